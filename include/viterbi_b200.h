@@ -1,0 +1,126 @@
+/*
+ * viterbi_b200.h -- C ABI of the B200 (sm_100a) batched Viterbi decoder.
+ *
+ * Drop-in CUDA backend for the hot path of williamyang98/ViterbiDecoderCpp:
+ *     reset -> update (add-compare-select) -> get_error -> chainback
+ * The reference is a header-only C++ library with no FFI of its own; each entry point below names the reference interface
+ * it replaces (paths relative to the reference tree).  The header-only C++ facade in include/viterbi_cuda/ wraps this ABI
+ * in the reference's template shapes; INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; every function returns 0 (VITB_OK) or a negative vitb_status;
+ * host pointers are never retained after return; a handle is single-threaded mutable state (like ViterbiDecoder_Core), make
+ * one per host thread / per GPU.  There is no CPU fallback: without a CUDA device every call fails with VITB_ERR_CUDA.
+ */
+#ifndef VITERBI_B200_H
+#define VITERBI_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VITB_MAX_R 16
+
+typedef enum vitb_status {
+    VITB_OK = 0,
+    VITB_ERR_ARG = -1,          /* violates a reference assert (symbol count not multiple of R, too many bits, bad state ...) */
+    VITB_ERR_UNSUPPORTED = -2,  /* (K, R, types) combination has no kernel (the analogue of Decoder::is_valid == false)      */
+    VITB_ERR_CUDA = -3,         /* CUDA runtime error; vitb_last_cuda_error() has the cudaError_t                             */
+    VITB_ERR_STATE = -4,        /* call protocol violated (e.g. chainback before enough update steps)                        */
+    VITB_ERR_NOMEM = -5
+} vitb_status;
+
+/* tie-break of the compare-select */
+#define VITB_TIE_SCALAR 0   /* decision = path0 >  path1  (viterbi_decoder_scalar.h:123-124) -- the parity oracle            */
+#define VITB_TIE_SIMD   1   /* decision = path0 >= path1  (x86/viterbi_decoder_avx_u16.h:112-115, SSE/NEON alike)            */
+
+/* Everything the reference passes to ViterbiBranchTable<K,R,soft_t>(G, high, low) (viterbi_branch_table.h:33-35) and
+ * ViterbiDecoder_Core<K,R,error_t,soft_t>(branch_table, config) (viterbi_decoder_core.h:170), flattened. */
+typedef struct vitb_params {
+    int32_t K;                          /* constraint length                                                     */
+    int32_t R;                          /* code rate 1/R                                                         */
+    uint32_t G[VITB_MAX_R];             /* generator polynomials, LSB = newest input bit (viterbi_branch_table.h:31) */
+    int32_t soft_bytes;                 /* 2: soft_t=int16_t, error_t=uint16_t;  1: soft_t=int8_t, error_t=uint8_t */
+    int32_t soft_decision_high;         /* viterbi_branch_table.h:34                                             */
+    int32_t soft_decision_low;          /* viterbi_branch_table.h:35                                             */
+    uint32_t soft_decision_max_error;   /* viterbi_decoder_config.h:14                                           */
+    uint32_t initial_start_error;       /* viterbi_decoder_config.h:15                                           */
+    uint32_t initial_non_start_error;   /* viterbi_decoder_config.h:16                                           */
+    uint32_t renormalisation_threshold; /* viterbi_decoder_config.h:17                                           */
+    int32_t tie_break;                  /* VITB_TIE_SCALAR (default) or VITB_TIE_SIMD                            */
+    int32_t device;                     /* CUDA device ordinal                                                   */
+} vitb_params;
+
+typedef struct vitb_decoder vitb_decoder;
+
+/* ---- lifetime: replaces constructing ViterbiBranchTable + ViterbiDecoder_Core (core.h:170-177) ---- */
+int vitb_create(const vitb_params* params, vitb_decoder** out);
+int vitb_destroy(vitb_decoder* h);
+/* 1 if a compiled kernel exists for (K, R, G, soft_bytes): the analogue of `static constexpr bool Decoder::is_valid` (scalar.h:25) */
+int vitb_is_supported(const vitb_params* params);
+
+/* ---- single-frame streaming API: same call protocol as the reference (examples/run_simple.cpp:76-80) ---- */
+int vitb_set_traceback_length(vitb_decoder* h, size_t traceback_length);        /* core.h:180-186 */
+int vitb_get_traceback_length(const vitb_decoder* h, size_t* traceback_length); /* core.h:189-192 */
+int vitb_reset(vitb_decoder* h, size_t starting_state);                         /* core.h:202-211 */
+/* Decoder::update<uint64_t>(base, symbols, N) (scalar.h:28-55): `symbols` is a HOST array of N soft_t, N % R == 0, may be called
+ * repeatedly; *accumulated_error receives the sum of renormalisation minima of THIS call. */
+int vitb_update(vitb_decoder* h, const void* symbols, size_t n_symbols, uint64_t* accumulated_error);
+int vitb_get_error(vitb_decoder* h, size_t end_state, uint32_t* error);         /* core.h:195-199 */
+int vitb_chainback(vitb_decoder* h, uint8_t* bytes_out, size_t total_bits, size_t end_state); /* core.h:214-236 */
+/* public fields of the reference Core, copied out on request */
+int vitb_get_current_decoded_bit(const vitb_decoder* h, size_t* bit);           /* m_current_decoded_bit  core.h:242 */
+int vitb_get_metrics(vitb_decoder* h, uint32_t* metrics_out /* [2^(K-1)] */);   /* m_metrics.get_old()    core.h:240 */
+/* m_decisions[first_row .. first_row+n_rows) in the reference layout: max(2^(K-1)/64,1) uint64 per row, bit s%64 of word s/64 (core.h:49-83) */
+int vitb_get_decisions(vitb_decoder* h, size_t first_row, size_t n_rows, uint64_t* rows_out);
+
+/* ---- batched API: n_frames independent frames per call, each decoded as reset(start) + update(all) + get_error(end) +
+ *      chainback(L, end).  symbols: [n_frames][row_stride] soft_t with (L+K-1)*R symbols used per frame (or the punctured
+ *      count, see vitb_set_puncture_schedule); row_stride = 0 means densely packed.
+ *      out_bytes [n_frames][ceil(L/8)], acc_error [n_frames] (sum of renormalisation minima), final_error [n_frames]
+ *      (get_error(end_state)); any output pointer may be NULL.  Total path error of a frame = acc_error + final_error
+ *      (examples/run_simple.cpp:78-79). ---- */
+typedef struct vitb_batch_opts {
+    size_t row_stride;       /* elements between frames in `symbols`; 0 = dense */
+    size_t starting_state;   /* reset(starting_state)          core.h:202 */
+    size_t end_state;        /* get_error / chainback end_state core.h:195,214 */
+} vitb_batch_opts;
+
+/* host pointers: H2D copy, kernels, D2H copy, synchronous */
+int vitb_decode_batch(vitb_decoder* h, const void* symbols, size_t n_frames, size_t total_bits, const vitb_batch_opts* opts,
+                      uint8_t* out_bytes, uint64_t* acc_error, uint32_t* final_error);
+/* device pointers on the handle's device, enqueued on `stream` (a cudaStream_t passed as void*; NULL = default stream), asynchronous */
+int vitb_decode_batch_dev(vitb_decoder* h, const void* d_symbols, size_t n_frames, size_t total_bits, const vitb_batch_opts* opts,
+                          uint8_t* d_out_bytes, uint64_t* d_acc_error, uint32_t* d_final_error, void* stream);
+
+/* Punctured input for the batched API (examples/helpers/puncture_code_helpers.h:17-55, schedule as in
+ * examples/run_punctured_decoder.cpp:248-286): keep[i] != 0 means depunctured symbol i was transmitted and is taken from the
+ * frame's row in order; keep[i] == 0 inserts `unpunctured_value`.  n_depunctured must equal (L+K-1)*R of later batch calls.
+ * n_depunctured = 0 clears the schedule. */
+int vitb_set_puncture_schedule(vitb_decoder* h, const uint8_t* keep, size_t n_depunctured, int32_t unpunctured_value);
+
+/* ---- multi-GPU: frames are independent, so the batch is split into contiguous ranges, one per handle (each created on its own
+ *      device), decoded concurrently from host memory; no collective.  ---- */
+int vitb_decode_batch_multi(vitb_decoder* const* handles, int n_handles, const void* symbols, size_t n_frames, size_t total_bits,
+                            const vitb_batch_opts* opts, uint8_t* out_bytes, uint64_t* acc_error, uint32_t* final_error);
+
+/* ---- introspection ---- */
+/* bytes of device workspace a batch call of this shape needs (decision rows dominate: n_frames * (L+K-1) * 2^(K-1)/8) */
+int vitb_workspace_bytes(const vitb_decoder* h, size_t n_frames, size_t total_bits, size_t* bytes);
+/* cap on the workspace; larger batches are processed in chunks of frames.  0 = default (set by VITB_WORKSPACE_MB or 24 GiB) */
+int vitb_set_workspace_limit(vitb_decoder* h, size_t bytes);
+/* number of CUDA kernels this handle has launched so far (bench.py reports it as gpu_launches) */
+int vitb_kernel_launch_count(const vitb_decoder* h, uint64_t* count);
+/* name of the ACS kernel variant selected for this handle, e.g. "acs_pair<K7,R2,u8,scalar-tie>" */
+const char* vitb_kernel_name(const vitb_decoder* h);
+int vitb_last_cuda_error(const vitb_decoder* h);
+const char* vitb_status_string(int status);
+/* library-level: number of CUDA devices visible (0 when no driver/GPU: every create then fails with VITB_ERR_CUDA) */
+int vitb_device_count(void);
+const char* vitb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITERBI_B200_H */

@@ -1,0 +1,37 @@
+"""shared helpers for the parity tests"""
+import numpy as np
+
+import viterbidecodercpp_b200 as v
+from viterbidecodercpp_b200 import synth
+from oracle_binding import OracleDecoder, MODE_SCALAR, MODE_SIMD
+
+CODE_BY_NAME = {c.name: c for c in v.COMMON_CODES}
+PAIR_CODES = ["Basic K=3 R=1/2", "Basic K=5 R=1/2", "Voyager", "LTE", "DAB Radio"]
+
+
+def make_cuda_decoder(code, decode_type, tie_break=0, device=0, config_override=None):
+    dc = v.DECODE_TYPES[decode_type](code.R)
+    cfg = config_override or dc.decoder_config
+    bt = v.ViterbiBranchTable(code.K, code.R, code.G, dc.soft_decision_high, dc.soft_decision_low, dc.soft_bytes)
+    return v.ViterbiDecoder_CUDA(bt, cfg, device=device, tie_break=tie_break), dc
+
+
+def make_oracle(code, decode_type, mode=MODE_SCALAR, config_override=None):
+    dc = v.DECODE_TYPES[decode_type](code.R)
+    c = config_override or dc.decoder_config
+    cfg = [c.soft_decision_max_error, c.initial_start_error, c.initial_non_start_error, c.renormalisation_threshold]
+    return OracleDecoder(code.K, code.R, code.G, dc.soft_bytes, dc.soft_decision_high, dc.soft_decision_low, cfg, mode), dc
+
+
+def frames(code, dc, n_frames, total_bits, EbNo_dB, seed):
+    return synth.make_frames(code.K, code.R, code.G, n_frames, total_bits, dc.soft_decision_high, dc.soft_decision_low,
+                             dc.soft_bytes, EbNo_dB, seed)
+
+
+def assert_batch_equal(got, want, what=""):
+    gb, ga, gf = got
+    wb, wa, wf = want
+    bad = np.nonzero((gb != wb).any(axis=1))[0]
+    assert bad.size == 0, f"{what}: decoded bytes differ in {bad.size}/{gb.shape[0]} frames (first {bad[:5]})"
+    assert (ga == wa).all(), f"{what}: accumulated error differs in {int((ga != wa).sum())} frames"
+    assert (gf == wf).all(), f"{what}: final error differs in {int((gf != wf).sum())} frames"

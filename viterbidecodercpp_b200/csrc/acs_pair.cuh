@@ -1,0 +1,262 @@
+// acs_pair.cuh -- add-compare-select for short constraint lengths (K <= 7): ONE THREAD OWNS A PAIR OF FRAMES.
+//
+// Replaces ViterbiDecoder_Scalar::update / bfly / renormalise (include/viterbi/viterbi_decoder_scalar.h:28-153) for a batch.
+//
+// Mapping (B200-first, not a port of the SIMD lanes of x86/viterbi_decoder_avx_u16.h):
+//   * a thread holds ALL 2^(K-1) path metrics of two frames in registers: register q = (metric of frame A | metric of frame
+//     B << 16).  Every packed instruction (VIADD.16x2, VIMNMX.U16x2) therefore works on two independent frames and the
+//     butterfly needs no lane permutation at all - no __shfl, no PRMT.
+//   * the state permutation new[2j], new[2j+1] <- old[j], old[j+N/2] is done IN PLACE: after n steps logical state s lives
+//     in register rotr^n(s) (rotation of the (K-1)-bit index).  The step loop is unrolled over the K-1 phases so every
+//     register index, branch pattern and decision bit position is a compile-time constant.
+//   * error_t = uint16_t runs natively in the 16-bit halves (wrapping adds == the scalar reference's modular error_t).
+//     error_t = uint8_t is held as metric << 8 in the same halves, so 16-bit wrap-around is exactly 8-bit wrap-around
+//     (sm_100a has no native u8x4 add/min: __vaddus4/__vminu4 expand to 7-8 instructions).
+//   * compare-select is one VIMNMX.U16x2 with two predicate outputs (a <= b per half).  decision = !(a <= b) = (a > b):
+//     the scalar reference's strict '>' tie-break (scalar.h:123-124).  TIE_SIMD swaps the operands to get the SSE/AVX/NEON
+//     rule decision = (min == path1) (x86/viterbi_decoder_avx_u16.h:112-115).
+//   * decision bits: each predicate feeds one predicated FADD into a float accumulator (2^23 + sum of 2^k): the FP32 pipe is
+//     otherwise idle, while VIADD.16x2 (FMA-heavy pipe) and VIMNMX (ALU pipe) are the busy ones
+//     (profiles/microbench/r01_pipe_rates_v2.txt).  The mantissa is the decision bit mask.
+//   * renormalisation: trigger is state 0's metric >= threshold (scalar.h:48), evaluated per frame half; minimum over the
+//     64 registers with VIMNMX3.U16x2; only the triggered half is shifted; the minimum is accumulated in a uint64.
+#pragma once
+#include <cstdint>
+#include <utility>
+#include <cuda_runtime.h>
+#include "vitb_code.cuh"
+
+namespace vitb {
+
+struct AcsPairParams {
+    const uint32_t* pk;     // packed symbols [n_blocks][n_steps][R][32 lanes]; word = (sA << SH) & 0xffff | (sB << SH) << 16
+    uint64_t* dec;          // decision rows  [n_blocks][dec_rows][64 frames]; bit s of the word = decision of state s (reference bit order)
+    uint16_t* metrics;      // [n_blocks*64][NS] path metrics in logical state order (raw error_t values); in (resume) / out
+    uint64_t* acc;          // [n_blocks*64] sum of renormalisation minima; in (resume) / out
+    uint32_t n_steps;       // trellis steps to run in this launch
+    uint32_t dec_rows;      // rows allocated per frame in `dec`
+    uint32_t dec_row0;      // row index of this launch's first step (= m_current_decoded_bit)
+    uint32_t resume;        // 0: metrics := initial errors (core.h:202-211); 1: continue from `metrics`/`acc`
+    uint32_t start_state;
+    uint32_t c_low2;        // per half: (-low) << SH                  -> e_low  = s - low   = S + c_low2
+    uint32_t c_high2;       // per half: (high << SH) + 1              -> e_high = high - s  = ~S + c_high2
+    uint32_t c_inv2;        // per half: (max_error - R*(high-low)) << SH  (0 for every reference preset)
+    uint32_t thr2;          // per half: renormalisation_threshold << SH
+    uint32_t init_start2;   // per half: initial_start_error << SH
+    uint32_t init_other2;   // per half: initial_non_start_error << SH
+};
+
+template <class C>
+struct PairShape {
+    static constexpr int NS = C::NS;
+    static constexpr int NACC = NS >= 16 ? NS / 16 : 1;   // float accumulators per frame (16 decision bits each)
+};
+
+// ---- branch metric table for one step ------------------------------------------------------------------------------
+// T[p] = sum_i (bit_i(p) ? e_high_i : e_low_i), all in packed wrapping u16 arithmetic.  e_low_i = s_i - low,
+// e_high_i = high - s_i: the value of |branch - s| for s in [low, high], which is the reference's documented input range
+// (scalar.h:30-34).
+template <int R, int LEVEL>
+struct TableBuild {
+    // fills T[0 .. 2^LEVEL) using symbols 0..LEVEL-1
+    template <int NP>
+    static __device__ __forceinline__ void run(uint32_t (&T)[NP], const uint32_t (&lo)[R], const uint32_t (&hi)[R]) {
+        TableBuild<R, LEVEL - 1>::run(T, lo, hi);
+        constexpr int H = 1 << (LEVEL - 1);
+#pragma unroll
+        for (int p = 0; p < H; p++) {
+            T[p + H] = __vadd2(T[p], hi[LEVEL - 1]);
+            T[p] = __vadd2(T[p], lo[LEVEL - 1]);
+        }
+    }
+};
+template <int R>
+struct TableBuild<R, 1> {
+    template <int NP>
+    static __device__ __forceinline__ void run(uint32_t (&T)[NP], const uint32_t (&lo)[R], const uint32_t (&hi)[R]) {
+        T[0] = lo[0];
+        T[1] = hi[0];
+    }
+};
+
+// ---- one butterfly, everything about its position known at compile time ----------------------------------------------
+template <class C, int PH, bool TIE_SIMD, int Q>
+__device__ __forceinline__ void bfly_at(uint32_t (&x)[C::NS], const uint32_t (&T)[C::NP], float (&fa)[2][PairShape<C>::NACC],
+                                        const uint32_t c_inv2, const bool consistent) {
+    constexpr int SB = C::SB;
+    constexpr int bit = 1 << (SB - 1 - PH);
+    if constexpr ((Q & bit) == 0) {
+        constexpr int q0 = Q, q1 = Q | bit;
+        constexpr uint32_t j = rotl_bits(uint32_t(q0), PH, SB);     // logical old state (leading bit 0)
+        static_assert(j < uint32_t(C::NS / 2), "butterfly index must have leading bit 0");
+        constexpr uint32_t pat = bfly_pattern<C>(j);
+        constexpr uint32_t ipat = (~pat) & uint32_t(C::NP - 1);
+        constexpr uint32_t s0 = 2 * j, s1 = 2 * j + 1;              // logical new states -> decision bit positions
+        const uint32_t tot = T[pat];
+        // inverted_error = max_error - total_error (scalar.h:107) = T[~pat] + c_inv2
+        const uint32_t inv = consistent ? T[ipat] : __vadd2(T[ipat], c_inv2);
+        const uint32_t a0 = __vadd2(x[q0], tot);   // (0|X) -> (X|0)   scalar.h:113
+        const uint32_t b0 = __vadd2(x[q1], inv);   // (1|X) -> (X|0)   scalar.h:114
+        const uint32_t a1 = __vadd2(x[q0], inv);   // (0|X) -> (X|1)   scalar.h:115
+        const uint32_t b1 = __vadd2(x[q1], tot);   // (1|X) -> (X|1)   scalar.h:116
+        bool h0, l0, h1, l1;
+        bool dA0, dB0, dA1, dB1;
+        if constexpr (!TIE_SIMD) {
+            x[q0] = __vibmin_u16x2(a0, b0, &h0, &l0);   // pred = (a <= b); decision = a > b
+            x[q1] = __vibmin_u16x2(a1, b1, &h1, &l1);
+            dA0 = !l0; dB0 = !h0; dA1 = !l1; dB1 = !h1;
+        } else {
+            x[q0] = __vibmin_u16x2(b0, a0, &h0, &l0);   // pred = (b <= a) = (min == b)
+            x[q1] = __vibmin_u16x2(b1, a1, &h1, &l1);
+            dA0 = l0; dB0 = h0; dA1 = l1; dB1 = h1;
+        }
+        constexpr int acc0 = int(s0 >> 4) % PairShape<C>::NACC, acc1 = int(s1 >> 4) % PairShape<C>::NACC;
+        constexpr float w0 = float(1u << (s0 & 15)), w1 = float(1u << (s1 & 15));
+        if (dA0) fa[0][acc0] += w0;
+        if (dB0) fa[1][acc0] += w0;
+        if (dA1) fa[0][acc1] += w1;
+        if (dB1) fa[1][acc1] += w1;
+    }
+}
+
+template <class C, int PH, bool TIE_SIMD, int... Qs>
+__device__ __forceinline__ void bfly_all(uint32_t (&x)[C::NS], const uint32_t (&T)[C::NP], float (&fa)[2][PairShape<C>::NACC],
+                                         const uint32_t c_inv2, const bool consistent, std::integer_sequence<int, Qs...>) {
+    (bfly_at<C, PH, TIE_SIMD, Qs>(x, T, fa, c_inv2, consistent), ...);
+}
+
+// minimum over all registers, per half
+template <int NS>
+__device__ __forceinline__ uint32_t packed_min(const uint32_t (&x)[NS]) {
+    uint32_t m = x[0];
+#pragma unroll
+    for (int q = 1; q + 1 < NS; q += 2) m = __vimin3_u16x2(m, x[q], x[q + 1]);
+    if (NS % 2 == 0) m = __vminu2(m, x[NS - 1]);
+    return m;
+}
+
+// ---- one trellis step at compile-time phase PH ---------------------------------------------------------------------
+template <class C, int SH, bool TIE_SIMD, bool CONSISTENT, int PH>
+__device__ __forceinline__ void acs_pair_step(uint32_t (&x)[C::NS], const uint32_t* sym /* R packed words */, const AcsPairParams& p,
+                                              uint64_t* dec_row /* this lane's 16 bytes of the row */, uint64_t& accA, uint64_t& accB) {
+    constexpr int R = C::R, NP = C::NP, NS = C::NS, NACC = PairShape<C>::NACC;
+    // per-symbol errors against low / high
+    uint32_t lo[R], hi[R];
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+        lo[i] = __vadd2(sym[i], p.c_low2);
+        hi[i] = __vadd2(~sym[i], p.c_high2);
+    }
+    uint32_t T[NP];
+    TableBuild<R, R>::run(T, lo, hi);
+
+    float fa[2][NACC];
+#pragma unroll
+    for (int a = 0; a < NACC; a++) { fa[0][a] = 8388608.f; fa[1][a] = 8388608.f; }
+
+    bfly_all<C, PH, TIE_SIMD>(x, T, fa, p.c_inv2, CONSISTENT, std::make_integer_sequence<int, NS>{});
+
+    // decision row: bit s of the 64-bit word = decision of logical state s (same bit order as core.h:49-83 / scalar.h:131-134)
+    uint32_t wA0, wA1 = 0, wB0, wB1 = 0;
+    if constexpr (NACC == 4) {
+        wA0 = __byte_perm(__float_as_uint(fa[0][0]), __float_as_uint(fa[0][1]), 0x5410);
+        wA1 = __byte_perm(__float_as_uint(fa[0][2]), __float_as_uint(fa[0][3]), 0x5410);
+        wB0 = __byte_perm(__float_as_uint(fa[1][0]), __float_as_uint(fa[1][1]), 0x5410);
+        wB1 = __byte_perm(__float_as_uint(fa[1][2]), __float_as_uint(fa[1][3]), 0x5410);
+    } else if constexpr (NACC == 2) {
+        wA0 = __byte_perm(__float_as_uint(fa[0][0]), __float_as_uint(fa[0][1]), 0x5410);
+        wB0 = __byte_perm(__float_as_uint(fa[1][0]), __float_as_uint(fa[1][1]), 0x5410);
+    } else {
+        wA0 = __float_as_uint(fa[0][0]) & 0xffffu;
+        wB0 = __float_as_uint(fa[1][0]) & 0xffffu;
+    }
+    *reinterpret_cast<uint4*>(dec_row) = make_uint4(wA0, wA1, wB0, wB1);
+
+    // renormalisation: "if (new_metric[0] >= renormalisation_threshold)" (scalar.h:48) - state 0 always sits in register 0
+    bool trigB, trigA;
+    (void)__vibmin_u16x2(p.thr2, x[0], &trigB, &trigA);      // pred = thr <= x0
+    if (trigA || trigB) {
+        const uint32_t m = packed_min<NS>(x);                   // scalar.h:140-146
+        const uint32_t mA = m & 0xffffu, mB = m >> 16;
+        const uint32_t sub = (trigA ? mA : 0u) | ((trigB ? mB : 0u) << 16);
+        const uint32_t neg = __vsub2(0u, sub);
+#pragma unroll
+        for (int q = 0; q < NS; q++) x[q] = __vadd2(x[q], neg);  // scalar.h:148-150
+        if (trigA) accA += uint64_t(mA >> SH);                  // scalar.h:49, 152
+        if (trigB) accB += uint64_t(mB >> SH);
+    }
+}
+
+template <class C, int SH, bool TIE_SIMD, bool CONSISTENT>
+struct PairRunner {
+    static constexpr int P = C::SB, R = C::R, NS = C::NS;
+
+    template <int PH>
+    static __device__ __forceinline__ bool phase(uint32_t (&x)[NS], const uint32_t (&cur)[P * R], const AcsPairParams& p, uint32_t t0,
+                                                 uint64_t* dec_lane, uint64_t& accA, uint64_t& accB) {
+        if (t0 + PH >= p.n_steps) return false;
+        acs_pair_step<C, SH, TIE_SIMD, CONSISTENT, PH>(x, &cur[PH * R], p, dec_lane + size_t(t0 + PH) * 64, accA, accB);
+        return true;
+    }
+
+    template <int... PHs>
+    static __device__ __forceinline__ void group(uint32_t (&x)[NS], const uint32_t (&cur)[P * R], const AcsPairParams& p, uint32_t t0,
+                                                 uint64_t* dec_lane, uint64_t& accA, uint64_t& accB, std::integer_sequence<int, PHs...>) {
+        (void)(phase<PHs>(x, cur, p, t0, dec_lane, accA, accB) && ...);
+    }
+};
+
+// grid = n_blocks (64 frames each), block = 32 threads (one warp; lane l owns frames 64*blk + 2l and 64*blk + 2l + 1)
+template <class C, int SH, bool TIE_SIMD, bool CONSISTENT>
+__global__ void __launch_bounds__(32) acs_pair_kernel(const AcsPairParams p) {
+    constexpr int P = C::SB, R = C::R, NS = C::NS, SB = C::SB;
+    using Run = PairRunner<C, SH, TIE_SIMD, CONSISTENT>;
+    const uint32_t lane = threadIdx.x, blk = blockIdx.x;
+    const size_t fA = size_t(blk) * 64 + 2 * lane, fB = fA + 1;
+
+    uint32_t x[NS];
+    uint64_t accA = 0, accB = 0;
+    if (p.resume) {
+        const uint16_t* mA = p.metrics + fA * NS;
+        const uint16_t* mB = p.metrics + fB * NS;
+#pragma unroll
+        for (int q = 0; q < NS; q++) x[q] = ((uint32_t(mA[q]) << SH) & 0xffffu) | (uint32_t(mB[q]) << (16 + SH));
+        accA = p.acc[fA];
+        accB = p.acc[fB];
+    } else {
+        const uint32_t s = p.start_state & uint32_t(NS - 1);       // core.h:209-210
+#pragma unroll
+        for (int q = 0; q < NS; q++) x[q] = (uint32_t(q) == s) ? p.init_start2 : p.init_other2;
+    }
+
+    const uint32_t* pk = p.pk + size_t(blk) * p.n_steps * R * 32 + lane;
+    uint64_t* dec_lane = p.dec + (size_t(blk) * p.dec_rows + p.dec_row0) * 64 + 2 * lane;
+
+    uint32_t cur[P * R], nxt[P * R];
+#pragma unroll
+    for (int k = 0; k < P * R; k++) nxt[k] = (uint32_t(k / R) < p.n_steps) ? __ldg(pk + size_t(k) * 32) : 0u;
+
+    for (uint32_t t0 = 0; t0 < p.n_steps; t0 += P) {
+#pragma unroll
+        for (int k = 0; k < P * R; k++) cur[k] = nxt[k];
+        const uint32_t tn = t0 + P;
+#pragma unroll
+        for (int k = 0; k < P * R; k++) nxt[k] = (tn + uint32_t(k / R) < p.n_steps) ? __ldg(pk + (size_t(tn) * R + k) * 32) : 0u;
+        Run::group(x, cur, p, t0, dec_lane, accA, accB, std::make_integer_sequence<int, P>{});
+    }
+
+    // after n steps logical state s sits in register rotr^n(s); write back in logical order (core.h:195-199 reads old_metrics[end_state])
+    const int ph = int(p.n_steps % uint32_t(P));
+    uint16_t* mA = p.metrics + fA * NS;
+    uint16_t* mB = p.metrics + fB * NS;
+#pragma unroll
+    for (int q = 0; q < NS; q++) {
+        const uint32_t s = rotl_bits(uint32_t(q), ph, SB);
+        mA[s] = uint16_t((x[q] & 0xffffu) >> SH);
+        mB[s] = uint16_t(x[q] >> (16 + SH));
+    }
+    p.acc[fA] = accA;
+    p.acc[fB] = accB;
+}
+
+}  // namespace vitb

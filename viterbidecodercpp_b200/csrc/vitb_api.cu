@@ -1,0 +1,540 @@
+// vitb_api.cu -- extern "C" boundary (include/viterbi_b200.h) and host-side orchestration of the decode pipeline
+//     ingest (layout + depuncture) -> ACS (add-compare-select, decision rows to HBM) -> traceback -> result gather
+// No CPU fallback: every entry point needs a CUDA device.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+#include <cuda_runtime.h>
+
+#include "../../include/viterbi_b200.h"
+#include "vitb_registry.h"
+#include "ingest.cuh"
+#include "traceback.cuh"
+
+namespace vitb {
+
+static const std::vector<KernelEntry>& registry() {
+    static std::vector<KernelEntry> entries;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        register_small(entries);
+        register_k7r2(entries);
+        register_k7r3(entries);
+        register_k7r4(entries);
+    });
+    return entries;
+}
+
+// per-frame results picked out of the workspace: acc_error[f], final_error[f] = metrics[f][end_state]
+__global__ void gather_results_kernel(const uint64_t* acc, const uint16_t* metrics, uint32_t n_states, uint32_t end_state,
+                                      uint32_t n_frames, uint64_t* acc_out, uint32_t* final_out) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_frames) return;
+    if (acc_out) acc_out[f] = acc[f];
+    if (final_out) final_out[f] = metrics[size_t(f) * n_states + end_state];
+}
+
+struct DeviceBuffer {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    cudaError_t reserve(size_t need) {
+        if (need <= bytes) return cudaSuccess;
+        if (ptr) { cudaFree(ptr); ptr = nullptr; bytes = 0; }
+        const cudaError_t e = cudaMalloc(&ptr, need);
+        if (e == cudaSuccess) bytes = need;
+        return e;
+    }
+    void release() { if (ptr) cudaFree(ptr); ptr = nullptr; bytes = 0; }
+};
+
+}  // namespace vitb
+
+using namespace vitb;
+
+struct vitb_decoder {
+    vitb_params prm{};
+    const KernelEntry* entry = nullptr;
+    int n_states = 0;
+    int sh = 0;
+    int last_cuda = 0;
+    uint64_t launches = 0;
+    size_t ws_limit = 0;
+    cudaStream_t stream = nullptr;    // owned; used by the host-pointer entry points
+    // batch workspace
+    DeviceBuffer pk, dec, metrics, acc, d_in, d_out, d_accout, d_finout, map;
+    size_t n_depunctured = 0, n_received = 0;
+    int32_t unpunctured_value = 0;
+    // single-frame streaming state (one 64-frame block, frame 0 is the user's)
+    DeviceBuffer s_pk, s_dec, s_metrics, s_acc, s_in, s_out;
+    size_t traceback_length = 0;
+    size_t current_decoded_bit = 0;
+};
+
+namespace {
+
+inline uint32_t pack2(uint32_t v) { return (v & 0xffffu) | (v << 16); }
+
+int cuda_fail(vitb_decoder* h, cudaError_t e) {
+    if (h) h->last_cuda = int(e);
+    return VITB_ERR_CUDA;
+}
+#define VITB_CUDA(h, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail((h), e__); } while (0)
+
+const KernelEntry* find_entry(const vitb_params& p) {
+    if (p.K < 2 || p.R < 1 || p.R > VITB_MAX_R) return nullptr;
+    const int sh = (p.soft_bytes == 1) ? 8 : 0;
+    const uint32_t span = uint32_t(p.soft_decision_high - p.soft_decision_low);
+    const uint32_t mask = (p.soft_bytes == 1) ? 0xffu : 0xffffu;
+    const int consistent = ((p.soft_decision_max_error & mask) == ((span * uint32_t(p.R)) & mask)) ? 1 : 0;
+    const uint32_t kmask = (p.K >= 32) ? 0xffffffffu : ((1u << p.K) - 1u);
+    for (const KernelEntry& e : registry()) {
+        if (e.K != p.K || e.R != p.R || e.sh != sh || e.tie != (p.tie_break ? 1 : 0) || e.consistent != consistent) continue;
+        bool same = true;
+        for (int i = 0; i < p.R; i++) same = same && ((e.G[i] & kmask) == (p.G[i] & kmask));
+        if (same) return &e;
+    }
+    return nullptr;
+}
+
+bool params_valid(const vitb_params& p) {
+    if (p.K < 2 || p.K > 24 || p.R < 1 || p.R > VITB_MAX_R) return false;
+    if (p.soft_bytes != 1 && p.soft_bytes != 2) return false;
+    if (p.soft_decision_high <= p.soft_decision_low) return false;        // viterbi_branch_table.h:43
+    const int lim = (p.soft_bytes == 1) ? 127 : 32767;
+    if (p.soft_decision_high > lim || p.soft_decision_low < -lim - 1) return false;
+    return true;
+}
+
+void fill_acs_params(const vitb_decoder* h, AcsPairParams& a) {
+    const vitb_params& p = h->prm;
+    const int sh = h->sh;
+    const uint32_t emask = (p.soft_bytes == 1) ? 0xffu : 0xffffu;
+    a.c_low2 = pack2(uint32_t(-p.soft_decision_low) << sh);
+    a.c_high2 = pack2((uint32_t(p.soft_decision_high) << sh) + 1u);
+    const uint32_t span = uint32_t(p.soft_decision_high - p.soft_decision_low);
+    a.c_inv2 = pack2(((p.soft_decision_max_error - span * uint32_t(p.R)) & emask) << sh);
+    a.thr2 = pack2((p.renormalisation_threshold & emask) << sh);
+    a.init_start2 = pack2((p.initial_start_error & emask) << sh);
+    a.init_other2 = pack2((p.initial_non_start_error & emask) << sh);
+}
+
+template <typename soft_t, int SH>
+cudaError_t launch_ingest(const IngestParams& ip, unsigned n_blocks, cudaStream_t s) {
+    dim3 grid((ip.n_sym + INGEST_TILE - 1) / INGEST_TILE, n_blocks);
+    ingest_pairs_kernel<soft_t, SH><<<grid, INGEST_TILE, 0, s>>>(ip);
+    return cudaGetLastError();
+}
+
+cudaError_t run_ingest(vitb_decoder* h, const IngestParams& ip, unsigned n_blocks, cudaStream_t s) {
+    h->launches++;
+    return (h->prm.soft_bytes == 1) ? launch_ingest<int8_t, 8>(ip, n_blocks, s) : launch_ingest<int16_t, 0>(ip, n_blocks, s);
+}
+
+size_t default_ws_limit() {
+    if (const char* e = getenv("VITB_WORKSPACE_MB")) {
+        const long long mb = atoll(e);
+        if (mb > 0) return size_t(mb) << 20;
+    }
+    return size_t(24) << 30;
+}
+
+// workspace bytes per 64-frame block for a frame of S steps
+size_t block_bytes(const vitb_decoder* h, size_t S) {
+    const size_t n_sym = S * size_t(h->prm.R);
+    return n_sym * 32 * 4                     // packed symbols
+         + S * 64 * 8                         // decision rows
+         + size_t(64) * h->n_states * 2       // metrics
+         + 64 * 8;                            // accumulated error
+}
+
+// One chunk of frames, everything on device, asynchronous on `s`.
+int decode_chunk_dev(vitb_decoder* h, const void* d_symbols, size_t row_stride, size_t n_frames, size_t L, size_t start_state,
+                     size_t end_state, uint8_t* d_out, uint64_t* d_acc, uint32_t* d_final, cudaStream_t s) {
+    const size_t K = size_t(h->prm.K), R = size_t(h->prm.R), S = L + K - 1, n_sym = S * R;
+    const unsigned n_blocks = unsigned((n_frames + 63) / 64);
+    VITB_CUDA(h, h->pk.reserve(size_t(n_blocks) * n_sym * 32 * 4));
+    VITB_CUDA(h, h->dec.reserve(size_t(n_blocks) * S * 64 * 8));
+    VITB_CUDA(h, h->metrics.reserve(size_t(n_blocks) * 64 * h->n_states * 2));
+    VITB_CUDA(h, h->acc.reserve(size_t(n_blocks) * 64 * 8));
+
+    IngestParams ip{};
+    ip.symbols = d_symbols; ip.row_stride = row_stride; ip.n_frames = uint32_t(n_frames); ip.n_sym = uint32_t(n_sym);
+    ip.depuncture_map = h->n_depunctured ? static_cast<const int32_t*>(h->map.ptr) : nullptr;
+    ip.fill_value = h->unpunctured_value; ip.pk = static_cast<uint32_t*>(h->pk.ptr);
+    VITB_CUDA(h, run_ingest(h, ip, n_blocks, s));
+
+    AcsPairParams a{};
+    fill_acs_params(h, a);
+    a.pk = static_cast<const uint32_t*>(h->pk.ptr); a.dec = static_cast<uint64_t*>(h->dec.ptr);
+    a.metrics = static_cast<uint16_t*>(h->metrics.ptr); a.acc = static_cast<uint64_t*>(h->acc.ptr);
+    a.n_steps = uint32_t(S); a.dec_rows = uint32_t(S); a.dec_row0 = 0; a.resume = 0; a.start_state = uint32_t(start_state);
+    h->launches++;
+    VITB_CUDA(h, h->entry->launch_pair(a, n_blocks, s));
+
+    if (d_out) {
+        TracebackParams t{};
+        t.dec = a.dec; t.dec_rows = a.dec_rows; t.n_frames = uint32_t(n_frames); t.total_bits = uint32_t(L);
+        t.state_bits = uint32_t(K - 1); t.end_state = uint32_t(end_state); t.out = d_out; t.out_stride = (L + 7) / 8;
+        h->launches++;
+        traceback_u64_kernel<32><<<unsigned((n_frames + 127) / 128), 128, 0, s>>>(t);
+        VITB_CUDA(h, cudaGetLastError());
+    }
+    if (d_acc || d_final) {
+        h->launches++;
+        gather_results_kernel<<<unsigned((n_frames + 255) / 256), 256, 0, s>>>(a.acc, a.metrics, uint32_t(h->n_states), uint32_t(end_state),
+                                                                              uint32_t(n_frames), d_acc, d_final);
+        VITB_CUDA(h, cudaGetLastError());
+    }
+    return VITB_OK;
+}
+
+int check_batch_args(const vitb_decoder* h, size_t n_frames, size_t L, const vitb_batch_opts* o, size_t* row_stride, size_t* start, size_t* end) {
+    if (!h) return VITB_ERR_ARG;
+    const size_t K = size_t(h->prm.K), R = size_t(h->prm.R), n_sym = (L + K - 1) * R;
+    if (n_frames == 0) return VITB_OK;
+    if (n_frames > 0x7fffffffu || L > 0x3fffffffu) return VITB_ERR_ARG;
+    size_t used = n_sym;
+    if (h->n_depunctured) {
+        if (h->n_depunctured != n_sym) return VITB_ERR_ARG;
+        used = h->n_received;
+    }
+    *row_stride = (o && o->row_stride) ? o->row_stride : used;
+    if (*row_stride < used) return VITB_ERR_ARG;
+    *start = o ? o->starting_state : 0;
+    *end = o ? o->end_state : 0;
+    if (*end >= size_t(h->n_states)) return VITB_ERR_ARG;      // core.h:196, 218
+    return VITB_OK;
+}
+
+size_t chunk_frames_for(const vitb_decoder* h, size_t L) {
+    const size_t S = L + size_t(h->prm.K) - 1;
+    const size_t limit = h->ws_limit ? h->ws_limit : default_ws_limit();
+    size_t blocks = limit / block_bytes(h, S);
+    if (blocks < 1) blocks = 1;
+    return blocks * 64;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vitb_version(void) { return "viterbi_b200 0.1 (sm_100a)"; }
+
+int vitb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* vitb_status_string(int status) {
+    switch (status) {
+    case VITB_OK: return "ok";
+    case VITB_ERR_ARG: return "invalid argument (violates a reference precondition)";
+    case VITB_ERR_UNSUPPORTED: return "no kernel compiled for this (K, R, G, types) combination";
+    case VITB_ERR_CUDA: return "CUDA runtime error";
+    case VITB_ERR_STATE: return "call protocol violated";
+    case VITB_ERR_NOMEM: return "out of memory";
+    default: return "unknown status";
+    }
+}
+
+int vitb_is_supported(const vitb_params* p) { return (p && params_valid(*p) && find_entry(*p)) ? 1 : 0; }
+
+int vitb_create(const vitb_params* p, vitb_decoder** out) {
+    if (!p || !out) return VITB_ERR_ARG;
+    *out = nullptr;
+    if (!params_valid(*p)) return VITB_ERR_ARG;
+    const KernelEntry* e = find_entry(*p);
+    if (!e) return VITB_ERR_UNSUPPORTED;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) { cudaGetLastError(); return VITB_ERR_CUDA; }
+    if (p->device < 0 || p->device >= n_dev) return VITB_ERR_ARG;
+    vitb_decoder* h = new (std::nothrow) vitb_decoder();
+    if (!h) return VITB_ERR_NOMEM;
+    h->prm = *p;
+    h->entry = e;
+    h->n_states = 1 << (p->K - 1);
+    h->sh = e->sh;
+    cudaError_t ce = cudaSetDevice(p->device);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (ce != cudaSuccess) { delete h; return VITB_ERR_CUDA; }
+    *out = h;
+    // core.h:175-176: the constructor leaves the decoder reset with traceback length 0
+    int rc = vitb_set_traceback_length(h, 0);
+    if (rc == VITB_OK) rc = vitb_reset(h, 0);
+    if (rc != VITB_OK) { vitb_destroy(h); *out = nullptr; }
+    return rc;
+}
+
+int vitb_destroy(vitb_decoder* h) {
+    if (!h) return VITB_OK;
+    cudaSetDevice(h->prm.device);
+    for (DeviceBuffer* b : {&h->pk, &h->dec, &h->metrics, &h->acc, &h->d_in, &h->d_out, &h->d_accout, &h->d_finout, &h->map,
+                            &h->s_pk, &h->s_dec, &h->s_metrics, &h->s_acc, &h->s_in, &h->s_out}) b->release();
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return VITB_OK;
+}
+
+int vitb_last_cuda_error(const vitb_decoder* h) { return h ? h->last_cuda : 0; }
+const char* vitb_kernel_name(const vitb_decoder* h) { return (h && h->entry) ? h->entry->name : ""; }
+int vitb_kernel_launch_count(const vitb_decoder* h, uint64_t* count) {
+    if (!h || !count) return VITB_ERR_ARG;
+    *count = h->launches;
+    return VITB_OK;
+}
+
+int vitb_set_workspace_limit(vitb_decoder* h, size_t bytes) {
+    if (!h) return VITB_ERR_ARG;
+    h->ws_limit = bytes;
+    return VITB_OK;
+}
+
+int vitb_workspace_bytes(const vitb_decoder* h, size_t n_frames, size_t L, size_t* bytes) {
+    if (!h || !bytes) return VITB_ERR_ARG;
+    const size_t S = L + size_t(h->prm.K) - 1;
+    *bytes = ((n_frames + 63) / 64) * block_bytes(h, S);
+    return VITB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// single-frame streaming API
+// ------------------------------------------------------------------------------------------------------------------
+int vitb_set_traceback_length(vitb_decoder* h, size_t traceback_length) {
+    if (!h) return VITB_ERR_ARG;
+    VITB_CUDA(h, cudaSetDevice(h->prm.device));
+    const size_t rows = traceback_length + size_t(h->prm.K - 1);       // core.h:181
+    const size_t old_rows = h->traceback_length + size_t(h->prm.K - 1);
+    if (!h->s_dec.ptr || rows != old_rows) {
+        // std::vector::resize keeps the leading rows (core.h:182): so do we
+        DeviceBuffer nb;
+        VITB_CUDA(h, nb.reserve(rows * 64 * 8));
+        VITB_CUDA(h, cudaMemsetAsync(nb.ptr, 0, rows * 64 * 8, h->stream));
+        if (h->s_dec.ptr) {
+            const size_t keep = rows < old_rows ? rows : old_rows;
+            VITB_CUDA(h, cudaMemcpyAsync(nb.ptr, h->s_dec.ptr, keep * 64 * 8, cudaMemcpyDeviceToDevice, h->stream));
+        }
+        VITB_CUDA(h, cudaStreamSynchronize(h->stream));
+        h->s_dec.release();
+        h->s_dec = nb;
+    }
+    h->traceback_length = traceback_length;
+    if (h->current_decoded_bit > rows) h->current_decoded_bit = rows;   // core.h:183-185
+    return VITB_OK;
+}
+
+int vitb_get_traceback_length(const vitb_decoder* h, size_t* traceback_length) {
+    if (!h || !traceback_length) return VITB_ERR_ARG;
+    *traceback_length = h->traceback_length;
+    return VITB_OK;
+}
+
+int vitb_get_current_decoded_bit(const vitb_decoder* h, size_t* bit) {
+    if (!h || !bit) return VITB_ERR_ARG;
+    *bit = h->current_decoded_bit;
+    return VITB_OK;
+}
+
+int vitb_reset(vitb_decoder* h, size_t starting_state) {
+    if (!h) return VITB_ERR_ARG;
+    VITB_CUDA(h, cudaSetDevice(h->prm.device));
+    const size_t ns = size_t(h->n_states);
+    const uint32_t emask = (h->prm.soft_bytes == 1) ? 0xffu : 0xffffu;
+    std::vector<uint16_t> m(64 * ns, uint16_t(h->prm.initial_non_start_error & emask));     // core.h:205-208
+    for (size_t f = 0; f < 64; f++) m[f * ns + (starting_state & (ns - 1))] = uint16_t(h->prm.initial_start_error & emask);  // core.h:209-210
+    VITB_CUDA(h, h->s_metrics.reserve(m.size() * 2));
+    VITB_CUDA(h, h->s_acc.reserve(64 * 8));
+    VITB_CUDA(h, cudaMemcpyAsync(h->s_metrics.ptr, m.data(), m.size() * 2, cudaMemcpyHostToDevice, h->stream));
+    VITB_CUDA(h, cudaMemsetAsync(h->s_acc.ptr, 0, 64 * 8, h->stream));
+    VITB_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->current_decoded_bit = 0;                                                             // core.h:203
+    return VITB_OK;
+}
+
+int vitb_update(vitb_decoder* h, const void* symbols, size_t n_symbols, uint64_t* accumulated_error) {
+    if (!h || (!symbols && n_symbols)) return VITB_ERR_ARG;
+    const size_t R = size_t(h->prm.R);
+    if (n_symbols % R) return VITB_ERR_ARG;                                                 // scalar.h:37
+    const size_t steps = n_symbols / R;
+    const size_t rows = h->traceback_length + size_t(h->prm.K - 1);
+    if (steps + h->current_decoded_bit > rows) return VITB_ERR_ARG;                         // scalar.h:38-40
+    if (accumulated_error) *accumulated_error = 0;
+    if (steps == 0) return VITB_OK;
+    VITB_CUDA(h, cudaSetDevice(h->prm.device));
+    const size_t sb = size_t(h->prm.soft_bytes);
+    VITB_CUDA(h, h->s_in.reserve(n_symbols * sb));
+    VITB_CUDA(h, h->s_pk.reserve(n_symbols * 32 * 4));
+    VITB_CUDA(h, cudaMemcpyAsync(h->s_in.ptr, symbols, n_symbols * sb, cudaMemcpyHostToDevice, h->stream));
+    VITB_CUDA(h, cudaMemsetAsync(h->s_acc.ptr, 0, 64 * 8, h->stream));       // update() returns the minima of THIS call (scalar.h:42)
+
+    IngestParams ip{};
+    ip.symbols = h->s_in.ptr; ip.row_stride = n_symbols; ip.n_frames = 1; ip.n_sym = uint32_t(n_symbols);
+    ip.depuncture_map = nullptr; ip.fill_value = 0; ip.pk = static_cast<uint32_t*>(h->s_pk.ptr);
+    VITB_CUDA(h, run_ingest(h, ip, 1, h->stream));
+
+    AcsPairParams a{};
+    fill_acs_params(h, a);
+    a.pk = static_cast<const uint32_t*>(h->s_pk.ptr); a.dec = static_cast<uint64_t*>(h->s_dec.ptr);
+    a.metrics = static_cast<uint16_t*>(h->s_metrics.ptr); a.acc = static_cast<uint64_t*>(h->s_acc.ptr);
+    a.n_steps = uint32_t(steps); a.dec_rows = uint32_t(rows); a.dec_row0 = uint32_t(h->current_decoded_bit);
+    a.resume = 1; a.start_state = 0;
+    h->launches++;
+    VITB_CUDA(h, h->entry->launch_pair(a, 1, h->stream));
+    uint64_t acc = 0;
+    VITB_CUDA(h, cudaMemcpyAsync(&acc, h->s_acc.ptr, 8, cudaMemcpyDeviceToHost, h->stream));
+    VITB_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->current_decoded_bit += steps;                                                        // scalar.h:52
+    if (accumulated_error) *accumulated_error = acc;
+    return VITB_OK;
+}
+
+int vitb_get_error(vitb_decoder* h, size_t end_state, uint32_t* error) {
+    if (!h || !error) return VITB_ERR_ARG;
+    if (end_state >= size_t(h->n_states)) return VITB_ERR_ARG;                              // core.h:196
+    VITB_CUDA(h, cudaSetDevice(h->prm.device));
+    uint16_t v = 0;
+    VITB_CUDA(h, cudaMemcpyAsync(&v, static_cast<uint16_t*>(h->s_metrics.ptr) + end_state, 2, cudaMemcpyDeviceToHost, h->stream));
+    VITB_CUDA(h, cudaStreamSynchronize(h->stream));
+    *error = v;
+    return VITB_OK;
+}
+
+int vitb_get_metrics(vitb_decoder* h, uint32_t* metrics_out) {
+    if (!h || !metrics_out) return VITB_ERR_ARG;
+    VITB_CUDA(h, cudaSetDevice(h->prm.device));
+    std::vector<uint16_t> m(size_t(h->n_states));
+    VITB_CUDA(h, cudaMemcpyAsync(m.data(), h->s_metrics.ptr, m.size() * 2, cudaMemcpyDeviceToHost, h->stream));
+    VITB_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (size_t i = 0; i < m.size(); i++) metrics_out[i] = m[i];
+    return VITB_OK;
+}
+
+int vitb_get_decisions(vitb_decoder* h, size_t first_row, size_t n_rows, uint64_t* rows_out) {
+    if (!h || (!rows_out && n_rows)) return VITB_ERR_ARG;
+    const size_t rows = h->traceback_length + size_t(h->prm.K - 1);
+    if (first_row + n_rows > rows) return VITB_ERR_ARG;
+    if (!n_rows) return VITB_OK;
+    VITB_CUDA(h, cudaSetDevice(h->prm.device));
+    // frame 0 of the block: one uint64 every 64 words
+    VITB_CUDA(h, cudaMemcpy2DAsync(rows_out, 8, static_cast<uint64_t*>(h->s_dec.ptr) + first_row * 64, 64 * 8, 8, n_rows,
+                                   cudaMemcpyDeviceToHost, h->stream));
+    VITB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return VITB_OK;
+}
+
+int vitb_chainback(vitb_decoder* h, uint8_t* bytes_out, size_t total_bits, size_t end_state) {
+    if (!h || (!bytes_out && total_bits)) return VITB_ERR_ARG;
+    if (h->traceback_length < total_bits) return VITB_ERR_ARG;                              // core.h:216
+    if (h->current_decoded_bit < size_t(h->prm.K - 1) + total_bits) return VITB_ERR_STATE;  // core.h:217
+    if (end_state >= size_t(h->n_states)) return VITB_ERR_ARG;                              // core.h:218
+    if (!total_bits) return VITB_OK;
+    VITB_CUDA(h, cudaSetDevice(h->prm.device));
+    const size_t nbytes = (total_bits + 7) / 8;
+    VITB_CUDA(h, h->s_out.reserve(nbytes));
+    TracebackParams t{};
+    t.dec = static_cast<const uint64_t*>(h->s_dec.ptr); t.dec_rows = uint32_t(h->traceback_length + size_t(h->prm.K - 1));
+    t.n_frames = 1; t.total_bits = uint32_t(total_bits); t.state_bits = uint32_t(h->prm.K - 1); t.end_state = uint32_t(end_state);
+    t.out = static_cast<uint8_t*>(h->s_out.ptr); t.out_stride = nbytes;
+    h->launches++;
+    traceback_u64_kernel<32><<<1, 128, 0, h->stream>>>(t);
+    VITB_CUDA(h, cudaGetLastError());
+    VITB_CUDA(h, cudaMemcpyAsync(bytes_out, h->s_out.ptr, nbytes, cudaMemcpyDeviceToHost, h->stream));
+    VITB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return VITB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// batched API
+// ------------------------------------------------------------------------------------------------------------------
+int vitb_set_puncture_schedule(vitb_decoder* h, const uint8_t* keep, size_t n_depunctured, int32_t unpunctured_value) {
+    if (!h) return VITB_ERR_ARG;
+    if (n_depunctured == 0) { h->n_depunctured = 0; h->n_received = 0; return VITB_OK; }
+    if (!keep || n_depunctured % size_t(h->prm.R) || n_depunctured > 0x7fffffffu) return VITB_ERR_ARG;
+    VITB_CUDA(h, cudaSetDevice(h->prm.device));
+    std::vector<int32_t> map(n_depunctured);
+    int32_t next = 0;
+    for (size_t i = 0; i < n_depunctured; i++) map[i] = keep[i] ? next++ : -1;               // puncture_code_helpers.h:29-45
+    VITB_CUDA(h, h->map.reserve(n_depunctured * 4));
+    VITB_CUDA(h, cudaMemcpy(h->map.ptr, map.data(), n_depunctured * 4, cudaMemcpyHostToDevice));
+    h->n_depunctured = n_depunctured;
+    h->n_received = size_t(next);
+    h->unpunctured_value = unpunctured_value;
+    return VITB_OK;
+}
+
+int vitb_decode_batch_dev(vitb_decoder* h, const void* d_symbols, size_t n_frames, size_t L, const vitb_batch_opts* opts,
+                          uint8_t* d_out, uint64_t* d_acc, uint32_t* d_final, void* stream) {
+    size_t row_stride = 0, start = 0, end = 0;
+    const int rc = check_batch_args(h, n_frames, L, opts, &row_stride, &start, &end);
+    if (rc != VITB_OK || n_frames == 0) return rc;
+    if (!d_symbols) return VITB_ERR_ARG;
+    VITB_CUDA(h, cudaSetDevice(h->prm.device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t chunk = chunk_frames_for(h, L), out_stride = (L + 7) / 8, sb = size_t(h->prm.soft_bytes);
+    for (size_t f0 = 0; f0 < n_frames; f0 += chunk) {
+        const size_t nf = (n_frames - f0 < chunk) ? (n_frames - f0) : chunk;
+        const int r = decode_chunk_dev(h, static_cast<const uint8_t*>(d_symbols) + f0 * row_stride * sb, row_stride, nf, L, start, end,
+                                       d_out ? d_out + f0 * out_stride : nullptr, d_acc ? d_acc + f0 : nullptr,
+                                       d_final ? d_final + f0 : nullptr, s);
+        if (r != VITB_OK) return r;
+    }
+    return VITB_OK;
+}
+
+int vitb_decode_batch(vitb_decoder* h, const void* symbols, size_t n_frames, size_t L, const vitb_batch_opts* opts,
+                      uint8_t* out_bytes, uint64_t* acc_error, uint32_t* final_error) {
+    size_t row_stride = 0, start = 0, end = 0;
+    const int rc = check_batch_args(h, n_frames, L, opts, &row_stride, &start, &end);
+    if (rc != VITB_OK || n_frames == 0) return rc;
+    if (!symbols) return VITB_ERR_ARG;
+    VITB_CUDA(h, cudaSetDevice(h->prm.device));
+    const size_t sb = size_t(h->prm.soft_bytes), out_stride = (L + 7) / 8;
+    const size_t in_bytes = n_frames * row_stride * sb;
+    VITB_CUDA(h, h->d_in.reserve(in_bytes));
+    if (out_bytes) VITB_CUDA(h, h->d_out.reserve(n_frames * out_stride));
+    if (acc_error) VITB_CUDA(h, h->d_accout.reserve(n_frames * 8));
+    if (final_error) VITB_CUDA(h, h->d_finout.reserve(n_frames * 4));
+    VITB_CUDA(h, cudaMemcpyAsync(h->d_in.ptr, symbols, in_bytes, cudaMemcpyHostToDevice, h->stream));
+    vitb_batch_opts o{}; o.row_stride = row_stride; o.starting_state = start; o.end_state = end;
+    const int r = vitb_decode_batch_dev(h, h->d_in.ptr, n_frames, L, &o, out_bytes ? static_cast<uint8_t*>(h->d_out.ptr) : nullptr,
+                                        acc_error ? static_cast<uint64_t*>(h->d_accout.ptr) : nullptr,
+                                        final_error ? static_cast<uint32_t*>(h->d_finout.ptr) : nullptr, h->stream);
+    if (r != VITB_OK) return r;
+    if (out_bytes) VITB_CUDA(h, cudaMemcpyAsync(out_bytes, h->d_out.ptr, n_frames * out_stride, cudaMemcpyDeviceToHost, h->stream));
+    if (acc_error) VITB_CUDA(h, cudaMemcpyAsync(acc_error, h->d_accout.ptr, n_frames * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (final_error) VITB_CUDA(h, cudaMemcpyAsync(final_error, h->d_finout.ptr, n_frames * 4, cudaMemcpyDeviceToHost, h->stream));
+    VITB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return VITB_OK;
+}
+
+int vitb_decode_batch_multi(vitb_decoder* const* handles, int n_handles, const void* symbols, size_t n_frames, size_t L,
+                            const vitb_batch_opts* opts, uint8_t* out_bytes, uint64_t* acc_error, uint32_t* final_error) {
+    if (!handles || n_handles < 1) return VITB_ERR_ARG;
+    for (int i = 0; i < n_handles; i++) if (!handles[i]) return VITB_ERR_ARG;
+    size_t row_stride = 0, start = 0, end = 0;
+    const int rc = check_batch_args(handles[0], n_frames, L, opts, &row_stride, &start, &end);
+    if (rc != VITB_OK || n_frames == 0) return rc;
+    const size_t sb = size_t(handles[0]->prm.soft_bytes), out_stride = (L + 7) / 8;
+    vitb_batch_opts o{}; o.row_stride = row_stride; o.starting_state = start; o.end_state = end;
+    std::vector<int> results(size_t(n_handles), VITB_OK);
+    std::vector<std::thread> threads;
+    for (int i = 0; i < n_handles; i++) {
+        // contiguous range of frames per device, no exchange between devices
+        const size_t f0 = n_frames * size_t(i) / size_t(n_handles), f1 = n_frames * size_t(i + 1) / size_t(n_handles);
+        if (f1 == f0) continue;
+        threads.emplace_back([&, i, f0, f1] {
+            results[size_t(i)] = vitb_decode_batch(handles[i], static_cast<const uint8_t*>(symbols) + f0 * row_stride * sb, f1 - f0, L, &o,
+                                                   out_bytes ? out_bytes + f0 * out_stride : nullptr, acc_error ? acc_error + f0 : nullptr,
+                                                   final_error ? final_error + f0 : nullptr);
+        });
+    }
+    for (auto& t : threads) t.join();
+    for (int r : results) if (r != VITB_OK) return r;
+    return VITB_OK;
+}
+
+}  // extern "C"
