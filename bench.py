@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 batched Viterbi decoder (contract: see the task statement / DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl ours|reference]
+
+A "step" is one pass of the hot path (ingest -> add-compare-select -> traceback -> result gather) over one batch of synthetic
+BPSK-over-AWGN frames (viterbidecodercpp_b200/synth.py, the statistics of the reference's run_snr_ber generator).
+`value`  : decoded Mbit/s with the soft symbols already resident in HBM (device-pointer C ABI call, CUDA events).
+`e2e`    : the same metric through the host-pointer C ABI call (pinned host buffers; H2D and D2H inside the timed region).
+`roofline`: the dominant kernel (add-compare-select) against the measured HBM copy bandwidth; `roofline_alu` against the
+            packed-integer issue roofline the north star names.
+`cpu_baseline`: the reference's own AVX2 decoder (oracle/_ref, built from /root/reference in place) on all host threads.
+--impl reference times that same CPU implementation as the reference arm.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+# BASELINE.json configs.  cfg2 is the configuration the metric is quoted on.
+WORKLOADS = {
+    "cfg1": dict(code="Voyager", decode="SOFT16", frames=16384, bits=1024, ebno=4.0, desc="K=7 R=1/2 u16 soft, 16384 x 1024-bit frames"),
+    "cfg2": dict(code="Voyager", decode="HARD8", frames=65536, bits=2048, ebno=4.0, desc="K=7 R=1/2 u8 hard, 65536 x 2048-bit frames"),
+    "cfg3": dict(code="CDMA IS-95A", decode="SOFT16", frames=16384, bits=8192, ebno=4.0, desc="K=9 R=1/2 u16 soft, 16384 x 8192-bit frames"),
+    "cfg4": dict(code="DAB Radio", decode="SOFT16", frames=65536, bits=768, ebno=0.0, punctured=True,
+                 desc="DAB K=7 R=1/4 u16 soft punctured FIC frames, 65536 x 768-bit"),
+    "cfg5": dict(code="Cassini", decode="SOFT16", frames=1024, bits=16384, ebno=4.0, desc="Cassini K=15 R=1/6 u16 soft, 1024 x 16384-bit frames"),
+    "run_simple": dict(code="DAB Radio", decode="SOFT16", frames=8192, bits=8192, ebno=None, desc="run_simple: K=7 R=1/4 u16 soft, 8192-bit frames"),
+}
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region (B200_PROFILING.md recipe)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_workload(name, seed, n_frames=None):
+    import viterbidecodercpp_b200 as v
+    from viterbidecodercpp_b200 import synth
+    w = dict(WORKLOADS[name])
+    if n_frames:
+        w["frames"] = n_frames
+    code = {c.name: c for c in v.COMMON_CODES}[w["code"]]
+    dc = v.DECODE_TYPES[w["decode"]](code.R)
+    F, L = w["frames"], w["bits"]
+    dtype = np.int8 if dc.soft_bytes == 1 else np.int16
+    keep = np.asarray(v.dab_fic_keep_schedule(), dtype=bool) if w.get("punctured") else None
+    # generated in slabs to bound host memory; every frame is unique
+    tx_all, sym_all = [], []
+    slab = 4096
+    for f0 in range(0, F, slab):
+        n = min(slab, F - f0)
+        tx, sym = synth.make_frames(code.K, code.R, code.G, n, L, dc.soft_decision_high, dc.soft_decision_low, dc.soft_bytes,
+                                    w["ebno"], seed + f0)
+        if keep is not None:
+            sym = synth.puncture(sym, keep)
+        tx_all.append(tx); sym_all.append(sym.astype(dtype))
+    w.update(code_obj=code, dc=dc, tx=np.concatenate(tx_all), sym=np.concatenate(sym_all), keep=keep)
+    return w
+
+
+def algorithmic_bytes(w):
+    """per frame  symbols read + decision bits written (ACS kernel)  [+ traceback read + output + 16 for the pipeline]"""
+    code, dc = w["code_obj"], w["dc"]
+    L, S, N = w["bits"], w["bits"] + code.K - 1, 1 << (code.K - 1)
+    sym = w["sym"].shape[1] * dc.soft_bytes
+    dec = S * N // 8
+    return {"acs_kernel": sym + dec + 16, "pipeline": sym + dec + 4 * L + L // 8 + 16, "acs_ops": S * N}
+
+
+def run_reference(args, rank):
+    """reference arm: the reference's AVX2 decoder (unmodified headers, oracle/_ref/libvitref.so) on all host threads"""
+    if rank != 0:
+        return
+    import oracle_binding as ob
+    if not ob.have_ref():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libvitref.so missing (built from /root/reference by oracle/Makefile)"}))
+        return
+    sample_frames = {"cfg2": 16384, "cfg1": 16384, "cfg3": 1024, "cfg4": 16384, "cfg5": 16, "run_simple": 1024}[args.workload]
+    w = build_workload(args.workload, 1234, sample_frames)
+    code, dc, cfg = w["code_obj"], w["dc"], w["dc"].decoder_config
+    sym = w["sym"]
+    if w["keep"] is not None:      # the reference decodes the depunctured stream (zeros inserted); same trellis work
+        dep = np.zeros((sym.shape[0], w["keep"].size), dtype=sym.dtype)
+        dep[:, w["keep"]] = sym
+        sym = dep
+    threads = ob.ref_lib().vitref_host_threads()
+    cfgl = [cfg.soft_decision_max_error, cfg.initial_start_error, cfg.initial_non_start_error, cfg.renormalisation_threshold]
+
+    def step():
+        r = ob.ref_decode(code.K, code.R, code.G, dc.soft_bytes, dc.soft_decision_high, dc.soft_decision_low, cfgl, ob.IMPL_AVX,
+                          sym, sym.shape[0], w["bits"], n_threads=threads)
+        return r["seconds"]
+    for _ in range(args.warmup):
+        step()
+    secs = [step() for _ in range(args.steps)]
+    t = float(np.mean(secs))
+    mbit = sym.shape[0] * w["bits"] / t / 1e6
+    ab = algorithmic_bytes(w)
+    line = {
+        "impl": "reference", "metric": "decoded_mbit_per_s", "value": mbit, "unit": "Mbit/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8" if dc.soft_bytes == 1 else "u16", "data": "synthetic BPSK/AWGN, fixed seed",
+        "config": {"workload": f"{args.workload}: {w['desc']}", "sample_frames": int(sym.shape[0])},
+        "acs_gops": sym.shape[0] * ab["acs_ops"] / t / 1e9,
+        "cpu_baseline": {"value": mbit, "unit": "Mbit/s", "cores": threads, "kind": "reference",
+                         "sample": f"{sym.shape[0]} frames x {w['bits']} bits per step, ViterbiDecoder_AVX_{'u8' if dc.soft_bytes == 1 else 'u16'}, reset+update+chainback, {threads} pinned threads"},
+        "e2e": {"value": mbit, "unit": "Mbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=0, help="override the number of frames (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import viterbidecodercpp_b200 as v
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- workload: every rank decodes a full batch of its own frames (weak scaling, no data-path collective) ----
+    w = build_workload(args.workload, 1234 + 1000003 * rank, args.frames or None)
+    code, dc = w["code_obj"], w["dc"]
+    F, L = w["sym"].shape[0], w["bits"]
+    bt = v.ViterbiBranchTable(code.K, code.R, code.G, dc.soft_decision_high, dc.soft_decision_low, dc.soft_bytes)
+    dec = v.ViterbiDecoder_CUDA(bt, dc.decoder_config, device=local_rank)
+    if w["keep"] is not None:
+        dec.set_puncture_schedule(w["keep"].astype(np.uint8), 0)
+    dec.set_profiling(True)
+
+    out_stride = (L + 7) // 8
+    h_sym = torch.from_numpy(w["sym"]).pin_memory()
+    h_out = torch.zeros((F, out_stride), dtype=torch.uint8).pin_memory()
+    h_acc = torch.zeros(F, dtype=torch.int64).pin_memory()
+    h_fin = torch.zeros(F, dtype=torch.int32).pin_memory()
+    d_sym = h_sym.to(dev)
+    d_out = torch.zeros((F, out_stride), dtype=torch.uint8, device=dev)
+    d_acc = torch.zeros(F, dtype=torch.int64, device=dev)
+    d_fin = torch.zeros(F, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+
+    def step_dev():
+        dec.decode_batch_dev(d_sym.data_ptr(), F, L, d_out.data_ptr(), d_acc.data_ptr(), d_fin.data_ptr(), stream=sptr,
+                             row_stride=w["sym"].shape[1])
+
+    def step_e2e():
+        dec.decode_batch_async(h_sym.data_ptr(), F, L, h_out.data_ptr(), h_acc.data_ptr(), h_fin.data_ptr(), stream=sptr,
+                               row_stride=w["sym"].shape[1])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, collect_stages=False):
+        stages = {"ingest": 0.0, "acs": 0.0, "traceback": 0.0, "gather": 0.0}
+        barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for k in range(steps):
+            evs[k][0].record(stream)
+            fn()
+            evs[k][1].record(stream)
+            if collect_stages:                 # per-stage CUDA events live inside the library, on the same stream
+                evs[k][1].synchronize()
+                for name, ms in dec.stage_ms().items():
+                    stages[name] += ms
+        barrier()
+        total_ms = sum(a.elapsed_time(b) for a, b in evs)
+        if world > 1:
+            t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)       # max over ranks
+            total_ms = float(t.item())
+        return total_ms / steps, {k2: v2 / steps for k2, v2 in stages.items()}
+
+    # ---- warm-up, then the timed region (inputs 269 MB >> 126 MB L2, so no explicit L2 flush is needed for cfg2) ----
+    for _ in range(args.warmup):
+        step_dev()
+    launches0 = dec.kernel_launch_count
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_step, stages = timed(step_dev, args.steps, collect_stages=True)
+    clocks = sampler.stop()
+    launches = dec.kernel_launch_count - launches0
+
+    # sanity: the timed path really decoded the frames (bit error rate against the transmitted bytes)
+    torch.cuda.synchronize()
+    ber = float(np.unpackbits(d_out.cpu().numpy() ^ w["tx"]).mean())
+
+    for _ in range(2):
+        step_e2e()
+    e2e_steps = max(3, min(args.steps, 10))
+    ms_e2e, _ = timed(step_e2e, e2e_steps)
+    torch.cuda.synchronize()
+    assert (h_out.numpy() == d_out.cpu().numpy()).all(), "host-pointer path and device-pointer path disagree"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, peak_src, sm_max = read_peaks()
+    ab = algorithmic_bytes(w)
+    bits_total = world * F * L
+    value = bits_total / (ms_step * 1e-3) / 1e6
+    acs_ms = stages["acs"]
+    achieved_gbs = F * ab["acs_kernel"] / (acs_ms * 1e-3) / 1e9
+    # packed-integer issue roofline (north star): 1.5 native packed instructions per ACS, 16 lanes/clk/SMSP for VIADD.16x2
+    # (measured: profiles/microbench/r01_pipe_rates_v2.txt), 148 SMs x 4 SMSPs, at the max SM clock
+    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    alu_peak_gacs = n_sm * 4 * 16 * sm_max * 1e6 / 1.5 / 1e9
+    acs_gacs = F * ab["acs_ops"] / (acs_ms * 1e-3) / 1e9
+    line = {
+        "metric": "decoded_mbit_per_s", "value": value, "unit": "Mbit/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8" if dc.soft_bytes == 1 else "u16", "data": "synthetic BPSK/AWGN (run_snr_ber statistics), fixed seed, every frame unique",
+        "config": {"workload": f"{args.workload}: {w['desc']}", "frames_per_gpu": F, "bits_per_frame": L, "EbNo_dB": w["ebno"],
+                   "l2": "inputs larger than L2 (no flush)" if w["sym"].nbytes > 130e6 else "inputs smaller than L2; decision buffer larger than L2",
+                   "kernel": dec.kernel_name, "parallelism": f"frames sharded over {world} GPU(s), no collective"},
+        "acs_gops": world * F * ab["acs_ops"] / (ms_step * 1e-3) / 1e9,
+        "ber": ber,
+        "stage_ms": stages,
+        "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+                     "traffic": None, "kernel": "add-compare-select", "peak_source": peak_src,
+                     "algorithmic_bytes_per_frame": ab["acs_kernel"], "kernel_ms": acs_ms},
+        "roofline_alu": {"bound": "packed-int16x2 issue (1.5 instr/ACS, 16 lanes/clk/SMSP)", "achieved": acs_gacs, "peak": alu_peak_gacs,
+                         "unit": "GACS/s", "frac": acs_gacs / alu_peak_gacs},
+        "pipeline_hbm": {"achieved": F * ab["pipeline"] / (ms_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": F * ab["pipeline"] / (ms_step * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_frame": ab["pipeline"]},
+        "e2e": {"value": bits_total / (ms_e2e * 1e-3) / 1e6, "unit": "Mbit/s", "h2d_bytes_per_step": int(w["sym"].nbytes),
+                "d2h_bytes_per_step": int(h_out.numel() + h_acc.numel() * 8 + h_fin.numel() * 4), "ms_per_step": ms_e2e},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            import oracle_binding as ob
+            if ob.have_ref():
+                cfg = dc.decoder_config
+                cfgl = [cfg.soft_decision_max_error, cfg.initial_start_error, cfg.initial_non_start_error, cfg.renormalisation_threshold]
+                sym = w["sym"]
+                if w["keep"] is not None:
+                    dep = np.zeros((sym.shape[0], w["keep"].size), dtype=sym.dtype)
+                    dep[:, w["keep"]] = sym
+                    sym = dep
+                threads = ob.ref_lib().vitref_host_threads()
+                n_cpu = min(sym.shape[0], {"cfg3": 2048, "cfg5": 32}.get(args.workload, sym.shape[0]))
+                t_total, reps = 0.0, 0
+                while t_total < 2.0 and reps < 50:          # >= 2 s of wall time on all threads (pinned)
+                    r = ob.ref_decode(code.K, code.R, code.G, dc.soft_bytes, dc.soft_decision_high, dc.soft_decision_low, cfgl,
+                                      ob.IMPL_AVX, sym[:n_cpu], n_cpu, L, n_threads=threads)
+                    t_total += r["seconds"]; reps += 1
+                cpu_mbit = reps * n_cpu * L / t_total / 1e6
+                mism = int((r["bytes"] != d_out.cpu().numpy()[:n_cpu]).any(axis=1).sum())
+                line["cpu_baseline"] = {"value": cpu_mbit, "unit": "Mbit/s", "cores": threads, "kind": "reference",
+                                        "sample": f"{n_cpu} frames x {L} bits, {reps} passes, reference AVX2 decoder (reset+update+chainback), "
+                                                  f"{threads} pinned threads; AVX2 tie-break differs from the scalar oracle: {mism}/{n_cpu} frames "
+                                                  f"decode to different bytes than the GPU (scalar-exact) output",
+                                        "acs_gops": reps * n_cpu * ab["acs_ops"] / t_total / 1e9}
+            else:
+                line["cpu_baseline"] = {"value": None, "unit": "Mbit/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
+        except Exception as e:   # the baseline must never take the bench line down with it
+            line["cpu_baseline"] = {"value": None, "unit": "Mbit/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

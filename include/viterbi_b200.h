@@ -94,6 +94,11 @@ int vitb_decode_batch(vitb_decoder* h, const void* symbols, size_t n_frames, siz
 int vitb_decode_batch_dev(vitb_decoder* h, const void* d_symbols, size_t n_frames, size_t total_bits, const vitb_batch_opts* opts,
                           uint8_t* d_out_bytes, uint64_t* d_acc_error, uint32_t* d_final_error, void* stream);
 
+/* pinned host pointers, enqueued on `stream`: H2D copy, kernels and D2H copies are all asynchronous; the caller synchronises the
+ * stream before reading the outputs (pageable memory works too but then the copies block). */
+int vitb_decode_batch_async(vitb_decoder* h, const void* symbols, size_t n_frames, size_t total_bits, const vitb_batch_opts* opts,
+                            uint8_t* out_bytes, uint64_t* acc_error, uint32_t* final_error, void* stream);
+
 /* Punctured input for the batched API (examples/helpers/puncture_code_helpers.h:17-55, schedule as in
  * examples/run_punctured_decoder.cpp:248-286): keep[i] != 0 means depunctured symbol i was transmitted and is taken from the
  * frame's row in order; keep[i] == 0 inserts `unpunctured_value`.  n_depunctured must equal (L+K-1)*R of later batch calls.
@@ -112,6 +117,11 @@ int vitb_workspace_bytes(const vitb_decoder* h, size_t n_frames, size_t total_bi
 int vitb_set_workspace_limit(vitb_decoder* h, size_t bytes);
 /* number of CUDA kernels this handle has launched so far (bench.py reports it as gpu_launches) */
 int vitb_kernel_launch_count(const vitb_decoder* h, uint64_t* count);
+/* stage profiling: when enabled every batch chunk records CUDA events around its stages on the launching stream.
+ * vitb_get_stage_ms (call after synchronising the stream) returns the summed device time of the LAST batch call per stage:
+ * ms[0] ingest, ms[1] add-compare-select, ms[2] traceback, ms[3] result gather. */
+int vitb_set_profiling(vitb_decoder* h, int enabled);
+int vitb_get_stage_ms(vitb_decoder* h, float ms[4]);
 /* name of the ACS kernel variant selected for this handle, e.g. "acs_pair<K7,R2,u8,scalar-tie>" */
 const char* vitb_kernel_name(const vitb_decoder* h);
 int vitb_last_cuda_error(const vitb_decoder* h);

@@ -1,0 +1,131 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol include/viterbi_b200.h declares, argument
+checking works without a GPU, nothing routes through a CPU fallback, and the multi-process sharding helpers behave (gloo, world 2)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import viterbidecodercpp_b200 as v
+from viterbidecodercpp_b200 import _lib, sharding
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SUPPORTED_K = {3, 5, 7}     # constraint lengths with compiled kernels so far (grows as kernel families land)
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "viterbi_b200.h")).read()
+    declared = set(re.findall(r"\b(vitb_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"vitb_status", "vitb_params", "vitb_decoder", "vitb_batch_opts"}
+    assert len(declared) >= 25
+    lib = C.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/viterbi_b200.h but not exported"
+    bound = {n for n, _, _ in _lib.API}
+    assert declared == bound, f"python binding out of sync: {declared ^ bound}"
+
+
+def test_library_is_built_for_sm_100a():
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_is_supported_matches_catalogue():
+    lib = v.load_library()
+    for code in v.COMMON_CODES:
+        for name, factory in v.DECODE_TYPES.items():
+            dc = factory(code.R)
+            bt = v.ViterbiBranchTable(code.K, code.R, code.G, dc.soft_decision_high, dc.soft_decision_low, dc.soft_bytes)
+            assert v.ViterbiDecoder_CUDA.is_valid(bt, dc.decoder_config) == (code.K in SUPPORTED_K), (code.name, name)
+    bt = v.ViterbiBranchTable(7, 2, [0o133, 0o165], 127, -127)
+    assert not v.ViterbiDecoder_CUDA.is_valid(bt, v.get_soft16_decoding_config(2).decoder_config)
+    assert lib.vitb_version().startswith(b"viterbi_b200")
+
+
+@pytest.mark.skipif(v.load_library().vitb_device_count() > 0, reason="only meaningful on a box without a GPU")
+def test_no_cpu_fallback_without_a_gpu():
+    dc = v.get_soft16_decoding_config(2)
+    bt = v.ViterbiBranchTable(7, 2, [109, 79], 127, -127)
+    with pytest.raises(v.ViterbiError) as e:
+        v.ViterbiDecoder_CUDA(bt, dc.decoder_config)
+    assert e.value.status == _lib.VITB_ERR_CUDA
+
+
+def test_create_argument_checking():
+    lib = v.load_library()
+    p = _lib.vitb_params()
+    h = C.c_void_p()
+    p.K, p.R, p.soft_bytes, p.soft_decision_high, p.soft_decision_low = 7, 2, 3, 127, -127
+    assert lib.vitb_create(C.byref(p), C.byref(h)) == _lib.VITB_ERR_ARG          # soft_bytes must be 1 or 2
+    p.soft_bytes, p.soft_decision_high, p.soft_decision_low = 2, -5, 5
+    assert lib.vitb_create(C.byref(p), C.byref(h)) == _lib.VITB_ERR_ARG          # high must exceed low (viterbi_branch_table.h:43)
+    p.soft_decision_high, p.soft_decision_low = 127, -127
+    p.G[0], p.G[1] = 1, 3
+    assert lib.vitb_create(C.byref(p), C.byref(h)) == _lib.VITB_ERR_UNSUPPORTED  # uncatalogued polynomials
+    assert lib.vitb_create(None, C.byref(h)) == _lib.VITB_ERR_ARG
+    assert lib.vitb_status_string(_lib.VITB_ERR_UNSUPPORTED)
+
+
+def test_branch_table_mirror_matches_reference_definition():
+    """BT[i][j] = parity((j << 1) & G[i]) ? high : low  (viterbi_branch_table.h:45-54), checked against the oracle's table"""
+    import oracle_binding as ob
+    for code in v.COMMON_CODES:
+        bt = v.ViterbiBranchTable(code.K, code.R, code.G, 127, -127)
+        ora = ob.OracleDecoder(code.K, code.R, code.G, 2, 127, -127, [0, 0, 0, 0])
+        ref = np.zeros((code.R, bt.NUMSTATES), dtype=np.int32)
+        ora.L.vo_branch_table(ora.h, ref.ctypes.data)
+        for i in range(code.R):
+            assert (bt[i] == ref[i]).all()
+
+
+def test_presets_match_reference_values():
+    """SOFT16 R=2: 508/0/2540/62995, R=4: 1016/0/5080/60455, R=6: 1524/0/7620/57915; HARD8 R=2: 4/0/12/243"""
+    def tup(dc):
+        c = dc.decoder_config
+        return (c.soft_decision_max_error, c.initial_start_error, c.initial_non_start_error, c.renormalisation_threshold)
+    assert tup(v.get_soft16_decoding_config(2)) == (508, 0, 2540, 62995)
+    assert tup(v.get_soft16_decoding_config(4)) == (1016, 0, 5080, 60455)
+    assert tup(v.get_soft16_decoding_config(6)) == (1524, 0, 7620, 57915)
+    assert tup(v.get_hard8_decoding_config(2)) == (4, 0, 12, 243)
+    assert tup(v.get_soft8_decoding_config(2)) == (12, 0, 24, 231)
+
+
+def test_frame_range_partitions_exactly():
+    for world in (1, 2, 3, 4, 8):
+        for n in (0, 1, 7, 64, 65536, 1000003):
+            spans = [sharding.frame_range(r, world, n) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import torch, torch.distributed as dist
+from viterbidecodercpp_b200 import sharding
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+f0, f1 = sharding.frame_range(rank, world, 1001)
+total = sharding.sum_over_ranks(f1 - f0)
+worst = sharding.max_over_ranks(10.0 + rank)
+dist.barrier()
+assert total == 1001 and worst == 10.0 + world - 1, (total, worst)
+if rank == 0:
+    print("OK", int(total), worst)
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_gloo_sharding(tmp_path):
+    """the N>1 plumbing bench.py uses (shard frames, barrier, max over ranks) with world_size 2 on CPU"""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", str(script), ROOT], capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "OK 1001 11.0" in r.stdout

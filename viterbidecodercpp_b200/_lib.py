@@ -42,11 +42,14 @@ API = [
     ("vitb_get_decisions", C.c_int, [_P, C.c_size_t, C.c_size_t, _P]),
     ("vitb_decode_batch", C.c_int, [_P, _P, C.c_size_t, C.c_size_t, C.POINTER(vitb_batch_opts), _P, _P, _P]),
     ("vitb_decode_batch_dev", C.c_int, [_P, _P, C.c_size_t, C.c_size_t, C.POINTER(vitb_batch_opts), _P, _P, _P, _P]),
+    ("vitb_decode_batch_async", C.c_int, [_P, _P, C.c_size_t, C.c_size_t, C.POINTER(vitb_batch_opts), _P, _P, _P, _P]),
     ("vitb_set_puncture_schedule", C.c_int, [_P, _P, C.c_size_t, C.c_int32]),
     ("vitb_decode_batch_multi", C.c_int, [C.POINTER(_P), C.c_int, _P, C.c_size_t, C.c_size_t, C.POINTER(vitb_batch_opts), _P, _P, _P]),
     ("vitb_workspace_bytes", C.c_int, [_P, C.c_size_t, C.c_size_t, C.POINTER(C.c_size_t)]),
     ("vitb_set_workspace_limit", C.c_int, [_P, C.c_size_t]),
     ("vitb_kernel_launch_count", C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    ("vitb_set_profiling", C.c_int, [_P, C.c_int]),
+    ("vitb_get_stage_ms", C.c_int, [_P, C.POINTER(C.c_float * 4)]),
     ("vitb_kernel_name", C.c_char_p, [_P]),
     ("vitb_last_cuda_error", C.c_int, [_P]),
     ("vitb_status_string", C.c_char_p, [C.c_int]),

@@ -33,6 +33,7 @@ struct AcsPairParams {
     uint64_t* dec;          // decision rows  [n_blocks][dec_rows][64 frames]; bit s of the word = decision of state s (reference bit order)
     uint16_t* metrics;      // [n_blocks*64][NS] path metrics in logical state order (raw error_t values); in (resume) / out
     uint64_t* acc;          // [n_blocks*64] sum of renormalisation minima; in (resume) / out
+    uint32_t n_blocks;      // 64-frame blocks
     uint32_t n_steps;       // trellis steps to run in this launch
     uint32_t dec_rows;      // rows allocated per frame in `dec`
     uint32_t dec_row0;      // row index of this launch's first step (= m_current_decoded_bit)
@@ -206,12 +207,15 @@ struct PairRunner {
     }
 };
 
-// grid = n_blocks (64 frames each), block = 32 threads (one warp; lane l owns frames 64*blk + 2l and 64*blk + 2l + 1)
+// One warp per 64-frame block (lane l owns frames 64*blk + 2l and 64*blk + 2l + 1); PAIR_WARPS warps per CTA so that the warps of
+// a CTA land on all four SM sub-partitions evenly.  grid = ceil(n_blocks / PAIR_WARPS).
+constexpr int PAIR_WARPS = 4;
 template <class C, int SH, bool TIE_SIMD, bool CONSISTENT>
-__global__ void __launch_bounds__(32) acs_pair_kernel(const AcsPairParams p) {
+__global__ void __launch_bounds__(32 * PAIR_WARPS) acs_pair_kernel(const AcsPairParams p) {
     constexpr int P = C::SB, R = C::R, NS = C::NS, SB = C::SB;
     using Run = PairRunner<C, SH, TIE_SIMD, CONSISTENT>;
-    const uint32_t lane = threadIdx.x, blk = blockIdx.x;
+    const uint32_t lane = threadIdx.x & 31, blk = blockIdx.x * PAIR_WARPS + (threadIdx.x >> 5);
+    if (blk >= p.n_blocks) return;
     const size_t fA = size_t(blk) * 64 + 2 * lane, fB = fA + 1;
 
     uint32_t x[NS];

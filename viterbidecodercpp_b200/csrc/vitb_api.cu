@@ -72,6 +72,10 @@ struct vitb_decoder {
     DeviceBuffer s_pk, s_dec, s_metrics, s_acc, s_in, s_out;
     size_t traceback_length = 0;
     size_t current_decoded_bit = 0;
+    // stage profiling
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev;      // 5 events per chunk of the last batch call
+    size_t ev_used = 0;
 };
 
 namespace {
@@ -151,6 +155,17 @@ size_t block_bytes(const vitb_decoder* h, size_t S) {
          + 64 * 8;                            // accumulated error
 }
 
+cudaError_t mark(vitb_decoder* h, cudaStream_t s) {
+    if (!h->profiling) return cudaSuccess;
+    if (h->ev_used == h->ev.size()) {
+        cudaEvent_t e;
+        const cudaError_t r = cudaEventCreate(&e);
+        if (r != cudaSuccess) return r;
+        h->ev.push_back(e);
+    }
+    return cudaEventRecord(h->ev[h->ev_used++], s);
+}
+
 // One chunk of frames, everything on device, asynchronous on `s`.
 int decode_chunk_dev(vitb_decoder* h, const void* d_symbols, size_t row_stride, size_t n_frames, size_t L, size_t start_state,
                      size_t end_state, uint8_t* d_out, uint64_t* d_acc, uint32_t* d_final, cudaStream_t s) {
@@ -165,7 +180,9 @@ int decode_chunk_dev(vitb_decoder* h, const void* d_symbols, size_t row_stride, 
     ip.symbols = d_symbols; ip.row_stride = row_stride; ip.n_frames = uint32_t(n_frames); ip.n_sym = uint32_t(n_sym);
     ip.depuncture_map = h->n_depunctured ? static_cast<const int32_t*>(h->map.ptr) : nullptr;
     ip.fill_value = h->unpunctured_value; ip.pk = static_cast<uint32_t*>(h->pk.ptr);
+    VITB_CUDA(h, mark(h, s));
     VITB_CUDA(h, run_ingest(h, ip, n_blocks, s));
+    VITB_CUDA(h, mark(h, s));
 
     AcsPairParams a{};
     fill_acs_params(h, a);
@@ -174,6 +191,7 @@ int decode_chunk_dev(vitb_decoder* h, const void* d_symbols, size_t row_stride, 
     a.n_steps = uint32_t(S); a.dec_rows = uint32_t(S); a.dec_row0 = 0; a.resume = 0; a.start_state = uint32_t(start_state);
     h->launches++;
     VITB_CUDA(h, h->entry->launch_pair(a, n_blocks, s));
+    VITB_CUDA(h, mark(h, s));
 
     if (d_out) {
         TracebackParams t{};
@@ -183,12 +201,14 @@ int decode_chunk_dev(vitb_decoder* h, const void* d_symbols, size_t row_stride, 
         traceback_u64_kernel<32><<<unsigned((n_frames + 127) / 128), 128, 0, s>>>(t);
         VITB_CUDA(h, cudaGetLastError());
     }
+    VITB_CUDA(h, mark(h, s));
     if (d_acc || d_final) {
         h->launches++;
         gather_results_kernel<<<unsigned((n_frames + 255) / 256), 256, 0, s>>>(a.acc, a.metrics, uint32_t(h->n_states), uint32_t(end_state),
                                                                               uint32_t(n_frames), d_acc, d_final);
         VITB_CUDA(h, cudaGetLastError());
     }
+    VITB_CUDA(h, mark(h, s));
     return VITB_OK;
 }
 
@@ -275,6 +295,7 @@ int vitb_destroy(vitb_decoder* h) {
     cudaSetDevice(h->prm.device);
     for (DeviceBuffer* b : {&h->pk, &h->dec, &h->metrics, &h->acc, &h->d_in, &h->d_out, &h->d_accout, &h->d_finout, &h->map,
                             &h->s_pk, &h->s_dec, &h->s_metrics, &h->s_acc, &h->s_in, &h->s_out}) b->release();
+    for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return VITB_OK;
@@ -474,6 +495,7 @@ int vitb_decode_batch_dev(vitb_decoder* h, const void* d_symbols, size_t n_frame
     if (!d_symbols) return VITB_ERR_ARG;
     VITB_CUDA(h, cudaSetDevice(h->prm.device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    h->ev_used = 0;
     const size_t chunk = chunk_frames_for(h, L), out_stride = (L + 7) / 8, sb = size_t(h->prm.soft_bytes);
     for (size_t f0 = 0; f0 < n_frames; f0 += chunk) {
         const size_t nf = (n_frames - f0 < chunk) ? (n_frames - f0) : chunk;
@@ -485,29 +507,59 @@ int vitb_decode_batch_dev(vitb_decoder* h, const void* d_symbols, size_t n_frame
     return VITB_OK;
 }
 
-int vitb_decode_batch(vitb_decoder* h, const void* symbols, size_t n_frames, size_t L, const vitb_batch_opts* opts,
-                      uint8_t* out_bytes, uint64_t* acc_error, uint32_t* final_error) {
+int vitb_decode_batch_async(vitb_decoder* h, const void* symbols, size_t n_frames, size_t L, const vitb_batch_opts* opts,
+                            uint8_t* out_bytes, uint64_t* acc_error, uint32_t* final_error, void* stream) {
     size_t row_stride = 0, start = 0, end = 0;
     const int rc = check_batch_args(h, n_frames, L, opts, &row_stride, &start, &end);
     if (rc != VITB_OK || n_frames == 0) return rc;
     if (!symbols) return VITB_ERR_ARG;
     VITB_CUDA(h, cudaSetDevice(h->prm.device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t sb = size_t(h->prm.soft_bytes), out_stride = (L + 7) / 8;
     const size_t in_bytes = n_frames * row_stride * sb;
     VITB_CUDA(h, h->d_in.reserve(in_bytes));
     if (out_bytes) VITB_CUDA(h, h->d_out.reserve(n_frames * out_stride));
     if (acc_error) VITB_CUDA(h, h->d_accout.reserve(n_frames * 8));
     if (final_error) VITB_CUDA(h, h->d_finout.reserve(n_frames * 4));
-    VITB_CUDA(h, cudaMemcpyAsync(h->d_in.ptr, symbols, in_bytes, cudaMemcpyHostToDevice, h->stream));
+    VITB_CUDA(h, cudaMemcpyAsync(h->d_in.ptr, symbols, in_bytes, cudaMemcpyHostToDevice, s));
     vitb_batch_opts o{}; o.row_stride = row_stride; o.starting_state = start; o.end_state = end;
     const int r = vitb_decode_batch_dev(h, h->d_in.ptr, n_frames, L, &o, out_bytes ? static_cast<uint8_t*>(h->d_out.ptr) : nullptr,
                                         acc_error ? static_cast<uint64_t*>(h->d_accout.ptr) : nullptr,
-                                        final_error ? static_cast<uint32_t*>(h->d_finout.ptr) : nullptr, h->stream);
+                                        final_error ? static_cast<uint32_t*>(h->d_finout.ptr) : nullptr, s);
     if (r != VITB_OK) return r;
-    if (out_bytes) VITB_CUDA(h, cudaMemcpyAsync(out_bytes, h->d_out.ptr, n_frames * out_stride, cudaMemcpyDeviceToHost, h->stream));
-    if (acc_error) VITB_CUDA(h, cudaMemcpyAsync(acc_error, h->d_accout.ptr, n_frames * 8, cudaMemcpyDeviceToHost, h->stream));
-    if (final_error) VITB_CUDA(h, cudaMemcpyAsync(final_error, h->d_finout.ptr, n_frames * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (out_bytes) VITB_CUDA(h, cudaMemcpyAsync(out_bytes, h->d_out.ptr, n_frames * out_stride, cudaMemcpyDeviceToHost, s));
+    if (acc_error) VITB_CUDA(h, cudaMemcpyAsync(acc_error, h->d_accout.ptr, n_frames * 8, cudaMemcpyDeviceToHost, s));
+    if (final_error) VITB_CUDA(h, cudaMemcpyAsync(final_error, h->d_finout.ptr, n_frames * 4, cudaMemcpyDeviceToHost, s));
+    return VITB_OK;
+}
+
+int vitb_decode_batch(vitb_decoder* h, const void* symbols, size_t n_frames, size_t L, const vitb_batch_opts* opts,
+                      uint8_t* out_bytes, uint64_t* acc_error, uint32_t* final_error) {
+    if (!h) return VITB_ERR_ARG;
+    const int r = vitb_decode_batch_async(h, symbols, n_frames, L, opts, out_bytes, acc_error, final_error, h->stream);
+    if (r != VITB_OK) return r;
     VITB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return VITB_OK;
+}
+
+int vitb_set_profiling(vitb_decoder* h, int enabled) {
+    if (!h) return VITB_ERR_ARG;
+    h->profiling = enabled != 0;
+    h->ev_used = 0;
+    return VITB_OK;
+}
+
+int vitb_get_stage_ms(vitb_decoder* h, float ms[4]) {
+    if (!h || !ms) return VITB_ERR_ARG;
+    for (int k = 0; k < 4; k++) ms[k] = 0.f;
+    VITB_CUDA(h, cudaSetDevice(h->prm.device));
+    for (size_t c = 0; c + 5 <= h->ev_used; c += 5) {
+        for (int k = 0; k < 4; k++) {
+            float t = 0.f;
+            VITB_CUDA(h, cudaEventElapsedTime(&t, h->ev[c + k], h->ev[c + k + 1]));
+            ms[k] += t;
+        }
+    }
     return VITB_OK;
 }
 

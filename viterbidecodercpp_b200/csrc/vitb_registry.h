@@ -24,7 +24,9 @@ struct KernelEntry {
 
 template <class C, int SH, bool TIE_SIMD, bool CONSISTENT>
 cudaError_t launch_pair(const AcsPairParams& p, unsigned n_blocks, cudaStream_t s) {
-    acs_pair_kernel<C, SH, TIE_SIMD, CONSISTENT><<<n_blocks, 32, 0, s>>>(p);
+    AcsPairParams q = p;
+    q.n_blocks = n_blocks;
+    acs_pair_kernel<C, SH, TIE_SIMD, CONSISTENT><<<(n_blocks + PAIR_WARPS - 1) / PAIR_WARPS, 32 * PAIR_WARPS, 0, s>>>(q);
     return cudaGetLastError();
 }
 

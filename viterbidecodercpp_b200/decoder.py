@@ -192,6 +192,21 @@ class ViterbiDecoder_CUDA:
         _check(self._L.vitb_decode_batch_dev(self._h, d_symbols, n_frames, total_bits, C.byref(o), d_out, d_acc, d_final, stream),
                "decode_batch_dev")
 
+    def decode_batch_async(self, h_symbols, n_frames, total_bits, h_out, h_acc, h_final, stream=0, row_stride=0, starting_state=0, end_state=0):
+        """raw (pinned) HOST pointers (ints); H2D, kernels and D2H are enqueued on `stream`"""
+        o = self._opts(row_stride, starting_state, end_state)
+        _check(self._L.vitb_decode_batch_async(self._h, h_symbols, n_frames, total_bits, C.byref(o), h_out, h_acc, h_final, stream),
+               "decode_batch_async")
+
+    def set_profiling(self, enabled=True):
+        _check(self._L.vitb_set_profiling(self._h, 1 if enabled else 0))
+
+    def stage_ms(self):
+        """device ms of the last batch call: {ingest, acs, traceback, gather}; synchronise the stream first"""
+        ms = (C.c_float * 4)()
+        _check(self._L.vitb_get_stage_ms(self._h, C.byref(ms)))
+        return {"ingest": ms[0], "acs": ms[1], "traceback": ms[2], "gather": ms[3]}
+
     # -- introspection ---------------------------------------------------------------------------------------------------------
     def workspace_bytes(self, n_frames, total_bits):
         n = C.c_size_t()
