@@ -122,6 +122,11 @@ int vitb_kernel_launch_count(const vitb_decoder* h, uint64_t* count);
  * ms[0] ingest, ms[1] add-compare-select, ms[2] traceback, ms[3] result gather. */
 int vitb_set_profiling(vitb_decoder* h, int enabled);
 int vitb_get_stage_ms(vitb_decoder* h, float ms[4]);
+/* Kernel variants: a frame pair can be spread over 1, 2, 4 ... lanes (more lanes = more warps for small batches).  By default the
+ * variant is chosen per batch call from the batch size; vitb_set_variant pins it (0 = automatic).  vitb_get_variants lists the
+ * compiled lanes-per-pair settings of this handle's code and returns their number. */
+int vitb_set_variant(vitb_decoder* h, int lanes_per_pair);
+int vitb_get_variants(const vitb_decoder* h, int* lanes_per_pair, int capacity);
 /* name of the ACS kernel variant selected for this handle, e.g. "acs_pair<K7,R2,u8,scalar-tie>" */
 const char* vitb_kernel_name(const vitb_decoder* h);
 int vitb_last_cuda_error(const vitb_decoder* h);

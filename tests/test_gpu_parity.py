@@ -6,29 +6,32 @@ import pytest
 
 import viterbidecodercpp_b200 as v
 from viterbidecodercpp_b200 import synth
-from common import CODE_BY_NAME, PAIR_CODES, assert_batch_equal, frames, make_cuda_decoder, make_oracle
+from common import CODE_BY_NAME, GPU_CODES, PAIR_CODES, assert_batch_equal, frames, make_cuda_decoder, make_oracle
 from oracle_binding import MODE_SCALAR, MODE_SIMD
 
 pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("decode_type", ["SOFT16", "SOFT8", "HARD8"])
-@pytest.mark.parametrize("name", PAIR_CODES)
+@pytest.mark.parametrize("name", GPU_CODES)
 def test_noise_free_round_trip(cuda_lib, name, decode_type):
     """examples/run_tests.cpp:153-191: 64-byte frames, noise free, 0 bit errors; run_simple.cpp:81-93: error metric 0"""
     code = CODE_BY_NAME[name]
     dec, dc = make_cuda_decoder(code, decode_type)
     tx, sym = frames(code, dc, 70, 512, None, seed=7)
-    out, acc, fin = dec.decode_batch(sym, 512)
-    assert (out == tx).all()
-    assert ((acc + fin) == 0).all()
     ora, _ = make_oracle(code, decode_type)
-    assert_batch_equal((out, acc, fin), ora.decode_frames(sym, 70, 512), f"{name} {decode_type}")
+    want = ora.decode_frames(sym, 70, 512)
+    for lanes in dec.variants:
+        dec.set_variant(lanes)
+        out, acc, fin = dec.decode_batch(sym, 512)
+        assert (out == tx).all(), lanes
+        assert ((acc + fin) == 0).all(), lanes
+        assert_batch_equal((out, acc, fin), want, f"{name} {decode_type} lanes/pair={lanes}")
 
 
 @pytest.mark.parametrize("EbNo_dB", [-3.0, 1.0, 4.0])
 @pytest.mark.parametrize("decode_type", ["SOFT16", "SOFT8", "HARD8"])
-@pytest.mark.parametrize("name", PAIR_CODES)
+@pytest.mark.parametrize("name", GPU_CODES)
 def test_batch_parity_awgn(cuda_lib, name, decode_type, EbNo_dB):
     """noisy frames: ties and renormalisations are exercised; ragged frame count (not a multiple of 64)"""
     code = CODE_BY_NAME[name]
@@ -36,14 +39,20 @@ def test_batch_parity_awgn(cuda_lib, name, decode_type, EbNo_dB):
     ora, _ = make_oracle(code, decode_type)
     n_frames, L = 149, 1000 if decode_type != "SOFT16" else 2048
     L = (L // 8) * 8
+    if code.K >= 9:
+        n_frames, L = 75, 1000
     tx, sym = frames(code, dc, n_frames, L, EbNo_dB, seed=1234)
-    got = dec.decode_batch(sym, L)
     want = ora.decode_frames(sym, n_frames, L)
-    assert_batch_equal(got, want, f"{name} {decode_type} {EbNo_dB} dB")
+    assert dec.variants, "no kernel variants"
+    for lanes in dec.variants:          # every compiled lanes-per-pair variant must be bit-exact
+        dec.set_variant(lanes)
+        got = dec.decode_batch(sym, L)
+        assert f"T{lanes}" in dec.kernel_name
+        assert_batch_equal(got, want, f"{name} {decode_type} {EbNo_dB} dB lanes/pair={lanes}")
 
 
 @pytest.mark.parametrize("decode_type", ["SOFT16", "HARD8"])
-@pytest.mark.parametrize("name", ["Voyager", "DAB Radio", "Basic K=5 R=1/2"])
+@pytest.mark.parametrize("name", ["Voyager", "DAB Radio", "Basic K=5 R=1/2", "CDMA IS-95A", "CDMA 2000"])
 def test_streaming_api_matches_oracle_state(cuda_lib, name, decode_type):
     """reset / update in ragged pieces / get_error / chainback + the public m_decisions and m_metrics fields"""
     code = CODE_BY_NAME[name]
@@ -138,21 +147,25 @@ def test_dab_fic_punctured_parity_awgn(cuda_lib, EbNo_dB):
     tx, sym = frames(code, dc, F, L, EbNo_dB, seed=77)
     rx = synth.puncture(sym, keep)
     dec.set_puncture_schedule(keep.astype(np.uint8), 0)
-    got = dec.decode_batch(rx, L)
     dep = np.zeros_like(sym)
     dep[:, keep] = rx
     want = ora.decode_frames(dep, F, L)
-    assert_batch_equal(got, want, f"FIC {EbNo_dB} dB")
+    for lanes in dec.variants:
+        dec.set_variant(lanes)
+        assert_batch_equal(dec.decode_batch(rx, L), want, f"FIC {EbNo_dB} dB lanes/pair={lanes}")
 
 
-@pytest.mark.parametrize("name,decode_type", [("Voyager", "SOFT16"), ("Voyager", "HARD8"), ("DAB Radio", "SOFT16")])
+@pytest.mark.parametrize("name,decode_type", [("Voyager", "SOFT16"), ("Voyager", "HARD8"), ("DAB Radio", "SOFT16"), ("CDMA IS-95A", "SOFT16")])
 def test_simd_tie_break_matches_simd_semantics(cuda_lib, name, decode_type):
     """VITB_TIE_SIMD reproduces the SSE/AVX decision rule (decision = min == path1); checked against the oracle's SIMD mode"""
     code = CODE_BY_NAME[name]
     dec, dc = make_cuda_decoder(code, decode_type, tie_break=v.VITB_TIE_SIMD)
     ora, _ = make_oracle(code, decode_type, mode=MODE_SIMD)
     tx, sym = frames(code, dc, 100, 1024, 0.0, seed=3)
-    assert_batch_equal(dec.decode_batch(sym, 1024), ora.decode_frames(sym, 100, 1024), f"{name} {decode_type} simd tie")
+    want = ora.decode_frames(sym, 100, 1024)
+    for lanes in dec.variants:
+        dec.set_variant(lanes)
+        assert_batch_equal(dec.decode_batch(sym, 1024), want, f"{name} {decode_type} simd tie lanes/pair={lanes}")
 
 
 def test_inconsistent_max_error_config(cuda_lib):
@@ -161,9 +174,12 @@ def test_inconsistent_max_error_config(cuda_lib):
     cfg = v.ViterbiDecoder_Config(600, 0, 3000, 60000)
     dec, dc = make_cuda_decoder(code, "SOFT16", config_override=cfg)
     ora, _ = make_oracle(code, "SOFT16", config_override=cfg)
-    assert "cinv" in dec.kernel_name
     tx, sym = frames(code, dc, 80, 1024, 1.0, seed=11)
-    assert_batch_equal(dec.decode_batch(sym, 1024), ora.decode_frames(sym, 80, 1024), "cinv")
+    want = ora.decode_frames(sym, 80, 1024)
+    for lanes in dec.variants:
+        dec.set_variant(lanes)
+        assert_batch_equal(dec.decode_batch(sym, 1024), want, f"cinv lanes/pair={lanes}")
+        assert "cinv" in dec.kernel_name
 
 
 def test_start_and_end_state_options(cuda_lib):
@@ -172,13 +188,15 @@ def test_start_and_end_state_options(cuda_lib):
     ora, _ = make_oracle(code, "SOFT16")
     L = 512
     tx, sym = frames(code, dc, 66, L, 3.0, seed=21)
-    out, acc, fin = dec.decode_batch(sym, L, starting_state=5, end_state=9)
-    ora.set_traceback_length(L)
-    for f in range(66):
-        ora.reset(5)
-        a = ora.update(sym[f])
-        assert a == acc[f] and ora.get_error(9) == fin[f]
-        assert (ora.chainback(L, 9) == out[f]).all()
+    for lanes in dec.variants:
+        dec.set_variant(lanes)
+        out, acc, fin = dec.decode_batch(sym, L, starting_state=5, end_state=9)
+        ora.set_traceback_length(L)
+        for f in range(66):
+            ora.reset(5)
+            a = ora.update(sym[f])
+            assert a == acc[f] and ora.get_error(9) == fin[f]
+            assert (ora.chainback(L, 9) == out[f]).all()
 
 
 def test_workspace_chunking_gives_identical_results(cuda_lib):

@@ -13,7 +13,7 @@ import viterbidecodercpp_b200 as v
 from viterbidecodercpp_b200 import _lib, sharding
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SUPPORTED_K = {3, 5, 7}     # constraint lengths with compiled kernels so far (grows as kernel families land)
+SUPPORTED_K = {3, 5, 7, 9}    # constraint lengths with compiled kernels so far (grows as kernel families land)
 
 
 def test_library_exports_every_declared_symbol():
@@ -91,6 +91,30 @@ def test_presets_match_reference_values():
     assert tup(v.get_soft16_decoding_config(6)) == (1524, 0, 7620, 57915)
     assert tup(v.get_hard8_decoding_config(2)) == (4, 0, 12, 243)
     assert tup(v.get_soft8_decoding_config(2)) == (12, 0, 24, 231)
+
+
+def test_exchange_swizzle_is_conflict_free():
+    """the shared-memory exchange of csrc/acs_group.cuh (GroupShape::slot): every warp-wide store and load hits 32 distinct banks
+    and the slots form a bijection, for every (state bits, lanes per pair) the kernels are compiled for"""
+    def check(SB, g):
+        T, LB = 1 << g, SB - g
+        NL = 1 << LB
+
+        def swz(qp):
+            return ((qp >> (LB - g)) & (T - 1)) if LB >= g else (qp & 31)
+
+        def slot(p, phi):
+            qp, tp = phi >> g, phi & (T - 1)
+            return qp * 32 + ((p * T + tp) ^ swz(qp))
+        seen = set()
+        for q in range(NL):
+            wr = {slot(lane // T, ((lane % T) << LB) | q) % 32 for lane in range(32)}
+            rd = {slot(lane // T, (q << g) | (lane % T)) % 32 for lane in range(32)}
+            assert len(wr) == 32 and len(rd) == 32, (SB, g, q)
+            seen |= {slot(lane // T, (q << g) | (lane % T)) for lane in range(32)}
+        assert seen == set(range(NL * 32))
+    for SB, g in [(4, 2), (6, 1), (6, 2), (6, 3), (8, 3), (8, 4), (8, 5)]:
+        check(SB, g)
 
 
 def test_frame_range_partitions_exactly():

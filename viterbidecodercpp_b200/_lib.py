@@ -50,6 +50,8 @@ API = [
     ("vitb_kernel_launch_count", C.c_int, [_P, C.POINTER(C.c_uint64)]),
     ("vitb_set_profiling", C.c_int, [_P, C.c_int]),
     ("vitb_get_stage_ms", C.c_int, [_P, C.POINTER(C.c_float * 4)]),
+    ("vitb_set_variant", C.c_int, [_P, C.c_int]),
+    ("vitb_get_variants", C.c_int, [_P, C.POINTER(C.c_int), C.c_int]),
     ("vitb_kernel_name", C.c_char_p, [_P]),
     ("vitb_last_cuda_error", C.c_int, [_P]),
     ("vitb_status_string", C.c_char_p, [C.c_int]),

@@ -28,12 +28,13 @@
 
 namespace vitb {
 
-struct AcsPairParams {
+struct AcsParams {
     const uint32_t* pk;     // packed symbols [n_blocks][n_steps][R][32 lanes]; word = (sA << SH) & 0xffff | (sB << SH) << 16
-    uint64_t* dec;          // decision rows  [n_blocks][dec_rows][64 frames]; bit s of the word = decision of state s (reference bit order)
+    void* dec;              // decision rows.  pair kernels: uint64 [n_blocks][dec_rows][64 frames], bit s = decision of state s
+                            // (reference bit order); group kernels: uint32 [n_blocks][dec_rows][32 lanes][W] (acs_group.cuh)
     uint16_t* metrics;      // [n_blocks*64][NS] path metrics in logical state order (raw error_t values); in (resume) / out
     uint64_t* acc;          // [n_blocks*64] sum of renormalisation minima; in (resume) / out
-    uint32_t n_blocks;      // 64-frame blocks
+    uint32_t n_blocks;      // warp blocks: 64 frames each (pair kernels) or 64/T frames each (group kernels, T lanes per pair)
     uint32_t n_steps;       // trellis steps to run in this launch
     uint32_t dec_rows;      // rows allocated per frame in `dec`
     uint32_t dec_row0;      // row index of this launch's first step (= m_current_decoded_bit)
@@ -138,7 +139,7 @@ __device__ __forceinline__ uint32_t packed_min(const uint32_t (&x)[NS]) {
 
 // ---- one trellis step at compile-time phase PH ---------------------------------------------------------------------
 template <class C, int SH, bool TIE_SIMD, bool CONSISTENT, int PH>
-__device__ __forceinline__ void acs_pair_step(uint32_t (&x)[C::NS], const uint32_t* sym /* R packed words */, const AcsPairParams& p,
+__device__ __forceinline__ void acs_pair_step(uint32_t (&x)[C::NS], const uint32_t* sym /* R packed words */, const AcsParams& p,
                                               uint64_t* dec_row /* this lane's 16 bytes of the row */, uint64_t& accA, uint64_t& accB) {
     constexpr int R = C::R, NP = C::NP, NS = C::NS, NACC = PairShape<C>::NACC;
     // per-symbol errors against low / high
@@ -193,7 +194,7 @@ struct PairRunner {
     static constexpr int P = C::SB, R = C::R, NS = C::NS;
 
     template <int PH>
-    static __device__ __forceinline__ bool phase(uint32_t (&x)[NS], const uint32_t (&cur)[P * R], const AcsPairParams& p, uint32_t t0,
+    static __device__ __forceinline__ bool phase(uint32_t (&x)[NS], const uint32_t (&cur)[P * R], const AcsParams& p, uint32_t t0,
                                                  uint64_t* dec_lane, uint64_t& accA, uint64_t& accB) {
         if (t0 + PH >= p.n_steps) return false;
         acs_pair_step<C, SH, TIE_SIMD, CONSISTENT, PH>(x, &cur[PH * R], p, dec_lane + size_t(t0 + PH) * 64, accA, accB);
@@ -201,7 +202,7 @@ struct PairRunner {
     }
 
     template <int... PHs>
-    static __device__ __forceinline__ void group(uint32_t (&x)[NS], const uint32_t (&cur)[P * R], const AcsPairParams& p, uint32_t t0,
+    static __device__ __forceinline__ void group(uint32_t (&x)[NS], const uint32_t (&cur)[P * R], const AcsParams& p, uint32_t t0,
                                                  uint64_t* dec_lane, uint64_t& accA, uint64_t& accB, std::integer_sequence<int, PHs...>) {
         (void)(phase<PHs>(x, cur, p, t0, dec_lane, accA, accB) && ...);
     }
@@ -211,7 +212,7 @@ struct PairRunner {
 // a CTA land on all four SM sub-partitions evenly.  grid = ceil(n_blocks / PAIR_WARPS).
 constexpr int PAIR_WARPS = 4;
 template <class C, int SH, bool TIE_SIMD, bool CONSISTENT>
-__global__ void __launch_bounds__(32 * PAIR_WARPS) acs_pair_kernel(const AcsPairParams p) {
+__global__ void __launch_bounds__(32 * PAIR_WARPS) acs_pair_kernel(const AcsParams p) {
     constexpr int P = C::SB, R = C::R, NS = C::NS, SB = C::SB;
     using Run = PairRunner<C, SH, TIE_SIMD, CONSISTENT>;
     const uint32_t lane = threadIdx.x & 31, blk = blockIdx.x * PAIR_WARPS + (threadIdx.x >> 5);
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(32 * PAIR_WARPS) acs_pair_kernel(const AcsPair
     }
 
     const uint32_t* pk = p.pk + size_t(blk) * p.n_steps * R * 32 + lane;
-    uint64_t* dec_lane = p.dec + (size_t(blk) * p.dec_rows + p.dec_row0) * 64 + 2 * lane;
+    uint64_t* dec_lane = static_cast<uint64_t*>(p.dec) + (size_t(blk) * p.dec_rows + p.dec_row0) * 64 + 2 * lane;
 
     uint32_t cur[P * R], nxt[P * R];
 #pragma unroll

@@ -6,8 +6,10 @@
 // every depunctured symbol index, the index of the received symbol in the frame's row or -1 for "insert the unpunctured
 // value", which is decode_punctured_symbols' behaviour (examples/helpers/puncture_code_helpers.h:17-55) done as a gather.
 //
-// Pair stream (K <= 7 kernels): word[(blk * n_sym + e) * 32 + lane] = (sA << SH) & 0xffff | (sB << SH) << 16 where
-// e = step*R + i, frames A/B = 64*blk + 2*lane + {0,1}.  SH = 8 for uint8_t error metrics (held as metric << 8), else 0.
+// Pair stream: frame pair gp = (frames 2gp, 2gp+1) belongs to warp block gp / PPW at slot gp % PPW (PPW = pairs per warp of the
+// ACS kernel: 32 for one-thread-per-pair, 32/T when a pair spans T lanes);
+//     word[(wblk * n_sym + e) * PPW + slot] = (sA << SH) & 0xffff | (sB << SH) << 16,   e = step*R + i.
+// SH = 8 for uint8_t error metrics (held as metric << 8), else 0.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -22,11 +24,12 @@ struct IngestParams {
     const int32_t* depuncture_map;  // nullable; [n_sym] -> received index or -1
     int32_t fill_value;       // unpunctured symbol value
     uint32_t* pk;             // output
+    uint32_t ppw;             // pairs per warp block (power of two, 1..32)
 };
 
 constexpr int INGEST_TILE = 256;
 
-// grid = (ceil(n_sym / 256), n_blocks), block = 256 threads.  64 x 256 tile transposed through shared memory.
+// grid = (ceil(n_sym / 256), ceil(n_frames / 64)), block = 256 threads.  64 frames x 256 symbols transposed through shared memory.
 template <typename soft_t, int SH>
 __global__ void __launch_bounds__(INGEST_TILE) ingest_pairs_kernel(const IngestParams p) {
     constexpr int RS = INGEST_TILE + 1;        // odd row stride (in int16) -> conflict-free column reads
@@ -48,13 +51,17 @@ __global__ void __launch_bounds__(INGEST_TILE) ingest_pairs_kernel(const IngestP
         tile[r * RS + tid] = uint16_t(uint32_t(v) << SH);
     }
     __syncthreads();
-    const uint32_t lane = tid & 31, k0 = tid >> 5;
-    uint32_t* out = p.pk + (size_t(blk) * p.n_sym + e0) * 32 + lane;
+    // 32 pairs x 256 symbols leave as (256 * ppw)-word runs, one run per warp block touched by this tile
+    const uint32_t ppw = p.ppw, run = INGEST_TILE * ppw;
+    const uint32_t n_valid = (p.n_sym - e0 < uint32_t(INGEST_TILE)) ? (p.n_sym - e0) : uint32_t(INGEST_TILE);
 #pragma unroll 4
-    for (int k = k0; k < INGEST_TILE; k += INGEST_TILE / 32) {
-        if (e0 + k < p.n_sym) {
-            const uint32_t a = tile[(2 * lane) * RS + k], b = tile[(2 * lane + 1) * RS + k];
-            out[size_t(k) * 32] = a | (b << 16);
+    for (uint32_t l = tid; l < 32u * INGEST_TILE; l += INGEST_TILE) {
+        const uint32_t wb = l / run, rem = l % run, k = rem / ppw, slot = rem % ppw;
+        if (k < n_valid) {
+            const uint32_t pr = wb * ppw + slot;                 // pair inside the tile
+            const uint32_t a = tile[(2 * pr) * RS + k], b = tile[(2 * pr + 1) * RS + k];
+            const size_t wblk = size_t(blk) * (32 / ppw) + wb;
+            p.pk[(wblk * p.n_sym + e0 + k) * ppw + slot] = a | (b << 16);
         }
     }
 }

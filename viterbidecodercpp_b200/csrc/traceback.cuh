@@ -72,4 +72,95 @@ __global__ void __launch_bounds__(128) traceback_u64_kernel(const TracebackParam
     }
 }
 
+// ---- decision rows written by acs_group_kernel (acs_group.cuh) -------------------------------------------------------------
+// T = 2^logt lanes serve one frame pair, with the same lane <-> group mapping as the ACS kernel: lane t loads ITS OWN decision
+// words (coalesced, addresses independent of the state, so whole batches of rows are in flight), and the word that holds the
+// decision of the current state is fetched from lane t(state) with one __shfl per frame and row.  All lanes of the group track
+// both states redundantly; lane 0 writes frame A's bytes, lane 1 frame B's.
+struct TracebackGroupParams {
+    const uint32_t* dec;      // [n_wblocks][dec_rows][32][W]
+    uint32_t dec_rows;
+    uint32_t n_frames;
+    uint32_t total_bits;
+    uint32_t state_bits;      // SB = K-1
+    uint32_t logt;            // lanes per pair = 1 << logt (>= 1)
+    uint32_t end_state;
+    uint8_t* out;
+    size_t out_stride;
+};
+
+__device__ __forceinline__ uint32_t rotr_rt(uint32_t v, uint32_t r, uint32_t n) {
+    r %= n;
+    return r == 0 ? v : (((v >> r) | (v << (n - r))) & ((1u << n) - 1u));
+}
+
+// grid = ceil(n_wblocks / 4), block = 128 (4 warps, one warp block each)
+template <int W, int BATCH>
+__global__ void __launch_bounds__(128) traceback_group_kernel(const TracebackGroupParams p) {
+    const uint32_t lane = threadIdx.x & 31, wblk = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const uint32_t SB = p.state_bits, g = p.logt, T = 1u << g, LB = SB - g, PPW = 32u >> g, L = p.total_bits;
+    const uint32_t n_pairs = (p.n_frames + 1) / 2;
+    if (size_t(wblk) * PPW >= n_pairs) return;
+    const uint32_t pw = lane >> g, t = lane & (T - 1), grp0 = lane & ~(T - 1);
+    const size_t fA = (size_t(wblk) * PPW + pw) * 2;
+    const uint32_t* d = p.dec + (size_t(wblk) * p.dec_rows * 32 + lane) * W;      // this lane's word(s) of row 0
+    uint32_t stA = p.end_state, stB = p.end_state;
+    uint32_t byteA = 0, byteB = 0;
+    const bool writerA = (t == 0) && (fA < p.n_frames), writerB = (t == 1) && (fA + 1 < p.n_frames);
+    uint8_t* outA = p.out + fA * p.out_stride;
+    uint8_t* outB = outA + p.out_stride;
+    if (L & 7) {
+        for (uint32_t jj = L; jj < ((L + 7) & ~7u); jj++) {
+            const uint32_t k = jj - L;
+            const uint32_t b = (k < SB) ? ((p.end_state >> (SB - 1 - k)) & 1u) : 0u;
+            byteA |= b << (7 - (jj & 7));
+        }
+        byteB = byteA;
+    }
+    auto one_row = [&](int64_t j, uint32_t w0, uint32_t w1) {
+        const uint32_t row = uint32_t(j) + SB, n = row % LB;
+        const uint32_t phiA = rotr_rt(stA, n + 1, SB), phiB = rotr_rt(stB, n + 1, SB);
+        const uint32_t qA = phiA >> g, qB = phiB >> g;
+        uint32_t bitA, bitB;
+        if (W == 1) {
+            const uint32_t wA = __shfl_sync(0xffffffffu, w0, int(grp0 + (phiA & (T - 1))));
+            const uint32_t wB = __shfl_sync(0xffffffffu, w0, int(grp0 + (phiB & (T - 1))));
+            bitA = (wA >> qA) & 1u;
+            bitB = (wB >> (16 + qB)) & 1u;
+        } else {
+            const uint32_t wA = __shfl_sync(0xffffffffu, w0, int(grp0 + (phiA & (T - 1))));
+            const uint32_t wB = __shfl_sync(0xffffffffu, w1, int(grp0 + (phiB & (T - 1))));
+            bitA = (wA >> qA) & 1u;
+            bitB = (wB >> qB) & 1u;
+        }
+        stA = (bitA << (SB - 1)) | (stA >> 1);
+        stB = (bitB << (SB - 1)) | (stB >> 1);
+        byteA |= bitA << (7 - (uint32_t(j) & 7));
+        byteB |= bitB << (7 - (uint32_t(j) & 7));
+        if ((j & 7) == 0) {
+            if (writerA) outA[j >> 3] = uint8_t(byteA);
+            if (writerB) outB[j >> 3] = uint8_t(byteB);
+            byteA = 0; byteB = 0;
+        }
+    };
+    int64_t j = int64_t(L) - 1;
+    while (j >= 0 && ((j + 1) % BATCH) != 0) {      // ragged head
+        const uint32_t* r = d + (size_t(j) + SB) * 32 * W;
+        one_row(j, r[0], W == 2 ? r[W - 1] : 0u);
+        j--;
+    }
+    while (j >= BATCH - 1) {
+        uint32_t w0[BATCH], w1[BATCH];
+#pragma unroll
+        for (int k = 0; k < BATCH; k++) {
+            const uint32_t* r = d + (size_t(j - k) + SB) * 32 * W;
+            if (W == 2) { const uint2 v = __ldcs(reinterpret_cast<const uint2*>(r)); w0[k] = v.x; w1[k] = v.y; }
+            else { w0[k] = __ldcs(r); w1[k] = 0u; }
+        }
+#pragma unroll
+        for (int k = 0; k < BATCH; k++) one_row(j - k, w0[k], w1[k]);
+        j -= BATCH;
+    }
+}
+
 }  // namespace vitb

@@ -1,6 +1,7 @@
 // vitb_api.cu -- extern "C" boundary (include/viterbi_b200.h) and host-side orchestration of the decode pipeline
 //     ingest (layout + depuncture) -> ACS (add-compare-select, decision rows to HBM) -> traceback -> result gather
 // No CPU fallback: every entry point needs a CUDA device.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -22,9 +23,11 @@ static const std::vector<KernelEntry>& registry() {
     static std::once_flag once;
     std::call_once(once, [] {
         register_small(entries);
-        register_k7r2(entries);
-        register_k7r3(entries);
-        register_k7r4(entries);
+        register_k7r2_t1(entries); register_k7r2_t2(entries); register_k7r2_t4(entries);
+        register_k7r3_t1(entries); register_k7r3_t4(entries);
+        register_k7r4_t1(entries); register_k7r4_t2(entries); register_k7r4_t4(entries);
+        register_k9r2_t8(entries); register_k9r2_t16(entries);
+        register_k9r4_t8(entries); register_k9r4_t16(entries);
     });
     return entries;
 }
@@ -57,7 +60,11 @@ using namespace vitb;
 
 struct vitb_decoder {
     vitb_params prm{};
-    const KernelEntry* entry = nullptr;
+    std::vector<const KernelEntry*> variants;   // every compiled lanes-per-pair variant of this code/config, ascending logt
+    const KernelEntry* entry = nullptr;         // variant used by the single-frame streaming API (fixes its decision layout)
+    const KernelEntry* last_batch = nullptr;    // variant the last batch call selected
+    int forced_logt = -1;                       // vitb_set_variant
+    int n_sm = 148;
     int n_states = 0;
     int sh = 0;
     int last_cuda = 0;
@@ -88,8 +95,9 @@ int cuda_fail(vitb_decoder* h, cudaError_t e) {
 }
 #define VITB_CUDA(h, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail((h), e__); } while (0)
 
-const KernelEntry* find_entry(const vitb_params& p) {
-    if (p.K < 2 || p.R < 1 || p.R > VITB_MAX_R) return nullptr;
+std::vector<const KernelEntry*> find_entries(const vitb_params& p) {
+    std::vector<const KernelEntry*> out;
+    if (p.K < 2 || p.R < 1 || p.R > VITB_MAX_R) return out;
     const int sh = (p.soft_bytes == 1) ? 8 : 0;
     const uint32_t span = uint32_t(p.soft_decision_high - p.soft_decision_low);
     const uint32_t mask = (p.soft_bytes == 1) ? 0xffu : 0xffffu;
@@ -99,9 +107,27 @@ const KernelEntry* find_entry(const vitb_params& p) {
         if (e.K != p.K || e.R != p.R || e.sh != sh || e.tie != (p.tie_break ? 1 : 0) || e.consistent != consistent) continue;
         bool same = true;
         for (int i = 0; i < p.R; i++) same = same && ((e.G[i] & kmask) == (p.G[i] & kmask));
-        if (same) return &e;
+        if (same) out.push_back(&e);
     }
-    return nullptr;
+    std::sort(out.begin(), out.end(), [](const KernelEntry* a, const KernelEntry* b) { return a->logt < b->logt; });
+    return out;
+}
+
+// Variant for a batch of n_frames: the fewest lanes per pair that still puts ~5 warps on every SM sub-partition (the 2-cycle
+// issue of VIADD.16x2 needs several warps to overlap, and the group kernels' hot loops are small enough for the instruction cache).
+const KernelEntry* choose_variant(const vitb_decoder* h, size_t n_frames) {
+    if (h->forced_logt >= 0) {
+        for (const KernelEntry* e : h->variants) if (e->logt == h->forced_logt) return e;
+    }
+    const size_t target_warps = size_t(h->n_sm) * 4 * 5;
+    const size_t pairs = (n_frames + 1) / 2;
+    const KernelEntry* best = h->variants.back();
+    for (const KernelEntry* e : h->variants) {
+        if (e->logt == 0 && h->variants.size() > 1) continue;      // the fully unrolled kernel is instruction-fetch bound: last resort
+        const size_t warps = ((pairs << e->logt) + 31) / 32;
+        if (warps >= target_warps) { best = e; break; }
+    }
+    return best;
 }
 
 bool params_valid(const vitb_params& p) {
@@ -113,7 +139,7 @@ bool params_valid(const vitb_params& p) {
     return true;
 }
 
-void fill_acs_params(const vitb_decoder* h, AcsPairParams& a) {
+void fill_acs_params(const vitb_decoder* h, AcsParams& a) {
     const vitb_params& p = h->prm;
     const int sh = h->sh;
     const uint32_t emask = (p.soft_bytes == 1) ? 0xffu : 0xffffu;
@@ -133,7 +159,7 @@ cudaError_t launch_ingest(const IngestParams& ip, unsigned n_blocks, cudaStream_
     return cudaGetLastError();
 }
 
-cudaError_t run_ingest(vitb_decoder* h, const IngestParams& ip, unsigned n_blocks, cudaStream_t s) {
+cudaError_t run_ingest(vitb_decoder* h, const IngestParams& ip, unsigned n_blocks, cudaStream_t s) {   // n_blocks: 64-frame tiles
     h->launches++;
     return (h->prm.soft_bytes == 1) ? launch_ingest<int8_t, 8>(ip, n_blocks, s) : launch_ingest<int16_t, 0>(ip, n_blocks, s);
 }
@@ -146,13 +172,40 @@ size_t default_ws_limit() {
     return size_t(24) << 30;
 }
 
-// workspace bytes per 64-frame block for a frame of S steps
+// workspace bytes per 64 frames for a frame of S steps (identical for every variant: decision rows are 2^(K-1) bits per frame-step)
 size_t block_bytes(const vitb_decoder* h, size_t S) {
     const size_t n_sym = S * size_t(h->prm.R);
-    return n_sym * 32 * 4                     // packed symbols
-         + S * 64 * 8                         // decision rows
-         + size_t(64) * h->n_states * 2       // metrics
-         + 64 * 8;                            // accumulated error
+    return n_sym * 32 * 4                                   // packed symbols
+         + S * 64 * (size_t(h->n_states) / 8 < 8 ? 8 : size_t(h->n_states) / 8)   // decision rows
+         + size_t(64) * h->n_states * 2                     // metrics
+         + 64 * 8;                                          // accumulated error
+}
+
+size_t dec_bytes_per_block64(const KernelEntry* e, size_t rows) {
+    if (e->logt == 0) return rows * 64 * 8;
+    return (size_t(1) << e->logt) * rows * 32 * size_t(e->dec_words) * 4;
+}
+
+cudaError_t launch_traceback(vitb_decoder* h, const KernelEntry* e, const void* dec, size_t dec_rows, size_t n_frames, size_t L,
+                             size_t end_state, uint8_t* d_out, size_t out_stride, cudaStream_t s) {
+    h->launches++;
+    if (e->logt == 0) {
+        TracebackParams t{};
+        t.dec = static_cast<const uint64_t*>(dec); t.dec_rows = uint32_t(dec_rows); t.n_frames = uint32_t(n_frames);
+        t.total_bits = uint32_t(L); t.state_bits = uint32_t(h->prm.K - 1); t.end_state = uint32_t(end_state);
+        t.out = d_out; t.out_stride = out_stride;
+        traceback_u64_kernel<32><<<unsigned((n_frames + 127) / 128), 128, 0, s>>>(t);
+    } else {
+        TracebackGroupParams t{};
+        t.dec = static_cast<const uint32_t*>(dec); t.dec_rows = uint32_t(dec_rows); t.n_frames = uint32_t(n_frames);
+        t.total_bits = uint32_t(L); t.state_bits = uint32_t(h->prm.K - 1); t.logt = uint32_t(e->logt); t.end_state = uint32_t(end_state);
+        t.out = d_out; t.out_stride = out_stride;
+        const size_t ppw = size_t(32) >> e->logt, n_pairs = (n_frames + 1) / 2, n_wblocks = (n_pairs + ppw - 1) / ppw;
+        const unsigned grid = unsigned((n_wblocks + 3) / 4);
+        if (e->dec_words == 1) traceback_group_kernel<1, 16><<<grid, 128, 0, s>>>(t);
+        else traceback_group_kernel<2, 16><<<grid, 128, 0, s>>>(t);
+    }
+    return cudaGetLastError();
 }
 
 cudaError_t mark(vitb_decoder* h, cudaStream_t s) {
@@ -167,40 +220,34 @@ cudaError_t mark(vitb_decoder* h, cudaStream_t s) {
 }
 
 // One chunk of frames, everything on device, asynchronous on `s`.
-int decode_chunk_dev(vitb_decoder* h, const void* d_symbols, size_t row_stride, size_t n_frames, size_t L, size_t start_state,
-                     size_t end_state, uint8_t* d_out, uint64_t* d_acc, uint32_t* d_final, cudaStream_t s) {
+int decode_chunk_dev(vitb_decoder* h, const KernelEntry* e, const void* d_symbols, size_t row_stride, size_t n_frames, size_t L,
+                     size_t start_state, size_t end_state, uint8_t* d_out, uint64_t* d_acc, uint32_t* d_final, cudaStream_t s) {
     const size_t K = size_t(h->prm.K), R = size_t(h->prm.R), S = L + K - 1, n_sym = S * R;
-    const unsigned n_blocks = unsigned((n_frames + 63) / 64);
-    VITB_CUDA(h, h->pk.reserve(size_t(n_blocks) * n_sym * 32 * 4));
-    VITB_CUDA(h, h->dec.reserve(size_t(n_blocks) * S * 64 * 8));
-    VITB_CUDA(h, h->metrics.reserve(size_t(n_blocks) * 64 * h->n_states * 2));
-    VITB_CUDA(h, h->acc.reserve(size_t(n_blocks) * 64 * 8));
+    const unsigned n_b64 = unsigned((n_frames + 63) / 64);
+    const unsigned n_wblocks = n_b64 << e->logt;
+    VITB_CUDA(h, h->pk.reserve(size_t(n_b64) * n_sym * 32 * 4));
+    VITB_CUDA(h, h->dec.reserve(size_t(n_b64) * dec_bytes_per_block64(e, S)));
+    VITB_CUDA(h, h->metrics.reserve(size_t(n_b64) * 64 * h->n_states * 2));
+    VITB_CUDA(h, h->acc.reserve(size_t(n_b64) * 64 * 8));
 
     IngestParams ip{};
     ip.symbols = d_symbols; ip.row_stride = row_stride; ip.n_frames = uint32_t(n_frames); ip.n_sym = uint32_t(n_sym);
     ip.depuncture_map = h->n_depunctured ? static_cast<const int32_t*>(h->map.ptr) : nullptr;
-    ip.fill_value = h->unpunctured_value; ip.pk = static_cast<uint32_t*>(h->pk.ptr);
+    ip.fill_value = h->unpunctured_value; ip.pk = static_cast<uint32_t*>(h->pk.ptr); ip.ppw = 32u >> e->logt;
     VITB_CUDA(h, mark(h, s));
-    VITB_CUDA(h, run_ingest(h, ip, n_blocks, s));
+    VITB_CUDA(h, run_ingest(h, ip, n_b64, s));
     VITB_CUDA(h, mark(h, s));
 
-    AcsPairParams a{};
+    AcsParams a{};
     fill_acs_params(h, a);
-    a.pk = static_cast<const uint32_t*>(h->pk.ptr); a.dec = static_cast<uint64_t*>(h->dec.ptr);
+    a.pk = static_cast<const uint32_t*>(h->pk.ptr); a.dec = h->dec.ptr;
     a.metrics = static_cast<uint16_t*>(h->metrics.ptr); a.acc = static_cast<uint64_t*>(h->acc.ptr);
-    a.n_steps = uint32_t(S); a.dec_rows = uint32_t(S); a.dec_row0 = 0; a.resume = 0; a.start_state = uint32_t(start_state);
+    a.n_blocks = n_wblocks; a.n_steps = uint32_t(S); a.dec_rows = uint32_t(S); a.dec_row0 = 0; a.resume = 0; a.start_state = uint32_t(start_state);
     h->launches++;
-    VITB_CUDA(h, h->entry->launch_pair(a, n_blocks, s));
+    VITB_CUDA(h, e->launch(a, s));
     VITB_CUDA(h, mark(h, s));
 
-    if (d_out) {
-        TracebackParams t{};
-        t.dec = a.dec; t.dec_rows = a.dec_rows; t.n_frames = uint32_t(n_frames); t.total_bits = uint32_t(L);
-        t.state_bits = uint32_t(K - 1); t.end_state = uint32_t(end_state); t.out = d_out; t.out_stride = (L + 7) / 8;
-        h->launches++;
-        traceback_u64_kernel<32><<<unsigned((n_frames + 127) / 128), 128, 0, s>>>(t);
-        VITB_CUDA(h, cudaGetLastError());
-    }
+    if (d_out) VITB_CUDA(h, launch_traceback(h, e, h->dec.ptr, S, n_frames, L, end_state, d_out, (L + 7) / 8, s));
     VITB_CUDA(h, mark(h, s));
     if (d_acc || d_final) {
         h->launches++;
@@ -262,24 +309,28 @@ const char* vitb_status_string(int status) {
     }
 }
 
-int vitb_is_supported(const vitb_params* p) { return (p && params_valid(*p) && find_entry(*p)) ? 1 : 0; }
+int vitb_is_supported(const vitb_params* p) { return (p && params_valid(*p) && !find_entries(*p).empty()) ? 1 : 0; }
 
 int vitb_create(const vitb_params* p, vitb_decoder** out) {
     if (!p || !out) return VITB_ERR_ARG;
     *out = nullptr;
     if (!params_valid(*p)) return VITB_ERR_ARG;
-    const KernelEntry* e = find_entry(*p);
-    if (!e) return VITB_ERR_UNSUPPORTED;
+    const std::vector<const KernelEntry*> found = find_entries(*p);
+    if (found.empty()) return VITB_ERR_UNSUPPORTED;
+    const KernelEntry* e = found.front();
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) { cudaGetLastError(); return VITB_ERR_CUDA; }
     if (p->device < 0 || p->device >= n_dev) return VITB_ERR_ARG;
     vitb_decoder* h = new (std::nothrow) vitb_decoder();
     if (!h) return VITB_ERR_NOMEM;
     h->prm = *p;
+    h->variants = found;
     h->entry = e;
+    if (const char* f = getenv("VITB_FORCE_LOGT")) h->forced_logt = atoi(f);
     h->n_states = 1 << (p->K - 1);
     h->sh = e->sh;
     cudaError_t ce = cudaSetDevice(p->device);
+    if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, p->device);
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (ce != cudaSuccess) { delete h; return VITB_ERR_CUDA; }
     *out = h;
@@ -302,7 +353,29 @@ int vitb_destroy(vitb_decoder* h) {
 }
 
 int vitb_last_cuda_error(const vitb_decoder* h) { return h ? h->last_cuda : 0; }
-const char* vitb_kernel_name(const vitb_decoder* h) { return (h && h->entry) ? h->entry->name : ""; }
+const char* vitb_kernel_name(const vitb_decoder* h) {
+    if (!h) return "";
+    return h->last_batch ? h->last_batch->name : (h->entry ? h->entry->name : "");
+}
+
+int vitb_set_variant(vitb_decoder* h, int lanes_per_pair) {
+    if (!h) return VITB_ERR_ARG;
+    if (lanes_per_pair <= 0) { h->forced_logt = -1; return VITB_OK; }
+    for (const KernelEntry* e : h->variants) {
+        if ((1 << e->logt) == lanes_per_pair) { h->forced_logt = e->logt; return VITB_OK; }
+    }
+    return VITB_ERR_UNSUPPORTED;
+}
+
+int vitb_get_variants(const vitb_decoder* h, int* lanes_per_pair, int capacity) {
+    if (!h) return VITB_ERR_ARG;
+    int n = 0;
+    for (const KernelEntry* e : h->variants) {
+        if (lanes_per_pair && n < capacity) lanes_per_pair[n] = 1 << e->logt;
+        n++;
+    }
+    return n;
+}
 int vitb_kernel_launch_count(const vitb_decoder* h, uint64_t* count) {
     if (!h || !count) return VITB_ERR_ARG;
     *count = h->launches;
@@ -331,13 +404,14 @@ int vitb_set_traceback_length(vitb_decoder* h, size_t traceback_length) {
     const size_t rows = traceback_length + size_t(h->prm.K - 1);       // core.h:181
     const size_t old_rows = h->traceback_length + size_t(h->prm.K - 1);
     if (!h->s_dec.ptr || rows != old_rows) {
-        // std::vector::resize keeps the leading rows (core.h:182): so do we
+        // std::vector::resize keeps the leading rows (core.h:182): so do we.  The streaming state is one warp block (block 0).
+        const size_t row_bytes = dec_bytes_per_block64(h->entry, 1) >> h->entry->logt;
         DeviceBuffer nb;
-        VITB_CUDA(h, nb.reserve(rows * 64 * 8));
-        VITB_CUDA(h, cudaMemsetAsync(nb.ptr, 0, rows * 64 * 8, h->stream));
+        VITB_CUDA(h, nb.reserve(rows * row_bytes + 16));
+        VITB_CUDA(h, cudaMemsetAsync(nb.ptr, 0, rows * row_bytes + 16, h->stream));
         if (h->s_dec.ptr) {
             const size_t keep = rows < old_rows ? rows : old_rows;
-            VITB_CUDA(h, cudaMemcpyAsync(nb.ptr, h->s_dec.ptr, keep * 64 * 8, cudaMemcpyDeviceToDevice, h->stream));
+            VITB_CUDA(h, cudaMemcpyAsync(nb.ptr, h->s_dec.ptr, keep * row_bytes, cudaMemcpyDeviceToDevice, h->stream));
         }
         VITB_CUDA(h, cudaStreamSynchronize(h->stream));
         h->s_dec.release();
@@ -394,17 +468,18 @@ int vitb_update(vitb_decoder* h, const void* symbols, size_t n_symbols, uint64_t
 
     IngestParams ip{};
     ip.symbols = h->s_in.ptr; ip.row_stride = n_symbols; ip.n_frames = 1; ip.n_sym = uint32_t(n_symbols);
-    ip.depuncture_map = nullptr; ip.fill_value = 0; ip.pk = static_cast<uint32_t*>(h->s_pk.ptr);
+    ip.depuncture_map = nullptr; ip.fill_value = 0; ip.pk = static_cast<uint32_t*>(h->s_pk.ptr); ip.ppw = 32u >> h->entry->logt;
     VITB_CUDA(h, run_ingest(h, ip, 1, h->stream));
 
-    AcsPairParams a{};
+    AcsParams a{};
     fill_acs_params(h, a);
-    a.pk = static_cast<const uint32_t*>(h->s_pk.ptr); a.dec = static_cast<uint64_t*>(h->s_dec.ptr);
+    a.pk = static_cast<const uint32_t*>(h->s_pk.ptr); a.dec = h->s_dec.ptr;
     a.metrics = static_cast<uint16_t*>(h->s_metrics.ptr); a.acc = static_cast<uint64_t*>(h->s_acc.ptr);
+    a.n_blocks = 1;      // warp block 0 holds the user's frame (frame 0); its other frames decode zeros and are ignored
     a.n_steps = uint32_t(steps); a.dec_rows = uint32_t(rows); a.dec_row0 = uint32_t(h->current_decoded_bit);
     a.resume = 1; a.start_state = 0;
     h->launches++;
-    VITB_CUDA(h, h->entry->launch_pair(a, 1, h->stream));
+    VITB_CUDA(h, h->entry->launch(a, h->stream));
     uint64_t acc = 0;
     VITB_CUDA(h, cudaMemcpyAsync(&acc, h->s_acc.ptr, 8, cudaMemcpyDeviceToHost, h->stream));
     VITB_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -440,10 +515,35 @@ int vitb_get_decisions(vitb_decoder* h, size_t first_row, size_t n_rows, uint64_
     if (first_row + n_rows > rows) return VITB_ERR_ARG;
     if (!n_rows) return VITB_OK;
     VITB_CUDA(h, cudaSetDevice(h->prm.device));
-    // frame 0 of the block: one uint64 every 64 words
-    VITB_CUDA(h, cudaMemcpy2DAsync(rows_out, 8, static_cast<uint64_t*>(h->s_dec.ptr) + first_row * 64, 64 * 8, 8, n_rows,
-                                   cudaMemcpyDeviceToHost, h->stream));
+    const KernelEntry* e = h->entry;
+    if (e->logt == 0) {
+        // frame 0 of the block: one uint64 every 64 words, already in the reference bit order
+        VITB_CUDA(h, cudaMemcpy2DAsync(rows_out, 8, static_cast<uint64_t*>(h->s_dec.ptr) + first_row * 64, 64 * 8, 8, n_rows,
+                                       cudaMemcpyDeviceToHost, h->stream));
+        VITB_CUDA(h, cudaStreamSynchronize(h->stream));
+        return VITB_OK;
+    }
+    // group layout (acs_group.cuh): lane t, bit q of row r holds the decision of state rotl^(n+1)((q << logt) | t), n = r % LB
+    const uint32_t g = uint32_t(e->logt), T = 1u << g, SB = uint32_t(h->prm.K - 1), LB = SB - g, NL = 1u << LB, W = uint32_t(e->dec_words);
+    const size_t words_per_row = size_t(32) * W, out_words = (size_t(h->n_states) + 63) / 64;
+    std::vector<uint32_t> raw(n_rows * words_per_row);
+    VITB_CUDA(h, cudaMemcpyAsync(raw.data(), static_cast<uint32_t*>(h->s_dec.ptr) + first_row * words_per_row, raw.size() * 4,
+                                 cudaMemcpyDeviceToHost, h->stream));
     VITB_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (size_t r = 0; r < n_rows; r++) {
+        uint64_t* out = rows_out + r * out_words;
+        for (size_t w = 0; w < out_words; w++) out[w] = 0;
+        const uint32_t n = uint32_t((first_row + r) % LB);
+        for (uint32_t t = 0; t < T; t++) {
+            const uint32_t* lane_words = &raw[r * words_per_row + size_t(t) * W];      // pair 0 = lanes 0..T-1, frame A
+            for (uint32_t q = 0; q < NL; q++) {
+                const uint32_t bit = (W == 1) ? ((lane_words[0] >> q) & 1u) : ((lane_words[0] >> q) & 1u);
+                if (!bit) continue;
+                const uint32_t s2 = rotl_bits((q << g) | t, int(n + 1), int(SB));
+                out[s2 / 64] |= uint64_t(1) << (s2 % 64);
+            }
+        }
+    }
     return VITB_OK;
 }
 
@@ -456,13 +556,8 @@ int vitb_chainback(vitb_decoder* h, uint8_t* bytes_out, size_t total_bits, size_
     VITB_CUDA(h, cudaSetDevice(h->prm.device));
     const size_t nbytes = (total_bits + 7) / 8;
     VITB_CUDA(h, h->s_out.reserve(nbytes));
-    TracebackParams t{};
-    t.dec = static_cast<const uint64_t*>(h->s_dec.ptr); t.dec_rows = uint32_t(h->traceback_length + size_t(h->prm.K - 1));
-    t.n_frames = 1; t.total_bits = uint32_t(total_bits); t.state_bits = uint32_t(h->prm.K - 1); t.end_state = uint32_t(end_state);
-    t.out = static_cast<uint8_t*>(h->s_out.ptr); t.out_stride = nbytes;
-    h->launches++;
-    traceback_u64_kernel<32><<<1, 128, 0, h->stream>>>(t);
-    VITB_CUDA(h, cudaGetLastError());
+    VITB_CUDA(h, launch_traceback(h, h->entry, h->s_dec.ptr, h->traceback_length + size_t(h->prm.K - 1), 1, total_bits, end_state,
+                                  static_cast<uint8_t*>(h->s_out.ptr), nbytes, h->stream));
     VITB_CUDA(h, cudaMemcpyAsync(bytes_out, h->s_out.ptr, nbytes, cudaMemcpyDeviceToHost, h->stream));
     VITB_CUDA(h, cudaStreamSynchronize(h->stream));
     return VITB_OK;
@@ -497,9 +592,11 @@ int vitb_decode_batch_dev(vitb_decoder* h, const void* d_symbols, size_t n_frame
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     h->ev_used = 0;
     const size_t chunk = chunk_frames_for(h, L), out_stride = (L + 7) / 8, sb = size_t(h->prm.soft_bytes);
+    const KernelEntry* e = choose_variant(h, n_frames < chunk ? n_frames : chunk);
+    h->last_batch = e;
     for (size_t f0 = 0; f0 < n_frames; f0 += chunk) {
         const size_t nf = (n_frames - f0 < chunk) ? (n_frames - f0) : chunk;
-        const int r = decode_chunk_dev(h, static_cast<const uint8_t*>(d_symbols) + f0 * row_stride * sb, row_stride, nf, L, start, end,
+        const int r = decode_chunk_dev(h, e, static_cast<const uint8_t*>(d_symbols) + f0 * row_stride * sb, row_stride, nf, L, start, end,
                                        d_out ? d_out + f0 * out_stride : nullptr, d_acc ? d_acc + f0 : nullptr,
                                        d_final ? d_final + f0 : nullptr, s);
         if (r != VITB_OK) return r;

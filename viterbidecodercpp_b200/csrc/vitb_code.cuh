@@ -34,6 +34,18 @@ __host__ __device__ constexpr uint32_t bfly_pattern(uint32_t j) {
     return p;
 }
 
+// same, for a run-time index (lane part of the pattern in the group kernels); G stays a compile-time constant
+template <class C, int... Is>
+__device__ __forceinline__ uint32_t bfly_pattern_dyn_impl(uint32_t j, std::integer_sequence<int, Is...>) {
+    uint32_t p = 0;
+    ((p |= (uint32_t(__popc((j << 1) & std::integral_constant<uint32_t, C::G[Is]>::value)) & 1u) << Is), ...);
+    return p;
+}
+template <class C>
+__device__ __forceinline__ uint32_t bfly_pattern_dyn(uint32_t j) {
+    return bfly_pattern_dyn_impl<C>(j, std::make_integer_sequence<int, C::R>{});
+}
+
 // runtime-G flavour of the same thing (generic kernels, host-side table checks)
 __host__ __device__ inline uint32_t bfly_pattern_rt(const uint32_t* G, int R, uint32_t j) {
     uint32_t p = 0;

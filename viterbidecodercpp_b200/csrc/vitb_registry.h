@@ -1,15 +1,14 @@
-// vitb_registry.h -- table of compiled ACS kernel variants; the host picks one at vitb_create time.
-// (One GPU backend, many template instantiations: this is the CUDA analogue of the reference's <K,R,error_t,soft_t> template
-// arguments, not a multi-backend dispatch.)
+// vitb_registry.h -- table of compiled ACS kernel variants; the host picks one per call (by batch size) from the variants of the
+// handle's code.  (One GPU backend, many template instantiations: this is the CUDA analogue of the reference's
+// <K,R,error_t,soft_t> template arguments, not a multi-backend dispatch.)
 #pragma once
 #include <cstdint>
 #include <vector>
 #include <cuda_runtime.h>
 #include "acs_pair.cuh"
+#include "acs_group.cuh"
 
 namespace vitb {
-
-enum KernelFamily { FAMILY_PAIR = 0 };
 
 struct KernelEntry {
     int K, R;
@@ -17,45 +16,65 @@ struct KernelEntry {
     int sh;            // 0: uint16_t metrics, 8: uint8_t metrics held as metric << 8
     int tie;           // VITB_TIE_*
     int consistent;    // max_error == R*(high-low): inverted error is the complementary table entry
-    int family;
+    int logt;          // lanes per frame pair = 1 << logt; 0 = one thread per pair (acs_pair.cuh), >= 1 = acs_group.cuh
+    int dec_words;     // 32-bit decision words per lane per step (group kernels); pair kernels: one uint64 per frame
     const char* name;
-    cudaError_t (*launch_pair)(const AcsPairParams&, unsigned n_blocks, cudaStream_t);
+    cudaError_t (*launch)(const AcsParams&, cudaStream_t);
 };
 
 template <class C, int SH, bool TIE_SIMD, bool CONSISTENT>
-cudaError_t launch_pair(const AcsPairParams& p, unsigned n_blocks, cudaStream_t s) {
-    AcsPairParams q = p;
-    q.n_blocks = n_blocks;
-    acs_pair_kernel<C, SH, TIE_SIMD, CONSISTENT><<<(n_blocks + PAIR_WARPS - 1) / PAIR_WARPS, 32 * PAIR_WARPS, 0, s>>>(q);
+cudaError_t launch_pair(const AcsParams& p, cudaStream_t s) {
+    acs_pair_kernel<C, SH, TIE_SIMD, CONSISTENT><<<(p.n_blocks + PAIR_WARPS - 1) / PAIR_WARPS, 32 * PAIR_WARPS, 0, s>>>(p);
     return cudaGetLastError();
 }
 
-template <class C, int SH, bool TIE_SIMD, bool CONSISTENT>
-KernelEntry make_pair_entry(const char* name) {
+template <class C, int LOGT, int SH, bool TIE_SIMD, bool CONSISTENT>
+cudaError_t launch_group(const AcsParams& p, cudaStream_t s) {
+    constexpr int WARPS = GroupShape<C, LOGT>::WARPS;
+    acs_group_kernel<C, LOGT, SH, TIE_SIMD, CONSISTENT><<<(p.n_blocks + WARPS - 1) / WARPS, 32 * WARPS, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+template <class C, int LOGT, int SH, bool TIE_SIMD, bool CONSISTENT>
+KernelEntry make_entry(const char* name) {
     KernelEntry e{};
     e.K = C::K; e.R = C::R;
     for (int i = 0; i < C::R; i++) e.G[i] = C::G[i];
-    e.sh = SH; e.tie = TIE_SIMD ? 1 : 0; e.consistent = CONSISTENT ? 1 : 0;
-    e.family = FAMILY_PAIR; e.name = name;
-    e.launch_pair = &launch_pair<C, SH, TIE_SIMD, CONSISTENT>;
+    e.sh = SH; e.tie = TIE_SIMD ? 1 : 0; e.consistent = CONSISTENT ? 1 : 0; e.logt = LOGT; e.name = name;
+    if constexpr (LOGT == 0) {
+        e.dec_words = 0;
+        e.launch = &launch_pair<C, SH, TIE_SIMD, CONSISTENT>;
+    } else {
+        e.dec_words = GroupShape<C, LOGT>::W;
+        e.launch = &launch_group<C, LOGT, SH, TIE_SIMD, CONSISTENT>;
+    }
     return e;
 }
 
-// all eight (metric type x tie-break x consistent-config) variants of one code
-#define VITB_PAIR_VARIANTS(VEC, CODE, TAG)                                                         \
-    VEC.push_back(make_pair_entry<CODE, 0, false, true>("acs_pair<" TAG ",u16,scalar-tie>"));       \
-    VEC.push_back(make_pair_entry<CODE, 8, false, true>("acs_pair<" TAG ",u8,scalar-tie>"));        \
-    VEC.push_back(make_pair_entry<CODE, 0, true, true>("acs_pair<" TAG ",u16,simd-tie>"));          \
-    VEC.push_back(make_pair_entry<CODE, 8, true, true>("acs_pair<" TAG ",u8,simd-tie>"));           \
-    VEC.push_back(make_pair_entry<CODE, 0, false, false>("acs_pair<" TAG ",u16,scalar-tie,cinv>")); \
-    VEC.push_back(make_pair_entry<CODE, 8, false, false>("acs_pair<" TAG ",u8,scalar-tie,cinv>"));  \
-    VEC.push_back(make_pair_entry<CODE, 0, true, false>("acs_pair<" TAG ",u16,simd-tie,cinv>"));    \
-    VEC.push_back(make_pair_entry<CODE, 8, true, false>("acs_pair<" TAG ",u8,simd-tie,cinv>"));
+// all eight (metric type x tie-break x consistent-config) variants of one code at one lanes-per-pair setting
+#define VITB_VARIANTS(VEC, CODE, LOGT, TAG)                                                        \
+    VEC.push_back(make_entry<CODE, LOGT, 0, false, true>("acs<" TAG ",u16,scalar-tie>"));           \
+    VEC.push_back(make_entry<CODE, LOGT, 8, false, true>("acs<" TAG ",u8,scalar-tie>"));            \
+    VEC.push_back(make_entry<CODE, LOGT, 0, true, true>("acs<" TAG ",u16,simd-tie>"));              \
+    VEC.push_back(make_entry<CODE, LOGT, 8, true, true>("acs<" TAG ",u8,simd-tie>"));               \
+    VEC.push_back(make_entry<CODE, LOGT, 0, false, false>("acs<" TAG ",u16,scalar-tie,cinv>"));     \
+    VEC.push_back(make_entry<CODE, LOGT, 8, false, false>("acs<" TAG ",u8,scalar-tie,cinv>"));      \
+    VEC.push_back(make_entry<CODE, LOGT, 0, true, false>("acs<" TAG ",u16,simd-tie,cinv>"));        \
+    VEC.push_back(make_entry<CODE, LOGT, 8, true, false>("acs<" TAG ",u8,simd-tie,cinv>"));
 
-// one translation unit per code family (parallel compilation)
-void register_k7r2(std::vector<KernelEntry>& v);
-void register_k7r3(std::vector<KernelEntry>& v);
-void register_k7r4(std::vector<KernelEntry>& v);
+// one translation unit per code family and lanes-per-pair setting (parallel compilation)
 void register_small(std::vector<KernelEntry>& v);
+void register_k7r2_t1(std::vector<KernelEntry>& v);
+void register_k7r2_t2(std::vector<KernelEntry>& v);
+void register_k7r2_t4(std::vector<KernelEntry>& v);
+void register_k7r3_t1(std::vector<KernelEntry>& v);
+void register_k7r3_t4(std::vector<KernelEntry>& v);
+void register_k7r4_t1(std::vector<KernelEntry>& v);
+void register_k7r4_t2(std::vector<KernelEntry>& v);
+void register_k7r4_t4(std::vector<KernelEntry>& v);
+void register_k9r2_t8(std::vector<KernelEntry>& v);
+void register_k9r2_t16(std::vector<KernelEntry>& v);
+void register_k9r4_t8(std::vector<KernelEntry>& v);
+void register_k9r4_t16(std::vector<KernelEntry>& v);
 
 }  // namespace vitb

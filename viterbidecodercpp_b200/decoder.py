@@ -216,6 +216,16 @@ class ViterbiDecoder_CUDA:
     def set_workspace_limit(self, nbytes):
         _check(self._L.vitb_set_workspace_limit(self._h, nbytes))
 
+    def set_variant(self, lanes_per_pair=0):
+        """pin the lanes-per-frame-pair kernel variant for batch calls (0 = choose by batch size)"""
+        _check(self._L.vitb_set_variant(self._h, lanes_per_pair), "set_variant")
+
+    @property
+    def variants(self):
+        buf = (C.c_int * 16)()
+        n = self._L.vitb_get_variants(self._h, buf, 16)
+        return [buf[i] for i in range(n)]
+
     @property
     def kernel_launch_count(self):
         n = C.c_uint64()
