@@ -180,6 +180,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=0, help="override the number of frames (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lanes", type=int, default=0, help="pin the lanes-per-frame-pair kernel variant (0 = automatic)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -210,6 +211,8 @@ def main():
     if w["keep"] is not None:
         dec.set_puncture_schedule(w["keep"].astype(np.uint8), 0)
     dec.set_profiling(True)
+    if args.lanes:
+        dec.set_variant(args.lanes)
 
     out_stride = (L + 7) // 8
     h_sym = torch.from_numpy(w["sym"]).pin_memory()

@@ -113,7 +113,7 @@ int vitb_decode_batch_multi(vitb_decoder* const* handles, int n_handles, const v
 /* ---- introspection ---- */
 /* bytes of device workspace a batch call of this shape needs (decision rows dominate: n_frames * (L+K-1) * 2^(K-1)/8) */
 int vitb_workspace_bytes(const vitb_decoder* h, size_t n_frames, size_t total_bits, size_t* bytes);
-/* cap on the workspace; larger batches are processed in chunks of frames.  0 = default (set by VITB_WORKSPACE_MB or 24 GiB) */
+/* cap on the workspace; larger batches are processed in chunks of frames.  0 = default (VITB_WORKSPACE_MB, else 60 % of device memory) */
 int vitb_set_workspace_limit(vitb_decoder* h, size_t bytes);
 /* number of CUDA kernels this handle has launched so far (bench.py reports it as gpu_launches) */
 int vitb_kernel_launch_count(const vitb_decoder* h, uint64_t* count);

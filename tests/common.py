@@ -7,7 +7,7 @@ from oracle_binding import OracleDecoder, MODE_SCALAR, MODE_SIMD
 
 CODE_BY_NAME = {c.name: c for c in v.COMMON_CODES}
 PAIR_CODES = ["Basic K=3 R=1/2", "Basic K=5 R=1/2", "Voyager", "LTE", "DAB Radio"]
-GPU_CODES = PAIR_CODES + ["CDMA IS-95A", "CDMA 2000"]      # codes with compiled kernels so far
+GPU_CODES = PAIR_CODES + ["CDMA IS-95A", "CDMA 2000", "Cassini"]      # the whole catalogue (examples/helpers/common_codes.h)
 
 
 def make_cuda_decoder(code, decode_type, tie_break=0, device=0, config_override=None):

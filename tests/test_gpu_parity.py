@@ -24,9 +24,11 @@ def test_noise_free_round_trip(cuda_lib, name, decode_type):
     for lanes in dec.variants:
         dec.set_variant(lanes)
         out, acc, fin = dec.decode_batch(sym, 512)
+        assert_batch_equal((out, acc, fin), want, f"{name} {decode_type} lanes/pair={lanes}")
+        if name == "Cassini" and decode_type == "SOFT8":
+            continue   # uint8 metrics wrap for K=15 (the reference skips this case too, run_tests.cpp:63-65); still bit-exact vs the oracle
         assert (out == tx).all(), lanes
         assert ((acc + fin) == 0).all(), lanes
-        assert_batch_equal((out, acc, fin), want, f"{name} {decode_type} lanes/pair={lanes}")
 
 
 @pytest.mark.parametrize("EbNo_dB", [-3.0, 1.0, 4.0])
@@ -41,18 +43,20 @@ def test_batch_parity_awgn(cuda_lib, name, decode_type, EbNo_dB):
     L = (L // 8) * 8
     if code.K >= 9:
         n_frames, L = 75, 1000
+    if code.K >= 15:
+        n_frames, L = 5, 2048          # long enough for several renormalisations (rollback + replay path of acs_cta.cuh)
     tx, sym = frames(code, dc, n_frames, L, EbNo_dB, seed=1234)
     want = ora.decode_frames(sym, n_frames, L)
     assert dec.variants, "no kernel variants"
     for lanes in dec.variants:          # every compiled lanes-per-pair variant must be bit-exact
         dec.set_variant(lanes)
         got = dec.decode_batch(sym, L)
-        assert f"T{lanes}" in dec.kernel_name
+        assert f"T{lanes}" in dec.kernel_name, dec.kernel_name
         assert_batch_equal(got, want, f"{name} {decode_type} {EbNo_dB} dB lanes/pair={lanes}")
 
 
 @pytest.mark.parametrize("decode_type", ["SOFT16", "HARD8"])
-@pytest.mark.parametrize("name", ["Voyager", "DAB Radio", "Basic K=5 R=1/2", "CDMA IS-95A", "CDMA 2000"])
+@pytest.mark.parametrize("name", ["Voyager", "DAB Radio", "Basic K=5 R=1/2", "CDMA IS-95A", "CDMA 2000", "Cassini"])
 def test_streaming_api_matches_oracle_state(cuda_lib, name, decode_type):
     """reset / update in ragged pieces / get_error / chainback + the public m_decisions and m_metrics fields"""
     code = CODE_BY_NAME[name]
@@ -79,6 +83,8 @@ def test_streaming_api_matches_oracle_state(cuda_lib, name, decode_type):
         assert dec.m_current_decoded_bit == pos
     assert acc_g == acc_o
     assert (dec.m_metrics == ora.metrics()).all()
+    if code.K >= 15 and decode_type == "SOFT16":
+        assert acc_o > 0, "test should cross the renormalisation threshold at least once"
     for end_state in (0, 1, (1 << (code.K - 1)) - 1):
         assert dec.get_error(end_state) == ora.get_error(end_state)
         assert (dec.chainback(L, end_state) == ora.chainback(L, end_state)).all()

@@ -1,0 +1,272 @@
+// acs_cta.cuh -- add-compare-select for long constraint lengths (K = 15, Cassini: 16384 states): ONE CTA PER FRAME PAIR.
+//
+// 512 threads hold the 16384 packed path metrics of two frames in registers (32 each).  Same position algebra as acs_group.cuh
+// with LOGT = 9: PHI = (q << 9) | t, after n steps state s sits at PHI = rotr^n(s), LB = 5 steps run with register-only
+// butterflies, then the CTA exchanges through 64 KB of shared memory (XOR-swizzled, conflict-free) under two __syncthreads.
+//
+// Differences from the warp-group kernel, all forced by the size of the problem:
+//   * branch metrics: R = 6 gives 64 patterns, too many for a per-thread register table.  The table of one whole group of steps
+//     (LB x 64 entries of {total, inverted total}) is built cooperatively into shared memory at each exchange, 320 threads
+//     computing one entry each; a butterfly fetches its entry with one LDS.64 at index (register part ^ lane part of the pattern).
+//   * renormalisation: the trigger (state 0's metric >= threshold, scalar.h:48) is only visible to thread 0.  Steps run
+//     SPECULATIVELY without it; thread 0 records a trigger, the CTA learns of it at the next exchange barrier, ROLLS BACK to the
+//     metrics at the start of the group (still in the exchange buffer) and replays the group one step at a time with a barrier
+//     after every step, renormalising at exactly the reference's step.  Rare (a handful of times per frame), so the common
+//     path has no per-step CTA synchronisation, and the replay makes the result exact whatever the speculative steps did.
+//   * decision rows: thread t writes 32 bits per frame and step (bit q = decision of the state in its register q after the
+//     step), 4 KB per pair and step = the reference's 2048 B per frame and step, fully coalesced.  traceback_cta_kernel reads it.
+#pragma once
+#include <cstdint>
+#include <utility>
+#include <cuda_runtime.h>
+#include "vitb_code.cuh"
+#include "acs_pair.cuh"
+
+namespace vitb {
+
+template <class C>
+struct CtaShape {
+    static constexpr int LOGT = 9;
+    static constexpr int T = 1 << LOGT;              // threads per CTA = per frame pair
+    static constexpr int SB = C::SB;
+    static constexpr int LB = SB - LOGT;             // steps between exchanges
+    static_assert(LB >= 1 && LB <= 5, "CtaShape is meant for K = 11..15");
+    static constexpr int NL = 1 << LB;               // packed registers per thread
+    static constexpr int NP = C::NP;                 // branch patterns
+    static constexpr int WARPS = T / 32;
+    static constexpr size_t XCH_WORDS = size_t(C::NS);
+    static constexpr size_t TBL_WORDS = size_t(LB) * NP * 2;
+    static constexpr size_t SMEM_BYTES = (XCH_WORDS + TBL_WORDS + 64) * 4;
+    static __host__ __device__ constexpr uint32_t slot(uint32_t phi) { return phi ^ ((phi >> 5) & 31u); }
+};
+
+template <class C, int PH, bool TIE_SIMD, int Q>
+__device__ __forceinline__ void cta_bfly_at(uint32_t (&x)[CtaShape<C>::NL], const uint2* tbl_ph, const uint32_t pt, float (&fa)[2][2]) {
+    using S = CtaShape<C>;
+    constexpr int bit = 1 << (S::LB - 1 - PH);
+    if constexpr ((Q & bit) == 0) {
+        constexpr int q0 = Q, q1 = Q | bit;
+        constexpr uint32_t jq = rotl_bits(uint32_t(q0) << S::LOGT, PH, S::SB);
+        constexpr uint32_t pq = bfly_pattern<C>(jq);
+        const uint2 e = tbl_ph[pq ^ pt];            // {total_error, inverted_error} of pattern pq ^ pt   (scalar.h:66-73, 107)
+        const uint32_t a0 = __vadd2(x[q0], e.x), b0 = __vadd2(x[q1], e.y);     // scalar.h:113-114
+        const uint32_t a1 = __vadd2(x[q0], e.y), b1 = __vadd2(x[q1], e.x);     // scalar.h:115-116
+        bool h0, l0, h1, l1, dA0, dB0, dA1, dB1;
+        if constexpr (!TIE_SIMD) {
+            x[q0] = __vibmin_u16x2(a0, b0, &h0, &l0);
+            x[q1] = __vibmin_u16x2(a1, b1, &h1, &l1);
+            dA0 = !l0; dB0 = !h0; dA1 = !l1; dB1 = !h1;
+        } else {
+            x[q0] = __vibmin_u16x2(b0, a0, &h0, &l0);
+            x[q1] = __vibmin_u16x2(b1, a1, &h1, &l1);
+            dA0 = l0; dB0 = h0; dA1 = l1; dB1 = h1;
+        }
+        constexpr int acc0 = (q0 >> 4) & 1, acc1 = (q1 >> 4) & 1;
+        constexpr float w0 = float(1u << (q0 & 15)), w1 = float(1u << (q1 & 15));
+        if (dA0) fa[0][acc0] += w0;
+        if (dB0) fa[1][acc0] += w0;
+        if (dA1) fa[0][acc1] += w1;
+        if (dB1) fa[1][acc1] += w1;
+    }
+}
+
+template <class C, int PH, bool TIE_SIMD, int... Qs>
+__device__ __forceinline__ void cta_bfly_all(uint32_t (&x)[CtaShape<C>::NL], const uint2* tbl_ph, const uint32_t pt, float (&fa)[2][2],
+                                             std::integer_sequence<int, Qs...>) {
+    (cta_bfly_at<C, PH, TIE_SIMD, Qs>(x, tbl_ph, pt, fa), ...);
+}
+
+template <class C, int SH, bool TIE_SIMD>
+struct CtaKernel {
+    using S = CtaShape<C>;
+    static constexpr int LB = S::LB, NL = S::NL, R = C::R, NP = C::NP, T = S::T, SB = S::SB;
+
+    // one trellis step at compile-time phase PH; decisions to dec_row (this thread's uint2 of the row)
+    template <int PH>
+    static __device__ __forceinline__ void step(uint32_t (&x)[NL], const uint2* tbl, const uint32_t (&pt)[LB], uint2* dec_row) {
+        float fa[2][2] = {{8388608.f, 8388608.f}, {8388608.f, 8388608.f}};
+        cta_bfly_all<C, PH, TIE_SIMD>(x, tbl + PH * NP, pt[PH], fa, std::make_integer_sequence<int, NL>{});
+        uint32_t wA, wB;
+        if constexpr (NL > 16) {
+            wA = __byte_perm(__float_as_uint(fa[0][0]), __float_as_uint(fa[0][1]), 0x5410);
+            wB = __byte_perm(__float_as_uint(fa[1][0]), __float_as_uint(fa[1][1]), 0x5410);
+        } else {
+            wA = __float_as_uint(fa[0][0]) & 0xffffu;
+            wB = __float_as_uint(fa[1][0]) & 0xffffu;
+        }
+        *dec_row = make_uint2(wA, wB);
+    }
+
+    // CTA-wide packed minimum of all path metrics (both halves); result in every thread
+    static __device__ __forceinline__ uint32_t cta_min(const uint32_t (&x)[NL], uint32_t* red /* WARPS words of smem */) {
+        uint32_t m = packed_min<NL>(x);
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) m = __vminu2(m, __shfl_xor_sync(0xffffffffu, m, d));
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+        __syncthreads();
+        uint32_t r = red[0];
+#pragma unroll
+        for (int w = 1; w < S::WARPS; w++) r = __vminu2(r, red[w]);
+        __syncthreads();
+        return r;
+    }
+};
+
+// grid = number of frame pairs, block = 512, dynamic shared memory = CtaShape::SMEM_BYTES
+template <class C, int SH, bool TIE_SIMD>
+__global__ void __launch_bounds__(CtaShape<C>::T, 1) acs_cta_kernel(const AcsParams p) {
+    using S = CtaShape<C>;
+    using Kn = CtaKernel<C, SH, TIE_SIMD>;
+    constexpr int LB = S::LB, NL = S::NL, R = C::R, NP = C::NP, SB = S::SB, LOGT = S::LOGT;
+    extern __shared__ uint32_t smem[];
+    uint32_t* xch = smem;                                             // [NS] exchange buffer = metrics at the start of the group
+    uint2* tbl = reinterpret_cast<uint2*>(smem + S::XCH_WORDS);       // [LB][NP] {total, inverted}
+    uint32_t* red = smem + S::XCH_WORDS + S::TBL_WORDS;               // [WARPS] reduction scratch
+    uint32_t* flag = red + S::WARPS;                                  // [2] trigger flags
+
+    const uint32_t t = threadIdx.x, pair = blockIdx.x;
+    const size_t fA = size_t(pair) * 2, fB = fA + 1;
+    uint16_t* mA = p.metrics + fA * C::NS;
+    uint16_t* mB = p.metrics + fB * C::NS;
+
+    // lane part of the branch pattern per phase
+    uint32_t pt[LB];
+#pragma unroll
+    for (int n = 0; n < LB; n++) pt[n] = bfly_pattern_dyn<C>(rotl_bits(t, n, SB));
+
+    int ph = int(p.dec_row0 % uint32_t(LB));
+    uint32_t x[NL];
+    uint64_t accA = 0, accB = 0;
+    if (p.resume) {
+#pragma unroll
+        for (int q = 0; q < NL; q++) {
+            const uint32_t s = rotl_bits((uint32_t(q) << LOGT) | t, ph, SB);
+            x[q] = ((uint32_t(mA[s]) << SH) & 0xffffu) | (uint32_t(mB[s]) << (16 + SH));
+        }
+        if (t == 0) { accA = p.acc[fA]; accB = p.acc[fB]; }
+    } else {
+        const uint32_t s0 = p.start_state & uint32_t(C::NS - 1);
+#pragma unroll
+        for (int q = 0; q < NL; q++) {
+            const uint32_t s = rotl_bits((uint32_t(q) << LOGT) | t, ph, SB);
+            x[q] = (s == s0) ? p.init_start2 : p.init_other2;
+        }
+    }
+
+    const uint32_t* pk = p.pk + size_t(pair) * p.n_steps * R;                                    // [n_steps][R]
+    uint2* dec = reinterpret_cast<uint2*>(p.dec) + (size_t(pair) * p.dec_rows + p.dec_row0) * S::T + t;
+
+    uint32_t done = 0;
+    bool need_save = true;       // after an exchange the buffer already holds the group's starting metrics in read layout
+    while (done < p.n_steps) {
+        const uint32_t left = p.n_steps - done;
+        const uint32_t span = uint32_t(LB - ph) < left ? uint32_t(LB - ph) : left;   // steps in this group: phases ph .. ph+span-1
+
+        // ---- group prologue: keep the group's starting metrics in the exchange buffer (registers stay valid), build the
+        //      branch metric tables of the group's steps
+        if (need_save) {
+#pragma unroll
+            for (int q = 0; q < NL; q++) xch[S::slot((uint32_t(q) << LOGT) | t)] = x[q];
+        }
+        if (t < uint32_t(LB * NP)) {
+            const int tph = int(t) / NP;
+            const uint32_t pat = t % NP;
+            const int k = tph - ph;
+            if (k >= 0 && uint32_t(k) < span) {
+                const uint32_t* sy = pk + size_t(done + uint32_t(k)) * R;
+                uint32_t tot = 0, inv = p.c_inv2;
+#pragma unroll
+                for (int i = 0; i < R; i++) {
+                    const uint32_t sv = __ldg(sy + i);
+                    const uint32_t lo = __vadd2(sv, p.c_low2), hi = __vadd2(~sv, p.c_high2);
+                    const bool b = (pat >> i) & 1u;
+                    tot = __vadd2(tot, b ? hi : lo);          // viterbi_branch_table.h:52 + scalar.h:66-73
+                    inv = __vadd2(inv, b ? lo : hi);          // scalar.h:107 (max_error - total), complementary pattern + c_inv
+                }
+                tbl[tph * NP + pat] = make_uint2(tot, inv);
+            }
+        }
+        __syncthreads();
+
+        // ---- speculative run of the group (no renormalisation); thread 0 remembers the first phase whose state-0 metric
+        //      reached the threshold
+        uint32_t trig_phase = 0xffffffffu;
+        auto run_phase = [&](auto PHc) {
+            constexpr int PH = decltype(PHc)::value;
+            if (PH >= ph && uint32_t(PH - ph) < span) {
+                Kn::template step<PH>(x, tbl, pt, dec + size_t(done + uint32_t(PH - ph)) * S::T);
+                bool tb, ta;
+                (void)__vibmin_u16x2(p.thr2, x[0], &tb, &ta);
+                if ((ta || tb) && trig_phase == 0xffffffffu) trig_phase = uint32_t(PH);
+            }
+        };
+        run_phase(std::integral_constant<int, 0>{});
+        if constexpr (LB > 1) run_phase(std::integral_constant<int, 1>{});
+        if constexpr (LB > 2) run_phase(std::integral_constant<int, 2>{});
+        if constexpr (LB > 3) run_phase(std::integral_constant<int, 3>{});
+        if constexpr (LB > 4) run_phase(std::integral_constant<int, 4>{});
+        if (t == 0) flag[0] = trig_phase;
+        __syncthreads();
+        const uint32_t first_trig = flag[0];
+
+        if (first_trig != 0xffffffffu) {
+            // ---- roll back and replay step by step with the reference's renormalisation (scalar.h:48-50, 139-153)
+#pragma unroll
+            for (int q = 0; q < NL; q++) x[q] = xch[S::slot((uint32_t(q) << LOGT) | t)];
+            auto replay_phase = [&](auto PHc) {
+                constexpr int PH = decltype(PHc)::value;
+                if (PH >= ph && uint32_t(PH - ph) < span) {
+                    Kn::template step<PH>(x, tbl, pt, dec + size_t(done + uint32_t(PH - ph)) * S::T);
+                    if (t == 0) flag[1] = x[0];
+                    __syncthreads();
+                    const uint32_t x00 = flag[1];
+                    bool tb, ta;
+                    (void)__vibmin_u16x2(p.thr2, x00, &tb, &ta);
+                    if (ta || tb) {                                    // uniform across the CTA
+                        const uint32_t m = Kn::cta_min(x, red);
+                        const uint32_t mAv = m & 0xffffu, mBv = m >> 16;
+                        const uint32_t sub = (ta ? mAv : 0u) | ((tb ? mBv : 0u) << 16);
+                        const uint32_t neg = __vsub2(0u, sub);
+#pragma unroll
+                        for (int q = 0; q < NL; q++) x[q] = __vadd2(x[q], neg);
+                        if (ta) accA += uint64_t(mAv >> SH);
+                        if (tb) accB += uint64_t(mBv >> SH);
+                    } else {
+                        __syncthreads();                               // flag[1] may be rewritten by the next phase
+                    }
+                }
+            };
+            replay_phase(std::integral_constant<int, 0>{});
+            if constexpr (LB > 1) replay_phase(std::integral_constant<int, 1>{});
+            if constexpr (LB > 2) replay_phase(std::integral_constant<int, 2>{});
+            if constexpr (LB > 3) replay_phase(std::integral_constant<int, 3>{});
+            if constexpr (LB > 4) replay_phase(std::integral_constant<int, 4>{});
+            __syncthreads();
+        }
+
+        done += span;
+        if (uint32_t(ph) + span == uint32_t(LB)) {
+            // ---- exchange: value at (q, t) moves to PHI' = (t << LB) | q, bringing the layout back to PHI = s
+#pragma unroll
+            for (int q = 0; q < NL; q++) xch[S::slot((t << LB) | uint32_t(q))] = x[q];
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < NL; q++) x[q] = xch[S::slot((uint32_t(q) << LOGT) | t)];
+            __syncthreads();
+            ph = 0;
+            need_save = false;
+        } else {
+            ph += int(span);
+        }
+    }
+
+#pragma unroll
+    for (int q = 0; q < NL; q++) {
+        const uint32_t s = rotl_bits((uint32_t(q) << LOGT) | t, ph, SB);
+        mA[s] = uint16_t((x[q] & 0xffffu) >> SH);
+        mB[s] = uint16_t(x[q] >> (16 + SH));
+    }
+    if (t == 0) { p.acc[fA] = accA; p.acc[fB] = accB; }
+}
+
+}  // namespace vitb

@@ -51,17 +51,31 @@ __global__ void __launch_bounds__(INGEST_TILE) ingest_pairs_kernel(const IngestP
         tile[r * RS + tid] = uint16_t(uint32_t(v) << SH);
     }
     __syncthreads();
-    // 32 pairs x 256 symbols leave as (256 * ppw)-word runs, one run per warp block touched by this tile
-    const uint32_t ppw = p.ppw, run = INGEST_TILE * ppw;
+    const uint32_t ppw = p.ppw;
     const uint32_t n_valid = (p.n_sym - e0 < uint32_t(INGEST_TILE)) ? (p.n_sym - e0) : uint32_t(INGEST_TILE);
+    if (ppw == 32) {
+        // one warp block per tile: lane = pair, 8 symbols in flight per pass
+        const uint32_t lane = tid & 31, k0 = tid >> 5;
+        uint32_t* out = p.pk + (size_t(blk) * p.n_sym + e0) * 32 + lane;
 #pragma unroll 4
-    for (uint32_t l = tid; l < 32u * INGEST_TILE; l += INGEST_TILE) {
-        const uint32_t wb = l / run, rem = l % run, k = rem / ppw, slot = rem % ppw;
-        if (k < n_valid) {
-            const uint32_t pr = wb * ppw + slot;                 // pair inside the tile
-            const uint32_t a = tile[(2 * pr) * RS + k], b = tile[(2 * pr + 1) * RS + k];
-            const size_t wblk = size_t(blk) * (32 / ppw) + wb;
-            p.pk[(wblk * p.n_sym + e0 + k) * ppw + slot] = a | (b << 16);
+        for (uint32_t k = k0; k < uint32_t(INGEST_TILE); k += INGEST_TILE / 32) {
+            if (k < n_valid) {
+                const uint32_t a = tile[(2 * lane) * RS + k], b = tile[(2 * lane + 1) * RS + k];
+                out[size_t(k) * 32] = a | (b << 16);
+            }
+        }
+    } else {
+        // 32 pairs x 256 symbols leave as (256 * ppw)-word runs, one run per warp block touched by this tile (ppw is a power of two)
+        const uint32_t lp = 31u - uint32_t(__clz(ppw)), run_shift = 8u + lp;
+#pragma unroll 4
+        for (uint32_t l = tid; l < 32u * INGEST_TILE; l += INGEST_TILE) {
+            const uint32_t wb = l >> run_shift, rem = l & ((1u << run_shift) - 1u), k = rem >> lp, slot = rem & (ppw - 1u);
+            if (k < n_valid) {
+                const uint32_t pr = (wb << lp) + slot;               // pair inside the tile
+                const uint32_t a = tile[(2 * pr) * RS + k], b = tile[(2 * pr + 1) * RS + k];
+                const size_t wblk = size_t(blk) * (32u >> lp) + wb;
+                p.pk[((wblk * p.n_sym + e0 + k) << lp) + slot] = a | (b << 16);
+            }
         }
     }
 }

@@ -163,4 +163,61 @@ __global__ void __launch_bounds__(128) traceback_group_kernel(const TracebackGro
     }
 }
 
+// ---- decision rows written by acs_cta_kernel (acs_cta.cuh): [pair][row][T threads] x {A word, B word} -----------------------
+// A row is 2 KB per frame, so unlike the short codes the walk must read only the word it needs: address = f(state).  Within one
+// exchange period (LB rows) the owning thread t(state) does not change, so the LB loads of a period are issued together; the
+// next period's address needs this period's decisions (a dependent chain of L/LB memory round trips per frame, all frames in
+// parallel).  One thread per frame.
+struct TracebackCtaParams {
+    const uint32_t* dec;
+    uint32_t dec_rows;
+    uint32_t n_frames;
+    uint32_t total_bits;
+    uint32_t state_bits;
+    uint32_t logt;
+    uint32_t end_state;
+    uint8_t* out;
+    size_t out_stride;
+};
+
+template <int MAXLB>
+__global__ void __launch_bounds__(64) traceback_cta_kernel(const TracebackCtaParams p) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= p.n_frames) return;
+    const uint32_t SB = p.state_bits, g = p.logt, T = 1u << g, LB = SB - g, L = p.total_bits, half = f & 1u;
+    const uint32_t* d = p.dec + size_t(f >> 1) * p.dec_rows * T * 2 + half;
+    uint8_t* out = p.out + size_t(f) * p.out_stride;
+    uint32_t state = p.end_state, byte = 0;
+    if (L & 7) {
+        for (uint32_t jj = L; jj < ((L + 7) & ~7u); jj++) {
+            const uint32_t k = jj - L;
+            const uint32_t b = (k < SB) ? ((p.end_state >> (SB - 1 - k)) & 1u) : 0u;
+            byte |= b << (7 - (jj & 7));
+        }
+    }
+    int64_t r = int64_t(L) + SB - 1;                       // top decision row
+    while (r >= int64_t(SB)) {
+        const uint32_t n = uint32_t(r) % LB;               // rows r, r-1, .., r-n belong to the same exchange period
+        int64_t r_lo = r - n;
+        if (r_lo < int64_t(SB)) r_lo = SB;
+        const uint32_t cnt = uint32_t(r - r_lo) + 1;
+        const uint32_t t = rotr_rt(state, n + 1, SB) & (T - 1);
+        uint32_t w[MAXLB];
+#pragma unroll
+        for (int k = 0; k < MAXLB; k++) w[k] = (uint32_t(k) < cnt) ? __ldcs(d + (size_t(r - k) * T + t) * 2) : 0u;
+#pragma unroll
+        for (int k = 0; k < MAXLB; k++) {
+            if (uint32_t(k) < cnt) {
+                const uint32_t q = rotr_rt(state, n - uint32_t(k) + 1, SB) >> g;
+                const uint32_t bit = (w[k] >> q) & 1u;
+                state = (bit << (SB - 1)) | (state >> 1);
+                const int64_t j = r - k - int64_t(SB);
+                byte |= bit << (7 - (uint32_t(j) & 7));
+                if ((j & 7) == 0) { out[j >> 3] = uint8_t(byte); byte = 0; }
+            }
+        }
+        r = r_lo - 1;
+    }
+}
+
 }  // namespace vitb

@@ -28,6 +28,7 @@ static const std::vector<KernelEntry>& registry() {
         register_k7r4_t1(entries); register_k7r4_t2(entries); register_k7r4_t4(entries);
         register_k9r2_t8(entries); register_k9r2_t16(entries);
         register_k9r4_t8(entries); register_k9r4_t16(entries);
+        register_k15r6_cta(entries);
     });
     return entries;
 }
@@ -113,21 +114,21 @@ std::vector<const KernelEntry*> find_entries(const vitb_params& p) {
     return out;
 }
 
-// Variant for a batch of n_frames: the fewest lanes per pair that still puts ~5 warps on every SM sub-partition (the 2-cycle
-// issue of VIADD.16x2 needs several warps to overlap, and the group kernels' hot loops are small enough for the instruction cache).
+// Variant for a batch of n_frames.  Measured on B200 (profiles/r01_variants.md): the one-thread-per-pair kernel executes the
+// fewest instructions and wins whenever it exists (K <= 7); for K = 9 a pair spans 8 lanes unless the batch is too small to give
+// every SM sub-partition ~4 warps, then 16.
 const KernelEntry* choose_variant(const vitb_decoder* h, size_t n_frames) {
     if (h->forced_logt >= 0) {
         for (const KernelEntry* e : h->variants) if (e->logt == h->forced_logt) return e;
     }
-    const size_t target_warps = size_t(h->n_sm) * 4 * 5;
+    if (h->variants.front()->logt == 0) return h->variants.front();
+    const size_t target_warps = size_t(h->n_sm) * 4 * 4;
     const size_t pairs = (n_frames + 1) / 2;
-    const KernelEntry* best = h->variants.back();
     for (const KernelEntry* e : h->variants) {
-        if (e->logt == 0 && h->variants.size() > 1) continue;      // the fully unrolled kernel is instruction-fetch bound: last resort
         const size_t warps = ((pairs << e->logt) + 31) / 32;
-        if (warps >= target_warps) { best = e; break; }
+        if (warps >= target_warps) return e;
     }
-    return best;
+    return h->variants.back();
 }
 
 bool params_valid(const vitb_params& p) {
@@ -169,6 +170,9 @@ size_t default_ws_limit() {
         const long long mb = atoll(e);
         if (mb > 0) return size_t(mb) << 20;
     }
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b) return total_b / 10 * 6;   // 60 % of HBM (108 GB of 180 GB)
+    cudaGetLastError();
     return size_t(24) << 30;
 }
 
@@ -182,14 +186,28 @@ size_t block_bytes(const vitb_decoder* h, size_t S) {
 }
 
 size_t dec_bytes_per_block64(const KernelEntry* e, size_t rows) {
-    if (e->logt == 0) return rows * 64 * 8;
+    if (e->layout == LAYOUT_PAIR) return rows * 64 * 8;
+    if (e->layout == LAYOUT_CTA) return size_t(32) * rows * (size_t(1) << e->logt) * size_t(e->dec_words) * 4;
     return (size_t(1) << e->logt) * rows * 32 * size_t(e->dec_words) * 4;
+}
+
+// bytes of one decision row of ONE warp block / CTA (the unit the streaming state keeps)
+size_t dec_row_bytes_unit(const KernelEntry* e) {
+    if (e->layout == LAYOUT_PAIR) return 64 * 8;
+    if (e->layout == LAYOUT_CTA) return (size_t(1) << e->logt) * size_t(e->dec_words) * 4;
+    return size_t(32) * size_t(e->dec_words) * 4;
 }
 
 cudaError_t launch_traceback(vitb_decoder* h, const KernelEntry* e, const void* dec, size_t dec_rows, size_t n_frames, size_t L,
                              size_t end_state, uint8_t* d_out, size_t out_stride, cudaStream_t s) {
     h->launches++;
-    if (e->logt == 0) {
+    if (e->layout == LAYOUT_CTA) {
+        TracebackCtaParams t{};
+        t.dec = static_cast<const uint32_t*>(dec); t.dec_rows = uint32_t(dec_rows); t.n_frames = uint32_t(n_frames);
+        t.total_bits = uint32_t(L); t.state_bits = uint32_t(h->prm.K - 1); t.logt = uint32_t(e->logt); t.end_state = uint32_t(end_state);
+        t.out = d_out; t.out_stride = out_stride;
+        traceback_cta_kernel<5><<<unsigned((n_frames + 63) / 64), 64, 0, s>>>(t);
+    } else if (e->layout == LAYOUT_PAIR) {
         TracebackParams t{};
         t.dec = static_cast<const uint64_t*>(dec); t.dec_rows = uint32_t(dec_rows); t.n_frames = uint32_t(n_frames);
         t.total_bits = uint32_t(L); t.state_bits = uint32_t(h->prm.K - 1); t.end_state = uint32_t(end_state);
@@ -224,7 +242,7 @@ int decode_chunk_dev(vitb_decoder* h, const KernelEntry* e, const void* d_symbol
                      size_t start_state, size_t end_state, uint8_t* d_out, uint64_t* d_acc, uint32_t* d_final, cudaStream_t s) {
     const size_t K = size_t(h->prm.K), R = size_t(h->prm.R), S = L + K - 1, n_sym = S * R;
     const unsigned n_b64 = unsigned((n_frames + 63) / 64);
-    const unsigned n_wblocks = n_b64 << e->logt;
+    const unsigned n_wblocks = n_b64 * unsigned(32 / e->ppw);
     VITB_CUDA(h, h->pk.reserve(size_t(n_b64) * n_sym * 32 * 4));
     VITB_CUDA(h, h->dec.reserve(size_t(n_b64) * dec_bytes_per_block64(e, S)));
     VITB_CUDA(h, h->metrics.reserve(size_t(n_b64) * 64 * h->n_states * 2));
@@ -233,7 +251,7 @@ int decode_chunk_dev(vitb_decoder* h, const KernelEntry* e, const void* d_symbol
     IngestParams ip{};
     ip.symbols = d_symbols; ip.row_stride = row_stride; ip.n_frames = uint32_t(n_frames); ip.n_sym = uint32_t(n_sym);
     ip.depuncture_map = h->n_depunctured ? static_cast<const int32_t*>(h->map.ptr) : nullptr;
-    ip.fill_value = h->unpunctured_value; ip.pk = static_cast<uint32_t*>(h->pk.ptr); ip.ppw = 32u >> e->logt;
+    ip.fill_value = h->unpunctured_value; ip.pk = static_cast<uint32_t*>(h->pk.ptr); ip.ppw = uint32_t(e->ppw);
     VITB_CUDA(h, mark(h, s));
     VITB_CUDA(h, run_ingest(h, ip, n_b64, s));
     VITB_CUDA(h, mark(h, s));
@@ -405,7 +423,7 @@ int vitb_set_traceback_length(vitb_decoder* h, size_t traceback_length) {
     const size_t old_rows = h->traceback_length + size_t(h->prm.K - 1);
     if (!h->s_dec.ptr || rows != old_rows) {
         // std::vector::resize keeps the leading rows (core.h:182): so do we.  The streaming state is one warp block (block 0).
-        const size_t row_bytes = dec_bytes_per_block64(h->entry, 1) >> h->entry->logt;
+        const size_t row_bytes = dec_row_bytes_unit(h->entry);
         DeviceBuffer nb;
         VITB_CUDA(h, nb.reserve(rows * row_bytes + 16));
         VITB_CUDA(h, cudaMemsetAsync(nb.ptr, 0, rows * row_bytes + 16, h->stream));
@@ -468,7 +486,7 @@ int vitb_update(vitb_decoder* h, const void* symbols, size_t n_symbols, uint64_t
 
     IngestParams ip{};
     ip.symbols = h->s_in.ptr; ip.row_stride = n_symbols; ip.n_frames = 1; ip.n_sym = uint32_t(n_symbols);
-    ip.depuncture_map = nullptr; ip.fill_value = 0; ip.pk = static_cast<uint32_t*>(h->s_pk.ptr); ip.ppw = 32u >> h->entry->logt;
+    ip.depuncture_map = nullptr; ip.fill_value = 0; ip.pk = static_cast<uint32_t*>(h->s_pk.ptr); ip.ppw = uint32_t(h->entry->ppw);
     VITB_CUDA(h, run_ingest(h, ip, 1, h->stream));
 
     AcsParams a{};
@@ -516,7 +534,7 @@ int vitb_get_decisions(vitb_decoder* h, size_t first_row, size_t n_rows, uint64_
     if (!n_rows) return VITB_OK;
     VITB_CUDA(h, cudaSetDevice(h->prm.device));
     const KernelEntry* e = h->entry;
-    if (e->logt == 0) {
+    if (e->layout == LAYOUT_PAIR) {
         // frame 0 of the block: one uint64 every 64 words, already in the reference bit order
         VITB_CUDA(h, cudaMemcpy2DAsync(rows_out, 8, static_cast<uint64_t*>(h->s_dec.ptr) + first_row * 64, 64 * 8, 8, n_rows,
                                        cudaMemcpyDeviceToHost, h->stream));
@@ -525,7 +543,7 @@ int vitb_get_decisions(vitb_decoder* h, size_t first_row, size_t n_rows, uint64_
     }
     // group layout (acs_group.cuh): lane t, bit q of row r holds the decision of state rotl^(n+1)((q << logt) | t), n = r % LB
     const uint32_t g = uint32_t(e->logt), T = 1u << g, SB = uint32_t(h->prm.K - 1), LB = SB - g, NL = 1u << LB, W = uint32_t(e->dec_words);
-    const size_t words_per_row = size_t(32) * W, out_words = (size_t(h->n_states) + 63) / 64;
+    const size_t words_per_row = dec_row_bytes_unit(e) / 4, out_words = (size_t(h->n_states) + 63) / 64;
     std::vector<uint32_t> raw(n_rows * words_per_row);
     VITB_CUDA(h, cudaMemcpyAsync(raw.data(), static_cast<uint32_t*>(h->s_dec.ptr) + first_row * words_per_row, raw.size() * 4,
                                  cudaMemcpyDeviceToHost, h->stream));
@@ -537,7 +555,7 @@ int vitb_get_decisions(vitb_decoder* h, size_t first_row, size_t n_rows, uint64_
         for (uint32_t t = 0; t < T; t++) {
             const uint32_t* lane_words = &raw[r * words_per_row + size_t(t) * W];      // pair 0 = lanes 0..T-1, frame A
             for (uint32_t q = 0; q < NL; q++) {
-                const uint32_t bit = (W == 1) ? ((lane_words[0] >> q) & 1u) : ((lane_words[0] >> q) & 1u);
+                const uint32_t bit = (lane_words[0] >> q) & 1u;
                 if (!bit) continue;
                 const uint32_t s2 = rotl_bits((q << g) | t, int(n + 1), int(SB));
                 out[s2 / 64] |= uint64_t(1) << (s2 % 64);

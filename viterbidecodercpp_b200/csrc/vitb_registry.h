@@ -7,8 +7,11 @@
 #include <cuda_runtime.h>
 #include "acs_pair.cuh"
 #include "acs_group.cuh"
+#include "acs_cta.cuh"
 
 namespace vitb {
+
+enum { LAYOUT_PAIR = 0, LAYOUT_GROUP = 1, LAYOUT_CTA = 2 };
 
 struct KernelEntry {
     int K, R;
@@ -16,8 +19,10 @@ struct KernelEntry {
     int sh;            // 0: uint16_t metrics, 8: uint8_t metrics held as metric << 8
     int tie;           // VITB_TIE_*
     int consistent;    // max_error == R*(high-low): inverted error is the complementary table entry
-    int logt;          // lanes per frame pair = 1 << logt; 0 = one thread per pair (acs_pair.cuh), >= 1 = acs_group.cuh
-    int dec_words;     // 32-bit decision words per lane per step (group kernels); pair kernels: one uint64 per frame
+    int logt;          // threads per frame pair = 1 << logt
+    int layout;        // LAYOUT_PAIR (acs_pair.cuh), LAYOUT_GROUP (acs_group.cuh), LAYOUT_CTA (acs_cta.cuh): decision row format
+    int ppw;           // frame pairs per warp block of the packed symbol stream (32 / lanes, 1 for CTA kernels)
+    int dec_words;     // 32-bit decision words per thread per step (group/CTA kernels); pair kernels: one uint64 per frame
     const char* name;
     cudaError_t (*launch)(const AcsParams&, cudaStream_t);
 };
@@ -35,6 +40,38 @@ cudaError_t launch_group(const AcsParams& p, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+// CONSISTENT is irrelevant for the CTA kernel (c_inv is folded into the shared-memory table)
+template <class C, int SH, bool TIE_SIMD>
+cudaError_t launch_cta(const AcsParams& p, cudaStream_t s) {
+    using S = CtaShape<C>;
+    static bool configured = false;      // per process; the attribute is per device, so set it every time a device may be new
+    cudaError_t e = cudaFuncSetAttribute(acs_cta_kernel<C, SH, TIE_SIMD>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(S::SMEM_BYTES));
+    if (e != cudaSuccess) return e;
+    configured = true;
+    (void)configured;
+    acs_cta_kernel<C, SH, TIE_SIMD><<<p.n_blocks, S::T, S::SMEM_BYTES, s>>>(p);
+    return cudaGetLastError();
+}
+
+template <class C, int SH, bool TIE_SIMD>
+KernelEntry make_cta_entry(const char* name, int consistent) {
+    KernelEntry e{};
+    e.K = C::K; e.R = C::R;
+    for (int i = 0; i < C::R; i++) e.G[i] = C::G[i];
+    e.sh = SH; e.tie = TIE_SIMD ? 1 : 0; e.consistent = consistent; e.logt = CtaShape<C>::LOGT; e.name = name;
+    e.layout = LAYOUT_CTA; e.ppw = 1; e.dec_words = 2;
+    e.launch = &launch_cta<C, SH, TIE_SIMD>;
+    return e;
+}
+
+#define VITB_CTA_VARIANTS(VEC, CODE, TAG)                                                   \
+    for (int cons = 0; cons < 2; cons++) {                                                  \
+        VEC.push_back(make_cta_entry<CODE, 0, false>("acs_cta<" TAG ",u16,scalar-tie>", cons)); \
+        VEC.push_back(make_cta_entry<CODE, 8, false>("acs_cta<" TAG ",u8,scalar-tie>", cons));  \
+        VEC.push_back(make_cta_entry<CODE, 0, true>("acs_cta<" TAG ",u16,simd-tie>", cons));    \
+        VEC.push_back(make_cta_entry<CODE, 8, true>("acs_cta<" TAG ",u8,simd-tie>", cons));     \
+    }
+
 template <class C, int LOGT, int SH, bool TIE_SIMD, bool CONSISTENT>
 KernelEntry make_entry(const char* name) {
     KernelEntry e{};
@@ -42,10 +79,10 @@ KernelEntry make_entry(const char* name) {
     for (int i = 0; i < C::R; i++) e.G[i] = C::G[i];
     e.sh = SH; e.tie = TIE_SIMD ? 1 : 0; e.consistent = CONSISTENT ? 1 : 0; e.logt = LOGT; e.name = name;
     if constexpr (LOGT == 0) {
-        e.dec_words = 0;
+        e.layout = LAYOUT_PAIR; e.ppw = 32; e.dec_words = 0;
         e.launch = &launch_pair<C, SH, TIE_SIMD, CONSISTENT>;
     } else {
-        e.dec_words = GroupShape<C, LOGT>::W;
+        e.layout = LAYOUT_GROUP; e.ppw = GroupShape<C, LOGT>::PPW; e.dec_words = GroupShape<C, LOGT>::W;
         e.launch = &launch_group<C, LOGT, SH, TIE_SIMD, CONSISTENT>;
     }
     return e;
@@ -76,5 +113,6 @@ void register_k9r2_t8(std::vector<KernelEntry>& v);
 void register_k9r2_t16(std::vector<KernelEntry>& v);
 void register_k9r4_t8(std::vector<KernelEntry>& v);
 void register_k9r4_t16(std::vector<KernelEntry>& v);
+void register_k15r6_cta(std::vector<KernelEntry>& v);
 
 }  // namespace vitb
