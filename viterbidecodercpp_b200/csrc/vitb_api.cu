@@ -70,7 +70,8 @@ struct vitb_decoder {
     int sh = 0;
     int last_cuda = 0;
     uint64_t launches = 0;
-    size_t ws_limit = 0;
+    size_t ws_limit = 0;                 // vitb_set_workspace_limit; 0 = ws_default
+    size_t ws_default = size_t(24) << 30;   // queried once at create time
     cudaStream_t stream = nullptr;    // owned; used by the host-pointer entry points
     // batch workspace
     DeviceBuffer pk, dec, metrics, acc, d_in, d_out, d_accout, d_finout, map;
@@ -297,7 +298,7 @@ int check_batch_args(const vitb_decoder* h, size_t n_frames, size_t L, const vit
 
 size_t chunk_frames_for(const vitb_decoder* h, size_t L) {
     const size_t S = L + size_t(h->prm.K) - 1;
-    const size_t limit = h->ws_limit ? h->ws_limit : default_ws_limit();
+    const size_t limit = h->ws_limit ? h->ws_limit : h->ws_default;
     size_t blocks = limit / block_bytes(h, S);
     if (blocks < 1) blocks = 1;
     return blocks * 64;
@@ -349,6 +350,7 @@ int vitb_create(const vitb_params* p, vitb_decoder** out) {
     h->sh = e->sh;
     cudaError_t ce = cudaSetDevice(p->device);
     if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, p->device);
+    if (ce == cudaSuccess) h->ws_default = default_ws_limit();
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (ce != cudaSuccess) { delete h; return VITB_ERR_CUDA; }
     *out = h;
