@@ -3,6 +3,7 @@
 // <K,R,error_t,soft_t> template arguments, not a multi-backend dispatch.)
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 #include <vector>
 #include <cuda_runtime.h>
 #include "acs_pair.cuh"
@@ -27,9 +28,15 @@ struct KernelEntry {
     cudaError_t (*launch)(const AcsParams&, cudaStream_t);
 };
 
+// The in-place kernel is the default.  VITB_PAIR_PINGPONG=1 selects the two-register-set variant (smaller hot loop, but ptxas
+// then schedules all compare-selects ahead of their predicated FADDs, runs out of predicate registers and spills them through
+// P2R/LOP3: measured 2.14 ms vs 1.42 ms on config 2, profiles/r01_summary.md).
 template <class C, int SH, bool TIE_SIMD, bool CONSISTENT>
 cudaError_t launch_pair(const AcsParams& p, cudaStream_t s) {
-    acs_pair_kernel<C, SH, TIE_SIMD, CONSISTENT><<<(p.n_blocks + PAIR_WARPS - 1) / PAIR_WARPS, 32 * PAIR_WARPS, 0, s>>>(p);
+    static const bool inplace = (getenv("VITB_PAIR_PINGPONG") == nullptr);
+    const unsigned grid = (p.n_blocks + PAIR_WARPS - 1) / PAIR_WARPS;
+    if (inplace) acs_pair_kernel<C, SH, TIE_SIMD, CONSISTENT><<<grid, 32 * PAIR_WARPS, 0, s>>>(p);
+    else acs_pair_pp_kernel<C, SH, TIE_SIMD, CONSISTENT><<<grid, 32 * PAIR_WARPS, 0, s>>>(p);
     return cudaGetLastError();
 }
 
