@@ -156,6 +156,14 @@ struct GroupKernel {
         step<PH>(x, &cur[PH * R], lc, p, dec_lane + size_t(tt) * 32 * S::W, accA, accB, lane, pair_mask);
     }
 
+    // a whole exchange period, no per-step bounds checks: the common path of batch decoding
+    template <int... PHs>
+    static __device__ __forceinline__ void fast_group(uint32_t (&x)[NL], const uint32_t (&cur)[LB * R], const LaneConsts<C, LOGT>& lc,
+                                                      const AcsParams& p, uint32_t* dec_rows, uint64_t& accA, uint64_t& accB,
+                                                      const uint32_t lane, const uint32_t pair_mask, std::integer_sequence<int, PHs...>) {
+        (step<PHs>(x, &cur[PHs * R], lc, p, dec_rows + PHs * 32 * S::W, accA, accB, lane, pair_mask), ...);
+    }
+
     template <int... PHs>
     static __device__ __forceinline__ void group(uint32_t (&x)[NL], const uint32_t (&cur)[LB * R], const LaneConsts<C, LOGT>& lc,
                                                  const AcsParams& p, uint32_t* dec_lane, const uint32_t done, const int ph0,
@@ -219,31 +227,62 @@ __global__ void __launch_bounds__(32 * GroupShape<C, LOGT>::WARPS) acs_group_ker
     const uint32_t* pk = p.pk + size_t(wblk) * p.n_steps * R * PPW + pw;
     uint32_t* dec_lane = static_cast<uint32_t*>(p.dec) + ((size_t(wblk) * p.dec_rows + p.dec_row0) * 32 + lane) * S::W;
 
+    auto exchange = [&]() {
+        // all LB phases done: rotate positions back to PHI = s.  Value at (q, t) moves to PHI' = (t << LB) | q.
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < NL; q++) my_xch[S::slot(pw, (t << LB) | uint32_t(q))] = x[q];
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < NL; q++) x[q] = my_xch[S::slot(pw, (uint32_t(q) << LOGT) | t)];
+    };
+
     uint32_t done = 0;
-    while (done < p.n_steps) {
+    // ---- head: a call that starts in the middle of an exchange period (streaming API) or is shorter than one period
+    if (ph != 0 || p.n_steps < uint32_t(LB)) {
         uint32_t cur[LB * R];
 #pragma unroll
         for (int k = 0; k < LB * R; k++) {
             const int PH = k / R;
-            const uint32_t tt = done + uint32_t(PH - ph);
+            const uint32_t tt = uint32_t(PH - ph);
             cur[k] = (PH >= ph && tt < p.n_steps) ? __ldg(pk + (size_t(tt) * R + (k % R)) * PPW) : 0u;
         }
-        Kn::group(x, cur, lc, p, dec_lane, done, ph, accA, accB, lane, pair_mask, std::make_integer_sequence<int, LB>{});
-        const uint32_t left = p.n_steps - done, span = uint32_t(LB - ph);
-        if (left >= span) {
-            // all LB phases done: rotate positions back to PHI = s.  Value at (q, t) moves to PHI' = (t << LB) | q.
-            done += span;
-            __syncwarp();
+        Kn::group(x, cur, lc, p, dec_lane, 0u, ph, accA, accB, lane, pair_mask, std::make_integer_sequence<int, LB>{});
+        const uint32_t span = uint32_t(LB - ph);
+        if (p.n_steps >= span) { done = span; exchange(); ph = 0; }
+        else { done = p.n_steps; ph += int(p.n_steps); }
+    }
+    // ---- body: whole periods, symbols of the next period prefetched while this one is computed
+    if (done + LB <= p.n_steps) {
+        uint32_t nxt[LB * R];
 #pragma unroll
-            for (int q = 0; q < NL; q++) my_xch[S::slot(pw, (t << LB) | uint32_t(q))] = x[q];
-            __syncwarp();
+        for (int k = 0; k < LB * R; k++) nxt[k] = __ldg(pk + (size_t(done) * R + k) * PPW);
+        uint32_t* drow = dec_lane + size_t(done) * 32 * S::W;
+#pragma unroll 1
+        while (done + LB <= p.n_steps) {
+            uint32_t cur[LB * R];
 #pragma unroll
-            for (int q = 0; q < NL; q++) x[q] = my_xch[S::slot(pw, (uint32_t(q) << LOGT) | t)];
-            ph = 0;
-        } else {
-            done += left;
-            ph += int(left);
+            for (int k = 0; k < LB * R; k++) cur[k] = nxt[k];
+            const uint32_t nb = done + LB;
+#pragma unroll
+            for (int k = 0; k < LB * R; k++) nxt[k] = (nb + uint32_t(k / R) < p.n_steps) ? __ldg(pk + (size_t(nb) * R + k) * PPW) : 0u;
+            Kn::fast_group(x, cur, lc, p, drow, accA, accB, lane, pair_mask, std::make_integer_sequence<int, LB>{});
+            exchange();
+            drow += LB * 32 * S::W;
+            done = nb;
         }
+    }
+    // ---- tail: fewer than LB steps left, phase 0
+    if (done < p.n_steps) {
+        uint32_t cur[LB * R];
+#pragma unroll
+        for (int k = 0; k < LB * R; k++) {
+            const uint32_t tt = done + uint32_t(k / R);
+            cur[k] = (tt < p.n_steps) ? __ldg(pk + (size_t(tt) * R + (k % R)) * PPW) : 0u;
+        }
+        Kn::group(x, cur, lc, p, dec_lane, done, 0, accA, accB, lane, pair_mask, std::make_integer_sequence<int, LB>{});
+        ph = int(p.n_steps - done);
+        done = p.n_steps;
     }
 
     // write back in logical order; state s sits at PHI = rotr^ph(s)

@@ -189,9 +189,16 @@ __device__ __forceinline__ void acs_pair_step(uint32_t (&x)[C::NS], const uint32
     }
 }
 
-template <class C, int SH, bool TIE_SIMD, bool CONSISTENT>
+// Number of in-place phases unrolled before the registers are renamed back to logical order (PHI = s).  SB phases need no
+// renaming at all but make the hot loop SB steps long (36 KB of SASS for K=7: instruction-fetch bound, "no_instruction" is the top
+// stall in profiles/r01_ncu_full_acs_pair_cfg2.txt); a shorter period trades 2^(K-1) register moves per period for a loop that
+// fits the instruction cache.
+template <class C>
+struct PairPeriod { static constexpr int value = (C::SB == 6) ? 3 : C::SB; };
+
+template <class C, int SH, bool TIE_SIMD, bool CONSISTENT, int PERIOD = PairPeriod<C>::value>
 struct PairRunner {
-    static constexpr int P = C::SB, R = C::R, NS = C::NS;
+    static constexpr int P = PERIOD, R = C::R, NS = C::NS;
 
     template <int PH>
     static __device__ __forceinline__ bool phase(uint32_t (&x)[NS], const uint32_t (&cur)[P * R], const AcsParams& p, uint32_t t0,
@@ -211,10 +218,10 @@ struct PairRunner {
 // One warp per 64-frame block (lane l owns frames 64*blk + 2l and 64*blk + 2l + 1); PAIR_WARPS warps per CTA so that the warps of
 // a CTA land on all four SM sub-partitions evenly.  grid = ceil(n_blocks / PAIR_WARPS).
 constexpr int PAIR_WARPS = 4;
-template <class C, int SH, bool TIE_SIMD, bool CONSISTENT>
+template <class C, int SH, bool TIE_SIMD, bool CONSISTENT, int PERIOD = PairPeriod<C>::value>
 __global__ void __launch_bounds__(32 * PAIR_WARPS) acs_pair_kernel(const AcsParams p) {
-    constexpr int P = C::SB, R = C::R, NS = C::NS, SB = C::SB;
-    using Run = PairRunner<C, SH, TIE_SIMD, CONSISTENT>;
+    constexpr int P = PERIOD, R = C::R, NS = C::NS, SB = C::SB;
+    using Run = PairRunner<C, SH, TIE_SIMD, CONSISTENT, PERIOD>;
     const uint32_t lane = threadIdx.x & 31, blk = blockIdx.x * PAIR_WARPS + (threadIdx.x >> 5);
     if (blk >= p.n_blocks) return;
     const size_t fA = size_t(blk) * 64 + 2 * lane, fB = fA + 1;
@@ -248,9 +255,19 @@ __global__ void __launch_bounds__(32 * PAIR_WARPS) acs_pair_kernel(const AcsPara
 #pragma unroll
         for (int k = 0; k < P * R; k++) nxt[k] = (tn + uint32_t(k / R) < p.n_steps) ? __ldg(pk + (size_t(tn) * R + k) * 32) : 0u;
         Run::group(x, cur, p, t0, dec_lane, accA, accB, std::make_integer_sequence<int, P>{});
+        if constexpr (P < SB) {
+            if (t0 + P <= p.n_steps) {          // a full period ran: state s sits in register rotr^P(s); rename back to register s
+                uint32_t y[NS];
+#pragma unroll
+                for (int q = 0; q < NS; q++) y[q] = x[rotr_bits(uint32_t(q), P, SB)];
+#pragma unroll
+                for (int q = 0; q < NS; q++) x[q] = y[q];
+            }
+        }
     }
 
-    // after n steps logical state s sits in register rotr^n(s); write back in logical order (core.h:195-199 reads old_metrics[end_state])
+    // after n steps (since the last renaming) logical state s sits in register rotr^n(s); write back in logical order
+    // (core.h:195-199 reads old_metrics[end_state])
     const int ph = int(p.n_steps % uint32_t(P));
     uint16_t* mA = p.metrics + fA * NS;
     uint16_t* mB = p.metrics + fB * NS;

@@ -117,22 +117,16 @@ __global__ void __launch_bounds__(128) traceback_group_kernel(const TracebackGro
         }
         byteB = byteA;
     }
-    auto one_row = [&](int64_t j, uint32_t w0, uint32_t w1) {
-        const uint32_t row = uint32_t(j) + SB, n = row % LB;
-        const uint32_t phiA = rotr_rt(stA, n + 1, SB), phiB = rotr_rt(stB, n + 1, SB);
+    const uint32_t smask = (1u << SB) - 1u;
+    // n = row % LB is carried along (rows are visited in decreasing order); rot = n + 1 is in [1, LB] so never 0 or SB
+    auto one_row = [&](int64_t j, uint32_t n, uint32_t w0, uint32_t w1) {
+        const uint32_t rot = n + 1;
+        const uint32_t phiA = ((stA >> rot) | (stA << (SB - rot))) & smask, phiB = ((stB >> rot) | (stB << (SB - rot))) & smask;
         const uint32_t qA = phiA >> g, qB = phiB >> g;
-        uint32_t bitA, bitB;
-        if (W == 1) {
-            const uint32_t wA = __shfl_sync(0xffffffffu, w0, int(grp0 + (phiA & (T - 1))));
-            const uint32_t wB = __shfl_sync(0xffffffffu, w0, int(grp0 + (phiB & (T - 1))));
-            bitA = (wA >> qA) & 1u;
-            bitB = (wB >> (16 + qB)) & 1u;
-        } else {
-            const uint32_t wA = __shfl_sync(0xffffffffu, w0, int(grp0 + (phiA & (T - 1))));
-            const uint32_t wB = __shfl_sync(0xffffffffu, w1, int(grp0 + (phiB & (T - 1))));
-            bitA = (wA >> qA) & 1u;
-            bitB = (wB >> qB) & 1u;
-        }
+        const uint32_t wA = __shfl_sync(0xffffffffu, w0, int(grp0 + (phiA & (T - 1))));
+        const uint32_t wB = __shfl_sync(0xffffffffu, W == 1 ? w0 : w1, int(grp0 + (phiB & (T - 1))));
+        const uint32_t bitA = (wA >> qA) & 1u;
+        const uint32_t bitB = (wB >> (W == 1 ? 16 + qB : qB)) & 1u;
         stA = (bitA << (SB - 1)) | (stA >> 1);
         stB = (bitB << (SB - 1)) | (stB >> 1);
         byteA |= bitA << (7 - (uint32_t(j) & 7));
@@ -144,21 +138,40 @@ __global__ void __launch_bounds__(128) traceback_group_kernel(const TracebackGro
         }
     };
     int64_t j = int64_t(L) - 1;
+    uint32_t n = uint32_t((uint64_t(j) + SB) % LB);     // phase of the top row
     while (j >= 0 && ((j + 1) % BATCH) != 0) {      // ragged head
         const uint32_t* r = d + (size_t(j) + SB) * 32 * W;
-        one_row(j, r[0], W == 2 ? r[W - 1] : 0u);
+        one_row(j, n, r[0], W == 2 ? r[W - 1] : 0u);
+        n = (n == 0) ? LB - 1 : n - 1;
         j--;
+    }
+    // main loop, software pipelined: the next batch of rows is already in flight while this one is walked
+    uint32_t nw0[BATCH], nw1[BATCH];
+    if (j >= BATCH - 1) {
+#pragma unroll
+        for (int k = 0; k < BATCH; k++) {
+            const uint32_t* r = d + (size_t(j - k) + SB) * 32 * W;
+            if (W == 2) { const uint2 v = __ldcs(reinterpret_cast<const uint2*>(r)); nw0[k] = v.x; nw1[k] = v.y; }
+            else { nw0[k] = __ldcs(r); nw1[k] = 0u; }
+        }
     }
     while (j >= BATCH - 1) {
         uint32_t w0[BATCH], w1[BATCH];
 #pragma unroll
-        for (int k = 0; k < BATCH; k++) {
-            const uint32_t* r = d + (size_t(j - k) + SB) * 32 * W;
-            if (W == 2) { const uint2 v = __ldcs(reinterpret_cast<const uint2*>(r)); w0[k] = v.x; w1[k] = v.y; }
-            else { w0[k] = __ldcs(r); w1[k] = 0u; }
+        for (int k = 0; k < BATCH; k++) { w0[k] = nw0[k]; w1[k] = nw1[k]; }
+        if (j - BATCH >= BATCH - 1) {
+#pragma unroll
+            for (int k = 0; k < BATCH; k++) {
+                const uint32_t* r = d + (size_t(j - BATCH - k) + SB) * 32 * W;
+                if (W == 2) { const uint2 v = __ldcs(reinterpret_cast<const uint2*>(r)); nw0[k] = v.x; nw1[k] = v.y; }
+                else { nw0[k] = __ldcs(r); nw1[k] = 0u; }
+            }
         }
 #pragma unroll
-        for (int k = 0; k < BATCH; k++) one_row(j - k, w0[k], w1[k]);
+        for (int k = 0; k < BATCH; k++) {
+            one_row(j - k, n, w0[k], w1[k]);
+            n = (n == 0) ? LB - 1 : n - 1;
+        }
         j -= BATCH;
     }
 }

@@ -117,13 +117,13 @@ std::vector<const KernelEntry*> find_entries(const vitb_params& p) {
 
 // Variant for a batch of n_frames.  Measured on B200 (profiles/r01_variants.md): the one-thread-per-pair kernel executes the
 // fewest instructions and wins whenever it exists (K <= 7); for K = 9 a pair spans 8 lanes unless the batch is too small to give
-// every SM sub-partition ~4 warps, then 16.
+// every SM sub-partition ~2 warps, then 16.
 const KernelEntry* choose_variant(const vitb_decoder* h, size_t n_frames) {
     if (h->forced_logt >= 0) {
         for (const KernelEntry* e : h->variants) if (e->logt == h->forced_logt) return e;
     }
     if (h->variants.front()->logt == 0) return h->variants.front();
-    const size_t target_warps = size_t(h->n_sm) * 4 * 4;
+    const size_t target_warps = size_t(h->n_sm) * 4 * 2;
     const size_t pairs = (n_frames + 1) / 2;
     for (const KernelEntry* e : h->variants) {
         const size_t warps = ((pairs << e->logt) + 31) / 32;

@@ -35,6 +35,14 @@ template <class C, int SH, bool TIE_SIMD, bool CONSISTENT>
 cudaError_t launch_pair(const AcsParams& p, cudaStream_t s) {
     static const bool inplace = (getenv("VITB_PAIR_PINGPONG") == nullptr);
     const unsigned grid = (p.n_blocks + PAIR_WARPS - 1) / PAIR_WARPS;
+#ifdef VITB_PERIOD_EXPERIMENT
+    static const int period = getenv("VITB_PAIR_PERIOD") ? atoi(getenv("VITB_PAIR_PERIOD")) : 0;
+    if constexpr (C::SB == 6 && SH == 8 && !TIE_SIMD && CONSISTENT) {
+        if (period == 1) { acs_pair_kernel<C, SH, TIE_SIMD, CONSISTENT, 1><<<grid, 32 * PAIR_WARPS, 0, s>>>(p); return cudaGetLastError(); }
+        if (period == 2) { acs_pair_kernel<C, SH, TIE_SIMD, CONSISTENT, 2><<<grid, 32 * PAIR_WARPS, 0, s>>>(p); return cudaGetLastError(); }
+        if (period == 6) { acs_pair_kernel<C, SH, TIE_SIMD, CONSISTENT, 6><<<grid, 32 * PAIR_WARPS, 0, s>>>(p); return cudaGetLastError(); }
+    }
+#endif
     if (inplace) acs_pair_kernel<C, SH, TIE_SIMD, CONSISTENT><<<grid, 32 * PAIR_WARPS, 0, s>>>(p);
     else acs_pair_pp_kernel<C, SH, TIE_SIMD, CONSISTENT><<<grid, 32 * PAIR_WARPS, 0, s>>>(p);
     return cudaGetLastError();
