@@ -39,6 +39,20 @@ WORKLOADS = {
 }
 
 
+def read_traffic(kernel_name, frames):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/r01_traffic.json), scaled
+    to this run's frame count; None when no capture exists for this kernel variant"""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        t = json.load(f)
+    e = t.get(kernel_name)
+    if not e:
+        return None
+    return (e["dram_read_bytes"] + e["dram_write_bytes"]) * frames / e["frames"]
+
+
 def read_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -274,6 +288,7 @@ def main():
     sampler.start()
     ms_step = timed(step_dev, args.steps)
     launches = dec.kernel_launch_count - launches0
+    kernel_name = dec.kernel_name
     stages = stage_breakdown(min(args.steps, 10))      # kernel-level times for the roofline, same inputs, live in this run
 
     # sanity: the timed path really decoded the frames (bit error rate against the transmitted bytes)
@@ -310,12 +325,12 @@ def main():
         "dtype": "u8" if dc.soft_bytes == 1 else "u16", "data": "synthetic BPSK/AWGN (run_snr_ber statistics), fixed seed, every frame unique",
         "config": {"workload": f"{args.workload}: {w['desc']}", "frames_per_gpu": F, "bits_per_frame": L, "EbNo_dB": w["ebno"],
                    "l2": "inputs larger than L2 (no flush)" if w["sym"].nbytes > 130e6 else "inputs smaller than L2; decision buffer larger than L2",
-                   "kernel": dec.kernel_name, "parallelism": f"frames sharded over {world} GPU(s), no collective"},
+                   "kernel": kernel_name, "parallelism": f"frames sharded over {world} GPU(s), no collective"},
         "acs_gops": world * F * ab["acs_ops"] / (ms_step * 1e-3) / 1e9,
         "ber": ber,
         "stage_ms": stages,
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                     "traffic": None, "kernel": "add-compare-select", "peak_source": peak_src,
+                     "traffic": read_traffic(kernel_name, F), "kernel": "add-compare-select", "peak_source": peak_src,
                      "algorithmic_bytes_per_frame": ab["acs_kernel"], "kernel_ms": acs_ms},
         "roofline_alu": {"bound": "packed-int16x2 issue (1.5 instr/ACS, 16 lanes/clk/SMSP)", "achieved": acs_gacs, "peak": alu_peak_gacs,
                          "unit": "GACS/s", "frac": acs_gacs / alu_peak_gacs},

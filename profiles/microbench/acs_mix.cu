@@ -125,6 +125,47 @@ __global__ void __launch_bounds__(1024) acs(uint32_t* out, long long* cycles, co
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
 
+// tagged butterfly (uint8 metrics << 8): tag byte on the path-1 operand, VIADDMNMX, PRMT + shift-accumulate, LOP3 mask
+// ACCMODE: 0 = acc*2 + t (compiler's choice), 1 = shift+or, 2 = no accumulate (only PRMT), 3 = no decisions at all (no mask either)
+template<int ACCMODE>
+__global__ void __launch_bounds__(1024) acs_tag(uint32_t* out, long long* cycles, const uint32_t* in) {
+    uint32_t x[16]; uint32_t T[4], TT[4];
+    uint32_t da[2] = {0, 0};
+    #pragma unroll
+    for (int i = 0; i < 16; i++) x[i] = (in[i] + threadIdx.x) & 0xff00ff00u;
+    #pragma unroll
+    for (int i = 0; i < 4; i++) { T[i] = in[16 + i] & 0xff00ff00u; TT[i] = T[i] + 0x00010001u; }
+    __syncthreads();
+    long long t0 = clock64();
+    #pragma unroll 1
+    for (int it = 0; it < ITER / 4; it++) {
+        #pragma unroll
+        for (int ph = 0; ph < 4; ph++) {
+            const int bit = 8 >> ph;
+            #pragma unroll
+            for (int q = 0; q < 16; q++) {
+                if (q & bit) continue;
+                uint32_t &x0 = x[q], &x1 = x[q | bit];
+                const int pi = (q * 5 + ph) & 3;
+                const uint32_t b0 = __vadd2(x1, TT[pi ^ 3]), b1 = __vadd2(x1, TT[pi]);
+                const uint32_t m0 = __viaddmin_u16x2(x0, T[pi], b0), m1 = __viaddmin_u16x2(x0, T[pi ^ 3], b1);
+                if (ACCMODE == 0) da[q & 1] = da[q & 1] + da[q & 1] + __byte_perm(m0, m1, 0x6420);
+                if (ACCMODE == 1) da[q & 1] = (da[q & 1] << 1) | __byte_perm(m0, m1, 0x6420);
+                if (ACCMODE == 2) da[q & 1] ^= __byte_perm(m0, m1, 0x6420);
+                if (ACCMODE == 3) { x0 = m0; x1 = m1; } else { x0 = m0 & 0xff00ff00u; x1 = m1 & 0xff00ff00u; }
+            }
+            T[ph] = __vadd2(T[ph], 0x01000100u); TT[ph] = __vadd2(TT[ph], 0x01000100u);
+        }
+    }
+    __syncthreads();
+    long long t1 = clock64();
+    uint32_t acc = da[0] ^ da[1];
+    #pragma unroll
+    for (int i = 0; i < 16; i++) acc ^= x[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
 template<typename F>
 void run(const char* name, int instr_per_bfly, F launch, int nsm, const uint32_t* din) {
     const int wl[] = {1, 2, 3, 4, 6, 8};
@@ -172,5 +213,10 @@ int main() {
     ACS(8, 8, "+ 2 @P FADD (lo pred of each VIMNMX)");
     ACS(9, 8, "+ 2 @P FADD (both preds of one VIMNMX)");
     ACS(10, 12, "+ 4 SEL + 2 IADD3 (3-input)");
+#define TAG(M, IPB, NAME) run(NAME, IPB, [](int g, int t, uint32_t* o, long long* c, const uint32_t* in) { acs_tag<M><<<g, t>>>(o, c, in); }, nsm, din)
+    TAG(3, 4, "tagged: 2 VIADD + 2 VIADDMNMX only");
+    TAG(2, 7, "tagged: + 2 LOP3 mask + PRMT");
+    TAG(0, 8, "tagged: + acc*2+t (compiler)");
+    TAG(1, 9, "tagged: + shift | or");
     return 0;
 }

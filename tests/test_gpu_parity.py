@@ -212,3 +212,32 @@ def test_workspace_chunking_gives_identical_results(cuda_lib):
     ref = dec.decode_batch(sym, 512)
     dec.set_workspace_limit(dec.workspace_bytes(64, 512) * 2)      # two 64-frame blocks per chunk
     assert_batch_equal(dec.decode_batch(sym, 512), ref, "chunked")
+
+
+def test_decode_batch_multi_matches_single(cuda_lib):
+    """vitb_decode_batch_multi: contiguous frame ranges, one handle per range (here both handles on device 0; on a multi-GPU box
+    each handle is created on its own device), no collective - results identical to one call"""
+    code = CODE_BY_NAME["Voyager"]
+    dec0, dc = make_cuda_decoder(code, "HARD8")
+    dec1, _ = make_cuda_decoder(code, "HARD8")
+    tx, sym = frames(code, dc, 333, 512, 3.0, seed=31)
+    want = dec0.decode_batch(sym, 512)
+    got = v.decode_batch_multi([dec0, dec1], sym, 512)
+    assert_batch_equal(got, want, "multi")
+
+
+def test_pipelined_host_path_matches_device_path(cuda_lib):
+    """large enough that the host-pointer call is cut into several copy/compute chunks (and picks a different kernel variant for
+    the smaller chunks); must agree with the oracle on a sample and with itself across variants"""
+    code = CODE_BY_NAME["Voyager"]
+    dec, dc = make_cuda_decoder(code, "HARD8")
+    ora, _ = make_oracle(code, "HARD8")
+    F, L = 20000, 2048
+    tx, sym = frames(code, dc, F, L, 4.0, seed=77)
+    got = dec.decode_batch(sym, L)
+    dec.set_variant(1)
+    ref = dec.decode_batch(sym, L)
+    assert_batch_equal(got, ref, "pipelined auto-variant vs T1")
+    idx = np.arange(0, F, 97)
+    want = ora.decode_frames(sym[idx], idx.size, L)
+    assert_batch_equal((got[0][idx], got[1][idx], got[2][idx]), want, "pipelined vs oracle sample")

@@ -40,8 +40,12 @@ struct CtaShape {
     static __host__ __device__ constexpr uint32_t slot(uint32_t phi) { return phi ^ ((phi >> 5) & 31u); }
 };
 
+// float accumulators per frame: 8 decision bits each keeps the predicated-FADD dependency chains short enough that ptxas does not
+// run out of predicate registers (with 2 x 16 bits it spilled predicates through LOP3 bit masks: +81 instructions per step)
+constexpr int CTA_NACC = 4;
+
 template <class C, int PH, bool TIE_SIMD, int Q>
-__device__ __forceinline__ void cta_bfly_at(uint32_t (&x)[CtaShape<C>::NL], const uint2* tbl_ph, const uint32_t pt, float (&fa)[2][2]) {
+__device__ __forceinline__ void cta_bfly_at(uint32_t (&x)[CtaShape<C>::NL], const uint2* tbl_ph, const uint32_t pt, float (&fa)[2][CTA_NACC]) {
     using S = CtaShape<C>;
     constexpr int bit = 1 << (S::LB - 1 - PH);
     if constexpr ((Q & bit) == 0) {
@@ -61,8 +65,8 @@ __device__ __forceinline__ void cta_bfly_at(uint32_t (&x)[CtaShape<C>::NL], cons
             x[q1] = __vibmin_u16x2(b1, a1, &h1, &l1);
             dA0 = l0; dB0 = h0; dA1 = l1; dB1 = h1;
         }
-        constexpr int acc0 = (q0 >> 4) & 1, acc1 = (q1 >> 4) & 1;
-        constexpr float w0 = float(1u << (q0 & 15)), w1 = float(1u << (q1 & 15));
+        constexpr int acc0 = (q0 >> 3) % CTA_NACC, acc1 = (q1 >> 3) % CTA_NACC;
+        constexpr float w0 = float(1u << (q0 & 7)), w1 = float(1u << (q1 & 7));
         if (dA0) fa[0][acc0] += w0;
         if (dB0) fa[1][acc0] += w0;
         if (dA1) fa[0][acc1] += w1;
@@ -71,7 +75,7 @@ __device__ __forceinline__ void cta_bfly_at(uint32_t (&x)[CtaShape<C>::NL], cons
 }
 
 template <class C, int PH, bool TIE_SIMD, int... Qs>
-__device__ __forceinline__ void cta_bfly_all(uint32_t (&x)[CtaShape<C>::NL], const uint2* tbl_ph, const uint32_t pt, float (&fa)[2][2],
+__device__ __forceinline__ void cta_bfly_all(uint32_t (&x)[CtaShape<C>::NL], const uint2* tbl_ph, const uint32_t pt, float (&fa)[2][CTA_NACC],
                                              std::integer_sequence<int, Qs...>) {
     (cta_bfly_at<C, PH, TIE_SIMD, Qs>(x, tbl_ph, pt, fa), ...);
 }
@@ -84,16 +88,17 @@ struct CtaKernel {
     // one trellis step at compile-time phase PH; decisions to dec_row (this thread's uint2 of the row)
     template <int PH>
     static __device__ __forceinline__ void step(uint32_t (&x)[NL], const uint2* tbl, const uint32_t (&pt)[LB], uint2* dec_row) {
-        float fa[2][2] = {{8388608.f, 8388608.f}, {8388608.f, 8388608.f}};
+        float fa[2][CTA_NACC];
+#pragma unroll
+        for (int a = 0; a < CTA_NACC; a++) { fa[0][a] = 8388608.f; fa[1][a] = 8388608.f; }
         cta_bfly_all<C, PH, TIE_SIMD>(x, tbl + PH * NP, pt[PH], fa, std::make_integer_sequence<int, NL>{});
-        uint32_t wA, wB;
-        if constexpr (NL > 16) {
-            wA = __byte_perm(__float_as_uint(fa[0][0]), __float_as_uint(fa[0][1]), 0x5410);
-            wB = __byte_perm(__float_as_uint(fa[1][0]), __float_as_uint(fa[1][1]), 0x5410);
-        } else {
-            wA = __float_as_uint(fa[0][0]) & 0xffffu;
-            wB = __float_as_uint(fa[1][0]) & 0xffffu;
-        }
+        // byte k of the word = mantissa byte 0 of accumulator k (registers 8k .. 8k+7)
+        static_assert(NL == 32 || NL <= 16, "decision word packing assumes 32 or <= 16 registers per thread");
+        const uint32_t a01 = __byte_perm(__float_as_uint(fa[0][0]), __float_as_uint(fa[0][1]), 0x0040);
+        const uint32_t a23 = __byte_perm(__float_as_uint(fa[0][2]), __float_as_uint(fa[0][3]), 0x0040);
+        const uint32_t b01 = __byte_perm(__float_as_uint(fa[1][0]), __float_as_uint(fa[1][1]), 0x0040);
+        const uint32_t b23 = __byte_perm(__float_as_uint(fa[1][2]), __float_as_uint(fa[1][3]), 0x0040);
+        const uint32_t wA = __byte_perm(a01, a23, 0x5410), wB = __byte_perm(b01, b23, 0x5410);
         *dec_row = make_uint2(wA, wB);
     }
 

@@ -38,6 +38,7 @@ struct GroupShape {
     static constexpr int NACC = NL > 16 ? 2 : 1;    // float accumulators per frame
     static constexpr int W = NL > 16 ? 2 : 1;       // 32-bit decision words per lane per step
     static constexpr int WARPS = 4;                 // warps per CTA
+    static constexpr int MIN_CTAS = NL <= 16 ? 4 : 3;   // register budget: 128 regs when a lane holds <= 16 metrics, else 168 (measured best, profiles/r01_summary.md)
     // exchange swizzle (verified conflict-free for reads and writes by tests/test_host_cpu.py::test_exchange_swizzle)
     static __host__ __device__ constexpr uint32_t swz(uint32_t qp) {
         return LB >= LOGT ? ((qp >> (LB - LOGT)) & uint32_t(T - 1)) : (qp & 31u);
@@ -93,9 +94,7 @@ __device__ __forceinline__ void group_bfly_all(uint32_t (&x)[GroupShape<C, LOGT>
 template <class C, int LOGT>
 struct LaneConsts {
     using S = GroupShape<C, LOGT>;
-    uint32_t m[S::LB][C::R];      // 0 or ~0: x = sym ^ m
-    uint32_t clo[S::LB][C::R];    // e(expected bit 0 of the folded table) = x + clo
-    uint32_t chi[S::LB][C::R];    // e(expected bit 1 of the folded table) = ~x + chi
+    uint32_t m[S::LB][C::R];      // 0 or ~0: x = sym ^ m;  e(folded bit 0) = x + (m ? c_high : c_low),  e(folded bit 1) = ~x + (m ? c_low : c_high)
 };
 
 template <class C, int LOGT, int SH, bool TIE_SIMD, bool CONSISTENT>
@@ -109,9 +108,10 @@ struct GroupKernel {
         uint32_t lo[R], hi[R];
 #pragma unroll
         for (int i = 0; i < R; i++) {
-            const uint32_t xs = sym[i] ^ lc.m[PH][i];
-            lo[i] = __vadd2(xs, lc.clo[PH][i]);
-            hi[i] = __vadd2(~xs, lc.chi[PH][i]);
+            const uint32_t mk = lc.m[PH][i], cd = p.c_low2 ^ p.c_high2;
+            const uint32_t xs = sym[i] ^ mk;
+            lo[i] = __vadd2(xs, p.c_low2 ^ (mk & cd));      // constants swap when the lane part of the pattern flips this symbol
+            hi[i] = __vadd2(~xs, p.c_high2 ^ (mk & cd));
         }
         uint32_t Tt[NP];
         TableBuild<R, R>::run(Tt, lo, hi);
@@ -175,7 +175,7 @@ struct GroupKernel {
 
 // grid = ceil(n_wblocks / WARPS), block = 32 * WARPS
 template <class C, int LOGT, int SH, bool TIE_SIMD, bool CONSISTENT>
-__global__ void __launch_bounds__(32 * GroupShape<C, LOGT>::WARPS) acs_group_kernel(const AcsParams p) {
+__global__ void __launch_bounds__(32 * GroupShape<C, LOGT>::WARPS, GroupShape<C, LOGT>::MIN_CTAS) acs_group_kernel(const AcsParams p) {
     using S = GroupShape<C, LOGT>;
     using Kn = GroupKernel<C, LOGT, SH, TIE_SIMD, CONSISTENT>;
     constexpr int LB = S::LB, NL = S::NL, R = C::R, T = S::T, SB = S::SB, PPW = S::PPW;
@@ -198,8 +198,6 @@ __global__ void __launch_bounds__(32 * GroupShape<C, LOGT>::WARPS) acs_group_ker
         for (int i = 0; i < R; i++) {
             const bool b = (pt >> i) & 1u;
             lc.m[n][i] = b ? 0xffffffffu : 0u;
-            lc.clo[n][i] = b ? p.c_high2 : p.c_low2;
-            lc.chi[n][i] = b ? p.c_low2 : p.c_high2;
         }
     }
 

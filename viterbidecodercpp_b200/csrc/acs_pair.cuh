@@ -127,6 +127,51 @@ __device__ __forceinline__ void bfly_all(uint32_t (&x)[C::NS], const uint32_t (&
     (bfly_at<C, PH, TIE_SIMD, Qs>(x, T, fa, c_inv2, consistent), ...);
 }
 
+// ---- tagged butterfly (uint8_t metrics only) --------------------------------------------------------------------------
+// With metric << 8 in each half the low byte of every register is free.  Give the inverted-error operand (path 1) a low byte
+// of 1 and the total-error operand (path 0) a low byte of 0: min() then breaks a metric tie in favour of path 0 - exactly the
+// reference's strict '>' (scalar.h:123-124) - and the low byte of the minimum IS the decision bit.  No predicates, so add and min
+// fuse into VIADDMNMX.U16x2 and the decision bits of two registers (4 frames x states) are collected with one PRMT and shifted
+// into a byte-lane accumulator with one 3-input add: 8 instructions per butterfly instead of 10, and spread over both integer
+// pipes (profiles/microbench/r01_acs_decision_mix.txt: the predicated FADDs cost more than the ACS arithmetic itself).
+// TIE_SIMD puts the tag on path 0 instead and the collected bits are inverted at the end.
+// T = total error by pattern, V = inverted error by pattern's complement index (V[k] = T[k] + c_inv), TT / VT = the same with the
+// tag byte set.  For consistent configurations V aliases T and VT aliases TT.
+template <class C, int PH, bool TIE_SIMD, int J>
+__device__ __forceinline__ void tag_bfly_at(uint32_t (&x)[C::NS], const uint32_t (&T)[C::NP], const uint32_t (&TT)[C::NP],
+                                            const uint32_t (&V)[C::NP], const uint32_t (&VT)[C::NP],
+                                            uint32_t (&dacc)[(C::NS / 2 + 7) / 8]) {
+    constexpr int SB = C::SB;
+    constexpr int q0 = int(rotr_bits(uint32_t(J), PH, SB));                 // register of logical old state J (leading bit 0)
+    constexpr int q1 = q0 | (1 << (SB - 1 - PH));
+    static_assert((q0 & (1 << (SB - 1 - PH))) == 0, "butterfly register must have the phase bit clear");
+    constexpr uint32_t pat = bfly_pattern<C>(uint32_t(J));
+    constexpr uint32_t ipat = (~pat) & uint32_t(C::NP - 1);
+    uint32_t m0, m1;
+    if constexpr (!TIE_SIMD) {
+        const uint32_t b0 = __vadd2(x[q1], VT[ipat]);                       // (1|X) + inverted, tag 1     scalar.h:114
+        const uint32_t b1 = __vadd2(x[q1], TT[pat]);                        // (1|X) + total,    tag 1     scalar.h:116
+        m0 = __viaddmin_u16x2(x[q0], T[pat], b0);                           // min((0|X) + total, b0)      scalar.h:113,127
+        m1 = __viaddmin_u16x2(x[q0], V[ipat], b1);                          // min((0|X) + inverted, b1)   scalar.h:115,128
+    } else {
+        const uint32_t a0 = __vadd2(x[q0], TT[pat]);                        // tag on path 0: a tie selects path 1 (avx_u16.h:112-115)
+        const uint32_t a1 = __vadd2(x[q0], VT[ipat]);
+        m0 = __viaddmin_u16x2(x[q1], V[ipat], a0);
+        m1 = __viaddmin_u16x2(x[q1], T[pat], a1);
+    }
+    // bytes: [A: state 2J, B: state 2J, A: state 2J+1, B: state 2J+1]; bit 7-(J%8) of each byte lane after 8 butterflies
+    dacc[J / 8] = dacc[J / 8] + dacc[J / 8] + __byte_perm(m0, m1, 0x6420);
+    x[q0] = m0 & 0xff00ff00u;
+    x[q1] = m1 & 0xff00ff00u;
+}
+
+template <class C, int PH, bool TIE_SIMD, int... Js>
+__device__ __forceinline__ void tag_bfly_all(uint32_t (&x)[C::NS], const uint32_t (&T)[C::NP], const uint32_t (&TT)[C::NP],
+                                             const uint32_t (&V)[C::NP], const uint32_t (&VT)[C::NP],
+                                             uint32_t (&dacc)[(C::NS / 2 + 7) / 8], std::integer_sequence<int, Js...>) {
+    (tag_bfly_at<C, PH, TIE_SIMD, Js>(x, T, TT, V, VT, dacc), ...);
+}
+
 // minimum over all registers, per half
 template <int NS>
 __device__ __forceinline__ uint32_t packed_min(const uint32_t (&x)[NS]) {
@@ -138,10 +183,11 @@ __device__ __forceinline__ uint32_t packed_min(const uint32_t (&x)[NS]) {
 }
 
 // ---- one trellis step at compile-time phase PH ---------------------------------------------------------------------
-template <class C, int SH, bool TIE_SIMD, bool CONSISTENT, int PH>
+template <class C, int SH, bool TIE_SIMD, bool CONSISTENT, int PH, bool TAG = (SH == 8)>
 __device__ __forceinline__ void acs_pair_step(uint32_t (&x)[C::NS], const uint32_t* sym /* R packed words */, const AcsParams& p,
                                               uint64_t* dec_row /* this lane's 16 bytes of the row */, uint64_t& accA, uint64_t& accB) {
     constexpr int R = C::R, NP = C::NP, NS = C::NS, NACC = PairShape<C>::NACC;
+    static_assert(!TAG || SH == 8, "the tagged butterfly needs the free low byte of uint8_t metrics held as metric << 8");
     // per-symbol errors against low / high
     uint32_t lo[R], hi[R];
 #pragma unroll
@@ -152,6 +198,41 @@ __device__ __forceinline__ void acs_pair_step(uint32_t (&x)[C::NS], const uint32
     uint32_t T[NP];
     TableBuild<R, R>::run(T, lo, hi);
 
+    uint32_t wA0, wA1 = 0, wB0, wB1 = 0;
+    if constexpr (TAG) {
+        uint32_t TT[NP];
+#pragma unroll
+        for (int k = 0; k < NP; k++) TT[k] = __vadd2(T[k], 0x00010001u);
+        constexpr int NDA = (NS / 2 + 7) / 8;
+        uint32_t dacc[NDA];
+#pragma unroll
+        for (int k = 0; k < NDA; k++) dacc[k] = 0u;
+        if constexpr (CONSISTENT) {
+            tag_bfly_all<C, PH, TIE_SIMD>(x, T, TT, T, TT, dacc, std::make_integer_sequence<int, NS / 2>{});
+        } else {
+            uint32_t V[NP], VT[NP];       // inverted_error = max_error - total_error (scalar.h:107) = T[~pattern] + c_inv
+#pragma unroll
+            for (int k = 0; k < NP; k++) { V[k] = __vadd2(T[k], p.c_inv2); VT[k] = __vadd2(TT[k], p.c_inv2); }
+            tag_bfly_all<C, PH, TIE_SIMD>(x, T, TT, V, VT, dacc, std::make_integer_sequence<int, NS / 2>{});
+        }
+        if constexpr (TIE_SIMD) {
+#pragma unroll
+            for (int k = 0; k < NDA; k++) dacc[k] = ~dacc[k];         // the tag marked path 0: decision = !tag
+        }
+        // tagged row layout (LAYOUT_PAIR_TAG): byte 2k+h of a frame's 64-bit word holds the decisions of states 2J+h, J = 8k..8k+7,
+        // first butterfly in the top bit.  Butterfly groups that do not exist (K < 7) leave zero bytes.
+        if constexpr (NDA == 4) {
+            wA0 = __byte_perm(dacc[0], dacc[1], 0x6420); wA1 = __byte_perm(dacc[2], dacc[3], 0x6420);
+            wB0 = __byte_perm(dacc[0], dacc[1], 0x7531); wB1 = __byte_perm(dacc[2], dacc[3], 0x7531);
+        } else if constexpr (NDA == 2) {
+            wA0 = __byte_perm(dacc[0], dacc[1], 0x6420); wB0 = __byte_perm(dacc[0], dacc[1], 0x7531);
+        } else {
+            wA0 = __byte_perm(dacc[0], 0u, 0x4420); wB0 = __byte_perm(dacc[0], 0u, 0x4431);
+        }
+        if constexpr (NS / 2 < 8) {    // fewer than 8 butterflies: the bits sit at the bottom of the byte, move them to the top
+            wA0 <<= (8 - NS / 2); wB0 <<= (8 - NS / 2);
+        }
+    } else {
     float fa[2][NACC];
 #pragma unroll
     for (int a = 0; a < NACC; a++) { fa[0][a] = 8388608.f; fa[1][a] = 8388608.f; }
@@ -159,7 +240,6 @@ __device__ __forceinline__ void acs_pair_step(uint32_t (&x)[C::NS], const uint32
     bfly_all<C, PH, TIE_SIMD>(x, T, fa, p.c_inv2, CONSISTENT, std::make_integer_sequence<int, NS>{});
 
     // decision row: bit s of the 64-bit word = decision of logical state s (same bit order as core.h:49-83 / scalar.h:131-134)
-    uint32_t wA0, wA1 = 0, wB0, wB1 = 0;
     if constexpr (NACC == 4) {
         wA0 = __byte_perm(__float_as_uint(fa[0][0]), __float_as_uint(fa[0][1]), 0x5410);
         wA1 = __byte_perm(__float_as_uint(fa[0][2]), __float_as_uint(fa[0][3]), 0x5410);
@@ -171,6 +251,7 @@ __device__ __forceinline__ void acs_pair_step(uint32_t (&x)[C::NS], const uint32
     } else {
         wA0 = __float_as_uint(fa[0][0]) & 0xffffu;
         wB0 = __float_as_uint(fa[1][0]) & 0xffffu;
+    }
     }
     *reinterpret_cast<uint4*>(dec_row) = make_uint4(wA0, wA1, wB0, wB1);
 

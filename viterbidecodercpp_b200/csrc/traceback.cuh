@@ -7,6 +7,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <cuda_pipeline.h>
 
 namespace vitb {
 
@@ -19,7 +20,16 @@ struct TracebackParams {
     uint32_t end_state;
     uint8_t* out;             // [n_frames][out_stride]
     size_t out_stride;
+    uint32_t tag_layout;      // 0: bit s of the word = state s;  1: rows written by the tagged butterfly (acs_pair.cuh):
+                              //    byte 2k+h holds states 2J+h for J = 8k..8k+7, first butterfly in the top bit
 };
+
+// bit position of state s inside a frame's 64-bit decision word
+__device__ __forceinline__ uint32_t dec_bit_index(uint32_t s, uint32_t tag_layout) {
+    if (!tag_layout) return s;
+    const uint32_t J = s >> 1;
+    return (((J >> 3) * 2 + (s & 1u)) << 3) + 7u - (J & 7u);
+}
 
 // Decoded bit j is the decision read from row j + (K-1) at the current state; state <- (bit << (K-2)) | (state >> 1)
 // (ViterbiTracebackBuffer::push_bit_in / get_state, core.h:96-113).  Bytes are MSB-first (core.h:234).  When
@@ -42,8 +52,9 @@ __global__ void __launch_bounds__(128) traceback_u64_kernel(const TracebackParam
         }
     }
     // ragged head so the main loop works on whole bytes
+    const uint32_t tagl = p.tag_layout;
     while (j >= 0 && ((j & 7) != 7)) {
-        const uint32_t bit = uint32_t(d[size_t(j) * 64] >> state) & 1u;
+        const uint32_t bit = uint32_t(d[size_t(j) * 64] >> dec_bit_index(state, tagl)) & 1u;
         state = (bit << (SB - 1)) | (state >> 1);
         byte |= bit << (7 - (uint32_t(j) & 7));
         if ((j & 7) == 0) { out[j >> 3] = uint8_t(byte); byte = 0; }
@@ -56,7 +67,7 @@ __global__ void __launch_bounds__(128) traceback_u64_kernel(const TracebackParam
         for (int k = 0; k < BATCH; k++) w[k] = __ldcs(d + size_t(j - k) * 64);
 #pragma unroll
         for (int k = 0; k < BATCH; k++) {
-            const uint32_t bit = uint32_t(w[k] >> state) & 1u;
+            const uint32_t bit = uint32_t(w[k] >> dec_bit_index(state, tagl)) & 1u;
             state = (bit << (SB - 1)) | (state >> 1);
             byte |= bit << (k & 7);                         // j-k has (j-k)&7 == 7-(k&7) because j&7 == 7 and BATCH%8 == 0
             if ((k & 7) == 7) { out[(j - k) >> 3] = uint8_t(byte); byte = 0; }
@@ -64,7 +75,7 @@ __global__ void __launch_bounds__(128) traceback_u64_kernel(const TracebackParam
         j -= BATCH;
     }
     while (j >= 0) {
-        const uint32_t bit = uint32_t(d[size_t(j) * 64] >> state) & 1u;
+        const uint32_t bit = uint32_t(d[size_t(j) * 64] >> dec_bit_index(state, tagl)) & 1u;
         state = (bit << (SB - 1)) | (state >> 1);
         byte |= bit << (7 - (uint32_t(j) & 7));
         if ((j & 7) == 0) { out[j >> 3] = uint8_t(byte); byte = 0; }
@@ -173,6 +184,95 @@ __global__ void __launch_bounds__(128) traceback_group_kernel(const TracebackGro
             n = (n == 0) ? LB - 1 : n - 1;
         }
         j -= BATCH;
+    }
+}
+
+// Staged variant of the above: a warp walks 32 FRAMES (16 pairs) at once instead of 32/T.  The decision rows of those pairs
+// (32 bytes per frame and row, state independent) are streamed into shared memory with cp.async, two batches of ROWS rows in
+// flight, and every lane picks the one word its state needs with a single LDS.  8-16x fewer instructions per frame than the
+// shuffle version, which replicates the walk in all T lanes of a pair.
+// grid = ceil(n_frames / 128), block = 128 (4 warps), dynamic smem = 4 * 2 * ROWS * row_words * 4 bytes
+template <int W, int ROWS>
+__global__ void __launch_bounds__(128) traceback_group_staged_kernel(const TracebackGroupParams p) {
+    extern __shared__ uint32_t tb_smem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t SB = p.state_bits, g = p.logt, T = 1u << g, LB = SB - g, PPW = 32u >> g, L = p.total_bits;
+    const uint32_t fbase = (blockIdx.x * 4 + warp) * 32;
+    if (fbase >= p.n_frames) return;
+    const uint32_t n_wb = 16u / PPW;                       // warp blocks covered by this warp's 16 pairs (PPW <= 16)
+    const uint32_t wb_words = 32u * W;                     // words of one warp block per row
+    const uint32_t row_words = n_wb * wb_words;            // = 16 * T * W
+    uint32_t* stage = tb_smem + size_t(warp) * 2 * ROWS * row_words;
+    const size_t wblk0 = size_t(fbase / 2) / PPW;
+    const uint32_t* dbase = p.dec + wblk0 * p.dec_rows * wb_words;     // row r of warp block w: dbase + (w * dec_rows + r) * wb_words
+
+    const uint32_t f = fbase + lane, pr = lane >> 1, half = lane & 1u;
+    const uint32_t my_off = ((pr / PPW) * 32u + (pr % PPW) * T) * W + (W == 2 ? half : 0u);   // + t * W selects the lane's word
+    const uint32_t bit_base = (W == 2) ? 0u : half * 16u;
+    const bool writer = f < p.n_frames;
+    uint8_t* out = p.out + size_t(f) * p.out_stride;
+    const uint32_t smask = (1u << SB) - 1u;
+
+    uint32_t byte = 0;
+    if (L & 7) {
+        for (uint32_t jj = L; jj < ((L + 7) & ~7u); jj++) {
+            const uint32_t k = jj - L;
+            const uint32_t b = (k < SB) ? ((p.end_state >> (SB - 1 - k)) & 1u) : 0u;
+            byte |= b << (7 - (jj & 7));
+        }
+    }
+    // batch b covers rows top - b*ROWS - (ROWS-1) .. top - b*ROWS (clamped at 0; rows below SB are loaded but not walked)
+    const int top = int(L + SB) - 1;
+    const int n_batches = int((L + ROWS - 1) / ROWS);
+    // all sizes are powers of two: 16-byte pieces per row, per warp block
+    const uint32_t lg_row_pieces = 31u - uint32_t(__clz(row_words / 4)), lg_wb_pieces = 31u - uint32_t(__clz(wb_words / 4));
+    const uint32_t pieces = uint32_t(ROWS) << lg_row_pieces;
+    auto issue = [&](int b) {
+        uint32_t* dst = stage + size_t(b & 1) * ROWS * row_words;
+        for (uint32_t pc = lane; pc < pieces; pc += 32) {
+            const uint32_t k = pc >> lg_row_pieces, in_row = pc & ((1u << lg_row_pieces) - 1u);   // k-th row from the top of the batch
+            int r = top - b * ROWS - int(k);
+            if (r < 0) r = 0;
+            const uint32_t w = in_row >> lg_wb_pieces, o = in_row & ((1u << lg_wb_pieces) - 1u);
+            __pipeline_memcpy_async(dst + pc * 4, dbase + (size_t(w) * p.dec_rows + size_t(r)) * wb_words + o * 4, 16);
+        }
+        __pipeline_commit();
+    };
+    issue(0);
+    // The walk tracks PHI = rotr^(n+1)(state) instead of the state: inside an exchange period going one row down only replaces
+    // the bit at position SB-1-n by the decision just read; at a period boundary PHI is re-rotated once.
+    uint32_t n = uint32_t(top) % LB;
+    uint32_t phi;
+    {
+        const uint32_t rot = n + 1, st = p.end_state;
+        phi = ((st >> rot) | (st << (SB - rot))) & smask;
+    }
+    const uint32_t lane_mask = T - 1;
+    for (int b = 0; b < n_batches; b++) {
+        if (b + 1 < n_batches) { issue(b + 1); __pipeline_wait_prior(1); } else { __pipeline_wait_prior(0); }
+        __syncwarp();
+        const uint32_t* src = stage + size_t(b & 1) * ROWS * row_words + my_off;
+        const int r_top = top - b * ROWS;
+#pragma unroll
+        for (int k = 0; k < ROWS; k++) {
+            const int r = r_top - k;
+            if (r < int(SB)) break;
+            const uint32_t wv = src[uint32_t(k) * row_words + (phi & lane_mask) * W];
+            const uint32_t bit = (wv >> (bit_base + (phi >> g))) & 1u;
+            if (n != 0) {                                     // uniform: n depends on the row only
+                const uint32_t pos = SB - 1 - n;
+                phi = (phi & ~(1u << pos)) | (bit << pos);
+                n--;
+            } else {                                          // PHI = rotr^1(state_r): replacing its top bit gives state_(r-1);
+                const uint32_t st = (phi & (smask >> 1)) | (bit << (SB - 1));   // the row below has phase LB-1: PHI = rotr^LB
+                phi = ((st >> LB) | (st << g)) & smask;       // SB - LB = g
+                n = LB - 1;
+            }
+            const uint32_t j = uint32_t(r) - SB;
+            byte |= bit << (7 - (j & 7));
+            if ((j & 7) == 0) { if (writer) out[j >> 3] = uint8_t(byte); byte = 0; }
+        }
+        __syncwarp();       // everyone done with this buffer before it is refilled two batches later
     }
 }
 

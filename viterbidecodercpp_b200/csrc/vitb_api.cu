@@ -73,6 +73,8 @@ struct vitb_decoder {
     size_t ws_limit = 0;                 // vitb_set_workspace_limit; 0 = ws_default
     size_t ws_default = size_t(24) << 30;   // queried once at create time
     cudaStream_t stream = nullptr;    // owned; used by the host-pointer entry points
+    cudaStream_t copy_stream = nullptr;   // owned; host->device copies of the pipelined host-pointer path
+    std::vector<cudaEvent_t> copy_ev;     // one per pipeline chunk + fork/join
     // batch workspace
     DeviceBuffer pk, dec, metrics, acc, d_in, d_out, d_accout, d_finout, map;
     size_t n_depunctured = 0, n_received = 0;
@@ -115,19 +117,19 @@ std::vector<const KernelEntry*> find_entries(const vitb_params& p) {
     return out;
 }
 
-// Variant for a batch of n_frames.  Measured on B200 (profiles/r01_variants.md): the one-thread-per-pair kernel executes the
-// fewest instructions and wins whenever it exists (K <= 7); for K = 9 a pair spans 8 lanes unless the batch is too small to give
-// every SM sub-partition ~2 warps, then 16.
+// Variant for a batch of n_frames.  Measured on B200 (profiles/r01_summary.md): fewer lanes per pair = fewer instructions per ACS,
+// but every SM sub-partition needs a few warps to overlap the 2-cycle dispatch of the packed-integer instructions.  Pick the
+// fewest lanes that still give `want` warps per sub-partition (1.5 for the one-thread-per-pair kernel, whose warps carry 32
+// independent butterflies each; 4 for the lane-group kernels), else the most parallel variant.
 const KernelEntry* choose_variant(const vitb_decoder* h, size_t n_frames) {
     if (h->forced_logt >= 0) {
         for (const KernelEntry* e : h->variants) if (e->logt == h->forced_logt) return e;
     }
-    if (h->variants.front()->logt == 0) return h->variants.front();
-    const size_t target_warps = size_t(h->n_sm) * 4 * 2;
-    const size_t pairs = (n_frames + 1) / 2;
+    const size_t pairs = (n_frames + 1) / 2, smsp = size_t(h->n_sm) * 4;
     for (const KernelEntry* e : h->variants) {
         const size_t warps = ((pairs << e->logt) + 31) / 32;
-        if (warps >= target_warps) return e;
+        const size_t want = (e->logt == 0) ? smsp * 3 / 2 : smsp * 4;
+        if (e->layout == LAYOUT_CTA || warps >= want) return e;
     }
     return h->variants.back();
 }
@@ -212,17 +214,33 @@ cudaError_t launch_traceback(vitb_decoder* h, const KernelEntry* e, const void* 
         TracebackParams t{};
         t.dec = static_cast<const uint64_t*>(dec); t.dec_rows = uint32_t(dec_rows); t.n_frames = uint32_t(n_frames);
         t.total_bits = uint32_t(L); t.state_bits = uint32_t(h->prm.K - 1); t.end_state = uint32_t(end_state);
-        t.out = d_out; t.out_stride = out_stride;
+        t.out = d_out; t.out_stride = out_stride; t.tag_layout = (e->sh == 8) ? 1u : 0u;     // uint8_t pair kernels use the tagged butterfly
         traceback_u64_kernel<32><<<unsigned((n_frames + 127) / 128), 128, 0, s>>>(t);
     } else {
         TracebackGroupParams t{};
         t.dec = static_cast<const uint32_t*>(dec); t.dec_rows = uint32_t(dec_rows); t.n_frames = uint32_t(n_frames);
         t.total_bits = uint32_t(L); t.state_bits = uint32_t(h->prm.K - 1); t.logt = uint32_t(e->logt); t.end_state = uint32_t(end_state);
         t.out = d_out; t.out_stride = out_stride;
-        const size_t ppw = size_t(32) >> e->logt, n_pairs = (n_frames + 1) / 2, n_wblocks = (n_pairs + ppw - 1) / ppw;
-        const unsigned grid = unsigned((n_wblocks + 3) / 4);
-        if (e->dec_words == 1) traceback_group_kernel<1, 16><<<grid, 128, 0, s>>>(t);
-        else traceback_group_kernel<2, 16><<<grid, 128, 0, s>>>(t);
+        // staged kernel: 32 frames per warp; needs the decision buffer padded to whole 64-frame blocks (it is) and PPW <= 16
+        constexpr int ROWS = 8;
+        const size_t row_words = size_t(16) * (size_t(1) << e->logt) * size_t(e->dec_words);
+        const size_t smem = size_t(4) * 2 * ROWS * row_words * 4;
+        const unsigned grid = unsigned((n_frames + 127) / 128);
+        static const bool force_shuffle = getenv("VITB_TRACEBACK_SHUFFLE") != nullptr;
+        // the streaming state holds a single warp block (not a padded 64-frame block): only the shuffle kernel stays inside it
+        const bool use_shuffle = force_shuffle || dec == h->s_dec.ptr;
+        if (use_shuffle) {
+            const size_t ppw = size_t(32) >> e->logt, n_pairs = (n_frames + 1) / 2, n_wblocks = (n_pairs + ppw - 1) / ppw;
+            const unsigned g2 = unsigned((n_wblocks + 3) / 4);
+            if (e->dec_words == 1) traceback_group_kernel<1, 16><<<g2, 128, 0, s>>>(t);
+            else traceback_group_kernel<2, 16><<<g2, 128, 0, s>>>(t);
+        } else if (e->dec_words == 1) {
+            if (smem > 48 * 1024) cudaFuncSetAttribute(traceback_group_staged_kernel<1, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            traceback_group_staged_kernel<1, ROWS><<<grid, 128, smem, s>>>(t);
+        } else {
+            if (smem > 48 * 1024) cudaFuncSetAttribute(traceback_group_staged_kernel<2, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            traceback_group_staged_kernel<2, ROWS><<<grid, 128, smem, s>>>(t);
+        }
     }
     return cudaGetLastError();
 }
@@ -352,6 +370,7 @@ int vitb_create(const vitb_params* p, vitb_decoder** out) {
     if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, p->device);
     if (ce == cudaSuccess) h->ws_default = default_ws_limit();
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
     if (ce != cudaSuccess) { delete h; return VITB_ERR_CUDA; }
     *out = h;
     // core.h:175-176: the constructor leaves the decoder reset with traceback length 0
@@ -367,6 +386,8 @@ int vitb_destroy(vitb_decoder* h) {
     for (DeviceBuffer* b : {&h->pk, &h->dec, &h->metrics, &h->acc, &h->d_in, &h->d_out, &h->d_accout, &h->d_finout, &h->map,
                             &h->s_pk, &h->s_dec, &h->s_metrics, &h->s_acc, &h->s_in, &h->s_out}) b->release();
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->copy_ev) cudaEventDestroy(e);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return VITB_OK;
@@ -541,6 +562,17 @@ int vitb_get_decisions(vitb_decoder* h, size_t first_row, size_t n_rows, uint64_
         VITB_CUDA(h, cudaMemcpy2DAsync(rows_out, 8, static_cast<uint64_t*>(h->s_dec.ptr) + first_row * 64, 64 * 8, 8, n_rows,
                                        cudaMemcpyDeviceToHost, h->stream));
         VITB_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (e->sh == 8) {      // tagged row layout -> reference bit order
+            for (size_t r = 0; r < n_rows; r++) {
+                const uint64_t w = rows_out[r];
+                uint64_t o = 0;
+                for (uint32_t st = 0; st < uint32_t(h->n_states); st++) {
+                    const uint32_t J = st >> 1, idx = (((J >> 3) * 2 + (st & 1u)) << 3) + 7u - (J & 7u);
+                    o |= ((w >> idx) & 1ull) << st;
+                }
+                rows_out[r] = o;
+            }
+        }
         return VITB_OK;
     }
     // group layout (acs_group.cuh): lane t, bit q of row r holds the decision of state rotl^(n+1)((q << logt) | t), n = r % LB
@@ -624,6 +656,9 @@ int vitb_decode_batch_dev(vitb_decoder* h, const void* d_symbols, size_t n_frame
     return VITB_OK;
 }
 
+// Host-pointer path, pipelined: the batch is cut into a few chunks of frames; chunk c+1 is copied host->device on the handle's copy
+// stream while chunk c is decoded on the caller's stream, and each chunk's results go back as soon as they exist.  End to end the
+// call then costs about max(PCIe copy, kernels) instead of their sum (config 2: 269 MB over PCIe ~ 5 ms vs 1.6 ms of kernels).
 int vitb_decode_batch_async(vitb_decoder* h, const void* symbols, size_t n_frames, size_t L, const vitb_batch_opts* opts,
                             uint8_t* out_bytes, uint64_t* acc_error, uint32_t* final_error, void* stream) {
     size_t row_stride = 0, start = 0, end = 0;
@@ -633,20 +668,51 @@ int vitb_decode_batch_async(vitb_decoder* h, const void* symbols, size_t n_frame
     VITB_CUDA(h, cudaSetDevice(h->prm.device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t sb = size_t(h->prm.soft_bytes), out_stride = (L + 7) / 8;
-    const size_t in_bytes = n_frames * row_stride * sb;
+    const size_t row_bytes = row_stride * sb, in_bytes = n_frames * row_bytes;
     VITB_CUDA(h, h->d_in.reserve(in_bytes));
     if (out_bytes) VITB_CUDA(h, h->d_out.reserve(n_frames * out_stride));
     if (acc_error) VITB_CUDA(h, h->d_accout.reserve(n_frames * 8));
     if (final_error) VITB_CUDA(h, h->d_finout.reserve(n_frames * 4));
-    VITB_CUDA(h, cudaMemcpyAsync(h->d_in.ptr, symbols, in_bytes, cudaMemcpyHostToDevice, s));
-    vitb_batch_opts o{}; o.row_stride = row_stride; o.starting_state = start; o.end_state = end;
-    const int r = vitb_decode_batch_dev(h, h->d_in.ptr, n_frames, L, &o, out_bytes ? static_cast<uint8_t*>(h->d_out.ptr) : nullptr,
-                                        acc_error ? static_cast<uint64_t*>(h->d_accout.ptr) : nullptr,
-                                        final_error ? static_cast<uint32_t*>(h->d_finout.ptr) : nullptr, s);
-    if (r != VITB_OK) return r;
-    if (out_bytes) VITB_CUDA(h, cudaMemcpyAsync(out_bytes, h->d_out.ptr, n_frames * out_stride, cudaMemcpyDeviceToHost, s));
-    if (acc_error) VITB_CUDA(h, cudaMemcpyAsync(acc_error, h->d_accout.ptr, n_frames * 8, cudaMemcpyDeviceToHost, s));
-    if (final_error) VITB_CUDA(h, cudaMemcpyAsync(final_error, h->d_finout.ptr, n_frames * 4, cudaMemcpyDeviceToHost, s));
+
+    // pipeline chunks: at least ~16 MB of input each (PCIe efficiency), at most 8 chunks, whole 64-frame blocks, and never larger
+    // than what the workspace allows
+    size_t chunk = (n_frames + 3) / 4;
+    const size_t min_chunk = (size_t(16) << 20) / (row_bytes ? row_bytes : 1) + 1;
+    if (chunk < min_chunk) chunk = min_chunk;
+    const size_t ws_chunk = chunk_frames_for(h, L);
+    if (chunk > ws_chunk) chunk = ws_chunk;
+    chunk = (chunk + 63) / 64 * 64;
+    const size_t n_chunks = (n_frames + chunk - 1) / chunk;
+    while (h->copy_ev.size() < n_chunks + 1) {
+        cudaEvent_t e;
+        VITB_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->copy_ev.push_back(e);
+    }
+    // fork: the copies must not start before the caller's earlier work on `s` (it may still be using the buffers of a previous call)
+    VITB_CUDA(h, cudaEventRecord(h->copy_ev[n_chunks], s));
+    VITB_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->copy_ev[n_chunks], 0));
+    for (size_t c = 0; c < n_chunks; c++) {
+        const size_t f0 = c * chunk, nf = (n_frames - f0 < chunk) ? (n_frames - f0) : chunk;
+        VITB_CUDA(h, cudaMemcpyAsync(static_cast<uint8_t*>(h->d_in.ptr) + f0 * row_bytes, static_cast<const uint8_t*>(symbols) + f0 * row_bytes,
+                                     nf * row_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+        VITB_CUDA(h, cudaEventRecord(h->copy_ev[c], h->copy_stream));
+    }
+    h->ev_used = 0;
+    const KernelEntry* e = choose_variant(h, n_frames < chunk ? n_frames : chunk);
+    h->last_batch = e;
+    for (size_t c = 0; c < n_chunks; c++) {
+        const size_t f0 = c * chunk, nf = (n_frames - f0 < chunk) ? (n_frames - f0) : chunk;
+        VITB_CUDA(h, cudaStreamWaitEvent(s, h->copy_ev[c], 0));
+        uint8_t* d_out = out_bytes ? static_cast<uint8_t*>(h->d_out.ptr) + f0 * out_stride : nullptr;
+        uint64_t* d_acc = acc_error ? static_cast<uint64_t*>(h->d_accout.ptr) + f0 : nullptr;
+        uint32_t* d_fin = final_error ? static_cast<uint32_t*>(h->d_finout.ptr) + f0 : nullptr;
+        const int r = decode_chunk_dev(h, e, static_cast<const uint8_t*>(h->d_in.ptr) + f0 * row_bytes, row_stride, nf, L, start, end,
+                                       d_out, d_acc, d_fin, s);
+        if (r != VITB_OK) return r;
+        if (out_bytes) VITB_CUDA(h, cudaMemcpyAsync(out_bytes + f0 * out_stride, d_out, nf * out_stride, cudaMemcpyDeviceToHost, s));
+        if (acc_error) VITB_CUDA(h, cudaMemcpyAsync(acc_error + f0, d_acc, nf * 8, cudaMemcpyDeviceToHost, s));
+        if (final_error) VITB_CUDA(h, cudaMemcpyAsync(final_error + f0, d_fin, nf * 4, cudaMemcpyDeviceToHost, s));
+    }
     return VITB_OK;
 }
 
