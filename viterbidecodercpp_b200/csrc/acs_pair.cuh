@@ -46,6 +46,11 @@ struct AcsParams {
     uint32_t thr2;          // per half: renormalisation_threshold << SH
     uint32_t init_start2;   // per half: initial_start_error << SH
     uint32_t init_other2;   // per half: initial_non_start_error << SH
+    // direct-symbol variant of the pair kernel (no ingest pass): the caller's rows, read where they lie
+    const void* sym;        // [n_frames][sym_row_bytes] soft_t, 4-byte aligned rows
+    uint64_t sym_row_bytes;
+    uint64_t sym_total_bytes;   // n_frames * sym_row_bytes (loads are clamped to stay inside)
+    uint32_t n_frames;
 };
 
 template <class C>
@@ -299,10 +304,62 @@ struct PairRunner {
 // One warp per 64-frame block (lane l owns frames 64*blk + 2l and 64*blk + 2l + 1); PAIR_WARPS warps per CTA so that the warps of
 // a CTA land on all four SM sub-partitions evenly.  grid = ceil(n_blocks / PAIR_WARPS).
 constexpr int PAIR_WARPS = 4;
-template <class C, int SH, bool TIE_SIMD, bool CONSISTENT, int PERIOD = PairPeriod<C>::value>
+
+// ---- direct symbol fetch ----------------------------------------------------------------------------------------------
+// Each lane streams its own two rows of the caller's [frame][step][R] array (the reference's layout, scalar.h:43-46) with 32-bit
+// loads, one period of steps ahead; a 128-byte line of a row serves ~20 periods from L1/L2, so DRAM traffic stays at the size of
+// the input.  Saves the ingest pass (one full read of the symbols plus a 2x larger write and re-read of the packed stream).
+// Requires 4-byte aligned rows and an even number of bytes per period; anything else (and punctured input) goes through ingest.
+template <class C, int SH, int P>
+struct DirectFetch {
+    static constexpr int SBY = (SH == 8) ? 1 : 2;       // bytes per soft symbol (int8_t with uint8_t metrics, else int16_t)
+    static constexpr int BS = C::R * SBY;               // bytes per trellis step
+    static constexpr int PB = P * BS;                   // bytes per period
+    static constexpr bool supported = (PB % 2) == 0;
+    static constexpr int NWA = (PB + 3) / 4;            // aligned words holding one period
+    static constexpr int NW = NWA + ((PB % 4) ? 1 : 0); // words loaded: one more when periods alternate between offsets 0 and 2
+
+    static __device__ __forceinline__ void load(uint32_t (&raw)[NW], const uint32_t* row_words, uint32_t period, uint32_t max_word) {
+        const uint32_t w0 = (period * uint32_t(PB)) >> 2;
+#pragma unroll
+        for (int j = 0; j < NW; j++) {
+            const uint32_t w = w0 + uint32_t(j);
+            raw[j] = __ldg(row_words + (w < max_word ? w : max_word));
+        }
+    }
+    // packed symbol words of the period: out[n * R + i] = (sA << SH) & 0xffff | (sB << SH) << 16
+    static __device__ __forceinline__ void convert(uint32_t (&out)[P * C::R], const uint32_t (&rawA)[NW], const uint32_t (&rawB)[NW],
+                                                   uint32_t period) {
+        uint32_t a[NWA], b[NWA];
+        if constexpr ((PB % 4) != 0) {
+            const uint32_t sh = ((period * uint32_t(PB)) & 2u) * 8u;      // 0 or 16
+#pragma unroll
+            for (int j = 0; j < NWA; j++) { a[j] = __funnelshift_r(rawA[j], rawA[j + 1], sh); b[j] = __funnelshift_r(rawB[j], rawB[j + 1], sh); }
+        } else {
+#pragma unroll
+            for (int j = 0; j < NWA; j++) { a[j] = rawA[j]; b[j] = rawB[j]; }
+        }
+#pragma unroll
+        for (int n = 0; n < P; n++) {
+#pragma unroll
+            for (int i = 0; i < C::R; i++) {
+                const int bp = n * BS + i * SBY, w = bp >> 2, o = bp & 3;
+                if constexpr (SBY == 1) {
+                    // byte o of A -> byte 1, byte o of B -> byte 3, low bytes cleared (the metrics are held as value << 8)
+                    out[n * C::R + i] = __byte_perm(a[w], b[w], uint32_t(((4 + o) << 12) | (o << 4))) & 0xff00ff00u;
+                } else {
+                    out[n * C::R + i] = __byte_perm(a[w], b[w], o ? 0x7632u : 0x5410u);
+                }
+            }
+        }
+    }
+};
+
+template <class C, int SH, bool TIE_SIMD, bool CONSISTENT, int PERIOD = PairPeriod<C>::value, bool DIRECT = false>
 __global__ void __launch_bounds__(32 * PAIR_WARPS) acs_pair_kernel(const AcsParams p) {
     constexpr int P = PERIOD, R = C::R, NS = C::NS, SB = C::SB;
     using Run = PairRunner<C, SH, TIE_SIMD, CONSISTENT, PERIOD>;
+    using DF = DirectFetch<C, SH, P>;
     const uint32_t lane = threadIdx.x & 31, blk = blockIdx.x * PAIR_WARPS + (threadIdx.x >> 5);
     if (blk >= p.n_blocks) return;
     const size_t fA = size_t(blk) * 64 + 2 * lane, fB = fA + 1;
@@ -325,16 +382,38 @@ __global__ void __launch_bounds__(32 * PAIR_WARPS) acs_pair_kernel(const AcsPara
     const uint32_t* pk = p.pk + size_t(blk) * p.n_steps * R * 32 + lane;
     uint64_t* dec_lane = static_cast<uint64_t*>(p.dec) + (size_t(blk) * p.dec_rows + p.dec_row0) * 64 + 2 * lane;
 
-    uint32_t cur[P * R], nxt[P * R];
+    uint32_t cur[P * R], nxt[DIRECT ? 1 : P * R];
+    uint32_t rawA[DIRECT ? DF::NW : 1], rawB[DIRECT ? DF::NW : 1];
+    const uint32_t* rowA = nullptr;
+    const uint32_t* rowB = nullptr;
+    uint32_t maxwA = 0, maxwB = 0;
+    if constexpr (DIRECT) {
+        static_assert(!DIRECT || DF::supported, "direct symbol fetch needs an even number of bytes per period");
+        const size_t lastf = size_t(p.n_frames) - 1;
+        const size_t ldA = fA < lastf ? fA : lastf, ldB = fB < lastf ? fB : lastf;     // padding lanes re-read the last frame
+        rowA = reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(p.sym) + ldA * p.sym_row_bytes);
+        rowB = reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(p.sym) + ldB * p.sym_row_bytes);
+        maxwA = uint32_t((p.sym_total_bytes - ldA * p.sym_row_bytes - 4) >> 2);
+        maxwB = uint32_t((p.sym_total_bytes - ldB * p.sym_row_bytes - 4) >> 2);
+        DF::load(rawA, rowA, 0u, maxwA);
+        DF::load(rawB, rowB, 0u, maxwB);
+    } else {
 #pragma unroll
-    for (int k = 0; k < P * R; k++) nxt[k] = (uint32_t(k / R) < p.n_steps) ? __ldg(pk + size_t(k) * 32) : 0u;
+        for (int k = 0; k < P * R; k++) nxt[k] = (uint32_t(k / R) < p.n_steps) ? __ldg(pk + size_t(k) * 32) : 0u;
+    }
 
-    for (uint32_t t0 = 0; t0 < p.n_steps; t0 += P) {
-#pragma unroll
-        for (int k = 0; k < P * R; k++) cur[k] = nxt[k];
+    uint32_t period = 0;
+    for (uint32_t t0 = 0; t0 < p.n_steps; t0 += P, period++) {
         const uint32_t tn = t0 + P;
+        if constexpr (DIRECT) {
+            DF::convert(cur, rawA, rawB, period);
+            if (tn < p.n_steps) { DF::load(rawA, rowA, period + 1, maxwA); DF::load(rawB, rowB, period + 1, maxwB); }
+        } else {
 #pragma unroll
-        for (int k = 0; k < P * R; k++) nxt[k] = (tn + uint32_t(k / R) < p.n_steps) ? __ldg(pk + (size_t(tn) * R + k) * 32) : 0u;
+            for (int k = 0; k < P * R; k++) cur[k] = nxt[k];
+#pragma unroll
+            for (int k = 0; k < P * R; k++) nxt[k] = (tn + uint32_t(k / R) < p.n_steps) ? __ldg(pk + (size_t(tn) * R + k) * 32) : 0u;
+        }
         Run::group(x, cur, p, t0, dec_lane, accA, accB, std::make_integer_sequence<int, P>{});
         if constexpr (P < SB) {
             if (t0 + P <= p.n_steps) {          // a full period ran: state s sits in register rotr^P(s); rename back to register s

@@ -267,21 +267,29 @@ int decode_chunk_dev(vitb_decoder* h, const KernelEntry* e, const void* d_symbol
     VITB_CUDA(h, h->metrics.reserve(size_t(n_b64) * 64 * h->n_states * 2));
     VITB_CUDA(h, h->acc.reserve(size_t(n_b64) * 64 * 8));
 
-    IngestParams ip{};
-    ip.symbols = d_symbols; ip.row_stride = row_stride; ip.n_frames = uint32_t(n_frames); ip.n_sym = uint32_t(n_sym);
-    ip.depuncture_map = h->n_depunctured ? static_cast<const int32_t*>(h->map.ptr) : nullptr;
-    ip.fill_value = h->unpunctured_value; ip.pk = static_cast<uint32_t*>(h->pk.ptr); ip.ppw = uint32_t(e->ppw);
+    // one-thread-per-pair kernels can read the caller's rows themselves when they are 4-byte aligned and not punctured
+    static const bool no_direct = getenv("VITB_NO_DIRECT") != nullptr;
+    const size_t row_bytes = row_stride * size_t(h->prm.soft_bytes);
+    const bool direct = !no_direct && e->launch_direct && !h->n_depunctured && (row_bytes % 4 == 0) &&
+                        (reinterpret_cast<uintptr_t>(d_symbols) % 4 == 0) && row_bytes >= 4;
     VITB_CUDA(h, mark(h, s));
-    VITB_CUDA(h, run_ingest(h, ip, n_b64, s));
+    if (!direct) {
+        IngestParams ip{};
+        ip.symbols = d_symbols; ip.row_stride = row_stride; ip.n_frames = uint32_t(n_frames); ip.n_sym = uint32_t(n_sym);
+        ip.depuncture_map = h->n_depunctured ? static_cast<const int32_t*>(h->map.ptr) : nullptr;
+        ip.fill_value = h->unpunctured_value; ip.pk = static_cast<uint32_t*>(h->pk.ptr); ip.ppw = uint32_t(e->ppw);
+        VITB_CUDA(h, run_ingest(h, ip, n_b64, s));
+    }
     VITB_CUDA(h, mark(h, s));
 
     AcsParams a{};
     fill_acs_params(h, a);
+    a.sym = d_symbols; a.sym_row_bytes = row_bytes; a.sym_total_bytes = row_bytes * n_frames; a.n_frames = uint32_t(n_frames);
     a.pk = static_cast<const uint32_t*>(h->pk.ptr); a.dec = h->dec.ptr;
     a.metrics = static_cast<uint16_t*>(h->metrics.ptr); a.acc = static_cast<uint64_t*>(h->acc.ptr);
     a.n_blocks = n_wblocks; a.n_steps = uint32_t(S); a.dec_rows = uint32_t(S); a.dec_row0 = 0; a.resume = 0; a.start_state = uint32_t(start_state);
     h->launches++;
-    VITB_CUDA(h, e->launch(a, s));
+    VITB_CUDA(h, direct ? e->launch_direct(a, s) : e->launch(a, s));
     VITB_CUDA(h, mark(h, s));
 
     if (d_out) VITB_CUDA(h, launch_traceback(h, e, h->dec.ptr, S, n_frames, L, end_state, d_out, (L + 7) / 8, s));

@@ -26,6 +26,7 @@ struct KernelEntry {
     int dec_words;     // 32-bit decision words per thread per step (group/CTA kernels); pair kernels: one uint64 per frame
     const char* name;
     cudaError_t (*launch)(const AcsParams&, cudaStream_t);
+    cudaError_t (*launch_direct)(const AcsParams&, cudaStream_t);   // pair kernels only: symbols read from the caller's rows (no ingest)
 };
 
 // The in-place kernel is the default.  VITB_PAIR_PINGPONG=1 selects the two-register-set variant (smaller hot loop, but ptxas
@@ -45,6 +46,13 @@ cudaError_t launch_pair(const AcsParams& p, cudaStream_t s) {
 #endif
     if (inplace) acs_pair_kernel<C, SH, TIE_SIMD, CONSISTENT><<<grid, 32 * PAIR_WARPS, 0, s>>>(p);
     else acs_pair_pp_kernel<C, SH, TIE_SIMD, CONSISTENT><<<grid, 32 * PAIR_WARPS, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+template <class C, int SH, bool TIE_SIMD, bool CONSISTENT>
+cudaError_t launch_pair_direct(const AcsParams& p, cudaStream_t s) {
+    const unsigned grid = (p.n_blocks + PAIR_WARPS - 1) / PAIR_WARPS;
+    acs_pair_kernel<C, SH, TIE_SIMD, CONSISTENT, PairPeriod<C>::value, true><<<grid, 32 * PAIR_WARPS, 0, s>>>(p);
     return cudaGetLastError();
 }
 
@@ -96,6 +104,7 @@ KernelEntry make_entry(const char* name) {
     if constexpr (LOGT == 0) {
         e.layout = LAYOUT_PAIR; e.ppw = 32; e.dec_words = 0;
         e.launch = &launch_pair<C, SH, TIE_SIMD, CONSISTENT>;
+        if constexpr (DirectFetch<C, SH, PairPeriod<C>::value>::supported) e.launch_direct = &launch_pair_direct<C, SH, TIE_SIMD, CONSISTENT>;
     } else {
         e.layout = LAYOUT_GROUP; e.ppw = GroupShape<C, LOGT>::PPW; e.dec_words = GroupShape<C, LOGT>::W;
         e.launch = &launch_group<C, LOGT, SH, TIE_SIMD, CONSISTENT>;
