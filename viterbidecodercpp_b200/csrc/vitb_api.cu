@@ -689,6 +689,8 @@ int vitb_decode_batch_async(vitb_decoder* h, const void* symbols, size_t n_frame
     if (chunk < min_chunk) chunk = min_chunk;
     const size_t ws_chunk = chunk_frames_for(h, L);
     if (chunk > ws_chunk) chunk = ws_chunk;
+    // one-CTA-per-pair kernels (K = 15) run a few waves of CTAs per batch: splitting only makes the wave quantisation worse
+    if (h->variants.front()->layout == LAYOUT_CTA && n_frames < size_t(h->n_sm) * 2 * 16) chunk = ws_chunk;
     chunk = (chunk + 63) / 64 * 64;
     const size_t n_chunks = (n_frames + chunk - 1) / chunk;
     while (h->copy_ev.size() < n_chunks + 1) {
