@@ -117,6 +117,23 @@ def test_exchange_swizzle_is_conflict_free():
         check(SB, g)
 
 
+def test_cta_exchange_skew_is_conflict_free():
+    """csrc/acs_cta.cuh CtaShape::slot(phi) = phi + (phi >> 5): the exchange's warp-wide stores ((t << LB) | q, fixed q) and loads
+    ((q << LOGT) | t, fixed q) hit 32 distinct banks, and slots never collide"""
+    SB = 14
+    for LOGT in (9, 10):
+        LB, T = SB - LOGT, 1 << LOGT
+        NL = 1 << LB
+        slot = lambda phi: phi + (phi >> 5)
+        assert len({slot(p) for p in range(1 << SB)}) == 1 << SB
+        assert max(slot(p) for p in range(1 << SB)) < (1 << SB) + (1 << SB) // 32 + 32
+        for w in range(T // 32):
+            lanes = range(32 * w, 32 * w + 32)
+            for q in range(NL):
+                assert len({slot((t << LB) | q) % 32 for t in lanes}) == 32
+                assert len({slot((q << LOGT) | t) % 32 for t in lanes}) == 32
+
+
 def test_frame_range_partitions_exactly():
     for world in (1, 2, 3, 4, 8):
         for n in (0, 1, 7, 64, 65536, 1000003):

@@ -24,29 +24,32 @@
 
 namespace vitb {
 
-template <class C>
+template <class C, int LT>
 struct CtaShape {
-    static constexpr int LOGT = 9;
+    static constexpr int LOGT = LT;                  // 9: 512 threads x 32 registers, 10: 1024 threads x 16 registers
     static constexpr int T = 1 << LOGT;              // threads per CTA = per frame pair
     static constexpr int SB = C::SB;
     static constexpr int LB = SB - LOGT;             // steps between exchanges
-    static_assert(LB >= 1 && LB <= 5, "CtaShape is meant for K = 11..15");
+    static_assert(LB >= 1 && LB <= 5 && LOGT >= 5 && LOGT <= 10, "CtaShape is meant for K = 11..15");
     static constexpr int NL = 1 << LB;               // packed registers per thread
     static constexpr int NP = C::NP;                 // branch patterns
     static constexpr int WARPS = T / 32;
-    static constexpr size_t XCH_WORDS = size_t(C::NS);
+    static constexpr size_t XCH_WORDS = size_t(C::NS) + size_t(C::NS) / 32 + 32;   // skewed by one word per 32
     static constexpr size_t TBL_WORDS = size_t(LB) * NP * 2;
     static constexpr size_t SMEM_BYTES = (XCH_WORDS + TBL_WORDS + 64) * 4;
-    static __host__ __device__ constexpr uint32_t slot(uint32_t phi) { return phi ^ ((phi >> 5) & 31u); }
+    // Skew instead of XOR so that every access is (per-thread base) + (compile-time offset): the exchange writes position
+    // (t << LB) | q -> word 33t + q (LB = 5) and reads (q << LOGT) | t -> word q * (T + T/32) + t + (t >> 5); both hit 32 distinct
+    // banks per warp (tests/test_host_cpu.py::test_cta_exchange_skew_is_conflict_free).
+    static __host__ __device__ constexpr uint32_t slot(uint32_t phi) { return phi + (phi >> 5); }
 };
 
 // float accumulators per frame: 8 decision bits each keeps the predicated-FADD dependency chains short enough that ptxas does not
 // run out of predicate registers (with 2 x 16 bits it spilled predicates through LOP3 bit masks: +81 instructions per step)
-constexpr int CTA_NACC = 4;
+template <int NL> struct CtaAcc { static constexpr int value = NL >= 32 ? 4 : (NL >= 16 ? 2 : 1); };
 
-template <class C, int PH, bool TIE_SIMD, int Q>
-__device__ __forceinline__ void cta_bfly_at(uint32_t (&x)[CtaShape<C>::NL], const uint2* tbl_ph, const uint32_t pt, float (&fa)[2][CTA_NACC]) {
-    using S = CtaShape<C>;
+template <class C, int LT, int PH, bool TIE_SIMD, int Q>
+__device__ __forceinline__ void cta_bfly_at(uint32_t (&x)[CtaShape<C, LT>::NL], const uint2* tbl_ph, const uint32_t pt, float (&fa)[2][CtaAcc<CtaShape<C, LT>::NL>::value]) {
+    using S = CtaShape<C, LT>;
     constexpr int bit = 1 << (S::LB - 1 - PH);
     if constexpr ((Q & bit) == 0) {
         constexpr int q0 = Q, q1 = Q | bit;
@@ -65,7 +68,8 @@ __device__ __forceinline__ void cta_bfly_at(uint32_t (&x)[CtaShape<C>::NL], cons
             x[q1] = __vibmin_u16x2(b1, a1, &h1, &l1);
             dA0 = l0; dB0 = h0; dA1 = l1; dB1 = h1;
         }
-        constexpr int acc0 = (q0 >> 3) % CTA_NACC, acc1 = (q1 >> 3) % CTA_NACC;
+        constexpr int NACC = CtaAcc<S::NL>::value;
+        constexpr int acc0 = (q0 >> 3) % NACC, acc1 = (q1 >> 3) % NACC;
         constexpr float w0 = float(1u << (q0 & 7)), w1 = float(1u << (q1 & 7));
         if (dA0) fa[0][acc0] += w0;
         if (dB0) fa[1][acc0] += w0;
@@ -74,32 +78,40 @@ __device__ __forceinline__ void cta_bfly_at(uint32_t (&x)[CtaShape<C>::NL], cons
     }
 }
 
-template <class C, int PH, bool TIE_SIMD, int... Qs>
-__device__ __forceinline__ void cta_bfly_all(uint32_t (&x)[CtaShape<C>::NL], const uint2* tbl_ph, const uint32_t pt, float (&fa)[2][CTA_NACC],
+template <class C, int LT, int PH, bool TIE_SIMD, int... Qs>
+__device__ __forceinline__ void cta_bfly_all(uint32_t (&x)[CtaShape<C, LT>::NL], const uint2* tbl_ph, const uint32_t pt, float (&fa)[2][CtaAcc<CtaShape<C, LT>::NL>::value],
                                              std::integer_sequence<int, Qs...>) {
-    (cta_bfly_at<C, PH, TIE_SIMD, Qs>(x, tbl_ph, pt, fa), ...);
+    (cta_bfly_at<C, LT, PH, TIE_SIMD, Qs>(x, tbl_ph, pt, fa), ...);
 }
 
-template <class C, int SH, bool TIE_SIMD>
+template <class C, int LT, int SH, bool TIE_SIMD>
 struct CtaKernel {
-    using S = CtaShape<C>;
+    using S = CtaShape<C, LT>;
     static constexpr int LB = S::LB, NL = S::NL, R = C::R, NP = C::NP, T = S::T, SB = S::SB;
 
     // one trellis step at compile-time phase PH; decisions to dec_row (this thread's uint2 of the row)
+    static constexpr int W = NL > 16 ? 2 : 1;     // 32-bit decision words per thread and step
+    // dec_row: this thread's W words of the row.  NL = 32: {A word, B word}; NL = 16: one word, A bits | B bits << 16
     template <int PH>
-    static __device__ __forceinline__ void step(uint32_t (&x)[NL], const uint2* tbl, const uint32_t (&pt)[LB], uint2* dec_row) {
-        float fa[2][CTA_NACC];
+    static __device__ __forceinline__ void step(uint32_t (&x)[NL], const uint2* tbl, const uint32_t (&pt)[LB], uint32_t* dec_row) {
+        constexpr int NACC = CtaAcc<NL>::value;
+        float fa[2][NACC];
 #pragma unroll
-        for (int a = 0; a < CTA_NACC; a++) { fa[0][a] = 8388608.f; fa[1][a] = 8388608.f; }
-        cta_bfly_all<C, PH, TIE_SIMD>(x, tbl + PH * NP, pt[PH], fa, std::make_integer_sequence<int, NL>{});
-        // byte k of the word = mantissa byte 0 of accumulator k (registers 8k .. 8k+7)
-        static_assert(NL == 32 || NL <= 16, "decision word packing assumes 32 or <= 16 registers per thread");
-        const uint32_t a01 = __byte_perm(__float_as_uint(fa[0][0]), __float_as_uint(fa[0][1]), 0x0040);
-        const uint32_t a23 = __byte_perm(__float_as_uint(fa[0][2]), __float_as_uint(fa[0][3]), 0x0040);
-        const uint32_t b01 = __byte_perm(__float_as_uint(fa[1][0]), __float_as_uint(fa[1][1]), 0x0040);
-        const uint32_t b23 = __byte_perm(__float_as_uint(fa[1][2]), __float_as_uint(fa[1][3]), 0x0040);
-        const uint32_t wA = __byte_perm(a01, a23, 0x5410), wB = __byte_perm(b01, b23, 0x5410);
-        *dec_row = make_uint2(wA, wB);
+        for (int a = 0; a < NACC; a++) { fa[0][a] = 8388608.f; fa[1][a] = 8388608.f; }
+        cta_bfly_all<C, LT, PH, TIE_SIMD>(x, tbl + PH * NP, pt[PH], fa, std::make_integer_sequence<int, NL>{});
+        // byte k of a frame's bits = mantissa byte 0 of accumulator k (registers 8k .. 8k+7)
+        static_assert(NL == 32 || NL == 16, "decision word packing assumes 32 or 16 registers per thread");
+        if constexpr (NL == 32) {
+            const uint32_t a01 = __byte_perm(__float_as_uint(fa[0][0]), __float_as_uint(fa[0][1]), 0x0040);
+            const uint32_t a23 = __byte_perm(__float_as_uint(fa[0][2]), __float_as_uint(fa[0][3]), 0x0040);
+            const uint32_t b01 = __byte_perm(__float_as_uint(fa[1][0]), __float_as_uint(fa[1][1]), 0x0040);
+            const uint32_t b23 = __byte_perm(__float_as_uint(fa[1][2]), __float_as_uint(fa[1][3]), 0x0040);
+            *reinterpret_cast<uint2*>(dec_row) = make_uint2(__byte_perm(a01, a23, 0x5410), __byte_perm(b01, b23, 0x5410));
+        } else {
+            const uint32_t a01 = __byte_perm(__float_as_uint(fa[0][0]), __float_as_uint(fa[0][1]), 0x0040);
+            const uint32_t b01 = __byte_perm(__float_as_uint(fa[1][0]), __float_as_uint(fa[1][1]), 0x0040);
+            dec_row[0] = __byte_perm(a01, b01, 0x5410);
+        }
     }
 
     // CTA-wide packed minimum of all path metrics (both halves); result in every thread
@@ -118,10 +130,10 @@ struct CtaKernel {
 };
 
 // grid = number of frame pairs, block = 512, dynamic shared memory = CtaShape::SMEM_BYTES
-template <class C, int SH, bool TIE_SIMD>
-__global__ void __launch_bounds__(CtaShape<C>::T, 1) acs_cta_kernel(const AcsParams p) {
-    using S = CtaShape<C>;
-    using Kn = CtaKernel<C, SH, TIE_SIMD>;
+template <class C, int LT, int SH, bool TIE_SIMD>
+__global__ void __launch_bounds__(CtaShape<C, LT>::T, 1) acs_cta_kernel(const AcsParams p) {
+    using S = CtaShape<C, LT>;
+    using Kn = CtaKernel<C, LT, SH, TIE_SIMD>;
     constexpr int LB = S::LB, NL = S::NL, R = C::R, NP = C::NP, SB = S::SB, LOGT = S::LOGT;
     extern __shared__ uint32_t smem[];
     uint32_t* xch = smem;                                             // [NS] exchange buffer = metrics at the start of the group
@@ -159,7 +171,8 @@ __global__ void __launch_bounds__(CtaShape<C>::T, 1) acs_cta_kernel(const AcsPar
     }
 
     const uint32_t* pk = p.pk + size_t(pair) * p.n_steps * R;                                    // [n_steps][R]
-    uint2* dec = reinterpret_cast<uint2*>(p.dec) + (size_t(pair) * p.dec_rows + p.dec_row0) * S::T + t;
+    constexpr int W = Kn::W;
+    uint32_t* dec = static_cast<uint32_t*>(p.dec) + ((size_t(pair) * p.dec_rows + p.dec_row0) * S::T + t) * W;
 
     uint32_t done = 0;
     bool need_save = true;       // after an exchange the buffer already holds the group's starting metrics in read layout
@@ -199,7 +212,7 @@ __global__ void __launch_bounds__(CtaShape<C>::T, 1) acs_cta_kernel(const AcsPar
         auto run_phase = [&](auto PHc) {
             constexpr int PH = decltype(PHc)::value;
             if (PH >= ph && uint32_t(PH - ph) < span) {
-                Kn::template step<PH>(x, tbl, pt, dec + size_t(done + uint32_t(PH - ph)) * S::T);
+                Kn::template step<PH>(x, tbl, pt, dec + size_t(done + uint32_t(PH - ph)) * S::T * W);
                 bool tb, ta;
                 (void)__vibmin_u16x2(p.thr2, x[0], &tb, &ta);
                 if ((ta || tb) && trig_phase == 0xffffffffu) trig_phase = uint32_t(PH);
@@ -221,7 +234,7 @@ __global__ void __launch_bounds__(CtaShape<C>::T, 1) acs_cta_kernel(const AcsPar
             auto replay_phase = [&](auto PHc) {
                 constexpr int PH = decltype(PHc)::value;
                 if (PH >= ph && uint32_t(PH - ph) < span) {
-                    Kn::template step<PH>(x, tbl, pt, dec + size_t(done + uint32_t(PH - ph)) * S::T);
+                    Kn::template step<PH>(x, tbl, pt, dec + size_t(done + uint32_t(PH - ph)) * S::T * W);
                     if (t == 0) flag[1] = x[0];
                     __syncthreads();
                     const uint32_t x00 = flag[1];

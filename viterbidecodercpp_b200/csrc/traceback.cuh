@@ -282,6 +282,7 @@ __global__ void __launch_bounds__(128) traceback_group_staged_kernel(const Trace
 // next period's address needs this period's decisions (a dependent chain of L/LB memory round trips per frame, all frames in
 // parallel).  One thread per frame.
 struct TracebackCtaParams {
+    uint32_t words;           // 2: {A word, B word} per thread and row (32 registers per thread); 1: A bits | B bits << 16 (16 registers)
     const uint32_t* dec;
     uint32_t dec_rows;
     uint32_t n_frames;
@@ -297,8 +298,9 @@ template <int MAXLB>
 __global__ void __launch_bounds__(64) traceback_cta_kernel(const TracebackCtaParams p) {
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= p.n_frames) return;
-    const uint32_t SB = p.state_bits, g = p.logt, T = 1u << g, LB = SB - g, L = p.total_bits, half = f & 1u;
-    const uint32_t* d = p.dec + size_t(f >> 1) * p.dec_rows * T * 2 + half;
+    const uint32_t SB = p.state_bits, g = p.logt, T = 1u << g, LB = SB - g, L = p.total_bits, half = f & 1u, W = p.words;
+    const uint32_t* d = p.dec + size_t(f >> 1) * p.dec_rows * T * W + (W == 2 ? half : 0u);
+    const uint32_t bit_base = (W == 2) ? 0u : half * 16u;
     uint8_t* out = p.out + size_t(f) * p.out_stride;
     uint32_t state = p.end_state, byte = 0;
     if (L & 7) {
@@ -317,12 +319,12 @@ __global__ void __launch_bounds__(64) traceback_cta_kernel(const TracebackCtaPar
         const uint32_t t = rotr_rt(state, n + 1, SB) & (T - 1);
         uint32_t w[MAXLB];
 #pragma unroll
-        for (int k = 0; k < MAXLB; k++) w[k] = (uint32_t(k) < cnt) ? __ldcs(d + (size_t(r - k) * T + t) * 2) : 0u;
+        for (int k = 0; k < MAXLB; k++) w[k] = (uint32_t(k) < cnt) ? __ldcs(d + (size_t(r - k) * T + t) * W) : 0u;
 #pragma unroll
         for (int k = 0; k < MAXLB; k++) {
             if (uint32_t(k) < cnt) {
                 const uint32_t q = rotr_rt(state, n - uint32_t(k) + 1, SB) >> g;
-                const uint32_t bit = (w[k] >> q) & 1u;
+                const uint32_t bit = (w[k] >> (bit_base + q)) & 1u;
                 state = (bit << (SB - 1)) | (state >> 1);
                 const int64_t j = r - k - int64_t(SB);
                 byte |= bit << (7 - (uint32_t(j) & 7));

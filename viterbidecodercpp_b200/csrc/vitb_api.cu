@@ -28,7 +28,7 @@ static const std::vector<KernelEntry>& registry() {
         register_k7r4_t1(entries); register_k7r4_t2(entries); register_k7r4_t4(entries);
         register_k9r2_t8(entries); register_k9r2_t16(entries);
         register_k9r4_t8(entries); register_k9r4_t16(entries);
-        register_k15r6_cta(entries);
+        register_k15r6_cta512(entries); register_k15r6_cta1024(entries);
     });
     return entries;
 }
@@ -208,7 +208,7 @@ cudaError_t launch_traceback(vitb_decoder* h, const KernelEntry* e, const void* 
         TracebackCtaParams t{};
         t.dec = static_cast<const uint32_t*>(dec); t.dec_rows = uint32_t(dec_rows); t.n_frames = uint32_t(n_frames);
         t.total_bits = uint32_t(L); t.state_bits = uint32_t(h->prm.K - 1); t.logt = uint32_t(e->logt); t.end_state = uint32_t(end_state);
-        t.out = d_out; t.out_stride = out_stride;
+        t.out = d_out; t.out_stride = out_stride; t.words = uint32_t(e->dec_words);
         traceback_cta_kernel<5><<<unsigned((n_frames + 63) / 64), 64, 0, s>>>(t);
     } else if (e->layout == LAYOUT_PAIR) {
         TracebackParams t{};

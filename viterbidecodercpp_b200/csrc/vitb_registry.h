@@ -64,35 +64,33 @@ cudaError_t launch_group(const AcsParams& p, cudaStream_t s) {
 }
 
 // CONSISTENT is irrelevant for the CTA kernel (c_inv is folded into the shared-memory table)
-template <class C, int SH, bool TIE_SIMD>
+template <class C, int LT, int SH, bool TIE_SIMD>
 cudaError_t launch_cta(const AcsParams& p, cudaStream_t s) {
-    using S = CtaShape<C>;
-    static bool configured = false;      // per process; the attribute is per device, so set it every time a device may be new
-    cudaError_t e = cudaFuncSetAttribute(acs_cta_kernel<C, SH, TIE_SIMD>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(S::SMEM_BYTES));
+    using S = CtaShape<C, LT>;
+    // the attribute is per device: set it on every launch (cheap) so that handles on different GPUs all get it
+    const cudaError_t e = cudaFuncSetAttribute(acs_cta_kernel<C, LT, SH, TIE_SIMD>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(S::SMEM_BYTES));
     if (e != cudaSuccess) return e;
-    configured = true;
-    (void)configured;
-    acs_cta_kernel<C, SH, TIE_SIMD><<<p.n_blocks, S::T, S::SMEM_BYTES, s>>>(p);
+    acs_cta_kernel<C, LT, SH, TIE_SIMD><<<p.n_blocks, S::T, S::SMEM_BYTES, s>>>(p);
     return cudaGetLastError();
 }
 
-template <class C, int SH, bool TIE_SIMD>
+template <class C, int LT, int SH, bool TIE_SIMD>
 KernelEntry make_cta_entry(const char* name, int consistent) {
     KernelEntry e{};
     e.K = C::K; e.R = C::R;
     for (int i = 0; i < C::R; i++) e.G[i] = C::G[i];
-    e.sh = SH; e.tie = TIE_SIMD ? 1 : 0; e.consistent = consistent; e.logt = CtaShape<C>::LOGT; e.name = name;
-    e.layout = LAYOUT_CTA; e.ppw = 1; e.dec_words = 2;
-    e.launch = &launch_cta<C, SH, TIE_SIMD>;
+    e.sh = SH; e.tie = TIE_SIMD ? 1 : 0; e.consistent = consistent; e.logt = LT; e.name = name;
+    e.layout = LAYOUT_CTA; e.ppw = 1; e.dec_words = CtaKernel<C, LT, SH, TIE_SIMD>::W;
+    e.launch = &launch_cta<C, LT, SH, TIE_SIMD>;
     return e;
 }
 
-#define VITB_CTA_VARIANTS(VEC, CODE, TAG)                                                   \
-    for (int cons = 0; cons < 2; cons++) {                                                  \
-        VEC.push_back(make_cta_entry<CODE, 0, false>("acs_cta<" TAG ",u16,scalar-tie>", cons)); \
-        VEC.push_back(make_cta_entry<CODE, 8, false>("acs_cta<" TAG ",u8,scalar-tie>", cons));  \
-        VEC.push_back(make_cta_entry<CODE, 0, true>("acs_cta<" TAG ",u16,simd-tie>", cons));    \
-        VEC.push_back(make_cta_entry<CODE, 8, true>("acs_cta<" TAG ",u8,simd-tie>", cons));     \
+#define VITB_CTA_VARIANTS(VEC, CODE, LT, TAG)                                                   \
+    for (int cons = 0; cons < 2; cons++) {                                                      \
+        VEC.push_back(make_cta_entry<CODE, LT, 0, false>("acs_cta<" TAG ",u16,scalar-tie>", cons)); \
+        VEC.push_back(make_cta_entry<CODE, LT, 8, false>("acs_cta<" TAG ",u8,scalar-tie>", cons));  \
+        VEC.push_back(make_cta_entry<CODE, LT, 0, true>("acs_cta<" TAG ",u16,simd-tie>", cons));    \
+        VEC.push_back(make_cta_entry<CODE, LT, 8, true>("acs_cta<" TAG ",u8,simd-tie>", cons));     \
     }
 
 template <class C, int LOGT, int SH, bool TIE_SIMD, bool CONSISTENT>
@@ -137,6 +135,7 @@ void register_k9r2_t8(std::vector<KernelEntry>& v);
 void register_k9r2_t16(std::vector<KernelEntry>& v);
 void register_k9r4_t8(std::vector<KernelEntry>& v);
 void register_k9r4_t16(std::vector<KernelEntry>& v);
-void register_k15r6_cta(std::vector<KernelEntry>& v);
+void register_k15r6_cta512(std::vector<KernelEntry>& v);
+void register_k15r6_cta1024(std::vector<KernelEntry>& v);
 
 }  // namespace vitb
