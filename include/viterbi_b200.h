@@ -105,6 +105,21 @@ int vitb_decode_batch_async(vitb_decoder* h, const void* symbols, size_t n_frame
  * n_depunctured = 0 clears the schedule. */
 int vitb_set_puncture_schedule(vitb_decoder* h, const uint8_t* keep, size_t n_depunctured, int32_t unpunctured_value);
 
+/* ---- device-side front end (the "next" row after the hot path: the producers of decoder input).  The test-data pipeline of the
+ *      reference's BER sweep (examples/run_snr_ber.cpp:311-359) on the GPU: random bytes -> convolutional encoder with K-1 zero tail
+ *      bits (include/viterbi/convolutional_encoder_shift_register.h:45-61) -> BPSK + AWGN at EbNo_dB (NaN = noise free) -> the
+ *      reference quantiser (round, clamp to [low, high]) -> soft_t rows, punctured if a schedule is set.  Encoder and quantiser are
+ *      exact; the random streams are Philox4x32-10, not std::mt19937. ---- */
+int vitb_synth_frames_dev(vitb_decoder* h, size_t n_frames, size_t total_bits, float EbNo_dB, uint64_t seed,
+                          uint8_t* d_tx_bytes /* [F][L/8] out */, void* d_symbols /* [F][row_stride] out */, size_t row_stride, void* stream);
+/* same, results copied to host arrays (tests, small runs) */
+int vitb_synth_frames(vitb_decoder* h, size_t n_frames, size_t total_bits, float EbNo_dB, uint64_t seed,
+                      uint8_t* tx_bytes, void* symbols, size_t row_stride);
+/* the quantiser alone on host arrays: soft = clamp(round(x * scale + mean), low, high)   (run_snr_ber.cpp:352-359) */
+int vitb_quantise(vitb_decoder* h, const float* x, size_t n, float scale, float mean, void* soft_out);
+/* generate n_frames frames at EbNo_dB, decode them and count bit errors, all on the device (run_snr_ber.cpp:336-372 for one batch) */
+int vitb_ber_trial(vitb_decoder* h, size_t n_frames, size_t total_bits, float EbNo_dB, uint64_t seed, uint64_t* bit_errors);
+
 /* ---- multi-GPU: frames are independent, so the batch is split into contiguous ranges, one per handle (each created on its own
  *      device), decoded concurrently from host memory; no collective.  ---- */
 int vitb_decode_batch_multi(vitb_decoder* const* handles, int n_handles, const void* symbols, size_t n_frames, size_t total_bits,

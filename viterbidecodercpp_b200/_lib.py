@@ -44,6 +44,10 @@ API = [
     ("vitb_decode_batch_dev", C.c_int, [_P, _P, C.c_size_t, C.c_size_t, C.POINTER(vitb_batch_opts), _P, _P, _P, _P]),
     ("vitb_decode_batch_async", C.c_int, [_P, _P, C.c_size_t, C.c_size_t, C.POINTER(vitb_batch_opts), _P, _P, _P, _P]),
     ("vitb_set_puncture_schedule", C.c_int, [_P, _P, C.c_size_t, C.c_int32]),
+    ("vitb_synth_frames_dev", C.c_int, [_P, C.c_size_t, C.c_size_t, C.c_float, C.c_uint64, _P, _P, C.c_size_t, _P]),
+    ("vitb_synth_frames", C.c_int, [_P, C.c_size_t, C.c_size_t, C.c_float, C.c_uint64, _P, _P, C.c_size_t]),
+    ("vitb_quantise", C.c_int, [_P, _P, C.c_size_t, C.c_float, C.c_float, _P]),
+    ("vitb_ber_trial", C.c_int, [_P, C.c_size_t, C.c_size_t, C.c_float, C.c_uint64, C.POINTER(C.c_uint64)]),
     ("vitb_decode_batch_multi", C.c_int, [C.POINTER(_P), C.c_int, _P, C.c_size_t, C.c_size_t, C.POINTER(vitb_batch_opts), _P, _P, _P]),
     ("vitb_workspace_bytes", C.c_int, [_P, C.c_size_t, C.c_size_t, C.POINTER(C.c_size_t)]),
     ("vitb_set_workspace_limit", C.c_int, [_P, C.c_size_t]),

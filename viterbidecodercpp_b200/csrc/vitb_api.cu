@@ -15,6 +15,8 @@
 #include "vitb_registry.h"
 #include "ingest.cuh"
 #include "traceback.cuh"
+#include "frontend.cuh"
+#include <cmath>
 
 namespace vitb {
 
@@ -81,6 +83,7 @@ struct vitb_decoder {
     int32_t unpunctured_value = 0;
     // single-frame streaming state (one 64-frame block, frame 0 is the user's)
     DeviceBuffer s_pk, s_dec, s_metrics, s_acc, s_in, s_out;
+    DeviceBuffer g_tx, g_sym, g_cnt;     // host-pointer conveniences of the device-side front end
     size_t traceback_length = 0;
     size_t current_decoded_bit = 0;
     // stage profiling
@@ -392,7 +395,7 @@ int vitb_destroy(vitb_decoder* h) {
     if (!h) return VITB_OK;
     cudaSetDevice(h->prm.device);
     for (DeviceBuffer* b : {&h->pk, &h->dec, &h->metrics, &h->acc, &h->d_in, &h->d_out, &h->d_accout, &h->d_finout, &h->map,
-                            &h->s_pk, &h->s_dec, &h->s_metrics, &h->s_acc, &h->s_in, &h->s_out}) b->release();
+                            &h->s_pk, &h->s_dec, &h->s_metrics, &h->s_acc, &h->s_in, &h->s_out, &h->g_tx, &h->g_sym, &h->g_cnt}) b->release();
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     for (cudaEvent_t e : h->copy_ev) cudaEventDestroy(e);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -753,6 +756,124 @@ int vitb_get_stage_ms(vitb_decoder* h, float ms[4]) {
             ms[k] += t;
         }
     }
+    return VITB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// device-side front end (frontend.cuh)
+// ------------------------------------------------------------------------------------------------------------------
+int vitb_synth_frames_dev(vitb_decoder* h, size_t n_frames, size_t total_bits, float EbNo_dB, uint64_t seed,
+                          uint8_t* d_tx_bytes, void* d_symbols, size_t row_stride, void* stream) {
+    if (!h || !d_tx_bytes || !d_symbols || (total_bits % 8) || n_frames > 0x7fffffffu || total_bits > 0x3fffffffu) return VITB_ERR_ARG;
+    if (n_frames == 0 || total_bits == 0) return VITB_OK;
+    const size_t K = size_t(h->prm.K), R = size_t(h->prm.R), steps = total_bits + K - 1, n_sym = steps * R;
+    size_t used = n_sym;
+    if (h->n_depunctured) {
+        if (h->n_depunctured != n_sym) return VITB_ERR_ARG;
+        used = h->n_received;
+    }
+    if (row_stride == 0) row_stride = used;
+    if (row_stride < used) return VITB_ERR_ARG;
+    VITB_CUDA(h, cudaSetDevice(h->prm.device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    SynthParams sp{};
+    sp.K = h->prm.K; sp.R = h->prm.R;
+    for (size_t i = 0; i < R; i++) sp.G[i] = h->prm.G[i];
+    sp.high = h->prm.soft_decision_high; sp.low = h->prm.soft_decision_low;
+    sp.n_frames = uint32_t(n_frames); sp.total_bits = uint32_t(total_bits);
+    const float mag = (float(sp.high) - float(sp.low)) / 2.0f;                       // run_snr_ber.cpp:311-312
+    sp.mean = (float(sp.high) + float(sp.low)) / 2.0f;
+    if (std::isnan(EbNo_dB)) {
+        sp.sigma = -1.f;
+        sp.scale = mag;
+    } else {
+        const float EsNo_dB = EbNo_dB - 10.0f * std::log10(float(R));               // run_snr_ber.cpp:320-325
+        const float noise_variance = std::pow(10.0f, -(EsNo_dB + 3.0f) / 10.0f);
+        sp.sigma = std::sqrt(noise_variance);
+        sp.scale = mag * (1.0f / std::sqrt(1.0f + noise_variance));
+    }
+    sp.seed = seed;
+    sp.depuncture_map = h->n_depunctured ? static_cast<const int32_t*>(h->map.ptr) : nullptr;
+    sp.tx_bytes = d_tx_bytes; sp.symbols = d_symbols; sp.row_stride = row_stride;
+    const size_t nb = n_frames * (total_bits / 8), ns = n_frames * steps;
+    h->launches += 2;
+    synth_bytes_kernel<<<unsigned((nb + 255) / 256), 256, 0, s>>>(sp);
+    VITB_CUDA(h, cudaGetLastError());
+    if (h->prm.soft_bytes == 1) synth_symbols_kernel<int8_t><<<unsigned((ns + 255) / 256), 256, 0, s>>>(sp);
+    else synth_symbols_kernel<int16_t><<<unsigned((ns + 255) / 256), 256, 0, s>>>(sp);
+    VITB_CUDA(h, cudaGetLastError());
+    return VITB_OK;
+}
+
+int vitb_synth_frames(vitb_decoder* h, size_t n_frames, size_t total_bits, float EbNo_dB, uint64_t seed,
+                      uint8_t* tx_bytes, void* symbols, size_t row_stride) {
+    if (!h || !tx_bytes || !symbols) return VITB_ERR_ARG;
+    const size_t K = size_t(h->prm.K), R = size_t(h->prm.R), n_sym = (total_bits + K - 1) * R;
+    const size_t used = h->n_depunctured ? h->n_received : n_sym;
+    if (row_stride == 0) row_stride = used;
+    const size_t sb = size_t(h->prm.soft_bytes), nb = n_frames * (total_bits / 8), sbytes = n_frames * row_stride * sb;
+    if (n_frames == 0) return VITB_OK;
+    VITB_CUDA(h, cudaSetDevice(h->prm.device));
+    VITB_CUDA(h, h->g_tx.reserve(nb ? nb : 1));
+    VITB_CUDA(h, h->g_sym.reserve(sbytes ? sbytes : 1));
+    VITB_CUDA(h, cudaMemsetAsync(h->g_sym.ptr, 0, sbytes, h->stream));
+    const int r = vitb_synth_frames_dev(h, n_frames, total_bits, EbNo_dB, seed, static_cast<uint8_t*>(h->g_tx.ptr), h->g_sym.ptr, row_stride, h->stream);
+    if (r != VITB_OK) return r;
+    VITB_CUDA(h, cudaMemcpyAsync(tx_bytes, h->g_tx.ptr, nb, cudaMemcpyDeviceToHost, h->stream));
+    VITB_CUDA(h, cudaMemcpyAsync(symbols, h->g_sym.ptr, sbytes, cudaMemcpyDeviceToHost, h->stream));
+    VITB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return VITB_OK;
+}
+
+int vitb_quantise(vitb_decoder* h, const float* x, size_t n, float scale, float mean, void* soft_out) {
+    if (!h || (!x && n) || (!soft_out && n)) return VITB_ERR_ARG;
+    if (!n) return VITB_OK;
+    VITB_CUDA(h, cudaSetDevice(h->prm.device));
+    const size_t sb = size_t(h->prm.soft_bytes);
+    VITB_CUDA(h, h->g_tx.reserve(n * 4));
+    VITB_CUDA(h, h->g_sym.reserve(n * sb));
+    VITB_CUDA(h, cudaMemcpyAsync(h->g_tx.ptr, x, n * 4, cudaMemcpyHostToDevice, h->stream));
+    h->launches++;
+    if (sb == 1) quantise_kernel<int8_t><<<unsigned((n + 255) / 256), 256, 0, h->stream>>>(static_cast<const float*>(h->g_tx.ptr), n, scale, mean,
+                                        h->prm.soft_decision_low, h->prm.soft_decision_high, static_cast<int8_t*>(h->g_sym.ptr));
+    else quantise_kernel<int16_t><<<unsigned((n + 255) / 256), 256, 0, h->stream>>>(static_cast<const float*>(h->g_tx.ptr), n, scale, mean,
+                                        h->prm.soft_decision_low, h->prm.soft_decision_high, static_cast<int16_t*>(h->g_sym.ptr));
+    VITB_CUDA(h, cudaGetLastError());
+    VITB_CUDA(h, cudaMemcpyAsync(soft_out, h->g_sym.ptr, n * sb, cudaMemcpyDeviceToHost, h->stream));
+    VITB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return VITB_OK;
+}
+
+// Generate, decode and count on the device: returns the number of bit errors of n_frames frames at EbNo_dB.  Nothing but the
+// count crosses PCIe (the inner loop of examples/run_snr_ber.cpp:336-372 for one batch).
+int vitb_ber_trial(vitb_decoder* h, size_t n_frames, size_t total_bits, float EbNo_dB, uint64_t seed, uint64_t* bit_errors) {
+    if (!h || !bit_errors || (total_bits % 8)) return VITB_ERR_ARG;
+    *bit_errors = 0;
+    if (n_frames == 0 || total_bits == 0) return VITB_OK;
+    const size_t K = size_t(h->prm.K), R = size_t(h->prm.R), n_sym = (total_bits + K - 1) * R;
+    const size_t used = h->n_depunctured ? h->n_received : n_sym;
+    const size_t row = (used * size_t(h->prm.soft_bytes) + 3) / 4 * 4 / size_t(h->prm.soft_bytes);      // 4-byte aligned rows: direct fetch
+    const size_t sb = size_t(h->prm.soft_bytes), nb = n_frames * (total_bits / 8);
+    VITB_CUDA(h, cudaSetDevice(h->prm.device));
+    VITB_CUDA(h, h->g_tx.reserve(nb));
+    VITB_CUDA(h, h->g_sym.reserve(n_frames * row * sb));
+    VITB_CUDA(h, h->g_cnt.reserve(8));
+    VITB_CUDA(h, h->d_out.reserve(nb));
+    VITB_CUDA(h, cudaMemsetAsync(h->g_cnt.ptr, 0, 8, h->stream));
+    VITB_CUDA(h, cudaMemsetAsync(h->g_sym.ptr, 0, n_frames * row * sb, h->stream));
+    int r = vitb_synth_frames_dev(h, n_frames, total_bits, EbNo_dB, seed, static_cast<uint8_t*>(h->g_tx.ptr), h->g_sym.ptr, row, h->stream);
+    if (r != VITB_OK) return r;
+    vitb_batch_opts o{}; o.row_stride = row;
+    r = vitb_decode_batch_dev(h, h->g_sym.ptr, n_frames, total_bits, &o, static_cast<uint8_t*>(h->d_out.ptr), nullptr, nullptr, h->stream);
+    if (r != VITB_OK) return r;
+    h->launches++;
+    bit_errors_kernel<<<296, 256, 0, h->stream>>>(static_cast<const uint8_t*>(h->g_tx.ptr), static_cast<const uint8_t*>(h->d_out.ptr), nb,
+                                                  static_cast<unsigned long long*>(h->g_cnt.ptr));
+    VITB_CUDA(h, cudaGetLastError());
+    unsigned long long c = 0;
+    VITB_CUDA(h, cudaMemcpyAsync(&c, h->g_cnt.ptr, 8, cudaMemcpyDeviceToHost, h->stream));
+    VITB_CUDA(h, cudaStreamSynchronize(h->stream));
+    *bit_errors = c;
     return VITB_OK;
 }
 

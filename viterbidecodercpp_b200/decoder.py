@@ -207,6 +207,30 @@ class ViterbiDecoder_CUDA:
         _check(self._L.vitb_get_stage_ms(self._h, C.byref(ms)))
         return {"ingest": ms[0], "acs": ms[1], "traceback": ms[2], "gather": ms[3]}
 
+    # -- device-side front end (include/viterbi_b200.h: vitb_synth_frames / vitb_quantise / vitb_ber_trial) ------------------
+    def synth_frames(self, n_frames, total_bits, EbNo_dB=None, seed=1, row=None):
+        """-> (tx_bytes [F, L/8], symbols [F, row]) generated on the GPU; EbNo_dB None = noise free"""
+        n_sym = (total_bits + self.K - 1) * self.R
+        row = row or n_sym
+        tx = np.zeros((n_frames, total_bits // 8), dtype=np.uint8)
+        sym = np.zeros((n_frames, row), dtype=_soft_dtype(self.soft_bytes))
+        e = float("nan") if EbNo_dB is None else float(EbNo_dB)
+        _check(self._L.vitb_synth_frames(self._h, n_frames, total_bits, e, seed, tx.ctypes.data, sym.ctypes.data, row), "synth_frames")
+        return tx, sym
+
+    def quantise(self, x, scale, mean):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        out = np.zeros(x.shape, dtype=_soft_dtype(self.soft_bytes))
+        _check(self._L.vitb_quantise(self._h, x.ctypes.data, x.size, scale, mean, out.ctypes.data), "quantise")
+        return out
+
+    def ber_trial(self, n_frames, total_bits, EbNo_dB, seed=1):
+        """bit errors of n_frames frames generated, decoded and counted on the device"""
+        c = C.c_uint64()
+        e = float("nan") if EbNo_dB is None else float(EbNo_dB)
+        _check(self._L.vitb_ber_trial(self._h, n_frames, total_bits, e, seed, C.byref(c)), "ber_trial")
+        return c.value
+
     # -- introspection ---------------------------------------------------------------------------------------------------------
     def workspace_bytes(self, n_frames, total_bits):
         n = C.c_size_t()
