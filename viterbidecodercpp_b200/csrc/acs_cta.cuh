@@ -174,67 +174,87 @@ __global__ void __launch_bounds__(CtaShape<C, LT>::T, 1) acs_cta_kernel(const Ac
     constexpr int W = Kn::W;
     uint32_t* dec = static_cast<uint32_t*>(p.dec) + ((size_t(pair) * p.dec_rows + p.dec_row0) * S::T + t) * W;
 
-    uint32_t done = 0;
-    bool need_save = true;       // after an exchange the buffer already holds the group's starting metrics in read layout
-    while (done < p.n_steps) {
-        const uint32_t left = p.n_steps - done;
-        const uint32_t span = uint32_t(LB - ph) < left ? uint32_t(LB - ph) : left;   // steps in this group: phases ph .. ph+span-1
-
-        // ---- group prologue: keep the group's starting metrics in the exchange buffer (registers stay valid), build the
-        //      branch metric tables of the group's steps
-        if (need_save) {
-#pragma unroll
-            for (int q = 0; q < NL; q++) xch[S::slot((uint32_t(q) << LOGT) | t)] = x[q];
-        }
+    // branch metric tables {total, inverted} of the steps of one group, built by the first LB*NP threads (one entry each)
+    auto build_tables = [&](uint32_t first_step, int first_phase, uint32_t n) {
         if (t < uint32_t(LB * NP)) {
             const int tph = int(t) / NP;
             const uint32_t pat = t % NP;
-            const int k = tph - ph;
-            if (k >= 0 && uint32_t(k) < span) {
-                const uint32_t* sy = pk + size_t(done + uint32_t(k)) * R;
+            const int k = tph - first_phase;
+            if (k >= 0 && uint32_t(k) < n) {
+                const uint32_t* sy = pk + size_t(first_step + uint32_t(k)) * R;
                 uint32_t tot = 0, inv = p.c_inv2;
 #pragma unroll
                 for (int i = 0; i < R; i++) {
                     const uint32_t sv = __ldg(sy + i);
                     const uint32_t lo = __vadd2(sv, p.c_low2), hi = __vadd2(~sv, p.c_high2);
-                    const bool b = (pat >> i) & 1u;
-                    tot = __vadd2(tot, b ? hi : lo);          // viterbi_branch_table.h:52 + scalar.h:66-73
-                    inv = __vadd2(inv, b ? lo : hi);          // scalar.h:107 (max_error - total), complementary pattern + c_inv
+                    const bool bb = (pat >> i) & 1u;
+                    tot = __vadd2(tot, bb ? hi : lo);          // viterbi_branch_table.h:52 + scalar.h:66-73
+                    inv = __vadd2(inv, bb ? lo : hi);          // scalar.h:107 (max_error - total), complementary pattern + c_inv
                 }
                 tbl[tph * NP + pat] = make_uint2(tot, inv);
             }
         }
-        __syncthreads();
+    };
+    auto group_span = [&](uint32_t done_, int ph_) {
+        const uint32_t left = p.n_steps - done_;
+        return uint32_t(LB - ph_) < left ? uint32_t(LB - ph_) : left;
+    };
 
-        // ---- speculative run of the group (no renormalisation); thread 0 remembers the first phase whose state-0 metric
-        //      reached the threshold
-        uint32_t trig_phase = 0xffffffffu;
-        auto run_phase = [&](auto PHc) {
-            constexpr int PH = decltype(PHc)::value;
-            if (PH >= ph && uint32_t(PH - ph) < span) {
-                Kn::template step<PH>(x, tbl, pt, dec + size_t(done + uint32_t(PH - ph)) * S::T * W);
-                bool tb, ta;
-                (void)__vibmin_u16x2(p.thr2, x[0], &tb, &ta);
-                if ((ta || tb) && trig_phase == 0xffffffffu) trig_phase = uint32_t(PH);
-            }
-        };
-        run_phase(std::integral_constant<int, 0>{});
-        if constexpr (LB > 1) run_phase(std::integral_constant<int, 1>{});
-        if constexpr (LB > 2) run_phase(std::integral_constant<int, 2>{});
-        if constexpr (LB > 3) run_phase(std::integral_constant<int, 3>{});
-        if constexpr (LB > 4) run_phase(std::integral_constant<int, 4>{});
-        if (t == 0) flag[0] = trig_phase;
-        __syncthreads();
-        const uint32_t first_trig = flag[0];
+    uint32_t done = 0;
+    // prologue: the exchange buffer always holds the metrics at the start of the current group (for the rollback)
+#pragma unroll
+    for (int q = 0; q < NL; q++) xch[S::slot((uint32_t(q) << LOGT) | t)] = x[q];
+    if (p.n_steps) build_tables(0u, ph, group_span(0u, ph));
+    __syncthreads();
 
-        if (first_trig != 0xffffffffu) {
+    while (done < p.n_steps) {
+        const uint32_t span = group_span(done, ph);        // steps in this group: phases ph .. ph+span-1
+        uint32_t* drow = dec + size_t(done) * S::T * W;
+
+        // ---- speculative run of the group (no renormalisation).  The running maximum of register 0 is all the trigger test
+        //      needs (thread 0 holds state 0 there): if it never reached the threshold, no step of the group renormalised.
+        uint32_t mx = 0u;
+        if (ph == 0 && span == uint32_t(LB)) {
+            auto fast_phase = [&](auto PHc) {
+                constexpr int PH = decltype(PHc)::value;
+                Kn::template step<PH>(x, tbl, pt, drow + size_t(PH) * S::T * W);
+                mx = __vmaxu2(mx, x[0]);
+            };
+            fast_phase(std::integral_constant<int, 0>{});
+            if constexpr (LB > 1) fast_phase(std::integral_constant<int, 1>{});
+            if constexpr (LB > 2) fast_phase(std::integral_constant<int, 2>{});
+            if constexpr (LB > 3) fast_phase(std::integral_constant<int, 3>{});
+            if constexpr (LB > 4) fast_phase(std::integral_constant<int, 4>{});
+        } else {
+            auto run_phase = [&](auto PHc) {
+                constexpr int PH = decltype(PHc)::value;
+                if (PH >= ph && uint32_t(PH - ph) < span) {
+                    Kn::template step<PH>(x, tbl, pt, drow + size_t(PH - ph) * S::T * W);
+                    mx = __vmaxu2(mx, x[0]);
+                }
+            };
+            run_phase(std::integral_constant<int, 0>{});
+            if constexpr (LB > 1) run_phase(std::integral_constant<int, 1>{});
+            if constexpr (LB > 2) run_phase(std::integral_constant<int, 2>{});
+            if constexpr (LB > 3) run_phase(std::integral_constant<int, 3>{});
+            if constexpr (LB > 4) run_phase(std::integral_constant<int, 4>{});
+        }
+        if (t == 0) {
+            bool tb, ta;
+            (void)__vibmin_u16x2(p.thr2, mx, &tb, &ta);     // thr <= max over the group of state 0's metric
+            flag[0] = (ta || tb) ? 1u : 0u;
+        }
+        __syncthreads();                                     // B1: all steps done, tables and exchange buffer free again
+        const uint32_t any_trig = flag[0];
+
+        if (any_trig) {
             // ---- roll back and replay step by step with the reference's renormalisation (scalar.h:48-50, 139-153)
 #pragma unroll
             for (int q = 0; q < NL; q++) x[q] = xch[S::slot((uint32_t(q) << LOGT) | t)];
             auto replay_phase = [&](auto PHc) {
                 constexpr int PH = decltype(PHc)::value;
                 if (PH >= ph && uint32_t(PH - ph) < span) {
-                    Kn::template step<PH>(x, tbl, pt, dec + size_t(done + uint32_t(PH - ph)) * S::T * W);
+                    Kn::template step<PH>(x, tbl, pt, drow + size_t(PH - ph) * S::T * W);
                     if (t == 0) flag[1] = x[0];
                     __syncthreads();
                     const uint32_t x00 = flag[1];
@@ -263,18 +283,22 @@ __global__ void __launch_bounds__(CtaShape<C, LT>::T, 1) acs_cta_kernel(const Ac
         }
 
         done += span;
-        if (uint32_t(ph) + span == uint32_t(LB)) {
+        const bool full = uint32_t(ph) + span == uint32_t(LB);
+        if (full) {
             // ---- exchange: value at (q, t) moves to PHI' = (t << LB) | q, bringing the layout back to PHI = s
 #pragma unroll
             for (int q = 0; q < NL; q++) xch[S::slot((t << LB) | uint32_t(q))] = x[q];
-            __syncthreads();
+            ph = 0;
+        } else {
+            ph += int(span);                                 // the call ends inside an exchange period (streaming API)
+        }
+        if (done < p.n_steps) build_tables(done, ph, group_span(done, ph));
+        __syncthreads();                                     // B2: exchange data and the next group's tables are in place
+        if (full) {
 #pragma unroll
             for (int q = 0; q < NL; q++) x[q] = xch[S::slot((uint32_t(q) << LOGT) | t)];
-            __syncthreads();
-            ph = 0;
-            need_save = false;
-        } else {
-            ph += int(span);
+            // no barrier needed here: the buffer is next written after B1 of the next group, which every thread reaches only
+            // after these loads; until then it doubles as the rollback copy of the group's starting metrics
         }
     }
 

@@ -129,6 +129,7 @@ const KernelEntry* choose_variant(const vitb_decoder* h, size_t n_frames) {
         for (const KernelEntry* e : h->variants) if (e->logt == h->forced_logt) return e;
     }
     const size_t pairs = (n_frames + 1) / 2, smsp = size_t(h->n_sm) * 4;
+    if (h->variants.front()->layout == LAYOUT_CTA) return h->variants.back();   // K = 15: 1024 threads x 16 registers measured fastest
     for (const KernelEntry* e : h->variants) {
         const size_t warps = ((pairs << e->logt) + 31) / 32;
         const size_t want = (e->logt == 0) ? smsp * 3 / 2 : smsp * 4;
