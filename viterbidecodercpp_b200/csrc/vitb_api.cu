@@ -266,8 +266,12 @@ int decode_chunk_dev(vitb_decoder* h, const KernelEntry* e, const void* d_symbol
     const size_t K = size_t(h->prm.K), R = size_t(h->prm.R), S = L + K - 1, n_sym = S * R;
     const unsigned n_b64 = unsigned((n_frames + 63) / 64);
     const unsigned n_wblocks = n_b64 * unsigned(32 / e->ppw);
+    // uint8_t one-thread-per-pair kernels: survivor-history records (acs_hist.cuh) instead of decision rows; same bytes per step
+    static const bool no_hist = getenv("VITB_NO_HIST") != nullptr;
+    const bool hist = !no_hist && e->launch_hist != nullptr;
+    const size_t n_periods = (S + 7) / 8;
     VITB_CUDA(h, h->pk.reserve(size_t(n_b64) * n_sym * 32 * 4));
-    VITB_CUDA(h, h->dec.reserve(size_t(n_b64) * dec_bytes_per_block64(e, S)));
+    VITB_CUDA(h, h->dec.reserve(hist ? size_t(n_b64) * n_periods * 64 * size_t(h->n_states) : size_t(n_b64) * dec_bytes_per_block64(e, S)));
     VITB_CUDA(h, h->metrics.reserve(size_t(n_b64) * 64 * h->n_states * 2));
     VITB_CUDA(h, h->acc.reserve(size_t(n_b64) * 64 * 8));
 
@@ -292,11 +296,22 @@ int decode_chunk_dev(vitb_decoder* h, const KernelEntry* e, const void* d_symbol
     a.pk = static_cast<const uint32_t*>(h->pk.ptr); a.dec = h->dec.ptr;
     a.metrics = static_cast<uint16_t*>(h->metrics.ptr); a.acc = static_cast<uint64_t*>(h->acc.ptr);
     a.n_blocks = n_wblocks; a.n_steps = uint32_t(S); a.dec_rows = uint32_t(S); a.dec_row0 = 0; a.resume = 0; a.start_state = uint32_t(start_state);
+    static const uint32_t pf_words = getenv("VITB_HIST_PF") ? uint32_t(atoi(getenv("VITB_HIST_PF"))) : 16u;
+    a.pf_words = pf_words;
     h->launches++;
-    VITB_CUDA(h, direct ? e->launch_direct(a, s) : e->launch(a, s));
+    if (hist) VITB_CUDA(h, direct ? e->launch_hist_direct(a, s) : e->launch_hist(a, s));
+    else VITB_CUDA(h, direct ? e->launch_direct(a, s) : e->launch(a, s));
     VITB_CUDA(h, mark(h, s));
 
-    if (d_out) VITB_CUDA(h, launch_traceback(h, e, h->dec.ptr, S, n_frames, L, end_state, d_out, (L + 7) / 8, s));
+    if (d_out && hist) {
+        h->launches++;
+        TracebackHistParams t{};
+        t.dec = static_cast<const uint8_t*>(h->dec.ptr); t.n_periods = uint32_t(n_periods); t.n_frames = uint32_t(n_frames);
+        t.total_bits = uint32_t(L); t.state_bits = uint32_t(K - 1); t.end_state = uint32_t(end_state); t.n_steps = uint32_t(S);
+        t.out = d_out; t.out_stride = (L + 7) / 8;
+        traceback_hist_kernel<<<unsigned((n_frames + 127) / 128), 128, 0, s>>>(t);
+        VITB_CUDA(h, cudaGetLastError());
+    } else if (d_out) VITB_CUDA(h, launch_traceback(h, e, h->dec.ptr, S, n_frames, L, end_state, d_out, (L + 7) / 8, s));
     VITB_CUDA(h, mark(h, s));
     if (d_acc || d_final) {
         h->launches++;

@@ -7,6 +7,7 @@
 #include <vector>
 #include <cuda_runtime.h>
 #include "acs_pair.cuh"
+#include "acs_hist.cuh"
 #include "acs_group.cuh"
 #include "acs_cta.cuh"
 
@@ -27,6 +28,9 @@ struct KernelEntry {
     const char* name;
     cudaError_t (*launch)(const AcsParams&, cudaStream_t);
     cudaError_t (*launch_direct)(const AcsParams&, cudaStream_t);   // pair kernels only: symbols read from the caller's rows (no ingest)
+    // uint8_t pair kernels only: whole-frame batch decode with survivor-history records instead of decision rows (acs_hist.cuh)
+    cudaError_t (*launch_hist)(const AcsParams&, cudaStream_t);
+    cudaError_t (*launch_hist_direct)(const AcsParams&, cudaStream_t);
 };
 
 // The in-place kernel is the default.  VITB_PAIR_PINGPONG=1 selects the two-register-set variant (smaller hot loop, but ptxas
@@ -53,6 +57,13 @@ template <class C, int SH, bool TIE_SIMD, bool CONSISTENT>
 cudaError_t launch_pair_direct(const AcsParams& p, cudaStream_t s) {
     const unsigned grid = (p.n_blocks + PAIR_WARPS - 1) / PAIR_WARPS;
     acs_pair_kernel<C, SH, TIE_SIMD, CONSISTENT, PairPeriod<C>::value, true><<<grid, 32 * PAIR_WARPS, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+template <class C, bool TIE_SIMD, bool CONSISTENT, bool DIRECT>
+cudaError_t launch_hist(const AcsParams& p, cudaStream_t s) {
+    const unsigned grid = (p.n_blocks + HIST_WARPS - 1) / HIST_WARPS;
+    acs_hist_kernel<C, TIE_SIMD, CONSISTENT, DIRECT><<<grid, 32 * HIST_WARPS, 0, s>>>(p);
     return cudaGetLastError();
 }
 
@@ -103,6 +114,10 @@ KernelEntry make_entry(const char* name) {
         e.layout = LAYOUT_PAIR; e.ppw = 32; e.dec_words = 0;
         e.launch = &launch_pair<C, SH, TIE_SIMD, CONSISTENT>;
         if constexpr (DirectFetch<C, SH, PairPeriod<C>::value>::supported) e.launch_direct = &launch_pair_direct<C, SH, TIE_SIMD, CONSISTENT>;
+        if constexpr (SH == 8) {
+            e.launch_hist = &launch_hist<C, TIE_SIMD, CONSISTENT, false>;
+            e.launch_hist_direct = &launch_hist<C, TIE_SIMD, CONSISTENT, true>;
+        }
     } else {
         e.layout = LAYOUT_GROUP; e.ppw = GroupShape<C, LOGT>::PPW; e.dec_words = GroupShape<C, LOGT>::W;
         e.launch = &launch_group<C, LOGT, SH, TIE_SIMD, CONSISTENT>;
