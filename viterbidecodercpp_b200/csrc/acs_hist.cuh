@@ -1,29 +1,36 @@
-// acs_hist.cuh -- add-compare-select with SURVIVOR-HISTORY TAGS for uint8_t error metrics (K <= 7), batch decode only.
+// acs_hist.cuh -- add-compare-select with SURVIVOR-HISTORY TAGS (K <= 7), whole-frame batch decode.
 //
 // Replaces ViterbiDecoder_Scalar::update / bfly / renormalise (include/viterbi/viterbi_decoder_scalar.h:28-153) for a batch, like
-// acs_pair.cuh, with the same mapping (one thread owns a frame pair, register q = metric of state q of frame A | frame B << 16,
-// uint8_t metrics held as metric << 8) but a different way of producing the decisions:
+// acs_pair.cuh, but with a different way of producing the decisions.  Every path metric register carries, BELOW the metric, the
+// last decisions of the SURVIVOR PATH that ends in that state:
 //
-//   * the free low byte of every 16-bit half carries the last <= 8 decisions of the SURVIVOR PATH that ends in that state.
-//     At step k of an 8-step period the path-1 operand of each compare gets the tag 2^k added (low bytes of the operands hold
-//     only bits < k, so the low byte never carries into the metric), and min() then
-//       - compares the metrics exactly (high bytes differ -> the low bytes are irrelevant),
-//       - breaks a metric tie in favour of path 0, because low(a) < 2^k <= low(b): the reference's strict '>' (scalar.h:123-124),
-//       - and keeps the winner's low byte: bit k of the new state's low byte IS the decision, bits < k are the decisions along the
+//     FMT 0 (uint8_t  error metrics): register q = [metric A << 8 | history A (8 bits)] | [metric B << 8 | history B] << 16
+//                                     two frames per thread, packed 16x2 arithmetic (VIADD.16x2 / VIADDMNMX.U16x2), period 8 steps
+//     FMT 1 (uint16_t error metrics): register q =  metric << 16 | history (16 bits)
+//                                     one frame per thread, 32-bit arithmetic (IADD / VIADDMNMX.U32), period 16 steps
+//
+//   * At step k of a period the path-1 operand of each compare gets the tag 2^k added (the history fields of the operands hold only
+//     bits < k, so the field never carries into the metric), and min() then
+//       - compares the metrics exactly (metric fields differ -> the history fields are irrelevant),
+//       - breaks a metric tie in favour of path 0, because hist(a) < 2^k <= hist(b): the reference's strict '>' (scalar.h:123-124),
+//       - and keeps the winner's history: bit k of the new state's history IS the decision, bits < k are the decisions along the
 //         winner's own survivor path.
-//     So a butterfly is 2 VIADD.16x2 + 2 VIADDMNMX.U16x2 = FOUR instructions for 4 add-compare-selects of 2 frames each: no
-//     predicates, no per-step bit collection, no tag clearing (acs_pair.cuh's tagged butterfly needs 8, its predicate form 10).
+//     So a butterfly is 2 adds + 2 fused add-min = FOUR instructions for its 4 add-compare-selects (x2 frames for FMT 0): no
+//     predicates, no per-step bit collection, no tag clearing (acs_pair.cuh's predicate form needs 10, its tagged form 8).
+//     Metric arithmetic wraps modulo 2^8 / 2^16 exactly like the reference's error_t.
 //     TIE_SIMD tags path 0 instead (a tie selects path 1, x86/viterbi_decoder_avx_u16.h:112-115) and the bits are inverted on output.
-//   * every 8 steps the 2^(K-1) low bytes of a frame are written out as one "history record" (2^(K-1) bytes per frame and period -
-//     exactly the size of 8 reference decision rows, core.h:49-83) and cleared.  Traceback (traceback_hist_kernel) then moves 8
-//     steps per lookup: the byte of the current state holds the 8 decisions of its survivor path, which are the decoded bits
-//     AND determine the state 8 steps earlier (core.h:96-113 applied 8 times).
+//   * every period the 2^(K-1) history fields of a frame are written out as one "history record" (2^(K-1) bits per frame and step -
+//     exactly the size of the reference's decision rows, core.h:49-83) and cleared.  Traceback (traceback_hist_kernel) then moves a
+//     whole period per lookup: the history of the current state holds the decisions of its survivor path, which are the decoded
+//     bits AND determine the state one period earlier (core.h:96-113 applied 8 / 16 times).
 //   * the metrics ping-pong between two register sets in logical state order, so the step code does not depend on the step index:
 //     the hot loop is two steps (about 5 KB of SASS) and there is no register renaming.
-//   * renormalisation (scalar.h:48, 139-153) works on the high bytes exactly as in acs_pair.cuh; the low bytes ride along.
+//   * renormalisation (scalar.h:48, 139-153) works on the metric fields; the history fields ride along.
 //
-// Record layout: NW = 2^(K-1)/2 32-bit words per thread and period, word w = [A:state 2w, B:state 2w, A:state 2w+1, B:state 2w+1];
-// dec = uint32 [n_blocks][n_periods][NW / VW][32 lanes][VW], VW = min(4, NW)  (coalesced 16-byte stores).
+// Record layout (both formats): NW = 2^(K-1)/2 32-bit words per thread and period;
+//     FMT 0: word w = bytes [A:state 2w, B:state 2w, A:state 2w+1, B:state 2w+1];   FMT 1: word w = halfwords [state 2w, state 2w+1]
+//     dec = uint32 [n_blocks][n_periods][NW / VW][32 lanes][VW], VW = min(4, NW)  (coalesced 16-byte stores);
+//     a block is one warp: 64 frames (FMT 0, lane l = frames 2l, 2l+1) or 32 frames (FMT 1, lane l = frame l).
 #pragma once
 #include <cstdint>
 #include <utility>
@@ -33,221 +40,322 @@
 
 namespace vitb {
 
+template <int FMT>
+struct HistLane;
+
+template <>
+struct HistLane<0> {
+    static constexpr int HB = 8, FPT = 2, SBY = 1;
+    static constexpr uint32_t TAG1 = 0x00010001u, METRIC_MASK = 0xff00ff00u;
+    static __device__ __forceinline__ uint32_t add(uint32_t a, uint32_t b) { return __vadd2(a, b); }
+    static __device__ __forceinline__ uint32_t addmin(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_u16x2(a, b, c); }
+    static __device__ __forceinline__ uint32_t min3(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u16x2(a, b, c); }
+    static __device__ __forceinline__ uint32_t min2(uint32_t a, uint32_t b) { return __vminu2(a, b); }
+};
+
+template <>
+struct HistLane<1> {
+    static constexpr int HB = 16, FPT = 1, SBY = 2;
+    static constexpr uint32_t TAG1 = 1u, METRIC_MASK = 0xffff0000u;
+    static __device__ __forceinline__ uint32_t add(uint32_t a, uint32_t b) { return a + b; }
+    static __device__ __forceinline__ uint32_t addmin(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_u32(a, b, c); }
+    static __device__ __forceinline__ uint32_t min3(uint32_t a, uint32_t b, uint32_t c) { return min(min(a, b), c); }
+    static __device__ __forceinline__ uint32_t min2(uint32_t a, uint32_t b) { return min(a, b); }
+};
+
+// kernel-uniform constants in the lane format (FMT 1 derives them from the packed 16x2 parameters the host fills for sh = 0)
+struct HistConsts {
+    uint32_t c_low, c_high, c_inv, thr, init_start, init_other;
+    uint32_t thr_m1;       // FMT 0: thr - 1 per half (trigger test with one packed max)
+    bool always;           // FMT 0: a threshold of 0 renormalises every step
+};
+
+template <int FMT>
+__device__ __forceinline__ HistConsts hist_consts(const AcsParams& p) {
+    HistConsts c;
+    if constexpr (FMT == 0) {
+        c.c_low = p.c_low2; c.c_high = p.c_high2; c.c_inv = p.c_inv2; c.thr = p.thr2; c.init_start = p.init_start2; c.init_other = p.init_other2;
+        c.always = (p.thr2 & 0xffffu) == 0u || (p.thr2 >> 16) == 0u;
+        c.thr_m1 = c.always ? 0xffffffffu : p.thr2 - 0x00010001u;
+    } else {
+        c.c_low = p.c_low2 & 0xffff0000u;                          // (-low) << 16
+        c.c_high = (p.c_high2 & 0xffff0000u) - 0x00010000u + 1u;   // (high << 16) + 1:  high - s = ~(s << 16) + c_high
+        c.c_inv = p.c_inv2 & 0xffff0000u; c.thr = p.thr2 & 0xffff0000u;
+        c.init_start = p.init_start2 & 0xffff0000u; c.init_other = p.init_other2 & 0xffff0000u;
+        c.always = false; c.thr_m1 = 0u;
+    }
+    return c;
+}
+
 template <class C>
 struct HistShape {
     static constexpr int NS = C::NS;
-    static constexpr int NW = NS / 2;                    // record words per thread (two frames) and period
+    static constexpr int NW = NS / 2;                    // record words per thread and period (both formats)
     static constexpr int VW = NW < 4 ? NW : 4;           // words per vector store
-    static constexpr int PERIOD = 8;                     // steps per record (bits of history per state)
-    static constexpr size_t BLOCK_RECORD_BYTES = size_t(64) * NS;     // one 64-frame block, one period
 };
 
-template <class C, bool TIE_SIMD, int J>
+template <class C, int FMT, bool TIE_SIMD, int J>
 __device__ __forceinline__ void hist_bfly_at(const uint32_t (&x)[C::NS], uint32_t (&y)[C::NS], const uint32_t (&T)[C::NP],
                                              const uint32_t (&TT)[C::NP], const uint32_t (&V)[C::NP], const uint32_t (&VT)[C::NP]) {
+    using LN = HistLane<FMT>;
     constexpr int H = C::NS / 2;
     constexpr uint32_t pat = bfly_pattern<C>(uint32_t(J));
     constexpr uint32_t ipat = (~pat) & uint32_t(C::NP - 1);
     if constexpr (!TIE_SIMD) {
-        const uint32_t b0 = __vadd2(x[J + H], VT[ipat]);                    // (1|X) + inverted, tagged    scalar.h:114
-        const uint32_t b1 = __vadd2(x[J + H], TT[pat]);                     // (1|X) + total,    tagged    scalar.h:116
-        y[2 * J] = __viaddmin_u16x2(x[J], T[pat], b0);                      // min((0|X) + total, b0)      scalar.h:113,127
-        y[2 * J + 1] = __viaddmin_u16x2(x[J], V[ipat], b1);                 // min((0|X) + inverted, b1)   scalar.h:115,128
+        const uint32_t b0 = LN::add(x[J + H], VT[ipat]);                    // (1|X) + inverted, tagged    scalar.h:114
+        const uint32_t b1 = LN::add(x[J + H], TT[pat]);                     // (1|X) + total,    tagged    scalar.h:116
+        y[2 * J] = LN::addmin(x[J], T[pat], b0);                            // min((0|X) + total, b0)      scalar.h:113,127
+        y[2 * J + 1] = LN::addmin(x[J], V[ipat], b1);                       // min((0|X) + inverted, b1)   scalar.h:115,128
     } else {
-        const uint32_t a0 = __vadd2(x[J], TT[pat]);                         // tag on path 0: a tie selects path 1
-        const uint32_t a1 = __vadd2(x[J], VT[ipat]);
-        y[2 * J] = __viaddmin_u16x2(x[J + H], V[ipat], a0);
-        y[2 * J + 1] = __viaddmin_u16x2(x[J + H], T[pat], a1);
+        const uint32_t a0 = LN::add(x[J], TT[pat]);                         // tag on path 0: a tie selects path 1
+        const uint32_t a1 = LN::add(x[J], VT[ipat]);
+        y[2 * J] = LN::addmin(x[J + H], V[ipat], a0);
+        y[2 * J + 1] = LN::addmin(x[J + H], T[pat], a1);
     }
 }
 
-template <class C, bool TIE_SIMD, int... Js>
+template <class C, int FMT, bool TIE_SIMD, int... Js>
 __device__ __forceinline__ void hist_bfly_all(const uint32_t (&x)[C::NS], uint32_t (&y)[C::NS], const uint32_t (&T)[C::NP],
                                               const uint32_t (&TT)[C::NP], const uint32_t (&V)[C::NP], const uint32_t (&VT)[C::NP],
                                               std::integer_sequence<int, Js...>) {
-    (hist_bfly_at<C, TIE_SIMD, Js>(x, y, T, TT, V, VT), ...);
+    (hist_bfly_at<C, FMT, TIE_SIMD, Js>(x, y, T, TT, V, VT), ...);
 }
 
-// one trellis step x -> y; tag2 = 2^k in both halves, k = step index inside the period
-template <class C, bool TIE_SIMD, bool CONSISTENT>
-__device__ __forceinline__ void hist_step(const uint32_t (&x)[C::NS], uint32_t (&y)[C::NS], const uint32_t* sym, const AcsParams& p,
-                                          const uint32_t tag2, const uint32_t thr_m1, const bool always, uint64_t& accA, uint64_t& accB) {
+// branch metric table in the lane format: T[p] = sum_i (bit_i(p) ? e_high_i : e_low_i)
+template <int FMT, int R, int LEVEL>
+struct HistTable {
+    template <int NP>
+    static __device__ __forceinline__ void run(uint32_t (&T)[NP], const uint32_t (&lo)[R], const uint32_t (&hi)[R]) {
+        HistTable<FMT, R, LEVEL - 1>::run(T, lo, hi);
+        constexpr int H = 1 << (LEVEL - 1);
+#pragma unroll
+        for (int p = 0; p < H; p++) {
+            T[p + H] = HistLane<FMT>::add(T[p], hi[LEVEL - 1]);
+            T[p] = HistLane<FMT>::add(T[p], lo[LEVEL - 1]);
+        }
+    }
+};
+template <int FMT, int R>
+struct HistTable<FMT, R, 1> {
+    template <int NP>
+    static __device__ __forceinline__ void run(uint32_t (&T)[NP], const uint32_t (&lo)[R], const uint32_t (&hi)[R]) {
+        T[0] = lo[0];
+        T[1] = hi[0];
+    }
+};
+
+// one trellis step x -> y; tag = 2^k in the history field(s), k = step index inside the period
+template <class C, int FMT, bool TIE_SIMD, bool CONSISTENT>
+__device__ __forceinline__ void hist_step(const uint32_t (&x)[C::NS], uint32_t (&y)[C::NS], const uint32_t* sym, const HistConsts& c,
+                                          const uint32_t tag, uint64_t& accA, uint64_t& accB) {
+    using LN = HistLane<FMT>;
     constexpr int R = C::R, NP = C::NP, NS = C::NS;
     uint32_t lo[R], hi[R];
 #pragma unroll
     for (int i = 0; i < R; i++) {
-        lo[i] = __vadd2(sym[i], p.c_low2);
-        hi[i] = __vadd2(~sym[i], p.c_high2);
+        lo[i] = LN::add(sym[i], c.c_low);          // s - low
+        hi[i] = LN::add(~sym[i], c.c_high);        // high - s  (|branch - s| for s in [low, high], scalar.h:30-34, 96-105)
     }
     uint32_t T[NP], TT[NP];
-    TableBuild<R, R>::run(T, lo, hi);
+    HistTable<FMT, R, R>::run(T, lo, hi);
 #pragma unroll
-    for (int k = 0; k < NP; k++) TT[k] = __vadd2(T[k], tag2);
+    for (int k = 0; k < NP; k++) TT[k] = LN::add(T[k], tag);
     if constexpr (CONSISTENT) {
-        hist_bfly_all<C, TIE_SIMD>(x, y, T, TT, T, TT, std::make_integer_sequence<int, NS / 2>{});
+        hist_bfly_all<C, FMT, TIE_SIMD>(x, y, T, TT, T, TT, std::make_integer_sequence<int, NS / 2>{});
     } else {
         uint32_t V[NP], VT[NP];       // inverted_error = max_error - total_error (scalar.h:107) = T[~pattern] + c_inv
 #pragma unroll
-        for (int k = 0; k < NP; k++) { V[k] = __vadd2(T[k], p.c_inv2); VT[k] = __vadd2(TT[k], p.c_inv2); }
-        hist_bfly_all<C, TIE_SIMD>(x, y, T, TT, V, VT, std::make_integer_sequence<int, NS / 2>{});
+        for (int k = 0; k < NP; k++) { V[k] = LN::add(T[k], c.c_inv); VT[k] = LN::add(TT[k], c.c_inv); }
+        hist_bfly_all<C, FMT, TIE_SIMD>(x, y, T, TT, V, VT, std::make_integer_sequence<int, NS / 2>{});
     }
-    // renormalisation: "if (new_metric[0] >= renormalisation_threshold)" (scalar.h:48).  The history byte below the metric cannot
-    // change the outcome: metric >= thr  <=>  y[0] half > (thr << 8) - 1.  One packed max + one compare decide whether EITHER frame
-    // triggers (thr == 0 means "always": thr_m1 is then unusable, `always` covers it); the exact per-frame work is in the rare branch.
-    if (always || __vmaxu2(y[0], thr_m1) != thr_m1) {
-        bool trigB, trigA;
-        (void)__vibmin_u16x2(p.thr2, y[0], &trigB, &trigA);     // pred = thr <= y0 per half
-        const uint32_t m = packed_min<NS>(y);                   // scalar.h:140-146: the high byte of the 16-bit minimum is the minimum metric
-        const uint32_t mA = m & 0xff00u, mB = (m >> 16) & 0xff00u;
-        const uint32_t sub = (trigA ? mA : 0u) | ((trigB ? mB : 0u) << 16);
-        const uint32_t neg = __vsub2(0u, sub);
+    // renormalisation: "if (new_metric[0] >= renormalisation_threshold)" (scalar.h:48).  The history field below the metric cannot
+    // change the outcome: metric >= thr  <=>  y[0] (field) > (thr << HB) - 1  <=>  y[0] (field) >= thr << HB.
+    bool any;
+    if constexpr (FMT == 0) any = c.always || __vmaxu2(y[0], c.thr_m1) != c.thr_m1;      // either frame (exact test in the rare branch)
+    else any = y[0] >= c.thr;
+    if (any) {
+        uint32_t m = y[0];                                        // scalar.h:140-146: the metric field of the minimum is the minimum metric
 #pragma unroll
-        for (int q = 0; q < NS; q++) y[q] = __vadd2(y[q], neg);  // scalar.h:148-150
-        if (trigA) accA += uint64_t(mA >> 8);                   // scalar.h:49, 152
-        if (trigB) accB += uint64_t(mB >> 8);
+        for (int q = 1; q + 1 < NS; q += 2) m = LN::min3(m, y[q], y[q + 1]);
+        m = LN::min2(m, y[NS - 1]);
+        uint32_t sub;
+        if constexpr (FMT == 0) {
+            bool trigB, trigA;
+            (void)__vibmin_u16x2(c.thr, y[0], &trigB, &trigA);     // pred = thr <= y0 per half
+            const uint32_t mA = m & 0xff00u, mB = (m >> 16) & 0xff00u;
+            sub = (trigA ? mA : 0u) | ((trigB ? mB : 0u) << 16);
+            if (trigA) accA += uint64_t(mA >> 8);                   // scalar.h:49, 152
+            if (trigB) accB += uint64_t(mB >> 8);
+        } else {
+            sub = m & 0xffff0000u;
+            accA += uint64_t(sub >> 16);
+        }
+        const uint32_t neg = (FMT == 0) ? __vsub2(0u, sub) : (0u - sub);
+#pragma unroll
+        for (int q = 0; q < NS; q++) y[q] = LN::add(y[q], neg);  // scalar.h:148-150
     }
 }
 
 constexpr int HIST_WARPS = 4;
 
-// grid = ceil(n_blocks / HIST_WARPS); one warp per 64-frame block, lane l owns frames 64*blk + 2l and 64*blk + 2l + 1.
-// Whole frames only: p.resume must be 0 and p.dec_row0 must be 0 (the streaming API keeps using acs_pair_kernel).
-template <class C, bool TIE_SIMD, bool CONSISTENT, bool DIRECT>
+// grid = ceil(n_blocks / HIST_WARPS); one warp per block of 64 (FMT 0) / 32 (FMT 1) frames.
+// Whole frames only: p.resume must be 0 and p.dec_row0 must be 0 (the streaming API keeps using acs_pair_kernel / acs_group_kernel).
+// FMT 1 reads the packed stream in the 16-pairs-per-warp-block layout (ingest with ppw = 16).
+template <class C, int FMT, bool TIE_SIMD, bool CONSISTENT, bool DIRECT>
 __global__ void __launch_bounds__(32 * HIST_WARPS) acs_hist_kernel(const AcsParams p) {
-    constexpr int R = C::R, NS = C::NS, NW = HistShape<C>::NW, VW = HistShape<C>::VW;
+    using LN = HistLane<FMT>;
+    constexpr int R = C::R, NS = C::NS, NW = HistShape<C>::NW, VW = HistShape<C>::VW, HB = LN::HB, FPT = LN::FPT;
     const uint32_t lane = threadIdx.x & 31, blk = blockIdx.x * HIST_WARPS + (threadIdx.x >> 5);
     if (blk >= p.n_blocks) return;
-    const size_t fA = size_t(blk) * 64 + 2 * lane, fB = fA + 1;
+    const size_t fA = size_t(blk) * (32 * FPT) + FPT * lane, fB = fA + 1;      // fB only exists for FMT 0
+    const HistConsts c = hist_consts<FMT>(p);
 
     uint32_t x[NS], y[NS];
     uint64_t accA = 0, accB = 0;
     {
         const uint32_t s = p.start_state & uint32_t(NS - 1);       // core.h:209-210
 #pragma unroll
-        for (int q = 0; q < NS; q++) x[q] = (uint32_t(q) == s) ? p.init_start2 : p.init_other2;
+        for (int q = 0; q < NS; q++) x[q] = (uint32_t(q) == s) ? c.init_start : c.init_other;
     }
 
-    // either half of the threshold zero: every step renormalises (thr - 1 would wrap)
-    const bool always = (p.thr2 & 0xffffu) == 0u || (p.thr2 >> 16) == 0u;
-    const uint32_t thr_m1 = always ? 0xffffffffu : p.thr2 - 0x00010001u;
-
-    const uint32_t n_periods = (p.n_steps + 7) / 8;
+    const uint32_t n_periods = (p.n_steps + HB - 1) / HB;
     uint32_t* rec = static_cast<uint32_t*>(p.dec) + size_t(blk) * n_periods * (32 * NW) + lane * VW;
-    const uint32_t* pk = p.pk + size_t(blk) * p.n_steps * R * 32 + lane;
+    // packed stream: FMT 0 [blk][e][32 pair slots], FMT 1 [blk][e][16 pair slots] (lane l = half l & 1 of slot l >> 1)
+    constexpr int SLOTS = (FMT == 0) ? 32 : 16;
+    const uint32_t* pk = p.pk + size_t(blk) * p.n_steps * R * SLOTS + (FMT == 0 ? lane : (lane >> 1));
+    const bool pk_hi = (lane & 1u) != 0u;
 
     // ---- symbol supply ------------------------------------------------------------------------------------------------------
-    // DIRECT: each lane streams its own two rows of the caller's [frame][step][R] int8_t array (the reference's layout, scalar.h:43-46).
-    // A period is 8 steps = 8R bytes = WPP whole words of a row; the words of period r+1 are loaded while period r runs (a full
-    // period ahead: about 2700 clocks, more than a DRAM miss), into registers that the step-pair loop consumes from the bottom and
-    // shifts down by 2R bytes per iteration (no dynamic register index).  A lane meets a new 32-byte sector of each row every 32/R
-    // steps, so nearly every warp-level load has a missing lane: one step pair of lookahead (tried first) left the kernel waiting
-    // on memory for a third of its time.
+    // DIRECT: each lane streams its own rows of the caller's [frame][step][R] soft_t array (the reference's layout, scalar.h:43-46):
+    // two int8_t rows (FMT 0) or one int16_t row (FMT 1).  A fetch group is 8 steps = WPG whole words of a row; the words of group g+1
+    // are loaded while group g runs (about 2700 clocks ahead, more than a DRAM miss), into registers that the step-pair loop consumes
+    // from the bottom and shifts down per iteration (no dynamic register index).  A lane meets a new 32-byte sector of a row every
+    // few steps, so nearly every warp-level load has a missing lane: one step pair of lookahead (tried first) left the kernel
+    // waiting on memory for a third of its time.
     // Packed stream (ingest output: punctured or unaligned input): words of the next step pair are loaded one iteration ahead and the
-    // lines of the period after next are prefetched with one prefetch instruction per period (a load would share a scoreboard with the
+    // lines of the group after next are prefetched with one prefetch instruction per group (a load would share a scoreboard with the
     // demand loads and make them wait for its DRAM latency).
-    constexpr int WPP = 2 * R;                               // words per row and period
-    uint32_t bufA[DIRECT ? WPP + 2 : 1], bufB[DIRECT ? WPP + 2 : 1], nxA[DIRECT ? WPP : 1], nxB[DIRECT ? WPP : 1], nxt[DIRECT ? 1 : 2 * R];
-    const uint32_t* rowA = nullptr;
-    const uint32_t* rowB = nullptr;
-    uint32_t maxwA = 0, maxwB = 0;
+    constexpr int NROW = FPT;                                      // rows per lane
+    constexpr int WPG = 8 * R * LN::SBY / 4;                       // words per row and fetch group
+    constexpr int BYTES = 2 * R * LN::SBY;                         // bytes of a row consumed per iteration (step pair)
+    constexpr int PAD = BYTES / 4 + 1;
+    uint32_t buf[DIRECT ? NROW : 1][DIRECT ? WPG + PAD : 1], nx[DIRECT ? NROW : 1][DIRECT ? WPG : 1], nxt[DIRECT ? 1 : 2 * R];
+    const uint32_t* row[NROW];
+    uint32_t maxw[NROW];
     if constexpr (DIRECT) {
         const size_t lastf = size_t(p.n_frames) - 1;
-        const size_t ldA = fA < lastf ? fA : lastf, ldB = fB < lastf ? fB : lastf;     // padding lanes re-read the last frame
-        rowA = reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(p.sym) + ldA * p.sym_row_bytes);
-        rowB = reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(p.sym) + ldB * p.sym_row_bytes);
-        maxwA = uint32_t((p.sym_total_bytes - ldA * p.sym_row_bytes - 4) >> 2);       // loads are clamped to stay inside the array
-        maxwB = uint32_t((p.sym_total_bytes - ldB * p.sym_row_bytes - 4) >> 2);
 #pragma unroll
-        for (int j = 0; j < WPP; j++) {
-            nxA[j] = __ldg(rowA + (uint32_t(j) < maxwA ? uint32_t(j) : maxwA));
-            nxB[j] = __ldg(rowB + (uint32_t(j) < maxwB ? uint32_t(j) : maxwB));
+        for (int a = 0; a < NROW; a++) {
+            const size_t f = fA + a, ld = f < lastf ? f : lastf;                      // padding lanes re-read the last frame
+            row[a] = reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(p.sym) + ld * p.sym_row_bytes);
+            maxw[a] = uint32_t((p.sym_total_bytes - ld * p.sym_row_bytes - 4) >> 2);    // loads are clamped to stay inside the array
+#pragma unroll
+            for (int j = 0; j < WPG; j++) nx[a][j] = __ldg(row[a] + (uint32_t(j) < maxw[a] ? uint32_t(j) : maxw[a]));
         }
     } else {
 #pragma unroll
-        for (int k = 0; k < 2 * R; k++) nxt[k] = (uint32_t(k / R) < p.n_steps) ? __ldg(pk + size_t(k) * 32) : 0u;
+        for (int k = 0; k < 2 * R; k++) nxt[k] = (uint32_t(k / R) < p.n_steps) ? __ldg(pk + size_t(k) * SLOTS) : 0u;
     }
 
-    // one step pair from the bottom of the period buffer: out[n * R + i] = (sA << 8) & 0xffff | (sB << 8) << 16, then shift down
+    // one step pair from the bottom of the group buffer, in the lane format, then shift the buffer down by the bytes consumed
     auto take_pair = [&](uint32_t (&out)[2 * R]) {
 #pragma unroll
-        for (int n = 0; n < 2; n++) {
-#pragma unroll
-            for (int i = 0; i < R; i++) {
-                const int bp = n * R + i, w = bp >> 2, o = bp & 3;
-                out[n * R + i] = __byte_perm(bufA[w], bufB[w], uint32_t(((4 + o) << 12) | (o << 4))) & 0xff00ff00u;
+        for (int e = 0; e < 2 * R; e++) {
+            if constexpr (FMT == 0) {
+                const int w = e >> 2, o = e & 3;          // byte o of A -> byte 1, byte o of B -> byte 3, history bytes cleared
+                out[e] = __byte_perm(buf[0][w], buf[NROW - 1][w], uint32_t(((4 + o) << 12) | (o << 4))) & 0xff00ff00u;
+            } else {
+                const int w = e >> 1;
+                out[e] = (e & 1) ? (buf[0][w] & 0xffff0000u) : (buf[0][w] << 16);
             }
         }
-        if constexpr ((2 * R) % 4 == 0) {
 #pragma unroll
-            for (int j = 0; j < WPP; j++) { bufA[j] = bufA[j + R / 2]; bufB[j] = bufB[j + R / 2]; }
-        } else {                                  // 2R = 4m + 2 bytes: shift by m words and 16 bits
+        for (int a = 0; a < NROW; a++) {
+            if constexpr (BYTES % 4 == 0) {
 #pragma unroll
-            for (int j = 0; j < WPP; j++) {
-                bufA[j] = __funnelshift_r(bufA[j + R / 2], bufA[j + R / 2 + 1], 16);
-                bufB[j] = __funnelshift_r(bufB[j + R / 2], bufB[j + R / 2 + 1], 16);
+                for (int j = 0; j < WPG; j++) buf[a][j] = buf[a][j + BYTES / 4];
+            } else {                                      // 4m + 2 bytes: shift by m words and 16 bits
+#pragma unroll
+                for (int j = 0; j < WPG; j++) buf[a][j] = __funnelshift_r(buf[a][j + BYTES / 4], buf[a][j + BYTES / 4 + 1], 16);
             }
         }
     };
-    static_assert((R % 2 == 0) ? (R / 2 <= 2) : (R / 2 <= 1), "period buffer padding covers R <= 3 (odd) / R <= 4 (even)");
+    auto unpack_pk = [&](uint32_t w) -> uint32_t {        // packed pair word -> lane format
+        if constexpr (FMT == 0) return w;
+        else return pk_hi ? (w & 0xffff0000u) : (w << 16);
+    };
 
     uint32_t t = 0;        // next step
     for (uint32_t r = 0; r < n_periods; r++) {
-        const uint32_t left = p.n_steps - t, nst = left < 8u ? left : 8u;
-        if constexpr (DIRECT) {
-#pragma unroll
-            for (int j = 0; j < WPP; j++) { bufA[j] = nxA[j]; bufB[j] = nxB[j]; }
-            bufA[WPP] = bufA[WPP + 1] = bufB[WPP] = bufB[WPP + 1] = 0u;
-            if (r + 1 < n_periods) {
-                const uint32_t w0 = (r + 1) * uint32_t(WPP);
-#pragma unroll
-                for (int j = 0; j < WPP; j++) {
-                    const uint32_t w = w0 + uint32_t(j);
-                    nxA[j] = __ldg(rowA + (w < maxwA ? w : maxwA));
-                    nxB[j] = __ldg(rowB + (w < maxwB ? w : maxwB));
-                }
-            }
-        } else {
-            const uint32_t line = (t + 16u) * uint32_t(R) + lane;          // lines of the period after next: 8 * R <= 32 of them
-            if (lane < 8u * uint32_t(R) && line < p.n_steps * uint32_t(R)) asm volatile("prefetch.global.L1 [%0];" :: "l"(pk + size_t(line) * 32 - lane));
-        }
-        uint32_t tag2 = 0x00010001u;
-        uint32_t k = 0;
+        const uint32_t pleft = p.n_steps - t, pst = pleft < uint32_t(HB) ? pleft : uint32_t(HB);     // steps in this period
+        uint32_t tag = LN::TAG1;
 #pragma unroll 1
-        for (; k + 2 <= nst; k += 2) {
-            uint32_t cur[2 * R];
+        for (uint32_t g0 = 0; g0 < pst; g0 += 8) {          // fetch groups of the period (one for FMT 0, up to two for FMT 1)
+            const uint32_t nst = (pst - g0) < 8u ? (pst - g0) : 8u;
             if constexpr (DIRECT) {
-                take_pair(cur);
+#pragma unroll
+                for (int a = 0; a < NROW; a++) {
+#pragma unroll
+                    for (int j = 0; j < WPG; j++) buf[a][j] = nx[a][j];
+#pragma unroll
+                    for (int j = WPG; j < WPG + PAD; j++) buf[a][j] = 0u;
+                }
+                if (t + 8 < p.n_steps) {
+                    const uint32_t w0 = ((t >> 3) + 1u) * uint32_t(WPG);
+#pragma unroll
+                    for (int a = 0; a < NROW; a++) {
+#pragma unroll
+                        for (int j = 0; j < WPG; j++) {
+                            const uint32_t w = w0 + uint32_t(j);
+                            nx[a][j] = __ldg(row[a] + (w < maxw[a] ? w : maxw[a]));
+                        }
+                    }
+                }
             } else {
-#pragma unroll
-                for (int i = 0; i < 2 * R; i++) cur[i] = nxt[i];
-#pragma unroll
-                for (int i = 0; i < 2 * R; i++) nxt[i] = (t + 2 + uint32_t(i / R) < p.n_steps) ? __ldg(pk + (size_t(t + 2) * R + i) * 32) : 0u;
+                const uint32_t line = (t + 16u) * uint32_t(R) + lane;          // lines of the group after next: 8 * R <= 32 of them
+                if (lane < 8u * uint32_t(R) && line < p.n_steps * uint32_t(R))
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(p.pk + (size_t(blk) * p.n_steps * R + line) * SLOTS));
             }
-            hist_step<C, TIE_SIMD, CONSISTENT>(x, y, &cur[0], p, tag2, thr_m1, always, accA, accB);
-            hist_step<C, TIE_SIMD, CONSISTENT>(y, x, &cur[R], p, tag2 << 1, thr_m1, always, accA, accB);
-            tag2 <<= 2;
-            t += 2;
-        }
-        if (k < nst) {          // odd number of steps in the (last) period: one more step, then back into x
-            uint32_t cur[2 * R];
-            if constexpr (DIRECT) {
-                take_pair(cur);
-            } else {
+            uint32_t k = 0;
+#pragma unroll 1
+            for (; k + 2 <= nst; k += 2) {
+                uint32_t cur[2 * R];
+                if constexpr (DIRECT) {
+                    take_pair(cur);
+                } else {
 #pragma unroll
-                for (int i = 0; i < 2 * R; i++) cur[i] = nxt[i];
+                    for (int i = 0; i < 2 * R; i++) cur[i] = unpack_pk(nxt[i]);
+#pragma unroll
+                    for (int i = 0; i < 2 * R; i++) nxt[i] = (t + 2 + uint32_t(i / R) < p.n_steps) ? __ldg(pk + (size_t(t + 2) * R + i) * SLOTS) : 0u;
+                }
+                hist_step<C, FMT, TIE_SIMD, CONSISTENT>(x, y, &cur[0], c, tag, accA, accB);
+                hist_step<C, FMT, TIE_SIMD, CONSISTENT>(y, x, &cur[R], c, tag << 1, accA, accB);
+                tag <<= 2;
+                t += 2;
             }
-            hist_step<C, TIE_SIMD, CONSISTENT>(x, y, &cur[0], p, tag2, thr_m1, always, accA, accB);
+            if (k < nst) {          // odd number of steps left (end of the frame): one more step, then back into x
+                uint32_t cur[2 * R];
+                if constexpr (DIRECT) {
+                    take_pair(cur);
+                } else {
 #pragma unroll
-            for (int q = 0; q < NS; q++) x[q] = y[q];
-            t += 1;
+                    for (int i = 0; i < 2 * R; i++) cur[i] = unpack_pk(nxt[i]);
+                }
+                hist_step<C, FMT, TIE_SIMD, CONSISTENT>(x, y, &cur[0], c, tag, accA, accB);
+#pragma unroll
+                for (int q = 0; q < NS; q++) x[q] = y[q];
+                t += 1;
+            }
         }
-        // history record of this period, then clear the low bytes
-        const uint32_t vmask = 0x01010101u * ((1u << nst) - 1u);
+        // history record of this period, then clear the history fields
         uint32_t w[NW];
 #pragma unroll
         for (int i = 0; i < NW; i++) {
-            w[i] = __byte_perm(x[2 * i], x[2 * i + 1], 0x6420);
-            if constexpr (TIE_SIMD) w[i] = ~w[i] & vmask;           // the tag marked path 0: decision = !tag
+            w[i] = __byte_perm(x[2 * i], x[2 * i + 1], FMT == 0 ? 0x6420u : 0x5410u);
+            if constexpr (TIE_SIMD) {                                  // the tag marked path 0: decision = !tag
+                const uint32_t vmask = (FMT == 0 ? 0x01010101u : 0x00010001u) * ((1u << pst) - 1u);
+                w[i] = ~w[i] & vmask;
+            }
         }
         uint32_t* dst = rec + size_t(r) * (32 * NW);
 #pragma unroll
@@ -257,19 +365,25 @@ __global__ void __launch_bounds__(32 * HIST_WARPS) acs_hist_kernel(const AcsPara
             else dst[v * 32] = w[v];
         }
 #pragma unroll
-        for (int q = 0; q < NS; q++) x[q] &= 0xff00ff00u;
+        for (int q = 0; q < NS; q++) x[q] &= LN::METRIC_MASK;
     }
 
     // final metrics in logical order (core.h:195-199 reads old_metrics[end_state])
     uint16_t* mA = p.metrics + fA * NS;
-    uint16_t* mB = p.metrics + fB * NS;
+    if constexpr (FMT == 0) {
+        uint16_t* mB = p.metrics + fB * NS;
 #pragma unroll
-    for (int q = 0; q < NS; q++) {
-        mA[q] = uint16_t((x[q] & 0xffffu) >> 8);
-        mB[q] = uint16_t(x[q] >> 24);
+        for (int q = 0; q < NS; q++) {
+            mA[q] = uint16_t((x[q] & 0xffffu) >> 8);
+            mB[q] = uint16_t(x[q] >> 24);
+        }
+        p.acc[fA] = accA;
+        p.acc[fB] = accB;
+    } else {
+#pragma unroll
+        for (int q = 0; q < NS; q++) mA[q] = uint16_t(x[q] >> 16);
+        p.acc[fA] = accA;
     }
-    p.acc[fA] = accA;
-    p.acc[fB] = accB;
 }
 
 }  // namespace vitb

@@ -340,11 +340,11 @@ __global__ void __launch_bounds__(64) traceback_cta_kernel(const TracebackCtaPar
 namespace vitb {
 
 // ---- history records written by acs_hist_kernel (acs_hist.cuh) ---------------------------------------------------------------
-// Record r of a frame holds, for every state s at time min(8(r+1), S), the decisions D[8r .. 8r+7] along the survivor path that
-// ends in s (bit k = step 8r + k).  chainback (core.h:214-236) reads, for decoded bit j, the decision of row j + (K-1) at the
-// current state and then moves to state (bit << (K-2)) | (state >> 1): along the survivor path those are exactly the bits of the
-// byte, so one byte lookup replaces 8 dependent row lookups:
-//     decoded[j] = D[j + SB];   state 8 steps earlier = bit-reversal of the low SB bits of the byte (SB <= 8).
+// Record r of a frame holds, for every state s at time min(HB(r+1), S), the decisions D[HB r .. HB r + HB-1] along the survivor path
+// that ends in s (bit k = step HB r + k; HB = 8 for uint8_t metrics, 16 for uint16_t metrics).  chainback (core.h:214-236) reads, for
+// decoded bit j, the decision of row j + (K-1) at the current state and then moves to state (bit << (K-2)) | (state >> 1): along
+// the survivor path those are exactly the bits of the history field, so one lookup replaces HB dependent row lookups:
+//     decoded[j] = D[j + SB];   state one period earlier = bit-reversal of the low SB bits of the field (SB <= 8 <= HB).
 // Bytes are MSB-first (core.h:234); when total_bits % 8 != 0 the last byte carries the leading bits of end_state below the decoded
 // bits (the reference's traceback buffer still holds them), modelled here as virtual decisions D[S + k] = bit (SB-1-k) of end_state.
 struct TracebackHistParams {
@@ -355,45 +355,52 @@ struct TracebackHistParams {
     uint32_t state_bits;      // SB = K-1 (<= 8)
     uint32_t end_state;
     uint32_t n_steps;         // S = L + SB
+    uint32_t hist_bits;       // HB: 8 (two frames per lane, 64 per block) or 16 (one frame per lane, 32 per block)
     uint8_t* out;
     size_t out_stride;
 };
-
-// byte offset of (lane, half, state) inside one 64-frame block record
-__device__ __forceinline__ uint32_t hist_byte_offset(uint32_t s, uint32_t lane, uint32_t half, uint32_t vw_log) {
-    const uint32_t w = s >> 1;
-    return ((((w >> vw_log) << 5) + lane) << (vw_log + 2)) + ((w & ((1u << vw_log) - 1u)) << 2) + ((s & 1u) << 1) + half;
-}
 
 // one thread per frame
 __global__ void __launch_bounds__(128) traceback_hist_kernel(const TracebackHistParams p) {
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= p.n_frames) return;
-    const uint32_t SB = p.state_bits, L = p.total_bits, S = p.n_steps, NS = 1u << SB;
+    const uint32_t SB = p.state_bits, L = p.total_bits, S = p.n_steps, NS = 1u << SB, HB = p.hist_bits;
     const uint32_t nw = NS / 2, vw_log = nw >= 4 ? 2u : (nw == 2 ? 1u : 0u);
-    const uint32_t lane = (f & 63u) >> 1, half = f & 1u;
-    const size_t rec_bytes = size_t(64) * NS;
-    const uint8_t* base = p.dec + size_t(f >> 6) * p.n_periods * rec_bytes;
+    const bool wide = HB == 16;
+    const uint32_t lane = wide ? (f & 31u) : ((f & 63u) >> 1), half = wide ? 0u : (f & 1u);
+    const size_t rec_bytes = size_t(64) * NS;                     // one warp block, one period (both formats)
+    const uint8_t* base = p.dec + size_t(wide ? (f >> 5) : (f >> 6)) * p.n_periods * rec_bytes;
     uint8_t* out = p.out + size_t(f) * p.out_stride;
-    const uint32_t n_out = (L + 7) / 8;
+    const uint32_t n_out = (L + 7) / 8, hmask = (1u << HB) - 1u;
 
-    const uint32_t r_last = (S - 1) / 8, nv = S - 8 * r_last;
+    const uint32_t r_last = (S - 1) / HB, nv = S - HB * r_last;
     // virtual decisions behind the last step
     const uint32_t E = SB ? (__brev(p.end_state) >> (32 - SB)) : 0u;
-    const uint32_t VS = E << nv;                       // relative to the first step of record r_last
+    const uint32_t VS = E << nv;                       // relative to the first step of record r_last (at most 16 + 8 bits)
     uint32_t state = p.end_state;
-    uint32_t hnext = (VS >> 8) & 0xffu;                // record r_last + 1 (purely virtual)
-    if (r_last + 1 < n_out) out[r_last + 1] = 0;       // cannot happen for SB >= 1 (n_out <= r_last + 1); kept for safety
+    uint32_t hnext = (VS >> HB) & hmask;               // record r_last + 1 (purely virtual)
     for (int64_t r = r_last; r >= 0; r--) {
-        const uint32_t h = base[size_t(r) * rec_bytes + hist_byte_offset(state, lane, half, vw_log)];
+        // word w = state >> 1 of the lane: FMT 0 bytes [A:2w, B:2w, A:2w+1, B:2w+1], FMT 1 halfwords [2w, 2w+1]
+        const uint32_t w = state >> 1;
+        const uint32_t off = ((((w >> vw_log) << 5) + lane) << (vw_log + 2)) + ((w & ((1u << vw_log) - 1u)) << 2) + ((state & 1u) << 1) + half;
+        const uint8_t* ptr = base + size_t(r) * rec_bytes + off;
+        const uint32_t h = wide ? uint32_t(*reinterpret_cast<const uint16_t*>(ptr)) : uint32_t(*ptr);
         uint32_t hext = h;
         if (uint32_t(r) == r_last) {
-            hext = (h & ((1u << nv) - 1u)) | (VS & 0xffu);
+            hext = (h & ((1u << nv) - 1u)) | (VS & hmask);
             for (int k = int(nv) - 1; k >= 0; k--) state = (((h >> k) & 1u) << (SB - 1)) | (state >> 1);
         } else {
-            state = __brev(h) >> (32 - SB);            // 8 steps back: the last SB pushed bits, newest on top
+            state = __brev(h) >> (32 - SB);            // one period back: the last SB pushed bits, newest on top
         }
-        if (uint32_t(r) < n_out) out[r] = uint8_t(__brev(((hext | (hnext << 8)) >> SB) & 0xffu) >> 24);
+        // decoded bits of this record's steps: window of 2 HB decisions shifted down by SB, MSB-first bytes
+        const uint64_t win = (uint64_t(hext) | (uint64_t(hnext) << HB)) >> SB;
+        if (!wide) {
+            if (uint32_t(r) < n_out) out[r] = uint8_t(__brev(uint32_t(win) & 0xffu) >> 24);
+        } else {
+            const uint32_t b0 = 2u * uint32_t(r);
+            if (b0 < n_out) out[b0] = uint8_t(__brev(uint32_t(win) & 0xffu) >> 24);
+            if (b0 + 1 < n_out) out[b0 + 1] = uint8_t(__brev(uint32_t(win >> 8) & 0xffu) >> 24);
+        }
         hnext = hext;
     }
 }

@@ -130,6 +130,14 @@ const KernelEntry* choose_variant(const vitb_decoder* h, size_t n_frames) {
     }
     const size_t pairs = (n_frames + 1) / 2, smsp = size_t(h->n_sm) * 4;
     if (h->variants.front()->layout == LAYOUT_CTA) return h->variants.back();   // K = 15: 1024 threads x 16 registers measured fastest
+    // survivor-history kernel (acs_hist.cuh, 4 instructions per butterfly): about twice as fast per add-compare-select as the
+    // predicate kernels, so it wins as soon as it can put a warp on half of the sub-partitions
+    static const bool no_hist = getenv("VITB_NO_HIST") != nullptr;
+    const KernelEntry* e0 = h->variants.front();
+    if (!no_hist && e0->logt == 0 && e0->launch_hist) {
+        const size_t fpw = (e0->sh == 8) ? 64 : 32;
+        if ((n_frames + fpw - 1) / fpw >= smsp / 2) return e0;
+    }
     for (const KernelEntry* e : h->variants) {
         const size_t warps = ((pairs << e->logt) + 31) / 32;
         const size_t want = (e->logt == 0) ? smsp * 3 / 2 : smsp * 4;
@@ -265,27 +273,30 @@ int decode_chunk_dev(vitb_decoder* h, const KernelEntry* e, const void* d_symbol
                      size_t start_state, size_t end_state, uint8_t* d_out, uint64_t* d_acc, uint32_t* d_final, cudaStream_t s) {
     const size_t K = size_t(h->prm.K), R = size_t(h->prm.R), S = L + K - 1, n_sym = S * R;
     const unsigned n_b64 = unsigned((n_frames + 63) / 64);
-    const unsigned n_wblocks = n_b64 * unsigned(32 / e->ppw);
-    // uint8_t one-thread-per-pair kernels: survivor-history records (acs_hist.cuh) instead of decision rows; same bytes per step
+    // one-thread-per-pair entries: survivor-history records (acs_hist.cuh) instead of decision rows; same bytes per frame and step.
+    // uint8_t metrics: warp block = 64 frames, 8-step records; uint16_t metrics: warp block = 32 frames, 16-step records.
     static const bool no_hist = getenv("VITB_NO_HIST") != nullptr;
     const bool hist = !no_hist && e->launch_hist != nullptr;
-    const size_t n_periods = (S + 7) / 8;
+    const bool hist_wide = hist && e->sh == 0;
+    const size_t hist_bits = hist_wide ? 16 : 8, n_periods = (S + hist_bits - 1) / hist_bits;
+    const unsigned ppw = hist_wide ? 16u : unsigned(e->ppw);
+    const unsigned n_wblocks = n_b64 * (32u / ppw);
     VITB_CUDA(h, h->pk.reserve(size_t(n_b64) * n_sym * 32 * 4));
-    VITB_CUDA(h, h->dec.reserve(hist ? size_t(n_b64) * n_periods * 64 * size_t(h->n_states) : size_t(n_b64) * dec_bytes_per_block64(e, S)));
+    VITB_CUDA(h, h->dec.reserve(hist ? size_t(n_wblocks) * n_periods * 64 * size_t(h->n_states) : size_t(n_b64) * dec_bytes_per_block64(e, S)));
     VITB_CUDA(h, h->metrics.reserve(size_t(n_b64) * 64 * h->n_states * 2));
     VITB_CUDA(h, h->acc.reserve(size_t(n_b64) * 64 * 8));
 
     // one-thread-per-pair kernels can read the caller's rows themselves when they are 4-byte aligned and not punctured
     static const bool no_direct = getenv("VITB_NO_DIRECT") != nullptr;
     const size_t row_bytes = row_stride * size_t(h->prm.soft_bytes);
-    const bool direct = !no_direct && e->launch_direct && !h->n_depunctured && (row_bytes % 4 == 0) &&
+    const bool direct = !no_direct && (hist || e->launch_direct) && !h->n_depunctured && (row_bytes % 4 == 0) &&
                         (reinterpret_cast<uintptr_t>(d_symbols) % 4 == 0) && row_bytes >= 4;
     VITB_CUDA(h, mark(h, s));
     if (!direct) {
         IngestParams ip{};
         ip.symbols = d_symbols; ip.row_stride = row_stride; ip.n_frames = uint32_t(n_frames); ip.n_sym = uint32_t(n_sym);
         ip.depuncture_map = h->n_depunctured ? static_cast<const int32_t*>(h->map.ptr) : nullptr;
-        ip.fill_value = h->unpunctured_value; ip.pk = static_cast<uint32_t*>(h->pk.ptr); ip.ppw = uint32_t(e->ppw);
+        ip.fill_value = h->unpunctured_value; ip.pk = static_cast<uint32_t*>(h->pk.ptr); ip.ppw = ppw;
         VITB_CUDA(h, run_ingest(h, ip, n_b64, s));
     }
     VITB_CUDA(h, mark(h, s));
@@ -308,7 +319,7 @@ int decode_chunk_dev(vitb_decoder* h, const KernelEntry* e, const void* d_symbol
         TracebackHistParams t{};
         t.dec = static_cast<const uint8_t*>(h->dec.ptr); t.n_periods = uint32_t(n_periods); t.n_frames = uint32_t(n_frames);
         t.total_bits = uint32_t(L); t.state_bits = uint32_t(K - 1); t.end_state = uint32_t(end_state); t.n_steps = uint32_t(S);
-        t.out = d_out; t.out_stride = (L + 7) / 8;
+        t.hist_bits = uint32_t(hist_bits); t.out = d_out; t.out_stride = (L + 7) / 8;
         traceback_hist_kernel<<<unsigned((n_frames + 127) / 128), 128, 0, s>>>(t);
         VITB_CUDA(h, cudaGetLastError());
     } else if (d_out) VITB_CUDA(h, launch_traceback(h, e, h->dec.ptr, S, n_frames, L, end_state, d_out, (L + 7) / 8, s));

@@ -28,7 +28,9 @@ struct KernelEntry {
     const char* name;
     cudaError_t (*launch)(const AcsParams&, cudaStream_t);
     cudaError_t (*launch_direct)(const AcsParams&, cudaStream_t);   // pair kernels only: symbols read from the caller's rows (no ingest)
-    // uint8_t pair kernels only: whole-frame batch decode with survivor-history records instead of decision rows (acs_hist.cuh)
+    // one-thread-per-pair entries: whole-frame batch decode with survivor-history records instead of decision rows (acs_hist.cuh).
+    // uint8_t metrics: two frames per lane, 8-step records; uint16_t metrics: one frame per lane, 16-step records, packed stream in
+    // the 16-pairs-per-warp-block layout
     cudaError_t (*launch_hist)(const AcsParams&, cudaStream_t);
     cudaError_t (*launch_hist_direct)(const AcsParams&, cudaStream_t);
 };
@@ -60,10 +62,10 @@ cudaError_t launch_pair_direct(const AcsParams& p, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-template <class C, bool TIE_SIMD, bool CONSISTENT, bool DIRECT>
+template <class C, int FMT, bool TIE_SIMD, bool CONSISTENT, bool DIRECT>
 cudaError_t launch_hist(const AcsParams& p, cudaStream_t s) {
     const unsigned grid = (p.n_blocks + HIST_WARPS - 1) / HIST_WARPS;
-    acs_hist_kernel<C, TIE_SIMD, CONSISTENT, DIRECT><<<grid, 32 * HIST_WARPS, 0, s>>>(p);
+    acs_hist_kernel<C, FMT, TIE_SIMD, CONSISTENT, DIRECT><<<grid, 32 * HIST_WARPS, 0, s>>>(p);
     return cudaGetLastError();
 }
 
@@ -114,10 +116,8 @@ KernelEntry make_entry(const char* name) {
         e.layout = LAYOUT_PAIR; e.ppw = 32; e.dec_words = 0;
         e.launch = &launch_pair<C, SH, TIE_SIMD, CONSISTENT>;
         if constexpr (DirectFetch<C, SH, PairPeriod<C>::value>::supported) e.launch_direct = &launch_pair_direct<C, SH, TIE_SIMD, CONSISTENT>;
-        if constexpr (SH == 8) {
-            e.launch_hist = &launch_hist<C, TIE_SIMD, CONSISTENT, false>;
-            e.launch_hist_direct = &launch_hist<C, TIE_SIMD, CONSISTENT, true>;
-        }
+        e.launch_hist = &launch_hist<C, SH == 8 ? 0 : 1, TIE_SIMD, CONSISTENT, false>;
+        e.launch_hist_direct = &launch_hist<C, SH == 8 ? 0 : 1, TIE_SIMD, CONSISTENT, true>;
     } else {
         e.layout = LAYOUT_GROUP; e.ppw = GroupShape<C, LOGT>::PPW; e.dec_words = GroupShape<C, LOGT>::W;
         e.launch = &launch_group<C, LOGT, SH, TIE_SIMD, CONSISTENT>;
