@@ -1,0 +1,153 @@
+"""GPU parity tests aimed at the survivor-history kernel (csrc/acs_hist.cuh) and its traceback (traceback_hist_kernel):
+random soft symbols inside [low, high] (arbitrary survivor paths, many metric ties - the tie-break lives in the history tags),
+frame lengths around every record boundary (8 steps for uint8_t metrics, 16 for uint16_t), ragged bit counts, non-zero start and
+end states, both tie-break flavours, an inconsistent max_error, packed-stream input (unaligned rows), and agreement with the
+decision-row kernels.  Everything against the scalar oracle through the C ABI, bit-exact."""
+import numpy as np
+import pytest
+
+import viterbidecodercpp_b200 as v
+from common import CODE_BY_NAME, PAIR_CODES, assert_batch_equal, make_cuda_decoder, make_oracle
+from oracle_binding import MODE_SCALAR, MODE_SIMD
+
+pytestmark = pytest.mark.gpu
+
+
+def random_symbols(dc, n_frames, n_sym, seed, pad=0):
+    rng = np.random.default_rng(seed)
+    dt = np.int8 if dc.soft_bytes == 1 else np.int16
+    s = rng.integers(dc.soft_decision_low, dc.soft_decision_high + 1, size=(n_frames, n_sym + pad)).astype(dt)
+    return s
+
+
+def oracle_batch(ora, code, sym, L, start=0, end=0):
+    """the call protocol of run_simple.cpp:76-80 per frame, with explicit start / end states (core.h:195-236)"""
+    n = sym.shape[0]
+    out = np.zeros((n, (L + 7) // 8), dtype=np.uint8)
+    acc = np.zeros(n, dtype=np.uint64)
+    fin = np.zeros(n, dtype=np.uint32)
+    ora.set_traceback_length(L)
+    for f in range(n):
+        ora.reset(start)
+        acc[f] = ora.update(sym[f])
+        fin[f] = ora.get_error(end)
+        out[f] = ora.chainback(L, end)
+    return out, acc, fin
+
+
+@pytest.mark.parametrize("decode_type", ["SOFT16", "SOFT8", "HARD8"])
+@pytest.mark.parametrize("name", PAIR_CODES)
+def test_history_kernel_every_record_residue(cuda_lib, name, decode_type):
+    """total_bits from 1 to 40 (every residue of the step count modulo the 8 / 16-step record, ragged last bytes) and a long frame"""
+    code = CODE_BY_NAME[name]
+    dec, dc = make_cuda_decoder(code, decode_type)
+    ora, _ = make_oracle(code, decode_type)
+    dec.set_variant(1)
+    for L in list(range(1, 41)) + [257, 1003]:
+        n_sym = (L + code.K - 1) * code.R
+        n_frames = 70 if L < 100 else 67
+        sym = random_symbols(dc, n_frames, n_sym, seed=1000 + L)
+        want = ora.decode_frames(sym, n_frames, L)
+        got = dec.decode_batch(sym, L)
+        assert dec.kernel_name.startswith("acs_hist<"), dec.kernel_name
+        assert_batch_equal(got, want, f"{name} {decode_type} L={L}")
+
+
+@pytest.mark.parametrize("decode_type", ["SOFT16", "HARD8"])
+@pytest.mark.parametrize("name", ["Voyager", "DAB Radio", "Basic K=5 R=1/2"])
+def test_history_kernel_matches_decision_row_kernel(cuda_lib, name, decode_type):
+    code = CODE_BY_NAME[name]
+    dec, dc = make_cuda_decoder(code, decode_type)
+    dec.set_variant(1)
+    L = 777
+    sym = random_symbols(dc, 130, (L + code.K - 1) * code.R, seed=5)
+    a = dec.decode_batch(sym, L)
+    assert dec.kernel_name.startswith("acs_hist<")
+    dec.set_history_kernel(False)
+    b = dec.decode_batch(sym, L)
+    assert dec.kernel_name.startswith("acs<"), dec.kernel_name
+    dec.set_history_kernel(True)
+    assert_batch_equal(a, b, f"{name} {decode_type} history vs decision rows")
+
+
+@pytest.mark.parametrize("decode_type", ["SOFT16", "SOFT8", "HARD8"])
+@pytest.mark.parametrize("name", ["Voyager", "LTE", "DAB Radio"])
+def test_history_kernel_start_and_end_states(cuda_lib, name, decode_type):
+    code = CODE_BY_NAME[name]
+    dec, dc = make_cuda_decoder(code, decode_type)
+    ora, _ = make_oracle(code, decode_type)
+    dec.set_variant(1)
+    ns = 1 << (code.K - 1)
+    for L, start, end in [(100, 5, 0), (100, 0, ns - 1), (61, 9, 37 % ns), (203, ns - 1, 21 % ns)]:
+        sym = random_symbols(dc, 33, (L + code.K - 1) * code.R, seed=L + start + end)
+        want = oracle_batch(ora, code, sym, L, start, end)
+        got = dec.decode_batch(sym, L, starting_state=start, end_state=end)
+        assert dec.kernel_name.startswith("acs_hist<")
+        assert_batch_equal(got, want, f"{name} {decode_type} L={L} start={start} end={end}")
+
+
+@pytest.mark.parametrize("decode_type", ["SOFT16", "HARD8"])
+@pytest.mark.parametrize("name", ["Voyager", "LTE", "DAB Radio", "Basic K=3 R=1/2"])
+def test_history_kernel_simd_tie_break(cuda_lib, name, decode_type):
+    """VITB_TIE_SIMD: decision = (min == path 1), x86/viterbi_decoder_avx_u16.h:112-115; random symbols tie all the time"""
+    code = CODE_BY_NAME[name]
+    dc = v.DECODE_TYPES[decode_type](code.R)
+    c = dc.decoder_config
+    # the SIMD flavour saturates where the CUDA path wraps (only its tie-break is reproduced): renormalise early enough that no
+    # uint8_t metric gets near 255 with random symbols
+    thr = c.renormalisation_threshold if decode_type == "SOFT16" else 100
+    cfg = v.ViterbiDecoder_Config(c.soft_decision_max_error, c.initial_start_error, c.initial_non_start_error, thr)
+    dec, _ = make_cuda_decoder(code, decode_type, tie_break=v.VITB_TIE_SIMD, config_override=cfg)
+    ora, _ = make_oracle(code, decode_type, mode=MODE_SIMD, config_override=cfg)
+    dec.set_variant(1)
+    for L in (13, 64, 500):
+        sym = random_symbols(dc, 70, (L + code.K - 1) * code.R, seed=77 + L)
+        want = ora.decode_frames(sym, 70, L)
+        got = dec.decode_batch(sym, L)
+        assert dec.kernel_name.startswith("acs_hist<")
+        assert_batch_equal(got, want, f"{name} {decode_type} simd tie L={L}")
+
+
+@pytest.mark.parametrize("decode_type", ["SOFT16", "HARD8"])
+def test_history_kernel_inconsistent_max_error(cuda_lib, decode_type):
+    """soft_decision_max_error != R * (high - low): the inverted error is no longer the complementary table entry (scalar.h:107)"""
+    code = CODE_BY_NAME["Voyager"]
+    dc = v.DECODE_TYPES[decode_type](code.R)
+    c = dc.decoder_config
+    cfg = v.ViterbiDecoder_Config(c.soft_decision_max_error + 3, c.initial_start_error, c.initial_non_start_error, c.renormalisation_threshold)
+    dec, _ = make_cuda_decoder(code, decode_type, config_override=cfg)
+    ora, _ = make_oracle(code, decode_type, config_override=cfg)
+    dec.set_variant(1)
+    L = 300
+    sym = random_symbols(dc, 70, (L + code.K - 1) * code.R, seed=3)
+    want = ora.decode_frames(sym, 70, L)
+    got = dec.decode_batch(sym, L)
+    assert dec.kernel_name.startswith("acs_hist<")
+    assert_batch_equal(got, want, f"Voyager {decode_type} inconsistent max_error")
+
+
+@pytest.mark.parametrize("decode_type", ["SOFT16", "HARD8"])
+@pytest.mark.parametrize("name", ["Voyager", "LTE", "DAB Radio"])
+def test_history_kernel_packed_stream_input(cuda_lib, name, decode_type):
+    """rows whose stride is not a multiple of 4 bytes cannot be fetched directly: ingest -> packed stream -> history kernel"""
+    code = CODE_BY_NAME[name]
+    dec, dc = make_cuda_decoder(code, decode_type)
+    ora, _ = make_oracle(code, decode_type)
+    dec.set_variant(1)
+    L = 333
+    n_sym = (L + code.K - 1) * code.R
+    pad = 1 if (n_sym * dc.soft_bytes) % 4 != 3 else 2
+    if ((n_sym + pad) * dc.soft_bytes) % 4 == 0:
+        pad += 1
+    full = random_symbols(dc, 70, n_sym, seed=11, pad=pad)
+    want = ora.decode_frames(np.ascontiguousarray(full[:, :n_sym]), 70, L)
+    # decode_batch takes the row stride from the array's second dimension: the padded array gives unaligned rows
+    import ctypes as C
+    out = np.zeros((70, (L + 7) // 8), dtype=np.uint8)
+    acc = np.zeros(70, dtype=np.uint64)
+    fin = np.zeros(70, dtype=np.uint32)
+    o = dec._opts(full.shape[1], 0, 0)
+    rc = dec._L.vitb_decode_batch(dec._h, full.ctypes.data, 70, L, C.byref(o), out.ctypes.data, acc.ctypes.data, fin.ctypes.data)
+    assert rc == 0
+    assert dec.kernel_name.startswith("acs_hist<")
+    assert_batch_equal((out, acc, fin), want, f"{name} {decode_type} packed stream")

@@ -198,14 +198,14 @@ __device__ __forceinline__ void hist_step(const uint32_t (&x)[C::NS], uint32_t (
 
 constexpr int HIST_WARPS = 4;
 
-// grid = ceil(n_blocks / HIST_WARPS); one warp per block of 64 (FMT 0) / 32 (FMT 1) frames.
+// grid = ceil(n_blocks / warps per CTA), at most HIST_WARPS warps per CTA; one warp per block of 64 (FMT 0) / 32 (FMT 1) frames.
 // Whole frames only: p.resume must be 0 and p.dec_row0 must be 0 (the streaming API keeps using acs_pair_kernel / acs_group_kernel).
 // FMT 1 reads the packed stream in the 16-pairs-per-warp-block layout (ingest with ppw = 16).
 template <class C, int FMT, bool TIE_SIMD, bool CONSISTENT, bool DIRECT>
 __global__ void __launch_bounds__(32 * HIST_WARPS) acs_hist_kernel(const AcsParams p) {
     using LN = HistLane<FMT>;
     constexpr int R = C::R, NS = C::NS, NW = HistShape<C>::NW, VW = HistShape<C>::VW, HB = LN::HB, FPT = LN::FPT;
-    const uint32_t lane = threadIdx.x & 31, blk = blockIdx.x * HIST_WARPS + (threadIdx.x >> 5);
+    const uint32_t lane = threadIdx.x & 31, blk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (blk >= p.n_blocks) return;
     const size_t fA = size_t(blk) * (32 * FPT) + FPT * lane, fB = fA + 1;      // fB only exists for FMT 0
     const HistConsts c = hist_consts<FMT>(p);

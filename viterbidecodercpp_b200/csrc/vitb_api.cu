@@ -66,7 +66,10 @@ struct vitb_decoder {
     std::vector<const KernelEntry*> variants;   // every compiled lanes-per-pair variant of this code/config, ascending logt
     const KernelEntry* entry = nullptr;         // variant used by the single-frame streaming API (fixes its decision layout)
     const KernelEntry* last_batch = nullptr;    // variant the last batch call selected
+    bool last_batch_hist = false;               // ... and whether it ran as the survivor-history kernel (acs_hist.cuh)
+    std::string name_buf;
     int forced_logt = -1;                       // vitb_set_variant
+    bool use_hist = getenv("VITB_NO_HIST") == nullptr;   // vitb_set_history_kernel
     int n_sm = 148;
     int n_states = 0;
     int sh = 0;
@@ -132,9 +135,8 @@ const KernelEntry* choose_variant(const vitb_decoder* h, size_t n_frames) {
     if (h->variants.front()->layout == LAYOUT_CTA) return h->variants.back();   // K = 15: 1024 threads x 16 registers measured fastest
     // survivor-history kernel (acs_hist.cuh, 4 instructions per butterfly): about twice as fast per add-compare-select as the
     // predicate kernels, so it wins as soon as it can put a warp on half of the sub-partitions
-    static const bool no_hist = getenv("VITB_NO_HIST") != nullptr;
     const KernelEntry* e0 = h->variants.front();
-    if (!no_hist && e0->logt == 0 && e0->launch_hist) {
+    if (h->use_hist && e0->logt == 0 && e0->launch_hist) {
         const size_t fpw = (e0->sh == 8) ? 64 : 32;
         if ((n_frames + fpw - 1) / fpw >= smsp / 2) return e0;
     }
@@ -275,9 +277,9 @@ int decode_chunk_dev(vitb_decoder* h, const KernelEntry* e, const void* d_symbol
     const unsigned n_b64 = unsigned((n_frames + 63) / 64);
     // one-thread-per-pair entries: survivor-history records (acs_hist.cuh) instead of decision rows; same bytes per frame and step.
     // uint8_t metrics: warp block = 64 frames, 8-step records; uint16_t metrics: warp block = 32 frames, 16-step records.
-    static const bool no_hist = getenv("VITB_NO_HIST") != nullptr;
-    const bool hist = !no_hist && e->launch_hist != nullptr;
+    const bool hist = h->use_hist && e->launch_hist != nullptr;
     const bool hist_wide = hist && e->sh == 0;
+    h->last_batch_hist = hist;
     const size_t hist_bits = hist_wide ? 16 : 8, n_periods = (S + hist_bits - 1) / hist_bits;
     const unsigned ppw = hist_wide ? 16u : unsigned(e->ppw);
     const unsigned n_wblocks = n_b64 * (32u / ppw);
@@ -434,6 +436,11 @@ int vitb_destroy(vitb_decoder* h) {
 int vitb_last_cuda_error(const vitb_decoder* h) { return h ? h->last_cuda : 0; }
 const char* vitb_kernel_name(const vitb_decoder* h) {
     if (!h) return "";
+    if (h->last_batch && h->last_batch_hist) {      // "acs<...>" -> "acs_hist<...>"
+        vitb_decoder* m = const_cast<vitb_decoder*>(h);
+        m->name_buf = std::string("acs_hist") + (h->last_batch->name + 3);
+        return m->name_buf.c_str();
+    }
     return h->last_batch ? h->last_batch->name : (h->entry ? h->entry->name : "");
 }
 
@@ -444,6 +451,12 @@ int vitb_set_variant(vitb_decoder* h, int lanes_per_pair) {
         if ((1 << e->logt) == lanes_per_pair) { h->forced_logt = e->logt; return VITB_OK; }
     }
     return VITB_ERR_UNSUPPORTED;
+}
+
+int vitb_set_history_kernel(vitb_decoder* h, int enabled) {
+    if (!h) return VITB_ERR_ARG;
+    h->use_hist = enabled != 0;
+    return VITB_OK;
 }
 
 int vitb_get_variants(const vitb_decoder* h, int* lanes_per_pair, int capacity) {

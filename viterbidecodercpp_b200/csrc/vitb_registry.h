@@ -64,8 +64,10 @@ cudaError_t launch_pair_direct(const AcsParams& p, cudaStream_t s) {
 
 template <class C, int FMT, bool TIE_SIMD, bool CONSISTENT, bool DIRECT>
 cudaError_t launch_hist(const AcsParams& p, cudaStream_t s) {
-    const unsigned grid = (p.n_blocks + HIST_WARPS - 1) / HIST_WARPS;
-    acs_hist_kernel<C, FMT, TIE_SIMD, CONSISTENT, DIRECT><<<grid, 32 * HIST_WARPS, 0, s>>>(p);
+    static const unsigned warps = getenv("VITB_HIST_WARPS") ? unsigned(atoi(getenv("VITB_HIST_WARPS"))) : unsigned(HIST_WARPS);
+    const unsigned w = (warps >= 1 && warps <= unsigned(HIST_WARPS)) ? warps : unsigned(HIST_WARPS);
+    const unsigned grid = (p.n_blocks + w - 1) / w;
+    acs_hist_kernel<C, FMT, TIE_SIMD, CONSISTENT, DIRECT><<<grid, 32 * w, 0, s>>>(p);
     return cudaGetLastError();
 }
 

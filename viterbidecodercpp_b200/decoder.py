@@ -244,6 +244,10 @@ class ViterbiDecoder_CUDA:
         """pin the lanes-per-frame-pair kernel variant for batch calls (0 = choose by batch size)"""
         _check(self._L.vitb_set_variant(self._h, lanes_per_pair), "set_variant")
 
+    def set_history_kernel(self, enabled=True):
+        """batch calls of one-lane-per-pair variants: survivor-history kernel (default) or the decision-row kernels"""
+        _check(self._L.vitb_set_history_kernel(self._h, 1 if enabled else 0), "set_history_kernel")
+
     @property
     def variants(self):
         buf = (C.c_int * 16)()
