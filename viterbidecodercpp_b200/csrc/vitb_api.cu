@@ -134,11 +134,12 @@ const KernelEntry* choose_variant(const vitb_decoder* h, size_t n_frames) {
     const size_t pairs = (n_frames + 1) / 2, smsp = size_t(h->n_sm) * 4;
     if (h->variants.front()->layout == LAYOUT_CTA) return h->variants.back();   // K = 15: 1024 threads x 16 registers measured fastest
     // survivor-history kernel (acs_hist.cuh, 4 instructions per butterfly): about twice as fast per add-compare-select as the
-    // predicate kernels, so it wins as soon as it can put a warp on half of the sub-partitions
+    // predicate kernels and no ingest pass, so it wins unless the batch is so small that only the lane-group variants can spread
+    // it over the GPU (a warp of the history kernel runs alone at full speed: 16 384 config-2 frames = 256 warps take 0.34 ms)
     const KernelEntry* e0 = h->variants.front();
     if (h->use_hist && e0->logt == 0 && e0->launch_hist) {
         const size_t fpw = (e0->sh == 8) ? 64 : 32;
-        if ((n_frames + fpw - 1) / fpw >= smsp / 2) return e0;
+        if ((n_frames + fpw - 1) / fpw >= smsp / 8) return e0;
     }
     for (const KernelEntry* e : h->variants) {
         const size_t warps = ((pairs << e->logt) + 31) / 32;
