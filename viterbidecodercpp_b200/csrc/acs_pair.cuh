@@ -51,7 +51,6 @@ struct AcsParams {
     uint64_t sym_row_bytes;
     uint64_t sym_total_bytes;   // n_frames * sym_row_bytes (loads are clamped to stay inside)
     uint32_t n_frames;
-    uint32_t pf_words;      // acs_hist.cuh: far-prefetch distance of the direct symbol fetch, in 32-bit words
 };
 
 template <class C>

@@ -310,8 +310,6 @@ int decode_chunk_dev(vitb_decoder* h, const KernelEntry* e, const void* d_symbol
     a.pk = static_cast<const uint32_t*>(h->pk.ptr); a.dec = h->dec.ptr;
     a.metrics = static_cast<uint16_t*>(h->metrics.ptr); a.acc = static_cast<uint64_t*>(h->acc.ptr);
     a.n_blocks = n_wblocks; a.n_steps = uint32_t(S); a.dec_rows = uint32_t(S); a.dec_row0 = 0; a.resume = 0; a.start_state = uint32_t(start_state);
-    static const uint32_t pf_words = getenv("VITB_HIST_PF") ? uint32_t(atoi(getenv("VITB_HIST_PF"))) : 16u;
-    a.pf_words = pf_words;
     h->launches++;
     if (hist) VITB_CUDA(h, direct ? e->launch_hist_direct(a, s) : e->launch_hist(a, s));
     else VITB_CUDA(h, direct ? e->launch_direct(a, s) : e->launch(a, s));
