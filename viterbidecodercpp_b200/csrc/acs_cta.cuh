@@ -43,12 +43,18 @@ struct CtaShape {
     static __host__ __device__ constexpr uint32_t slot(uint32_t phi) { return phi + (phi >> 5); }
 };
 
-// float accumulators per frame: 8 decision bits each keeps the predicated-FADD dependency chains short enough that ptxas does not
-// run out of predicate registers (with 2 x 16 bits it spilled predicates through LOP3 bit masks: +81 instructions per step)
+// float accumulators per frame: one per 8 decision bits, each split into two chains of 4 predicated FADDs (low nibble starts at 2^23,
+// high nibble at 0, summed exactly at the end).  Short chains let ptxas consume the VIMNMX predicates quickly: with chains of 8 it
+// ran out of predicate registers and spilled them through pairs of LOP3 bit-mask updates (36 LOP3 of 171 instructions per step in
+// profiles/r01_ncu_full_acs_cta_cfg5.txt; with 2 x 16 bits per frame it was +81 instructions).
 template <int NL> struct CtaAcc { static constexpr int value = NL >= 32 ? 4 : (NL >= 16 ? 2 : 1); };
+#ifndef VITB_CTA_CHAINS
+#define VITB_CTA_CHAINS 2
+#endif
+constexpr int CTA_CHAINS = VITB_CTA_CHAINS;          // chains per decision byte (1, 2 or 4)
 
 template <class C, int LT, int PH, bool TIE_SIMD, int Q>
-__device__ __forceinline__ void cta_bfly_at(uint32_t (&x)[CtaShape<C, LT>::NL], const uint2* tbl_ph, const uint32_t pt, float (&fa)[2][CtaAcc<CtaShape<C, LT>::NL>::value]) {
+__device__ __forceinline__ void cta_bfly_at(uint32_t (&x)[CtaShape<C, LT>::NL], const uint2* tbl_ph, const uint32_t pt, float (&fa)[2][CtaAcc<CtaShape<C, LT>::NL>::value][CTA_CHAINS]) {
     using S = CtaShape<C, LT>;
     constexpr int bit = 1 << (S::LB - 1 - PH);
     if constexpr ((Q & bit) == 0) {
@@ -69,17 +75,17 @@ __device__ __forceinline__ void cta_bfly_at(uint32_t (&x)[CtaShape<C, LT>::NL], 
             dA0 = l0; dB0 = h0; dA1 = l1; dB1 = h1;
         }
         constexpr int NACC = CtaAcc<S::NL>::value;
-        constexpr int acc0 = (q0 >> 3) % NACC, acc1 = (q1 >> 3) % NACC;
+        constexpr int acc0 = (q0 >> 3) % NACC, acc1 = (q1 >> 3) % NACC, n0 = ((q0 & 7) * CTA_CHAINS) >> 3, n1 = ((q1 & 7) * CTA_CHAINS) >> 3;
         constexpr float w0 = float(1u << (q0 & 7)), w1 = float(1u << (q1 & 7));
-        if (dA0) fa[0][acc0] += w0;
-        if (dB0) fa[1][acc0] += w0;
-        if (dA1) fa[0][acc1] += w1;
-        if (dB1) fa[1][acc1] += w1;
+        if (dA0) fa[0][acc0][n0] += w0;
+        if (dB0) fa[1][acc0][n0] += w0;
+        if (dA1) fa[0][acc1][n1] += w1;
+        if (dB1) fa[1][acc1][n1] += w1;
     }
 }
 
 template <class C, int LT, int PH, bool TIE_SIMD, int... Qs>
-__device__ __forceinline__ void cta_bfly_all(uint32_t (&x)[CtaShape<C, LT>::NL], const uint2* tbl_ph, const uint32_t pt, float (&fa)[2][CtaAcc<CtaShape<C, LT>::NL>::value],
+__device__ __forceinline__ void cta_bfly_all(uint32_t (&x)[CtaShape<C, LT>::NL], const uint2* tbl_ph, const uint32_t pt, float (&fa)[2][CtaAcc<CtaShape<C, LT>::NL>::value][CTA_CHAINS],
                                              std::integer_sequence<int, Qs...>) {
     (cta_bfly_at<C, LT, PH, TIE_SIMD, Qs>(x, tbl_ph, pt, fa), ...);
 }
@@ -95,10 +101,23 @@ struct CtaKernel {
     template <int PH>
     static __device__ __forceinline__ void step(uint32_t (&x)[NL], const uint2* tbl, const uint32_t (&pt)[LB], uint32_t* dec_row) {
         constexpr int NACC = CtaAcc<NL>::value;
+        float fn[2][NACC][CTA_CHAINS];
+#pragma unroll
+        for (int a = 0; a < NACC; a++) {
+#pragma unroll
+            for (int c = 0; c < CTA_CHAINS; c++) { fn[0][a][c] = c ? 0.f : 8388608.f; fn[1][a][c] = c ? 0.f : 8388608.f; }
+        }
+        cta_bfly_all<C, LT, PH, TIE_SIMD>(x, tbl + PH * NP, pt[PH], fn, std::make_integer_sequence<int, NL>{});
         float fa[2][NACC];
 #pragma unroll
-        for (int a = 0; a < NACC; a++) { fa[0][a] = 8388608.f; fa[1][a] = 8388608.f; }
-        cta_bfly_all<C, LT, PH, TIE_SIMD>(x, tbl + PH * NP, pt[PH], fa, std::make_integer_sequence<int, NL>{});
+        for (int a = 0; a < NACC; a++) {
+#pragma unroll
+            for (int f = 0; f < 2; f++) {
+                if constexpr (CTA_CHAINS == 4) fa[f][a] = (fn[f][a][0] + fn[f][a][1]) + (fn[f][a][2] + fn[f][a][3]);
+                else if constexpr (CTA_CHAINS == 2) fa[f][a] = fn[f][a][0] + fn[f][a][1];
+                else fa[f][a] = fn[f][a][0];
+            }
+        }
         // byte k of a frame's bits = mantissa byte 0 of accumulator k (registers 8k .. 8k+7)
         static_assert(NL == 32 || NL == 16, "decision word packing assumes 32 or 16 registers per thread");
         if constexpr (NL == 32) {
