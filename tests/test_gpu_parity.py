@@ -109,8 +109,8 @@ def test_streaming_api_error_behaviour(cuda_lib):
         dec.chainback(64)                                       # not enough steps decoded yet
     with pytest.raises(v.ViterbiError):
         dec.get_error(64)                                       # end_state out of range
-    bt = v.ViterbiBranchTable(7, 2, [0o133, 0o165], 127, -127)
-    assert not v.ViterbiDecoder_CUDA.is_valid(bt, dc.decoder_config)   # uncatalogued polynomials: no kernel (yet)
+    bt = v.ViterbiBranchTable(9, 2, [0o561, 0o751], 127, -127)
+    assert not v.ViterbiDecoder_CUDA.is_valid(bt, dc.decoder_config)   # uncatalogued polynomials with K > 7: no kernel (yet)
 
 
 @pytest.mark.parametrize("decode_type,expected", [("SOFT16", 100584), ("SOFT8", 2376), ("HARD8", 792)])

@@ -40,8 +40,13 @@ def test_is_supported_matches_catalogue():
             dc = factory(code.R)
             bt = v.ViterbiBranchTable(code.K, code.R, code.G, dc.soft_decision_high, dc.soft_decision_low, dc.soft_bytes)
             assert v.ViterbiDecoder_CUDA.is_valid(bt, dc.decoder_config) == (code.K in SUPPORTED_K), (code.name, name)
+    # polynomials outside the compiled catalogue: the generic kernels cover 3 <= K <= 7 with R <= 6, nothing beyond
     bt = v.ViterbiBranchTable(7, 2, [0o133, 0o165], 127, -127)
+    assert v.ViterbiDecoder_CUDA.is_valid(bt, v.get_soft16_decoding_config(2).decoder_config)
+    bt = v.ViterbiBranchTable(9, 2, [0o561, 0o753 ^ 2], 127, -127)
     assert not v.ViterbiDecoder_CUDA.is_valid(bt, v.get_soft16_decoding_config(2).decoder_config)
+    bt = v.ViterbiBranchTable(5, 7, [19, 21, 23, 25, 27, 29, 31], 127, -127)
+    assert not v.ViterbiDecoder_CUDA.is_valid(bt, v.get_soft16_decoding_config(7).decoder_config)
     assert lib.vitb_version().startswith(b"viterbi_b200")
 
 
@@ -63,8 +68,9 @@ def test_create_argument_checking():
     p.soft_bytes, p.soft_decision_high, p.soft_decision_low = 2, -5, 5
     assert lib.vitb_create(C.byref(p), C.byref(h)) == _lib.VITB_ERR_ARG          # high must exceed low (viterbi_branch_table.h:43)
     p.soft_decision_high, p.soft_decision_low = 127, -127
-    p.G[0], p.G[1] = 1, 3
-    assert lib.vitb_create(C.byref(p), C.byref(h)) == _lib.VITB_ERR_UNSUPPORTED  # uncatalogued polynomials
+    p.K, p.G[0], p.G[1] = 9, 1, 3
+    assert lib.vitb_create(C.byref(p), C.byref(h)) == _lib.VITB_ERR_UNSUPPORTED  # uncatalogued polynomials beyond the generic kernels (K <= 7)
+    p.K = 7
     assert lib.vitb_create(None, C.byref(h)) == _lib.VITB_ERR_ARG
     assert lib.vitb_status_string(_lib.VITB_ERR_UNSUPPORTED)
 

@@ -31,6 +31,7 @@ static const std::vector<KernelEntry>& registry() {
         register_k9r2_t8(entries); register_k9r2_t16(entries);
         register_k9r4_t8(entries); register_k9r4_t16(entries);
         register_k15r6_cta512(entries); register_k15r6_cta1024(entries);
+        register_generic(entries);
     });
     return entries;
 }
@@ -70,6 +71,7 @@ struct vitb_decoder {
     std::string name_buf;
     int forced_logt = -1;                       // vitb_set_variant
     bool use_hist = getenv("VITB_NO_HIST") == nullptr;   // vitb_set_history_kernel
+    GenericCode gcode{};                        // branch patterns for the generic kernels (codes outside the compiled catalogue)
     int n_sm = 148;
     int n_states = 0;
     int sh = 0;
@@ -114,10 +116,14 @@ std::vector<const KernelEntry*> find_entries(const vitb_params& p) {
     const int consistent = ((p.soft_decision_max_error & mask) == ((span * uint32_t(p.R)) & mask)) ? 1 : 0;
     const uint32_t kmask = (p.K >= 32) ? 0xffffffffu : ((1u << p.K) - 1u);
     for (const KernelEntry& e : registry()) {
-        if (e.K != p.K || e.R != p.R || e.sh != sh || e.tie != (p.tie_break ? 1 : 0) || e.consistent != consistent) continue;
+        if (e.generic || e.K != p.K || e.R != p.R || e.sh != sh || e.tie != (p.tie_break ? 1 : 0) || e.consistent != consistent) continue;
         bool same = true;
         for (int i = 0; i < p.R; i++) same = same && ((e.G[i] & kmask) == (p.G[i] & kmask));
         if (same) out.push_back(&e);
+    }
+    if (out.empty() && p.R <= GENERIC_MAX_R) {      // not in the compiled catalogue: the generic kernel of this K, if there is one
+        for (const KernelEntry& e : registry())
+            if (e.generic && e.K == p.K && e.sh == sh && e.tie == (p.tie_break ? 1 : 0)) out.push_back(&e);
     }
     std::sort(out.begin(), out.end(), [](const KernelEntry* a, const KernelEntry* b) { return a->logt < b->logt; });
     return out;
@@ -229,7 +235,7 @@ cudaError_t launch_traceback(vitb_decoder* h, const KernelEntry* e, const void* 
         TracebackParams t{};
         t.dec = static_cast<const uint64_t*>(dec); t.dec_rows = uint32_t(dec_rows); t.n_frames = uint32_t(n_frames);
         t.total_bits = uint32_t(L); t.state_bits = uint32_t(h->prm.K - 1); t.end_state = uint32_t(end_state);
-        t.out = d_out; t.out_stride = out_stride; t.tag_layout = (e->sh == 8) ? 1u : 0u;     // uint8_t pair kernels use the tagged butterfly
+        t.out = d_out; t.out_stride = out_stride; t.tag_layout = (e->sh == 8 && !e->generic) ? 1u : 0u;     // uint8_t catalogue pair kernels use the tagged butterfly
         traceback_u64_kernel<32><<<unsigned((n_frames + 127) / 128), 128, 0, s>>>(t);
     } else {
         TracebackGroupParams t{};
@@ -312,6 +318,7 @@ int decode_chunk_dev(vitb_decoder* h, const KernelEntry* e, const void* d_symbol
     a.n_blocks = n_wblocks; a.n_steps = uint32_t(S); a.dec_rows = uint32_t(S); a.dec_row0 = 0; a.resume = 0; a.start_state = uint32_t(start_state);
     h->launches++;
     if (hist) VITB_CUDA(h, direct ? e->launch_hist_direct(a, s) : e->launch_hist(a, s));
+    else if (e->generic) VITB_CUDA(h, e->launch_generic(a, h->gcode, s));
     else VITB_CUDA(h, direct ? e->launch_direct(a, s) : e->launch(a, s));
     VITB_CUDA(h, mark(h, s));
 
@@ -405,6 +412,10 @@ int vitb_create(const vitb_params* p, vitb_decoder** out) {
     if (const char* f = getenv("VITB_FORCE_LOGT")) h->forced_logt = atoi(f);
     h->n_states = 1 << (p->K - 1);
     h->sh = e->sh;
+    if (e->generic) {
+        h->gcode.R = uint32_t(p->R);
+        for (uint32_t j = 0; j < uint32_t(h->n_states) / 2; j++) h->gcode.pat[j] = uint8_t(bfly_pattern_rt(p->G, p->R, j));
+    }
     cudaError_t ce = cudaSetDevice(p->device);
     if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, p->device);
     if (ce == cudaSuccess) h->ws_default = default_ws_limit();
@@ -570,7 +581,8 @@ int vitb_update(vitb_decoder* h, const void* symbols, size_t n_symbols, uint64_t
     a.n_steps = uint32_t(steps); a.dec_rows = uint32_t(rows); a.dec_row0 = uint32_t(h->current_decoded_bit);
     a.resume = 1; a.start_state = 0;
     h->launches++;
-    VITB_CUDA(h, h->entry->launch(a, h->stream));
+    if (h->entry->generic) VITB_CUDA(h, h->entry->launch_generic(a, h->gcode, h->stream));
+    else VITB_CUDA(h, h->entry->launch(a, h->stream));
     uint64_t acc = 0;
     VITB_CUDA(h, cudaMemcpyAsync(&acc, h->s_acc.ptr, 8, cudaMemcpyDeviceToHost, h->stream));
     VITB_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -612,7 +624,7 @@ int vitb_get_decisions(vitb_decoder* h, size_t first_row, size_t n_rows, uint64_
         VITB_CUDA(h, cudaMemcpy2DAsync(rows_out, 8, static_cast<uint64_t*>(h->s_dec.ptr) + first_row * 64, 64 * 8, 8, n_rows,
                                        cudaMemcpyDeviceToHost, h->stream));
         VITB_CUDA(h, cudaStreamSynchronize(h->stream));
-        if (e->sh == 8) {      // tagged row layout -> reference bit order
+        if (e->sh == 8 && !e->generic) {      // tagged row layout -> reference bit order
             for (size_t r = 0; r < n_rows; r++) {
                 const uint64_t w = rows_out[r];
                 uint64_t o = 0;

@@ -10,6 +10,7 @@
 #include "acs_hist.cuh"
 #include "acs_group.cuh"
 #include "acs_cta.cuh"
+#include "acs_generic.cuh"
 
 namespace vitb {
 
@@ -32,6 +33,10 @@ struct KernelEntry {
     // uint8_t metrics: two frames per lane, 8-step records; uint16_t metrics: one frame per lane, 16-step records, packed stream in
     // the 16-pairs-per-warp-block layout
     cudaError_t (*launch_hist)(const AcsParams&, cudaStream_t);
+    // generic entries (acs_generic.cuh): any generator polynomials and any rate R <= GENERIC_MAX_R for this K; R, G and consistent are
+    // wildcards in the table and the branch patterns travel as a kernel argument
+    int generic;
+    cudaError_t (*launch_generic)(const AcsParams&, const GenericCode&, cudaStream_t);
     cudaError_t (*launch_hist_direct)(const AcsParams&, cudaStream_t);
 };
 
@@ -138,8 +143,31 @@ KernelEntry make_entry(const char* name) {
     VEC.push_back(make_entry<CODE, LOGT, 0, true, false>("acs<" TAG ",u16,simd-tie,cinv>"));        \
     VEC.push_back(make_entry<CODE, LOGT, 8, true, false>("acs<" TAG ",u8,simd-tie,cinv>"));
 
+template <int K, int SH, bool TIE_SIMD>
+cudaError_t launch_generic(const AcsParams& p, const GenericCode& gc, cudaStream_t s) {
+    constexpr unsigned W = GENERIC_THREADS / 32;
+    acs_generic_kernel<K, SH, TIE_SIMD><<<(p.n_blocks + W - 1) / W, GENERIC_THREADS, 0, s>>>(p, gc);
+    return cudaGetLastError();
+}
+
+template <int K, int SH, bool TIE_SIMD>
+KernelEntry make_generic_entry(const char* name) {
+    KernelEntry e{};
+    e.K = K; e.R = 0; e.sh = SH; e.tie = TIE_SIMD ? 1 : 0; e.consistent = -1; e.logt = 0; e.name = name;
+    e.layout = LAYOUT_PAIR; e.ppw = 32; e.dec_words = 0; e.generic = 1;
+    e.launch_generic = &launch_generic<K, SH, TIE_SIMD>;
+    return e;
+}
+
+#define VITB_GENERIC_VARIANTS(VEC, KK, TAG)                                                              \
+    VEC.push_back(make_generic_entry<KK, 0, false>("acs_generic<" TAG ",T1,u16,scalar-tie>"));             \
+    VEC.push_back(make_generic_entry<KK, 8, false>("acs_generic<" TAG ",T1,u8,scalar-tie>"));              \
+    VEC.push_back(make_generic_entry<KK, 0, true>("acs_generic<" TAG ",T1,u16,simd-tie>"));                \
+    VEC.push_back(make_generic_entry<KK, 8, true>("acs_generic<" TAG ",T1,u8,simd-tie>"));
+
 // one translation unit per code family and lanes-per-pair setting (parallel compilation)
 void register_small(std::vector<KernelEntry>& v);
+void register_generic(std::vector<KernelEntry>& v);
 void register_k7r2_t1(std::vector<KernelEntry>& v);
 void register_k7r2_t2(std::vector<KernelEntry>& v);
 void register_k7r2_t4(std::vector<KernelEntry>& v);
