@@ -146,6 +146,11 @@ int vitb_get_variants(const vitb_decoder* h, int* lanes_per_pair, int capacity);
  * below the path metrics, traceback moves 8 / 16 steps per lookup) - same results, about twice the speed.  enabled = 0 keeps the
  * decision-row kernels for batch calls too (the streaming calls always use them); default 1, or 0 when VITB_NO_HIST is set. */
 int vitb_set_history_kernel(vitb_decoder* h, int enabled);
+/* Traceback of the survivor-history records walks every frame in concurrent segments: each segment warms up over overlap_records
+ * records from a guessed state (survivor paths merge) and is verified - and re-walked if it did not merge - against the segment
+ * above, so the result is exact.  seg_records = 0 / overlap_records = -1 choose automatically (by batch size / 96 steps); tests use
+ * overlap 0 to force the repair path. */
+int vitb_set_traceback_segments(vitb_decoder* h, int seg_records, int overlap_records);
 /* name of the ACS kernel variant selected for this handle, e.g. "acs_pair<K7,R2,u8,scalar-tie>" */
 const char* vitb_kernel_name(const vitb_decoder* h);
 int vitb_last_cuda_error(const vitb_decoder* h);

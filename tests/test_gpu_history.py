@@ -151,3 +151,24 @@ def test_history_kernel_packed_stream_input(cuda_lib, name, decode_type):
     assert rc == 0
     assert dec.kernel_name.startswith("acs_hist<")
     assert_batch_equal((out, acc, fin), want, f"{name} {decode_type} packed stream")
+
+
+@pytest.mark.parametrize("decode_type", ["SOFT16", "HARD8"])
+@pytest.mark.parametrize("name", ["Voyager", "DAB Radio", "Basic K=5 R=1/2"])
+def test_segmented_traceback_and_its_repair_path(cuda_lib, name, decode_type):
+    """the history-record traceback walks a frame in concurrent segments after a warm-up from a guessed state; with the warm-up
+    switched off (overlap 0) nearly every segment starts from the wrong state and must be repaired: results stay bit-exact"""
+    code = CODE_BY_NAME[name]
+    dec, dc = make_cuda_decoder(code, decode_type)
+    ora, _ = make_oracle(code, decode_type)
+    dec.set_variant(1)
+    for L, end in [(1000, 0), (2049, 3), (517, 1)]:
+        n_sym = (L + code.K - 1) * code.R
+        sym = random_symbols(dc, 40, n_sym, seed=L)
+        want = oracle_batch(ora, code, sym, L, 0, end)
+        for seg, ov in [(0, -1), (7, 0), (5, 1), (16, 3), (1, 0), (1000, 0)]:
+            dec.set_traceback_segments(seg, ov)
+            got = dec.decode_batch(sym, L, end_state=end)
+            assert dec.kernel_name.startswith("acs_hist<")
+            assert_batch_equal(got, want, f"{name} {decode_type} L={L} seg={seg} overlap={ov}")
+    dec.set_traceback_segments(0, -1)

@@ -56,6 +56,7 @@ API = [
     ("vitb_get_stage_ms", C.c_int, [_P, C.POINTER(C.c_float * 4)]),
     ("vitb_set_variant", C.c_int, [_P, C.c_int]),
     ("vitb_set_history_kernel", C.c_int, [_P, C.c_int]),
+    ("vitb_set_traceback_segments", C.c_int, [_P, C.c_int, C.c_int]),
     ("vitb_get_variants", C.c_int, [_P, C.POINTER(C.c_int), C.c_int]),
     ("vitb_kernel_name", C.c_char_p, [_P]),
     ("vitb_last_cuda_error", C.c_int, [_P]),

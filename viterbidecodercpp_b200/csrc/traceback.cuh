@@ -360,48 +360,124 @@ struct TracebackHistParams {
     size_t out_stride;
 };
 
-// one thread per frame
-__global__ void __launch_bounds__(128) traceback_hist_kernel(const TracebackHistParams p) {
-    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= p.n_frames) return;
-    const uint32_t SB = p.state_bits, L = p.total_bits, S = p.n_steps, NS = 1u << SB, HB = p.hist_bits;
-    const uint32_t nw = NS / 2, vw_log = nw >= 4 ? 2u : (nw == 2 ? 1u : 0u);
-    const bool wide = HB == 16;
-    const uint32_t lane = wide ? (f & 31u) : ((f & 63u) >> 1), half = wide ? 0u : (f & 1u);
-    const size_t rec_bytes = size_t(64) * NS;                     // one warp block, one period (both formats)
-    const uint8_t* base = p.dec + size_t(wide ? (f >> 5) : (f >> 6)) * p.n_periods * rec_bytes;
-    uint8_t* out = p.out + size_t(f) * p.out_stride;
-    const uint32_t n_out = (L + 7) / 8, hmask = (1u << HB) - 1u;
+// Walk records r_hi .. r_lo (downwards) of one frame.  `state` is the state at the boundary above r_hi (time min(HB (r_hi + 1), S)).
+// The history above a record only enters its output through its low SB bits, and those are the bit-reversed state at the
+// boundary between the two records, so a walk can start at any record boundary from the state alone.  Returns the state at the
+// boundary below r_lo.
+struct HistFrame {
+    const uint8_t* base;      // first record of the frame's warp block
+    uint8_t* out;
+    size_t rec_bytes;
+    uint32_t lane, half, vw_log, SB, HB, r_last, nv, VS, n_out;
+    bool wide;
+};
 
-    const uint32_t r_last = (S - 1) / HB, nv = S - HB * r_last;
-    // virtual decisions behind the last step
-    const uint32_t E = SB ? (__brev(p.end_state) >> (32 - SB)) : 0u;
-    const uint32_t VS = E << nv;                       // relative to the first step of record r_last (at most 16 + 8 bits)
-    uint32_t state = p.end_state;
-    uint32_t hnext = (VS >> HB) & hmask;               // record r_last + 1 (purely virtual)
-    for (int64_t r = r_last; r >= 0; r--) {
+__device__ __forceinline__ HistFrame hist_frame(const TracebackHistParams& p, uint32_t f) {
+    HistFrame c;
+    c.SB = p.state_bits; c.HB = p.hist_bits; c.wide = c.HB == 16;
+    const uint32_t NS = 1u << c.SB, nw = NS / 2;
+    c.vw_log = nw >= 4 ? 2u : (nw == 2 ? 1u : 0u);
+    c.lane = c.wide ? (f & 31u) : ((f & 63u) >> 1);
+    c.half = c.wide ? 0u : (f & 1u);
+    c.rec_bytes = size_t(64) * NS;                               // one warp block, one period (both formats)
+    c.base = p.dec + size_t(c.wide ? (f >> 5) : (f >> 6)) * p.n_periods * c.rec_bytes;
+    c.out = p.out + size_t(f) * p.out_stride;
+    c.n_out = (p.total_bits + 7) / 8;
+    c.r_last = (p.n_steps - 1) / c.HB;
+    c.nv = p.n_steps - c.HB * c.r_last;
+    const uint32_t E = c.SB ? (__brev(p.end_state) >> (32 - c.SB)) : 0u;     // virtual decisions behind the last step
+    c.VS = E << c.nv;                                            // relative to the first step of record r_last (at most 16 + 8 bits)
+    return c;
+}
+
+template <bool WRITE>
+__device__ __forceinline__ uint32_t hist_walk(const HistFrame& c, int64_t r_hi, int64_t r_lo, uint32_t state) {
+    const uint32_t SB = c.SB, HB = c.HB, hmask = (1u << HB) - 1u;
+    for (int64_t r = r_hi; r >= r_lo; r--) {
+        const bool last = uint32_t(r) == c.r_last;
+        // history of the record above, as far as this record's output needs it
+        const uint32_t hnext = last ? ((c.VS >> HB) & hmask) : (SB ? (__brev(state) >> (32 - SB)) : 0u);
         // word w = state >> 1 of the lane: FMT 0 bytes [A:2w, B:2w, A:2w+1, B:2w+1], FMT 1 halfwords [2w, 2w+1]
         const uint32_t w = state >> 1;
-        const uint32_t off = ((((w >> vw_log) << 5) + lane) << (vw_log + 2)) + ((w & ((1u << vw_log) - 1u)) << 2) + ((state & 1u) << 1) + half;
-        const uint8_t* ptr = base + size_t(r) * rec_bytes + off;
-        const uint32_t h = wide ? uint32_t(*reinterpret_cast<const uint16_t*>(ptr)) : uint32_t(*ptr);
+        const uint32_t off = ((((w >> c.vw_log) << 5) + c.lane) << (c.vw_log + 2)) + ((w & ((1u << c.vw_log) - 1u)) << 2) + ((state & 1u) << 1) + c.half;
+        const uint8_t* ptr = c.base + size_t(r) * c.rec_bytes + off;
+        const uint32_t h = c.wide ? uint32_t(*reinterpret_cast<const uint16_t*>(ptr)) : uint32_t(*ptr);
         uint32_t hext = h;
-        if (uint32_t(r) == r_last) {
-            hext = (h & ((1u << nv) - 1u)) | (VS & hmask);
-            for (int k = int(nv) - 1; k >= 0; k--) state = (((h >> k) & 1u) << (SB - 1)) | (state >> 1);
+        if (last) {
+            hext = (h & ((1u << c.nv) - 1u)) | (c.VS & hmask);
+            for (int k = int(c.nv) - 1; k >= 0; k--) state = (((h >> k) & 1u) << (SB - 1)) | (state >> 1);
         } else {
             state = __brev(h) >> (32 - SB);            // one period back: the last SB pushed bits, newest on top
         }
-        // decoded bits of this record's steps: window of 2 HB decisions shifted down by SB, MSB-first bytes
-        const uint64_t win = (uint64_t(hext) | (uint64_t(hnext) << HB)) >> SB;
-        if (!wide) {
-            if (uint32_t(r) < n_out) out[r] = uint8_t(__brev(uint32_t(win) & 0xffu) >> 24);
-        } else {
-            const uint32_t b0 = 2u * uint32_t(r);
-            if (b0 < n_out) out[b0] = uint8_t(__brev(uint32_t(win) & 0xffu) >> 24);
-            if (b0 + 1 < n_out) out[b0 + 1] = uint8_t(__brev(uint32_t(win >> 8) & 0xffu) >> 24);
+        if (WRITE) {
+            // decoded bits of this record's steps: window of 2 HB decisions shifted down by SB, MSB-first bytes
+            const uint64_t win = (uint64_t(hext) | (uint64_t(hnext) << HB)) >> SB;
+            if (!c.wide) {
+                if (uint32_t(r) < c.n_out) c.out[r] = uint8_t(__brev(uint32_t(win) & 0xffu) >> 24);
+            } else {
+                const uint32_t b0 = 2u * uint32_t(r);
+                if (b0 < c.n_out) c.out[b0] = uint8_t(__brev(uint32_t(win) & 0xffu) >> 24);
+                if (b0 + 1 < c.n_out) c.out[b0 + 1] = uint8_t(__brev(uint32_t(win >> 8) & 0xffu) >> 24);
+            }
         }
-        hnext = hext;
+    }
+    return state;
+}
+
+// one thread per frame, the whole chain
+__global__ void __launch_bounds__(128) traceback_hist_kernel(const TracebackHistParams p) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= p.n_frames) return;
+    const HistFrame c = hist_frame(p, f);
+    (void)hist_walk<true>(c, c.r_last, 0, p.end_state);
+}
+
+// ---- segmented walk -----------------------------------------------------------------------------------------------------------
+// The chain of a frame is S / HB dependent memory round trips (about 630 ns each on B200), which is what a traceback launch costs
+// when the batch has too few frames to saturate DRAM.  Survivor paths merge: a walk started `overlap` records above a segment from
+// ANY state has, with overwhelming probability, joined the true path by the time it reaches the segment.  So every frame is cut
+// into n_seg segments of seg_records records that are walked concurrently, each (except the top one, which starts from the true end
+// state) after a warm-up over `overlap` records from state 0; the state it arrives with is recorded next to the state the segment
+// above ended in, and traceback_hist_fix_kernel re-walks, serially and from the true state, any segment whose two states differ.
+// The result is therefore exact, not probabilistic.
+struct TracebackSegParams {
+    uint32_t n_seg, seg_records, overlap;
+    uint32_t* spec;           // [n_seg][n_frames] state a segment's warm-up arrived with (top segment: unused)
+    uint32_t* fin;            // [n_seg][n_frames] state at the segment's lower boundary
+};
+
+// grid = (ceil(n_frames / 128), n_seg)
+__global__ void __launch_bounds__(128) traceback_hist_seg_kernel(const TracebackHistParams p, const TracebackSegParams sp) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x, g = blockIdx.y;
+    if (f >= p.n_frames) return;
+    const HistFrame c = hist_frame(p, f);
+    const int64_t r_lo = int64_t(g) * sp.seg_records;
+    int64_t r_hi = r_lo + sp.seg_records - 1;
+    uint32_t state;
+    if (g + 1 == sp.n_seg || r_hi >= int64_t(c.r_last)) {
+        r_hi = c.r_last;
+        state = p.end_state;                                  // the top segment starts from the truth
+    } else {
+        int64_t r_warm = r_hi + sp.overlap;
+        if (r_warm >= int64_t(c.r_last)) { r_warm = c.r_last; state = p.end_state; }
+        else state = 0u;
+        state = hist_walk<false>(c, r_warm, r_hi + 1, state);
+        sp.spec[size_t(g) * p.n_frames + f] = state;
+    }
+    sp.fin[size_t(g) * p.n_frames + f] = hist_walk<true>(c, r_hi, r_lo, state);
+}
+
+// one thread per frame: top-down check of the segment boundaries, re-walk on mismatch
+__global__ void __launch_bounds__(128) traceback_hist_fix_kernel(const TracebackHistParams p, const TracebackSegParams sp) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= p.n_frames) return;
+    uint32_t truth = sp.fin[size_t(sp.n_seg - 1) * p.n_frames + f];
+    for (int g = int(sp.n_seg) - 2; g >= 0; g--) {
+        const size_t i = size_t(g) * p.n_frames + f;
+        if (sp.spec[i] == truth) { truth = sp.fin[i]; continue; }
+        const HistFrame c = hist_frame(p, f);
+        const int64_t r_lo = int64_t(g) * sp.seg_records;
+        truth = hist_walk<true>(c, r_lo + sp.seg_records - 1, r_lo, truth);
     }
 }
 

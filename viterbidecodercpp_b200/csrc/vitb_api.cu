@@ -71,6 +71,7 @@ struct vitb_decoder {
     std::string name_buf;
     int forced_logt = -1;                       // vitb_set_variant
     bool use_hist = getenv("VITB_NO_HIST") == nullptr;   // vitb_set_history_kernel
+    int seg_records_forced = 0, seg_overlap_forced = -1;   // vitb_set_traceback_segments (0 / -1 = automatic)
     GenericCode gcode{};                        // branch patterns for the generic kernels (codes outside the compiled catalogue)
     int n_sm = 148;
     int n_states = 0;
@@ -83,7 +84,7 @@ struct vitb_decoder {
     cudaStream_t copy_stream = nullptr;   // owned; host->device copies of the pipelined host-pointer path
     std::vector<cudaEvent_t> copy_ev;     // one per pipeline chunk + fork/join
     // batch workspace
-    DeviceBuffer pk, dec, metrics, acc, d_in, d_out, d_accout, d_finout, map;
+    DeviceBuffer pk, dec, metrics, acc, d_in, d_out, d_accout, d_finout, map, tb_spec, tb_fin;
     size_t n_depunctured = 0, n_received = 0;
     int32_t unpunctured_value = 0;
     // single-frame streaming state (one 64-frame block, frame 0 is the user's)
@@ -328,7 +329,31 @@ int decode_chunk_dev(vitb_decoder* h, const KernelEntry* e, const void* d_symbol
         t.dec = static_cast<const uint8_t*>(h->dec.ptr); t.n_periods = uint32_t(n_periods); t.n_frames = uint32_t(n_frames);
         t.total_bits = uint32_t(L); t.state_bits = uint32_t(K - 1); t.end_state = uint32_t(end_state); t.n_steps = uint32_t(S);
         t.hist_bits = uint32_t(hist_bits); t.out = d_out; t.out_stride = (L + 7) / 8;
-        traceback_hist_kernel<<<unsigned((n_frames + 127) / 128), 128, 0, s>>>(t);
+        // A frame's chain is n_periods dependent memory round trips; small batches cannot hide them, so the chain is cut into
+        // segments walked concurrently (warm-up over `overlap` records from a guessed state, verified and repaired afterwards:
+        // traceback.cuh).  About 128 K threads saturate DRAM; the warm-up is kept below a quarter of the walk.
+        static const bool no_seg = getenv("VITB_NO_SEG_TRACEBACK") != nullptr;
+        const size_t overlap = h->seg_overlap_forced >= 0 ? size_t(h->seg_overlap_forced) : ((hist_bits == 8) ? 12 : 6);   // 96 steps
+        static const size_t seg_target = getenv("VITB_SEG_TARGET") ? size_t(atoll(getenv("VITB_SEG_TARGET"))) : size_t(131072);
+        const size_t want_seg = (seg_target + n_frames - 1) / n_frames;
+        size_t seg_records = (n_periods + want_seg - 1) / want_seg;
+        if (seg_records < 4 * overlap) seg_records = 4 * overlap;
+        if (h->seg_records_forced > 0) seg_records = size_t(h->seg_records_forced);
+        if (seg_records == 0) seg_records = 1;
+        const size_t n_seg = no_seg ? 1 : (n_periods + seg_records - 1) / seg_records;
+        if (n_seg <= 1) {
+            traceback_hist_kernel<<<unsigned((n_frames + 127) / 128), 128, 0, s>>>(t);
+        } else {
+            VITB_CUDA(h, h->tb_spec.reserve(n_seg * n_frames * 4));
+            VITB_CUDA(h, h->tb_fin.reserve(n_seg * n_frames * 4));
+            TracebackSegParams sp{};
+            sp.n_seg = uint32_t(n_seg); sp.seg_records = uint32_t(seg_records); sp.overlap = uint32_t(overlap);
+            sp.spec = static_cast<uint32_t*>(h->tb_spec.ptr); sp.fin = static_cast<uint32_t*>(h->tb_fin.ptr);
+            traceback_hist_seg_kernel<<<dim3(unsigned((n_frames + 127) / 128), unsigned(n_seg)), 128, 0, s>>>(t, sp);
+            VITB_CUDA(h, cudaGetLastError());
+            h->launches++;
+            traceback_hist_fix_kernel<<<unsigned((n_frames + 127) / 128), 128, 0, s>>>(t, sp);
+        }
         VITB_CUDA(h, cudaGetLastError());
     } else if (d_out) VITB_CUDA(h, launch_traceback(h, e, h->dec.ptr, S, n_frames, L, end_state, d_out, (L + 7) / 8, s));
     VITB_CUDA(h, mark(h, s));
@@ -433,7 +458,7 @@ int vitb_create(const vitb_params* p, vitb_decoder** out) {
 int vitb_destroy(vitb_decoder* h) {
     if (!h) return VITB_OK;
     cudaSetDevice(h->prm.device);
-    for (DeviceBuffer* b : {&h->pk, &h->dec, &h->metrics, &h->acc, &h->d_in, &h->d_out, &h->d_accout, &h->d_finout, &h->map,
+    for (DeviceBuffer* b : {&h->pk, &h->dec, &h->metrics, &h->acc, &h->d_in, &h->d_out, &h->d_accout, &h->d_finout, &h->map, &h->tb_spec, &h->tb_fin,
                             &h->s_pk, &h->s_dec, &h->s_metrics, &h->s_acc, &h->s_in, &h->s_out, &h->g_tx, &h->g_sym, &h->g_cnt}) b->release();
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     for (cudaEvent_t e : h->copy_ev) cudaEventDestroy(e);
@@ -461,6 +486,13 @@ int vitb_set_variant(vitb_decoder* h, int lanes_per_pair) {
         if ((1 << e->logt) == lanes_per_pair) { h->forced_logt = e->logt; return VITB_OK; }
     }
     return VITB_ERR_UNSUPPORTED;
+}
+
+int vitb_set_traceback_segments(vitb_decoder* h, int seg_records, int overlap_records) {
+    if (!h || seg_records < 0 || overlap_records < -1) return VITB_ERR_ARG;
+    h->seg_records_forced = seg_records;
+    h->seg_overlap_forced = overlap_records;
+    return VITB_OK;
 }
 
 int vitb_set_history_kernel(vitb_decoder* h, int enabled) {

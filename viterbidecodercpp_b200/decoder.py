@@ -248,6 +248,10 @@ class ViterbiDecoder_CUDA:
         """batch calls of one-lane-per-pair variants: survivor-history kernel (default) or the decision-row kernels"""
         _check(self._L.vitb_set_history_kernel(self._h, 1 if enabled else 0), "set_history_kernel")
 
+    def set_traceback_segments(self, seg_records=0, overlap_records=-1):
+        """segment length / warm-up of the history-record traceback in records (0 / -1 = automatic)"""
+        _check(self._L.vitb_set_traceback_segments(self._h, seg_records, overlap_records), "set_traceback_segments")
+
     @property
     def variants(self):
         buf = (C.c_int * 16)()
