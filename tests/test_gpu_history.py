@@ -172,3 +172,25 @@ def test_segmented_traceback_and_its_repair_path(cuda_lib, name, decode_type):
             assert dec.kernel_name.startswith("acs_hist<")
             assert_batch_equal(got, want, f"{name} {decode_type} L={L} seg={seg} overlap={ov}")
     dec.set_traceback_segments(0, -1)
+
+
+@pytest.mark.parametrize("decode_type", ["SOFT16", "HARD8"])
+def test_segmented_traceback_k15(cuda_lib, decode_type):
+    """K = 15 decision rows: the same segmented walk (segments in units of 8 decoded bits, warm-up in units of 8 rows), automatic
+    setting and settings that force the repair path; ragged bit count and a non-zero end state"""
+    from common import frames
+    code = CODE_BY_NAME["Cassini"]
+    dec, dc = make_cuda_decoder(code, decode_type)
+    ora, _ = make_oracle(code, decode_type)
+    for L, end in [(2048, 0), (1003, 5)]:
+        n_sym = (L + code.K - 1) * code.R
+        if L % 8 == 0:
+            tx, sym = frames(code, dc, 6, L, 3.0, seed=L)
+        else:
+            sym = random_symbols(dc, 6, n_sym, seed=L)
+        want = oracle_batch(ora, code, sym, L, 0, end)
+        for seg, ov in [(0, -1), (8, 0), (16, 4), (3, 1)]:
+            dec.set_traceback_segments(seg, ov)
+            got = dec.decode_batch(sym, L, end_state=end)
+            assert_batch_equal(got, want, f"Cassini {decode_type} L={L} seg={seg} overlap={ov}")
+    dec.set_traceback_segments(0, -1)

@@ -294,28 +294,19 @@ struct TracebackCtaParams {
     size_t out_stride;
 };
 
-template <int MAXLB>
-__global__ void __launch_bounds__(64) traceback_cta_kernel(const TracebackCtaParams p) {
-    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= p.n_frames) return;
-    const uint32_t SB = p.state_bits, g = p.logt, T = 1u << g, LB = SB - g, L = p.total_bits, half = f & 1u, W = p.words;
-    const uint32_t* d = p.dec + size_t(f >> 1) * p.dec_rows * T * W + (W == 2 ? half : 0u);
-    const uint32_t bit_base = (W == 2) ? 0u : half * 16u;
-    uint8_t* out = p.out + size_t(f) * p.out_stride;
-    uint32_t state = p.end_state, byte = 0;
-    if (L & 7) {
-        for (uint32_t jj = L; jj < ((L + 7) & ~7u); jj++) {
-            const uint32_t k = jj - L;
-            const uint32_t b = (k < SB) ? ((p.end_state >> (SB - 1 - k)) & 1u) : 0u;
-            byte |= b << (7 - (jj & 7));
-        }
-    }
-    int64_t r = int64_t(L) + SB - 1;                       // top decision row
-    while (r >= int64_t(SB)) {
+// Walk decision rows r_hi .. r_lo (downwards) of one frame from `state` (the state after row r_hi); returns the state after row
+// r_lo - 1 ... i.e. the state the walk arrives with below r_lo.  WRITE: decoded bit j = r - SB goes to the output (MSB-first bytes,
+// flushed when j is a multiple of 8; `byte` carries the bits above r_hi that share its byte - only the ragged top of a frame has any).
+template <int MAXLB, bool WRITE>
+__device__ __forceinline__ uint32_t cta_walk(const TracebackCtaParams& p, const uint32_t* d, uint8_t* out, uint32_t bit_base,
+                                             int64_t r_hi, int64_t r_lo, uint32_t state, uint32_t byte) {
+    const uint32_t SB = p.state_bits, g = p.logt, T = 1u << g, LB = SB - g, W = p.words;
+    int64_t r = r_hi;
+    while (r >= r_lo) {
         const uint32_t n = uint32_t(r) % LB;               // rows r, r-1, .., r-n belong to the same exchange period
-        int64_t r_lo = r - n;
-        if (r_lo < int64_t(SB)) r_lo = SB;
-        const uint32_t cnt = uint32_t(r - r_lo) + 1;
+        int64_t r_lo_p = r - n;
+        if (r_lo_p < r_lo) r_lo_p = r_lo;
+        const uint32_t cnt = uint32_t(r - r_lo_p) + 1;
         const uint32_t t = rotr_rt(state, n + 1, SB) & (T - 1);
         uint32_t w[MAXLB];
 #pragma unroll
@@ -326,12 +317,92 @@ __global__ void __launch_bounds__(64) traceback_cta_kernel(const TracebackCtaPar
                 const uint32_t q = rotr_rt(state, n - uint32_t(k) + 1, SB) >> g;
                 const uint32_t bit = (w[k] >> (bit_base + q)) & 1u;
                 state = (bit << (SB - 1)) | (state >> 1);
-                const int64_t j = r - k - int64_t(SB);
-                byte |= bit << (7 - (uint32_t(j) & 7));
-                if ((j & 7) == 0) { out[j >> 3] = uint8_t(byte); byte = 0; }
+                if (WRITE) {
+                    const int64_t j = r - k - int64_t(SB);
+                    byte |= bit << (7 - (uint32_t(j) & 7));
+                    if ((j & 7) == 0) { out[j >> 3] = uint8_t(byte); byte = 0; }
+                }
             }
         }
-        r = r_lo - 1;
+        r = r_lo_p - 1;
+    }
+    return state;
+}
+
+// virtual bits L, L+1, ... of a ragged last byte = end_state from its top bit down, then zeros (the reference's traceback buffer
+// still holds them, core.h:96-113)
+__device__ __forceinline__ uint32_t ragged_top_byte(uint32_t L, uint32_t SB, uint32_t end_state) {
+    uint32_t byte = 0;
+    if (L & 7) {
+        for (uint32_t jj = L; jj < ((L + 7) & ~7u); jj++) {
+            const uint32_t k = jj - L;
+            const uint32_t b = (k < SB) ? ((end_state >> (SB - 1 - k)) & 1u) : 0u;
+            byte |= b << (7 - (jj & 7));
+        }
+    }
+    return byte;
+}
+
+// one thread per frame, the whole chain
+template <int MAXLB>
+__global__ void __launch_bounds__(64) traceback_cta_kernel(const TracebackCtaParams p) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= p.n_frames) return;
+    const uint32_t SB = p.state_bits, T = 1u << p.logt, L = p.total_bits, half = f & 1u, W = p.words;
+    const uint32_t* d = p.dec + size_t(f >> 1) * p.dec_rows * T * W + (W == 2 ? half : 0u);
+    const uint32_t bit_base = (W == 2) ? 0u : half * 16u;
+    uint8_t* out = p.out + size_t(f) * p.out_stride;
+    (void)cta_walk<MAXLB, true>(p, d, out, bit_base, int64_t(L) + SB - 1, SB, p.end_state, ragged_top_byte(L, SB, p.end_state));
+}
+
+// Segmented walk (same scheme as traceback_hist_seg_kernel below): segments of seg_bits decoded bits (a multiple of 8), warm-up over
+// `overlap` rows from state 0, the arriving state recorded for the check against the segment above.
+struct TracebackCtaSegParams {
+    uint32_t n_seg, seg_bits, overlap;
+    uint32_t* spec;           // [n_seg][n_frames]
+    uint32_t* fin;            // [n_seg][n_frames]
+};
+
+// grid = (ceil(n_frames / 64), n_seg)
+template <int MAXLB>
+__global__ void __launch_bounds__(64) traceback_cta_seg_kernel(const TracebackCtaParams p, const TracebackCtaSegParams sp) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x, g = blockIdx.y;
+    if (f >= p.n_frames) return;
+    const uint32_t SB = p.state_bits, T = 1u << p.logt, L = p.total_bits, half = f & 1u, W = p.words;
+    const uint32_t* d = p.dec + size_t(f >> 1) * p.dec_rows * T * W + (W == 2 ? half : 0u);
+    const uint32_t bit_base = (W == 2) ? 0u : half * 16u;
+    uint8_t* out = p.out + size_t(f) * p.out_stride;
+    const int64_t r_top = int64_t(L) + SB - 1;
+    const int64_t r_lo = int64_t(g) * sp.seg_bits + SB;
+    int64_t r_hi = r_lo + sp.seg_bits - 1;
+    uint32_t state, byte = 0;
+    if (g + 1 == sp.n_seg || r_hi >= r_top) {
+        r_hi = r_top;
+        state = p.end_state;                                  // the top segment starts from the truth
+        byte = ragged_top_byte(L, SB, p.end_state);
+    } else {
+        int64_t r_warm = r_hi + sp.overlap;
+        if (r_warm >= r_top) { r_warm = r_top; state = p.end_state; }
+        else state = 0u;
+        state = cta_walk<MAXLB, false>(p, d, out, bit_base, r_warm, r_hi + 1, state, 0u);
+        sp.spec[size_t(g) * p.n_frames + f] = state;
+    }
+    sp.fin[size_t(g) * p.n_frames + f] = cta_walk<MAXLB, true>(p, d, out, bit_base, r_hi, r_lo, state, byte);
+}
+
+// one thread per frame: top-down check of the segment boundaries, re-walk on mismatch
+template <int MAXLB>
+__global__ void __launch_bounds__(64) traceback_cta_fix_kernel(const TracebackCtaParams p, const TracebackCtaSegParams sp) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= p.n_frames) return;
+    uint32_t truth = sp.fin[size_t(sp.n_seg - 1) * p.n_frames + f];
+    for (int g = int(sp.n_seg) - 2; g >= 0; g--) {
+        const size_t i = size_t(g) * p.n_frames + f;
+        if (sp.spec[i] == truth) { truth = sp.fin[i]; continue; }
+        const uint32_t SB = p.state_bits, T = 1u << p.logt, half = f & 1u, W = p.words;
+        const uint32_t* d = p.dec + size_t(f >> 1) * p.dec_rows * T * W + (W == 2 ? half : 0u);
+        const int64_t r_lo = int64_t(g) * sp.seg_bits + SB;
+        truth = cta_walk<MAXLB, true>(p, d, p.out + size_t(f) * p.out_stride, (W == 2) ? 0u : half * 16u, r_lo + sp.seg_bits - 1, r_lo, truth, 0u);
     }
 }
 

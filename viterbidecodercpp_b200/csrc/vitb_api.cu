@@ -231,7 +231,28 @@ cudaError_t launch_traceback(vitb_decoder* h, const KernelEntry* e, const void* 
         t.dec = static_cast<const uint32_t*>(dec); t.dec_rows = uint32_t(dec_rows); t.n_frames = uint32_t(n_frames);
         t.total_bits = uint32_t(L); t.state_bits = uint32_t(h->prm.K - 1); t.logt = uint32_t(e->logt); t.end_state = uint32_t(end_state);
         t.out = d_out; t.out_stride = out_stride; t.words = uint32_t(e->dec_words);
-        traceback_cta_kernel<5><<<unsigned((n_frames + 63) / 64), 64, 0, s>>>(t);
+        // the chain of a K = 15 frame is L / 5 dependent memory round trips (16 384 bits: 5.7 ms): walk it in concurrent segments
+        // (warm-up from a guessed state, verified and repaired afterwards, traceback.cuh); the streaming state keeps the plain walk
+        static const bool no_seg = getenv("VITB_NO_SEG_TRACEBACK") != nullptr;
+        const size_t overlap = h->seg_overlap_forced >= 0 ? size_t(h->seg_overlap_forced) * 8 : size_t(16) * size_t(h->prm.K);     // rows
+        size_t seg_bits = h->seg_records_forced > 0 ? size_t(h->seg_records_forced) * 8 : ((4 * overlap + 7) / 8 * 8);
+        if (seg_bits < 8) seg_bits = 8;
+        const size_t n_seg = (no_seg || dec == h->s_dec.ptr) ? 1 : (L + seg_bits - 1) / seg_bits;
+        if (n_seg <= 1) {
+            traceback_cta_kernel<5><<<unsigned((n_frames + 63) / 64), 64, 0, s>>>(t);
+        } else {
+            cudaError_t ce = h->tb_spec.reserve(n_seg * n_frames * 4);
+            if (ce == cudaSuccess) ce = h->tb_fin.reserve(n_seg * n_frames * 4);
+            if (ce != cudaSuccess) return ce;
+            TracebackCtaSegParams sp{};
+            sp.n_seg = uint32_t(n_seg); sp.seg_bits = uint32_t(seg_bits); sp.overlap = uint32_t(overlap);
+            sp.spec = static_cast<uint32_t*>(h->tb_spec.ptr); sp.fin = static_cast<uint32_t*>(h->tb_fin.ptr);
+            traceback_cta_seg_kernel<5><<<dim3(unsigned((n_frames + 63) / 64), unsigned(n_seg)), 64, 0, s>>>(t, sp);
+            ce = cudaGetLastError();
+            if (ce != cudaSuccess) return ce;
+            h->launches++;
+            traceback_cta_fix_kernel<5><<<unsigned((n_frames + 63) / 64), 64, 0, s>>>(t, sp);
+        }
     } else if (e->layout == LAYOUT_PAIR) {
         TracebackParams t{};
         t.dec = static_cast<const uint64_t*>(dec); t.dec_rows = uint32_t(dec_rows); t.n_frames = uint32_t(n_frames);
