@@ -48,6 +48,7 @@ struct HistLane<0> {
     static constexpr int HB = 8, FPT = 2, SBY = 1;
     static constexpr uint32_t TAG1 = 0x00010001u, METRIC_MASK = 0xff00ff00u;
     static __device__ __forceinline__ uint32_t add(uint32_t a, uint32_t b) { return __vadd2(a, b); }
+    static __device__ __forceinline__ uint32_t sub(uint32_t a, uint32_t b) { return __vsub2(a, b); }
     static __device__ __forceinline__ uint32_t addmin(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_u16x2(a, b, c); }
     static __device__ __forceinline__ uint32_t min3(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u16x2(a, b, c); }
     static __device__ __forceinline__ uint32_t min2(uint32_t a, uint32_t b) { return __vminu2(a, b); }
@@ -58,6 +59,7 @@ struct HistLane<1> {
     static constexpr int HB = 16, FPT = 1, SBY = 2;
     static constexpr uint32_t TAG1 = 1u, METRIC_MASK = 0xffff0000u;
     static __device__ __forceinline__ uint32_t add(uint32_t a, uint32_t b) { return a + b; }
+    static __device__ __forceinline__ uint32_t sub(uint32_t a, uint32_t b) { return a - b; }
     static __device__ __forceinline__ uint32_t addmin(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_u32(a, b, c); }
     static __device__ __forceinline__ uint32_t min3(uint32_t a, uint32_t b, uint32_t c) { return min(min(a, b), c); }
     static __device__ __forceinline__ uint32_t min2(uint32_t a, uint32_t b) { return min(a, b); }
@@ -65,7 +67,7 @@ struct HistLane<1> {
 
 // kernel-uniform constants in the lane format (FMT 1 derives them from the packed 16x2 parameters the host fills for sh = 0)
 struct HistConsts {
-    uint32_t c_low, c_high, c_inv, thr, init_start, init_other;
+    uint32_t c_low, c_high, c_high_n, c_inv, thr, init_start, init_other;      // high - s = c_high - s = ~s + c_high_n
     uint32_t thr_m1;       // FMT 0: thr - 1 per half (trigger test with one packed max)
     bool always;           // FMT 0: a threshold of 0 renormalises every step
 };
@@ -74,12 +76,15 @@ template <int FMT>
 __device__ __forceinline__ HistConsts hist_consts(const AcsParams& p) {
     HistConsts c;
     if constexpr (FMT == 0) {
-        c.c_low = p.c_low2; c.c_high = p.c_high2; c.c_inv = p.c_inv2; c.thr = p.thr2; c.init_start = p.init_start2; c.init_other = p.init_other2;
+        c.c_low = p.c_low2; c.c_inv = p.c_inv2; c.thr = p.thr2; c.init_start = p.init_start2; c.init_other = p.init_other2;
+        c.c_high_n = p.c_high2;                                    // (high << 8) + 1 per half
+        c.c_high = p.c_high2 - 0x00010001u;                        // high << 8 per half
         c.always = (p.thr2 & 0xffffu) == 0u || (p.thr2 >> 16) == 0u;
         c.thr_m1 = c.always ? 0xffffffffu : p.thr2 - 0x00010001u;
     } else {
         c.c_low = p.c_low2 & 0xffff0000u;                          // (-low) << 16
-        c.c_high = (p.c_high2 & 0xffff0000u) - 0x00010000u + 1u;   // (high << 16) + 1:  high - s = ~(s << 16) + c_high
+        c.c_high = (p.c_high2 & 0xffff0000u) - 0x00010000u;        // high << 16  (c_high2 holds high + 1 per half)
+        c.c_high_n = c.c_high + 1u;
         c.c_inv = p.c_inv2 & 0xffff0000u; c.thr = p.thr2 & 0xffff0000u;
         c.init_start = p.init_start2 & 0xffff0000u; c.init_other = p.init_other2 & 0xffff0000u;
         c.always = false; c.thr_m1 = 0u;
@@ -145,7 +150,7 @@ struct HistTable<FMT, R, 1> {
 };
 
 // one trellis step x -> y; tag = 2^k in the history field(s), k = step index inside the period
-template <class C, int FMT, bool TIE_SIMD, bool CONSISTENT>
+template <class C, int FMT, bool TIE_SIMD, bool CONSISTENT, bool NEG_BY_NOT>
 __device__ __forceinline__ void hist_step(const uint32_t (&x)[C::NS], uint32_t (&y)[C::NS], const uint32_t* sym, const HistConsts& c,
                                           const uint32_t tag, uint64_t& accA, uint64_t& accB) {
     using LN = HistLane<FMT>;
@@ -154,7 +159,10 @@ __device__ __forceinline__ void hist_step(const uint32_t (&x)[C::NS], uint32_t (
 #pragma unroll
     for (int i = 0; i < R; i++) {
         lo[i] = LN::add(sym[i], c.c_low);          // s - low
-        hi[i] = LN::add(~sym[i], c.c_high);        // high - s  (|branch - s| for s in [low, high], scalar.h:30-34, 96-105)
+        // high - s  (|branch - s| for s in [low, high], scalar.h:30-34, 96-105).  Two equivalent forms; which one ptxas schedules
+        // better depends on where the symbols come from (measured on config 2 / 1 / 4: ~s + (c + 1) is 3 % faster behind the direct
+        // fetch, where the NOT fuses into the unpacking LOP3; c - s is 5 % faster behind the packed stream)
+        hi[i] = NEG_BY_NOT ? LN::add(~sym[i], c.c_high_n) : LN::sub(c.c_high, sym[i]);
     }
     uint32_t T[NP], TT[NP];
     HistTable<FMT, R, R>::run(T, lo, hi);
@@ -241,7 +249,7 @@ __global__ void __launch_bounds__(32 * HIST_WARPS) acs_hist_kernel(const AcsPara
     constexpr int PAD = BYTES / 4 + 1;
     uint32_t buf[DIRECT ? NROW : 1][DIRECT ? WPG + PAD : 1], nx[DIRECT ? NROW : 1][DIRECT ? WPG : 1], nxt[DIRECT ? 1 : 2 * R];
     const uint32_t* row[NROW];
-    uint32_t maxw[NROW];
+    uint32_t maxw[NROW] = {};
     if constexpr (DIRECT) {
         const size_t lastf = size_t(p.n_frames) - 1;
 #pragma unroll
@@ -328,8 +336,8 @@ __global__ void __launch_bounds__(32 * HIST_WARPS) acs_hist_kernel(const AcsPara
 #pragma unroll
                     for (int i = 0; i < 2 * R; i++) nxt[i] = (t + 2 + uint32_t(i / R) < p.n_steps) ? __ldg(pk + (size_t(t + 2) * R + i) * SLOTS) : 0u;
                 }
-                hist_step<C, FMT, TIE_SIMD, CONSISTENT>(x, y, &cur[0], c, tag, accA, accB);
-                hist_step<C, FMT, TIE_SIMD, CONSISTENT>(y, x, &cur[R], c, tag << 1, accA, accB);
+                hist_step<C, FMT, TIE_SIMD, CONSISTENT, DIRECT>(x, y, &cur[0], c, tag, accA, accB);
+                hist_step<C, FMT, TIE_SIMD, CONSISTENT, DIRECT>(y, x, &cur[R], c, tag << 1, accA, accB);
                 tag <<= 2;
                 t += 2;
             }
@@ -341,7 +349,7 @@ __global__ void __launch_bounds__(32 * HIST_WARPS) acs_hist_kernel(const AcsPara
 #pragma unroll
                     for (int i = 0; i < 2 * R; i++) cur[i] = unpack_pk(nxt[i]);
                 }
-                hist_step<C, FMT, TIE_SIMD, CONSISTENT>(x, y, &cur[0], c, tag, accA, accB);
+                hist_step<C, FMT, TIE_SIMD, CONSISTENT, DIRECT>(x, y, &cur[0], c, tag, accA, accB);
 #pragma unroll
                 for (int q = 0; q < NS; q++) x[q] = y[q];
                 t += 1;
