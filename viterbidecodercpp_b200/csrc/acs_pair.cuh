@@ -441,149 +441,4 @@ __global__ void __launch_bounds__(32 * PAIR_WARPS) acs_pair_kernel(const AcsPara
     p.acc[fB] = accB;
 }
 
-// =====================================================================================================================
-// Ping-pong variant: same arithmetic, but the metrics live in two register sets (X -> Y -> X) in LOGICAL state order, so a
-// step's code does not depend on the step index and the hot loop is two steps long (about 12 KB of SASS instead of 36 KB for
-// the K-1 unrolled phases of the in-place kernel above, which ncu shows stalled on instruction fetch: "no_instruction" is its
-// top stall reason, profiles/r01_ncu_full_acs_pair_cfg2.txt).  Costs 2^(K-1) more registers.
-// =====================================================================================================================
-template <class C, bool TIE_SIMD, int J>
-__device__ __forceinline__ void pp_bfly_at(const uint32_t (&x)[C::NS], uint32_t (&y)[C::NS], const uint32_t (&T)[C::NP],
-                                           float (&fa)[2][PairShape<C>::NACC], const uint32_t c_inv2, const bool consistent) {
-    constexpr int H = C::NS / 2;
-    constexpr uint32_t pat = bfly_pattern<C>(uint32_t(J));
-    constexpr uint32_t ipat = (~pat) & uint32_t(C::NP - 1);
-    constexpr int s0 = 2 * J, s1 = 2 * J + 1;
-    const uint32_t tot = T[pat];
-    const uint32_t inv = consistent ? T[ipat] : __vadd2(T[ipat], c_inv2);
-    const uint32_t a0 = __vadd2(x[J], tot), b0 = __vadd2(x[J + H], inv);     // scalar.h:113-114
-    const uint32_t a1 = __vadd2(x[J], inv), b1 = __vadd2(x[J + H], tot);     // scalar.h:115-116
-    bool h0, l0, h1, l1, dA0, dB0, dA1, dB1;
-    if constexpr (!TIE_SIMD) {
-        y[s0] = __vibmin_u16x2(a0, b0, &h0, &l0);
-        y[s1] = __vibmin_u16x2(a1, b1, &h1, &l1);
-        dA0 = !l0; dB0 = !h0; dA1 = !l1; dB1 = !h1;
-    } else {
-        y[s0] = __vibmin_u16x2(b0, a0, &h0, &l0);
-        y[s1] = __vibmin_u16x2(b1, a1, &h1, &l1);
-        dA0 = l0; dB0 = h0; dA1 = l1; dB1 = h1;
-    }
-    constexpr int acc0 = (s0 >> 4) % PairShape<C>::NACC, acc1 = (s1 >> 4) % PairShape<C>::NACC;
-    constexpr float w0 = float(1u << (s0 & 15)), w1 = float(1u << (s1 & 15));
-    if (dA0) fa[0][acc0] += w0;
-    if (dB0) fa[1][acc0] += w0;
-    if (dA1) fa[0][acc1] += w1;
-    if (dB1) fa[1][acc1] += w1;
-}
-
-template <class C, bool TIE_SIMD, int... Js>
-__device__ __forceinline__ void pp_bfly_all(const uint32_t (&x)[C::NS], uint32_t (&y)[C::NS], const uint32_t (&T)[C::NP],
-                                            float (&fa)[2][PairShape<C>::NACC], const uint32_t c_inv2, const bool consistent,
-                                            std::integer_sequence<int, Js...>) {
-    (pp_bfly_at<C, TIE_SIMD, Js>(x, y, T, fa, c_inv2, consistent), ...);
-}
-
-// one trellis step x -> y
-template <class C, int SH, bool TIE_SIMD, bool CONSISTENT>
-__device__ __forceinline__ void pp_step(const uint32_t (&x)[C::NS], uint32_t (&y)[C::NS], const uint32_t* sym, const AcsParams& p,
-                                        uint64_t* dec_row, uint64_t& accA, uint64_t& accB) {
-    constexpr int R = C::R, NP = C::NP, NS = C::NS, NACC = PairShape<C>::NACC;
-    uint32_t lo[R], hi[R];
-#pragma unroll
-    for (int i = 0; i < R; i++) {
-        lo[i] = __vadd2(sym[i], p.c_low2);
-        hi[i] = __vadd2(~sym[i], p.c_high2);
-    }
-    uint32_t T[NP];
-    TableBuild<R, R>::run(T, lo, hi);
-    float fa[2][NACC];
-#pragma unroll
-    for (int a = 0; a < NACC; a++) { fa[0][a] = 8388608.f; fa[1][a] = 8388608.f; }
-    pp_bfly_all<C, TIE_SIMD>(x, y, T, fa, p.c_inv2, CONSISTENT, std::make_integer_sequence<int, NS / 2>{});
-
-    uint32_t wA0, wA1 = 0, wB0, wB1 = 0;
-    if constexpr (NACC == 4) {
-        wA0 = __byte_perm(__float_as_uint(fa[0][0]), __float_as_uint(fa[0][1]), 0x5410);
-        wA1 = __byte_perm(__float_as_uint(fa[0][2]), __float_as_uint(fa[0][3]), 0x5410);
-        wB0 = __byte_perm(__float_as_uint(fa[1][0]), __float_as_uint(fa[1][1]), 0x5410);
-        wB1 = __byte_perm(__float_as_uint(fa[1][2]), __float_as_uint(fa[1][3]), 0x5410);
-    } else if constexpr (NACC == 2) {
-        wA0 = __byte_perm(__float_as_uint(fa[0][0]), __float_as_uint(fa[0][1]), 0x5410);
-        wB0 = __byte_perm(__float_as_uint(fa[1][0]), __float_as_uint(fa[1][1]), 0x5410);
-    } else {
-        wA0 = __float_as_uint(fa[0][0]) & 0xffffu;
-        wB0 = __float_as_uint(fa[1][0]) & 0xffffu;
-    }
-    *reinterpret_cast<uint4*>(dec_row) = make_uint4(wA0, wA1, wB0, wB1);
-
-    bool trigB, trigA;
-    (void)__vibmin_u16x2(p.thr2, y[0], &trigB, &trigA);      // scalar.h:48
-    if (trigA || trigB) {
-        const uint32_t m = packed_min<NS>(y);
-        const uint32_t mA = m & 0xffffu, mB = m >> 16;
-        const uint32_t sub = (trigA ? mA : 0u) | ((trigB ? mB : 0u) << 16);
-        const uint32_t neg = __vsub2(0u, sub);
-#pragma unroll
-        for (int q = 0; q < NS; q++) y[q] = __vadd2(y[q], neg);
-        if (trigA) accA += uint64_t(mA >> SH);
-        if (trigB) accB += uint64_t(mB >> SH);
-    }
-}
-
-constexpr int PP_CHUNK = 4;   // steps whose symbols are fetched together (2 iterations of the 2-step body)
-
-template <class C, int SH, bool TIE_SIMD, bool CONSISTENT>
-__global__ void __launch_bounds__(32 * PAIR_WARPS) acs_pair_pp_kernel(const AcsParams p) {
-    constexpr int R = C::R, NS = C::NS;
-    const uint32_t lane = threadIdx.x & 31, blk = blockIdx.x * PAIR_WARPS + (threadIdx.x >> 5);
-    if (blk >= p.n_blocks) return;
-    const size_t fA = size_t(blk) * 64 + 2 * lane, fB = fA + 1;
-
-    uint32_t x[NS], y[NS];
-    uint64_t accA = 0, accB = 0;
-    uint16_t* mA = p.metrics + fA * NS;
-    uint16_t* mB = p.metrics + fB * NS;
-    if (p.resume) {
-#pragma unroll
-        for (int q = 0; q < NS; q++) x[q] = ((uint32_t(mA[q]) << SH) & 0xffffu) | (uint32_t(mB[q]) << (16 + SH));
-        accA = p.acc[fA];
-        accB = p.acc[fB];
-    } else {
-        const uint32_t s = p.start_state & uint32_t(NS - 1);
-#pragma unroll
-        for (int q = 0; q < NS; q++) x[q] = (uint32_t(q) == s) ? p.init_start2 : p.init_other2;
-    }
-
-    const uint32_t* pk = p.pk + size_t(blk) * p.n_steps * R * 32 + lane;
-    uint64_t* dec_lane = static_cast<uint64_t*>(p.dec) + (size_t(blk) * p.dec_rows + p.dec_row0) * 64 + 2 * lane;
-
-    uint32_t nxt[2 * R];
-#pragma unroll
-    for (int k = 0; k < 2 * R; k++) nxt[k] = (uint32_t(k / R) < p.n_steps) ? __ldg(pk + size_t(k) * 32) : 0u;
-
-    uint32_t t = 0;
-#pragma unroll 1
-    for (; t + 2 <= p.n_steps; t += 2) {
-        uint32_t cur[2 * R];
-#pragma unroll
-        for (int k = 0; k < 2 * R; k++) cur[k] = nxt[k];
-#pragma unroll
-        for (int k = 0; k < 2 * R; k++) nxt[k] = (t + 2 + uint32_t(k / R) < p.n_steps) ? __ldg(pk + (size_t(t + 2) * R + k) * 32) : 0u;
-        pp_step<C, SH, TIE_SIMD, CONSISTENT>(x, y, &cur[0], p, dec_lane + size_t(t) * 64, accA, accB);
-        pp_step<C, SH, TIE_SIMD, CONSISTENT>(y, x, &cur[R], p, dec_lane + size_t(t + 1) * 64, accA, accB);
-    }
-    if (t < p.n_steps) {     // odd tail: one more step, result ends in y
-        pp_step<C, SH, TIE_SIMD, CONSISTENT>(x, y, &nxt[0], p, dec_lane + size_t(t) * 64, accA, accB);
-#pragma unroll
-        for (int q = 0; q < NS; q++) x[q] = y[q];
-    }
-#pragma unroll
-    for (int q = 0; q < NS; q++) {
-        mA[q] = uint16_t((x[q] & 0xffffu) >> SH);
-        mB[q] = uint16_t(x[q] >> (16 + SH));
-    }
-    p.acc[fA] = accA;
-    p.acc[fB] = accB;
-}
-
 }  // namespace vitb

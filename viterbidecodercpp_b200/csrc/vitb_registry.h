@@ -40,23 +40,13 @@ struct KernelEntry {
     cudaError_t (*launch_hist_direct)(const AcsParams&, cudaStream_t);
 };
 
-// The in-place kernel is the default.  VITB_PAIR_PINGPONG=1 selects the two-register-set variant (smaller hot loop, but ptxas
-// then schedules all compare-selects ahead of their predicated FADDs, runs out of predicate registers and spills them through
-// P2R/LOP3: measured 2.14 ms vs 1.42 ms on config 2, profiles/r01_summary.md).
+// Decision-row kernel of the one-thread-per-pair mapping (streaming calls; batch calls when the history kernel is switched off).
+// A two-register-set (ping-pong) variant of it was measured and dropped: ptxas scheduled all compare-selects ahead of their
+// predicated FADDs, ran out of predicate registers and spilled them (2.14 ms vs 1.42 ms on config 2, profiles/r01_summary.md).
 template <class C, int SH, bool TIE_SIMD, bool CONSISTENT>
 cudaError_t launch_pair(const AcsParams& p, cudaStream_t s) {
-    static const bool inplace = (getenv("VITB_PAIR_PINGPONG") == nullptr);
     const unsigned grid = (p.n_blocks + PAIR_WARPS - 1) / PAIR_WARPS;
-#ifdef VITB_PERIOD_EXPERIMENT
-    static const int period = getenv("VITB_PAIR_PERIOD") ? atoi(getenv("VITB_PAIR_PERIOD")) : 0;
-    if constexpr (C::SB == 6 && SH == 8 && !TIE_SIMD && CONSISTENT) {
-        if (period == 1) { acs_pair_kernel<C, SH, TIE_SIMD, CONSISTENT, 1><<<grid, 32 * PAIR_WARPS, 0, s>>>(p); return cudaGetLastError(); }
-        if (period == 2) { acs_pair_kernel<C, SH, TIE_SIMD, CONSISTENT, 2><<<grid, 32 * PAIR_WARPS, 0, s>>>(p); return cudaGetLastError(); }
-        if (period == 6) { acs_pair_kernel<C, SH, TIE_SIMD, CONSISTENT, 6><<<grid, 32 * PAIR_WARPS, 0, s>>>(p); return cudaGetLastError(); }
-    }
-#endif
-    if (inplace) acs_pair_kernel<C, SH, TIE_SIMD, CONSISTENT><<<grid, 32 * PAIR_WARPS, 0, s>>>(p);
-    else acs_pair_pp_kernel<C, SH, TIE_SIMD, CONSISTENT><<<grid, 32 * PAIR_WARPS, 0, s>>>(p);
+    acs_pair_kernel<C, SH, TIE_SIMD, CONSISTENT><<<grid, 32 * PAIR_WARPS, 0, s>>>(p);
     return cudaGetLastError();
 }
 
