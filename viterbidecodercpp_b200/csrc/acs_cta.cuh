@@ -49,7 +49,7 @@ struct CtaShape {
 // profiles/r01_ncu_full_acs_cta_cfg5.txt; with 2 x 16 bits per frame it was +81 instructions).
 template <int NL> struct CtaAcc { static constexpr int value = NL >= 32 ? 4 : (NL >= 16 ? 2 : 1); };
 #ifndef VITB_CTA_CHAINS
-#define VITB_CTA_CHAINS 2
+#define VITB_CTA_CHAINS 4
 #endif
 constexpr int CTA_CHAINS = VITB_CTA_CHAINS;          // chains per decision byte (1, 2 or 4)
 
@@ -113,7 +113,8 @@ struct CtaKernel {
         for (int a = 0; a < NACC; a++) {
 #pragma unroll
             for (int f = 0; f < 2; f++) {
-                if constexpr (CTA_CHAINS == 4) fa[f][a] = (fn[f][a][0] + fn[f][a][1]) + (fn[f][a][2] + fn[f][a][3]);
+                if constexpr (CTA_CHAINS == 8) fa[f][a] = ((fn[f][a][0] + fn[f][a][1]) + (fn[f][a][2] + fn[f][a][3])) + ((fn[f][a][4] + fn[f][a][5]) + (fn[f][a][6] + fn[f][a][7]));
+                else if constexpr (CTA_CHAINS == 4) fa[f][a] = (fn[f][a][0] + fn[f][a][1]) + (fn[f][a][2] + fn[f][a][3]);
                 else if constexpr (CTA_CHAINS == 2) fa[f][a] = fn[f][a][0] + fn[f][a][1];
                 else fa[f][a] = fn[f][a][0];
             }

@@ -139,7 +139,7 @@ const KernelEntry* choose_variant(const vitb_decoder* h, size_t n_frames) {
         for (const KernelEntry* e : h->variants) if (e->logt == h->forced_logt) return e;
     }
     const size_t pairs = (n_frames + 1) / 2, smsp = size_t(h->n_sm) * 4;
-    if (h->variants.front()->layout == LAYOUT_CTA) return h->variants.back();   // K = 15: 1024 threads x 16 registers measured fastest
+    if (h->variants.front()->layout == LAYOUT_CTA) return h->variants.front();  // K = 15: 512 threads x 32 registers measured fastest (56.0 vs 61.1 ms)
     // survivor-history kernel (acs_hist.cuh, 4 instructions per butterfly): about twice as fast per add-compare-select as the
     // predicate kernels and no ingest pass, so it wins unless the batch is so small that only the lane-group variants can spread
     // it over the GPU (a warp of the history kernel runs alone at full speed: 16 384 config-2 frames = 256 warps take 0.34 ms)
