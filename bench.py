@@ -108,6 +108,26 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def gpu_numa_cpus(torch, local_rank):
+    """(node, cpus) of the NUMA node this rank's GPU hangs off, from sysfs; (None, None) when that cannot be determined"""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read())
+        if node < 0:
+            return None, None
+        cpus = set()
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        return (node, cpus) if cpus else (None, None)
+    except Exception:
+        return None, None
+
+
 def build_workload(name, seed, n_frames=None):
     import viterbidecodercpp_b200 as v
     from viterbidecodercpp_b200 import synth
@@ -228,10 +248,18 @@ def main():
         dec.set_variant(args.lanes)
 
     out_stride = (L + 7) // 8
+    # pinned host buffers of the end-to-end leg: allocated (first touch) while this thread sits on the NUMA node of its GPU, so that
+    # with several ranks per box every GPU pulls its symbols from local memory instead of across the socket interconnect
+    affinity0 = os.sched_getaffinity(0)
+    numa_node, numa_cpus = gpu_numa_cpus(torch, local_rank)
+    if numa_cpus:
+        os.sched_setaffinity(0, numa_cpus)
     h_sym = torch.from_numpy(w["sym"]).pin_memory()
     h_out = torch.zeros((F, out_stride), dtype=torch.uint8).pin_memory()
     h_acc = torch.zeros(F, dtype=torch.int64).pin_memory()
     h_fin = torch.zeros(F, dtype=torch.int32).pin_memory()
+    if numa_cpus:
+        os.sched_setaffinity(0, affinity0)          # the CPU-baseline leg wants every host thread again
     d_sym = h_sym.to(dev)
     d_out = torch.zeros((F, out_stride), dtype=torch.uint8, device=dev)
     d_acc = torch.zeros(F, dtype=torch.int64, device=dev)
@@ -333,7 +361,8 @@ def main():
         "dtype": "u8" if dc.soft_bytes == 1 else "u16", "data": "synthetic BPSK/AWGN (run_snr_ber statistics), fixed seed, every frame unique",
         "config": {"workload": f"{args.workload}: {w['desc']}", "frames_per_gpu": F, "bits_per_frame": L, "EbNo_dB": w["ebno"],
                    "l2": "inputs larger than L2 (no flush)" if w["sym"].nbytes > 130e6 else "inputs smaller than L2; decision buffer larger than L2",
-                   "kernel": kernel_name, "parallelism": f"frames sharded over {world} GPU(s), no collective"},
+                   "kernel": kernel_name, "parallelism": f"frames sharded over {world} GPU(s), no collective",
+                   "host_numa_node": numa_node},
         "acs_gops": world * F * ab["acs_ops"] / (ms_step * 1e-3) / 1e9,
         "ber": ber,
         "stage_ms": stages,
