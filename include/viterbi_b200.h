@@ -21,6 +21,7 @@ extern "C" {
 #endif
 
 #define VITB_MAX_R 16
+#define VITB_END_STATE_BEST ((size_t)-1)
 
 typedef enum vitb_status {
     VITB_OK = 0,
@@ -84,7 +85,8 @@ int vitb_get_decisions(vitb_decoder* h, size_t first_row, size_t n_rows, uint64_
 typedef struct vitb_batch_opts {
     size_t row_stride;       /* elements between frames in `symbols`; 0 = dense */
     size_t starting_state;   /* reset(starting_state)          core.h:202 */
-    size_t end_state;        /* get_error / chainback end_state core.h:195,214 */
+    size_t end_state;        /* get_error / chainback end_state core.h:195,214; VITB_END_STATE_BEST = per frame, the state with
+                              * the smallest final path metric (lowest index on a tie) */
 } vitb_batch_opts;
 
 /* host pointers: H2D copy, kernels, D2H copy, synchronous */

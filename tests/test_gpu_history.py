@@ -194,3 +194,33 @@ def test_segmented_traceback_k15(cuda_lib, decode_type):
             got = dec.decode_batch(sym, L, end_state=end)
             assert_batch_equal(got, want, f"Cassini {decode_type} L={L} seg={seg} overlap={ov}")
     dec.set_traceback_segments(0, -1)
+
+
+@pytest.mark.parametrize("name,decode_type,lanes", [("Voyager", "SOFT16", 1), ("Voyager", "HARD8", 1), ("DAB Radio", "SOFT16", 4),
+                                                     ("Voyager", "HARD8", 2), ("CDMA IS-95A", "SOFT16", 16), ("CDMA IS-95A", "HARD8", 8),
+                                                     ("Cassini", "SOFT16", 0)])
+def test_best_end_state(cuda_lib, name, decode_type, lanes):
+    """end_state = VITB_END_STATE_BEST: every frame is traced back from its own best final state (smallest metric, lowest index on a
+    tie) - what a caller of the reference computes with get_error(s) over all s before chainback(..., s).  Random symbols, so the best
+    state differs from frame to frame; covers the history, lane-group and K = 15 traceback kernels, ragged bit counts included."""
+    code = CODE_BY_NAME[name]
+    dec, dc = make_cuda_decoder(code, decode_type)
+    ora, _ = make_oracle(code, decode_type)
+    if lanes:
+        dec.set_variant(lanes)
+    n_frames = 6 if code.K >= 15 else 37
+    for L in ([520, 1003] if code.K < 15 else [1003]):
+        sym = random_symbols(dc, n_frames, (L + code.K - 1) * code.R, seed=L + lanes)
+        out = np.zeros((n_frames, (L + 7) // 8), dtype=np.uint8); acc = np.zeros(n_frames, dtype=np.uint64); fin = np.zeros(n_frames, dtype=np.uint32)
+        ora.set_traceback_length(L)
+        bests = []
+        for f in range(n_frames):
+            ora.reset(0)
+            acc[f] = ora.update(sym[f])
+            best = int(np.argmin(np.asarray(ora.metrics())))
+            bests.append(best)
+            fin[f] = ora.get_error(best)
+            out[f] = ora.chainback(L, best)
+        assert len(set(bests)) > 1
+        got = dec.decode_batch(sym, L, end_state=v.VITB_END_STATE_BEST)
+        assert_batch_equal(got, (out, acc, fin), f"{name} {decode_type} lanes={lanes} L={L} best end state")

@@ -18,11 +18,18 @@ struct TracebackParams {
     uint32_t total_bits;      // L
     uint32_t state_bits;      // K-1
     uint32_t end_state;
+    const uint32_t* end_states;   // nullable: per-frame end states (VITB_END_STATE_BEST), overrides end_state
     uint8_t* out;             // [n_frames][out_stride]
     size_t out_stride;
     uint32_t tag_layout;      // 0: bit s of the word = state s;  1: rows written by the tagged butterfly (acs_pair.cuh):
                               //    byte 2k+h holds states 2J+h for J = 8k..8k+7, first butterfly in the top bit
 };
+
+// end state of frame f: the call's end_state, or the frame's own (argmin of its final metrics) when the caller asked for the best one
+template <class P>
+__device__ __forceinline__ uint32_t frame_end_state(const P& p, size_t f) {
+    return p.end_states ? p.end_states[f < p.n_frames ? f : p.n_frames - 1] : p.end_state;
+}
 
 // bit position of state s inside a frame's 64-bit decision word
 __device__ __forceinline__ uint32_t dec_bit_index(uint32_t s, uint32_t tag_layout) {
@@ -41,13 +48,14 @@ __global__ void __launch_bounds__(128) traceback_u64_kernel(const TracebackParam
     const uint32_t SB = p.state_bits, L = p.total_bits;
     const uint64_t* d = p.dec + (size_t(f >> 6) * p.dec_rows + SB) * 64 + (f & 63);   // row of decoded bit 0
     uint8_t* out = p.out + size_t(f) * p.out_stride;
-    uint32_t state = p.end_state;
+    const uint32_t es = frame_end_state(p, f);
+    uint32_t state = es;
     int64_t j = int64_t(L) - 1;
     uint32_t byte = 0;
     if (L & 7) {   // virtual bits L, L+1, ... = end_state from its top bit down, then zeros
         for (uint32_t jj = L; jj < ((L + 7) & ~7u); jj++) {
             const uint32_t k = jj - L;
-            const uint32_t b = (k < SB) ? ((p.end_state >> (SB - 1 - k)) & 1u) : 0u;
+            const uint32_t b = (k < SB) ? ((es >> (SB - 1 - k)) & 1u) : 0u;
             byte |= b << (7 - (jj & 7));
         }
     }
@@ -96,6 +104,7 @@ struct TracebackGroupParams {
     uint32_t state_bits;      // SB = K-1
     uint32_t logt;            // lanes per pair = 1 << logt (>= 1)
     uint32_t end_state;
+    const uint32_t* end_states;   // nullable: per-frame end states (VITB_END_STATE_BEST), overrides end_state
     uint8_t* out;
     size_t out_stride;
 };
@@ -115,7 +124,8 @@ __global__ void __launch_bounds__(128) traceback_group_kernel(const TracebackGro
     const uint32_t pw = lane >> g, t = lane & (T - 1), grp0 = lane & ~(T - 1);
     const size_t fA = (size_t(wblk) * PPW + pw) * 2;
     const uint32_t* d = p.dec + (size_t(wblk) * p.dec_rows * 32 + lane) * W;      // this lane's word(s) of row 0
-    uint32_t stA = p.end_state, stB = p.end_state;
+    const uint32_t esA = frame_end_state(p, fA), esB = frame_end_state(p, fA + 1);
+    uint32_t stA = esA, stB = esB;
     uint32_t byteA = 0, byteB = 0;
     const bool writerA = (t == 0) && (fA < p.n_frames), writerB = (t == 1) && (fA + 1 < p.n_frames);
     uint8_t* outA = p.out + fA * p.out_stride;
@@ -123,10 +133,9 @@ __global__ void __launch_bounds__(128) traceback_group_kernel(const TracebackGro
     if (L & 7) {
         for (uint32_t jj = L; jj < ((L + 7) & ~7u); jj++) {
             const uint32_t k = jj - L;
-            const uint32_t b = (k < SB) ? ((p.end_state >> (SB - 1 - k)) & 1u) : 0u;
-            byteA |= b << (7 - (jj & 7));
+            byteA |= ((k < SB) ? ((esA >> (SB - 1 - k)) & 1u) : 0u) << (7 - (jj & 7));
+            byteB |= ((k < SB) ? ((esB >> (SB - 1 - k)) & 1u) : 0u) << (7 - (jj & 7));
         }
-        byteB = byteA;
     }
     const uint32_t smask = (1u << SB) - 1u;
     // n = row % LB is carried along (rows are visited in decreasing order); rot = n + 1 is in [1, LB] so never 0 or SB
@@ -213,11 +222,12 @@ __global__ void __launch_bounds__(128) traceback_group_staged_kernel(const Trace
     uint8_t* out = p.out + size_t(f) * p.out_stride;
     const uint32_t smask = (1u << SB) - 1u;
 
+    const uint32_t es = frame_end_state(p, f);
     uint32_t byte = 0;
     if (L & 7) {
         for (uint32_t jj = L; jj < ((L + 7) & ~7u); jj++) {
             const uint32_t k = jj - L;
-            const uint32_t b = (k < SB) ? ((p.end_state >> (SB - 1 - k)) & 1u) : 0u;
+            const uint32_t b = (k < SB) ? ((es >> (SB - 1 - k)) & 1u) : 0u;
             byte |= b << (7 - (jj & 7));
         }
     }
@@ -244,7 +254,7 @@ __global__ void __launch_bounds__(128) traceback_group_staged_kernel(const Trace
     uint32_t n = uint32_t(top) % LB;
     uint32_t phi;
     {
-        const uint32_t rot = n + 1, st = p.end_state;
+        const uint32_t rot = n + 1, st = es;
         phi = ((st >> rot) | (st << (SB - rot))) & smask;
     }
     const uint32_t lane_mask = T - 1;
@@ -290,6 +300,7 @@ struct TracebackCtaParams {
     uint32_t state_bits;
     uint32_t logt;
     uint32_t end_state;
+    const uint32_t* end_states;   // nullable: per-frame end states (VITB_END_STATE_BEST), overrides end_state
     uint8_t* out;
     size_t out_stride;
 };
@@ -352,7 +363,8 @@ __global__ void __launch_bounds__(64) traceback_cta_kernel(const TracebackCtaPar
     const uint32_t* d = p.dec + size_t(f >> 1) * p.dec_rows * T * W + (W == 2 ? half : 0u);
     const uint32_t bit_base = (W == 2) ? 0u : half * 16u;
     uint8_t* out = p.out + size_t(f) * p.out_stride;
-    (void)cta_walk<MAXLB, true>(p, d, out, bit_base, int64_t(L) + SB - 1, SB, p.end_state, ragged_top_byte(L, SB, p.end_state));
+    const uint32_t es = frame_end_state(p, f);
+    (void)cta_walk<MAXLB, true>(p, d, out, bit_base, int64_t(L) + SB - 1, SB, es, ragged_top_byte(L, SB, es));
 }
 
 // Segmented walk (same scheme as traceback_hist_seg_kernel below): segments of seg_bits decoded bits (a multiple of 8), warm-up over
@@ -375,14 +387,15 @@ __global__ void __launch_bounds__(64) traceback_cta_seg_kernel(const TracebackCt
     const int64_t r_top = int64_t(L) + SB - 1;
     const int64_t r_lo = int64_t(g) * sp.seg_bits + SB;
     int64_t r_hi = r_lo + sp.seg_bits - 1;
+    const uint32_t es = frame_end_state(p, f);
     uint32_t state, byte = 0;
     if (g + 1 == sp.n_seg || r_hi >= r_top) {
         r_hi = r_top;
-        state = p.end_state;                                  // the top segment starts from the truth
-        byte = ragged_top_byte(L, SB, p.end_state);
+        state = es;                                           // the top segment starts from the truth
+        byte = ragged_top_byte(L, SB, es);
     } else {
         int64_t r_warm = r_hi + sp.overlap;
-        if (r_warm >= r_top) { r_warm = r_top; state = p.end_state; }
+        if (r_warm >= r_top) { r_warm = r_top; state = es; }
         else state = 0u;
         state = cta_walk<MAXLB, false>(p, d, out, bit_base, r_warm, r_hi + 1, state, 0u);
         sp.spec[size_t(g) * p.n_frames + f] = state;
@@ -425,6 +438,7 @@ struct TracebackHistParams {
     uint32_t total_bits;      // L
     uint32_t state_bits;      // SB = K-1 (<= 8)
     uint32_t end_state;
+    const uint32_t* end_states;   // nullable: per-frame end states (VITB_END_STATE_BEST), overrides end_state
     uint32_t n_steps;         // S = L + SB
     uint32_t hist_bits;       // HB: 8 (two frames per lane, 64 per block) or 16 (one frame per lane, 32 per block)
     uint8_t* out;
@@ -439,7 +453,7 @@ struct HistFrame {
     const uint8_t* base;      // first record of the frame's warp block
     uint8_t* out;
     size_t rec_bytes;
-    uint32_t lane, half, vw_log, SB, HB, r_last, nv, VS, n_out;
+    uint32_t lane, half, vw_log, SB, HB, r_last, nv, VS, n_out, end_state;
     bool wide;
 };
 
@@ -456,7 +470,8 @@ __device__ __forceinline__ HistFrame hist_frame(const TracebackHistParams& p, ui
     c.n_out = (p.total_bits + 7) / 8;
     c.r_last = (p.n_steps - 1) / c.HB;
     c.nv = p.n_steps - c.HB * c.r_last;
-    const uint32_t E = c.SB ? (__brev(p.end_state) >> (32 - c.SB)) : 0u;     // virtual decisions behind the last step
+    c.end_state = frame_end_state(p, f);
+    const uint32_t E = c.SB ? (__brev(c.end_state) >> (32 - c.SB)) : 0u;     // virtual decisions behind the last step
     c.VS = E << c.nv;                                            // relative to the first step of record r_last (at most 16 + 8 bits)
     return c;
 }
@@ -500,7 +515,7 @@ __global__ void __launch_bounds__(128) traceback_hist_kernel(const TracebackHist
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= p.n_frames) return;
     const HistFrame c = hist_frame(p, f);
-    (void)hist_walk<true>(c, c.r_last, 0, p.end_state);
+    (void)hist_walk<true>(c, c.r_last, 0, c.end_state);
 }
 
 // ---- segmented walk -----------------------------------------------------------------------------------------------------------
@@ -527,10 +542,10 @@ __global__ void __launch_bounds__(128) traceback_hist_seg_kernel(const Traceback
     uint32_t state;
     if (g + 1 == sp.n_seg || r_hi >= int64_t(c.r_last)) {
         r_hi = c.r_last;
-        state = p.end_state;                                  // the top segment starts from the truth
+        state = c.end_state;                                  // the top segment starts from the truth
     } else {
         int64_t r_warm = r_hi + sp.overlap;
-        if (r_warm >= int64_t(c.r_last)) { r_warm = c.r_last; state = p.end_state; }
+        if (r_warm >= int64_t(c.r_last)) { r_warm = c.r_last; state = c.end_state; }
         else state = 0u;
         state = hist_walk<false>(c, r_warm, r_hi + 1, state);
         sp.spec[size_t(g) * p.n_frames + f] = state;

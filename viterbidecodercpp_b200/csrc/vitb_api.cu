@@ -36,13 +36,33 @@ static const std::vector<KernelEntry>& registry() {
     return entries;
 }
 
-// per-frame results picked out of the workspace: acc_error[f], final_error[f] = metrics[f][end_state]
+// per-frame results picked out of the workspace: acc_error[f], final_error[f] = metrics[f][end_state of the frame]
 __global__ void gather_results_kernel(const uint64_t* acc, const uint16_t* metrics, uint32_t n_states, uint32_t end_state,
-                                      uint32_t n_frames, uint64_t* acc_out, uint32_t* final_out) {
+                                      const uint32_t* end_states, uint32_t n_frames, uint64_t* acc_out, uint32_t* final_out) {
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n_frames) return;
     if (acc_out) acc_out[f] = acc[f];
-    if (final_out) final_out[f] = metrics[size_t(f) * n_states + end_state];
+    if (final_out) final_out[f] = metrics[size_t(f) * n_states + (end_states ? end_states[f] : end_state)];
+}
+
+// VITB_END_STATE_BEST: the end state of a frame is the state with the smallest final path metric (lowest index on a tie): what a
+// caller of the reference does with get_error(s) over all s before chainback(..., s) when the encoder was not flushed to state 0.
+// One warp per frame.
+__global__ void __launch_bounds__(128) best_state_kernel(const uint16_t* metrics, uint32_t n_states, uint32_t n_frames, uint32_t* best) {
+    const uint32_t f = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (f >= n_frames) return;
+    const uint16_t* m = metrics + size_t(f) * n_states;
+    uint32_t key = 0xffffffffu;                         // metric << 16 | state for n_states <= 65536: min(key) = lowest metric, lowest state
+    for (uint32_t s = lane; s < n_states; s += 32) {
+        const uint32_t k = (uint32_t(m[s]) << 16) | (s & 0xffffu);
+        key = k < key ? k : key;
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        const uint32_t o = __shfl_xor_sync(0xffffffffu, key, d);
+        key = o < key ? o : key;
+    }
+    if (lane == 0) best[f] = key & 0xffffu;
 }
 
 struct DeviceBuffer {
@@ -84,7 +104,7 @@ struct vitb_decoder {
     cudaStream_t copy_stream = nullptr;   // owned; host->device copies of the pipelined host-pointer path
     std::vector<cudaEvent_t> copy_ev;     // one per pipeline chunk + fork/join
     // batch workspace
-    DeviceBuffer pk, dec, metrics, acc, d_in, d_out, d_accout, d_finout, map, tb_spec, tb_fin;
+    DeviceBuffer pk, dec, metrics, acc, d_in, d_out, d_accout, d_finout, map, tb_spec, tb_fin, end_states;
     size_t n_depunctured = 0, n_received = 0;
     int32_t unpunctured_value = 0;
     // single-frame streaming state (one 64-frame block, frame 0 is the user's)
@@ -224,12 +244,12 @@ size_t dec_row_bytes_unit(const KernelEntry* e) {
 }
 
 cudaError_t launch_traceback(vitb_decoder* h, const KernelEntry* e, const void* dec, size_t dec_rows, size_t n_frames, size_t L,
-                             size_t end_state, uint8_t* d_out, size_t out_stride, cudaStream_t s) {
+                             size_t end_state, uint8_t* d_out, size_t out_stride, cudaStream_t s, const uint32_t* end_states = nullptr) {
     h->launches++;
     if (e->layout == LAYOUT_CTA) {
         TracebackCtaParams t{};
         t.dec = static_cast<const uint32_t*>(dec); t.dec_rows = uint32_t(dec_rows); t.n_frames = uint32_t(n_frames);
-        t.total_bits = uint32_t(L); t.state_bits = uint32_t(h->prm.K - 1); t.logt = uint32_t(e->logt); t.end_state = uint32_t(end_state);
+        t.total_bits = uint32_t(L); t.state_bits = uint32_t(h->prm.K - 1); t.logt = uint32_t(e->logt); t.end_state = uint32_t(end_state); t.end_states = end_states;
         t.out = d_out; t.out_stride = out_stride; t.words = uint32_t(e->dec_words);
         // the chain of a K = 15 frame is L / 5 dependent memory round trips (16 384 bits: 5.7 ms): walk it in concurrent segments
         // (warm-up from a guessed state, verified and repaired afterwards, traceback.cuh); the streaming state keeps the plain walk
@@ -256,13 +276,13 @@ cudaError_t launch_traceback(vitb_decoder* h, const KernelEntry* e, const void* 
     } else if (e->layout == LAYOUT_PAIR) {
         TracebackParams t{};
         t.dec = static_cast<const uint64_t*>(dec); t.dec_rows = uint32_t(dec_rows); t.n_frames = uint32_t(n_frames);
-        t.total_bits = uint32_t(L); t.state_bits = uint32_t(h->prm.K - 1); t.end_state = uint32_t(end_state);
+        t.total_bits = uint32_t(L); t.state_bits = uint32_t(h->prm.K - 1); t.end_state = uint32_t(end_state); t.end_states = end_states;
         t.out = d_out; t.out_stride = out_stride; t.tag_layout = (e->sh == 8 && !e->generic) ? 1u : 0u;     // uint8_t catalogue pair kernels use the tagged butterfly
         traceback_u64_kernel<32><<<unsigned((n_frames + 127) / 128), 128, 0, s>>>(t);
     } else {
         TracebackGroupParams t{};
         t.dec = static_cast<const uint32_t*>(dec); t.dec_rows = uint32_t(dec_rows); t.n_frames = uint32_t(n_frames);
-        t.total_bits = uint32_t(L); t.state_bits = uint32_t(h->prm.K - 1); t.logt = uint32_t(e->logt); t.end_state = uint32_t(end_state);
+        t.total_bits = uint32_t(L); t.state_bits = uint32_t(h->prm.K - 1); t.logt = uint32_t(e->logt); t.end_state = uint32_t(end_state); t.end_states = end_states;
         t.out = d_out; t.out_stride = out_stride;
         // staged kernel: 32 frames per warp; needs the decision buffer padded to whole 64-frame blocks (it is) and PPW <= 16
         constexpr int ROWS = 8;
@@ -344,11 +364,21 @@ int decode_chunk_dev(vitb_decoder* h, const KernelEntry* e, const void* d_symbol
     else VITB_CUDA(h, direct ? e->launch_direct(a, s) : e->launch(a, s));
     VITB_CUDA(h, mark(h, s));
 
+    const uint32_t* end_states = nullptr;
+    if (end_state == VITB_END_STATE_BEST) {
+        VITB_CUDA(h, h->end_states.reserve(n_frames * 4));
+        h->launches++;
+        best_state_kernel<<<unsigned((n_frames + 3) / 4), 128, 0, s>>>(a.metrics, uint32_t(h->n_states), uint32_t(n_frames),
+                                                                        static_cast<uint32_t*>(h->end_states.ptr));
+        VITB_CUDA(h, cudaGetLastError());
+        end_states = static_cast<const uint32_t*>(h->end_states.ptr);
+        end_state = 0;
+    }
     if (d_out && hist) {
         h->launches++;
         TracebackHistParams t{};
         t.dec = static_cast<const uint8_t*>(h->dec.ptr); t.n_periods = uint32_t(n_periods); t.n_frames = uint32_t(n_frames);
-        t.total_bits = uint32_t(L); t.state_bits = uint32_t(K - 1); t.end_state = uint32_t(end_state); t.n_steps = uint32_t(S);
+        t.total_bits = uint32_t(L); t.state_bits = uint32_t(K - 1); t.end_state = uint32_t(end_state); t.end_states = end_states; t.n_steps = uint32_t(S);
         t.hist_bits = uint32_t(hist_bits); t.out = d_out; t.out_stride = (L + 7) / 8;
         // A frame's chain is n_periods dependent memory round trips; small batches cannot hide them, so the chain is cut into
         // segments walked concurrently (warm-up over `overlap` records from a guessed state, verified and repaired afterwards:
@@ -376,12 +406,12 @@ int decode_chunk_dev(vitb_decoder* h, const KernelEntry* e, const void* d_symbol
             traceback_hist_fix_kernel<<<unsigned((n_frames + 127) / 128), 128, 0, s>>>(t, sp);
         }
         VITB_CUDA(h, cudaGetLastError());
-    } else if (d_out) VITB_CUDA(h, launch_traceback(h, e, h->dec.ptr, S, n_frames, L, end_state, d_out, (L + 7) / 8, s));
+    } else if (d_out) VITB_CUDA(h, launch_traceback(h, e, h->dec.ptr, S, n_frames, L, end_state, d_out, (L + 7) / 8, s, end_states));
     VITB_CUDA(h, mark(h, s));
     if (d_acc || d_final) {
         h->launches++;
         gather_results_kernel<<<unsigned((n_frames + 255) / 256), 256, 0, s>>>(a.acc, a.metrics, uint32_t(h->n_states), uint32_t(end_state),
-                                                                              uint32_t(n_frames), d_acc, d_final);
+                                                                              end_states, uint32_t(n_frames), d_acc, d_final);
         VITB_CUDA(h, cudaGetLastError());
     }
     VITB_CUDA(h, mark(h, s));
@@ -402,7 +432,7 @@ int check_batch_args(const vitb_decoder* h, size_t n_frames, size_t L, const vit
     if (*row_stride < used) return VITB_ERR_ARG;
     *start = o ? o->starting_state : 0;
     *end = o ? o->end_state : 0;
-    if (*end >= size_t(h->n_states)) return VITB_ERR_ARG;      // core.h:196, 218
+    if (*end >= size_t(h->n_states) && *end != VITB_END_STATE_BEST) return VITB_ERR_ARG;      // core.h:196, 218
     return VITB_OK;
 }
 
@@ -479,7 +509,7 @@ int vitb_create(const vitb_params* p, vitb_decoder** out) {
 int vitb_destroy(vitb_decoder* h) {
     if (!h) return VITB_OK;
     cudaSetDevice(h->prm.device);
-    for (DeviceBuffer* b : {&h->pk, &h->dec, &h->metrics, &h->acc, &h->d_in, &h->d_out, &h->d_accout, &h->d_finout, &h->map, &h->tb_spec, &h->tb_fin,
+    for (DeviceBuffer* b : {&h->pk, &h->dec, &h->metrics, &h->acc, &h->d_in, &h->d_out, &h->d_accout, &h->d_finout, &h->map, &h->tb_spec, &h->tb_fin, &h->end_states,
                             &h->s_pk, &h->s_dec, &h->s_metrics, &h->s_acc, &h->s_in, &h->s_out, &h->g_tx, &h->g_sym, &h->g_cnt}) b->release();
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     for (cudaEvent_t e : h->copy_ev) cudaEventDestroy(e);
