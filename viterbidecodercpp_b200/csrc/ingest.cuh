@@ -40,42 +40,42 @@ __global__ void __launch_bounds__(INGEST_TILE) ingest_pairs_kernel(const IngestP
     const uint32_t e = e0 + tid;
     int32_t src = -2;                          // -2: beyond the row, -1: punctured
     if (e < p.n_sym) src = p.depuncture_map ? p.depuncture_map[e] : int32_t(e);
-#pragma unroll 8
-    for (int r = 0; r < 64; r++) {
-        const size_t f = size_t(blk) * 64 + r;
-        int32_t v = 0;
-        if (f < p.n_frames) {
-            if (src >= 0) v = int32_t(sym[f * p.row_stride + size_t(src)]);
-            else if (src == -1) v = p.fill_value;
+    // Column `tid` of the tile: one symbol position of 64 consecutive frames.  Everything about the position (received index,
+    // punctured or not) is loop invariant, so the loop over the frames is a pointer walk (this kernel was issue bound at 25
+    // instructions per element when the address was recomputed per frame: profiles/r01_summary.md).
+    const uint32_t rows = (p.n_frames - blk * 64u < 64u) ? (p.n_frames - blk * 64u) : 64u;
+    uint16_t* tcol = tile + tid;
+    if (src >= 0) {
+        const soft_t* q = sym + size_t(blk) * 64 * p.row_stride + size_t(src);
+        if (rows == 64u) {
+#pragma unroll 16
+            for (int r = 0; r < 64; r++) { tcol[r * RS] = uint16_t(uint32_t(int32_t(*q)) << SH); q += p.row_stride; }
+        } else {
+            for (uint32_t r = 0; r < 64u; r++) {
+                tcol[r * RS] = (r < rows) ? uint16_t(uint32_t(int32_t(*q)) << SH) : uint16_t(0);
+                q += p.row_stride;
+            }
         }
-        tile[r * RS + tid] = uint16_t(uint32_t(v) << SH);
+    } else {
+        const uint16_t v = (src == -1) ? uint16_t(uint32_t(p.fill_value) << SH) : uint16_t(0);
+#pragma unroll 16
+        for (uint32_t r = 0; r < 64u; r++) tcol[r * RS] = (r < rows) ? v : uint16_t(0);
     }
     __syncthreads();
     const uint32_t ppw = p.ppw;
     const uint32_t n_valid = (p.n_sym - e0 < uint32_t(INGEST_TILE)) ? (p.n_sym - e0) : uint32_t(INGEST_TILE);
-    if (ppw == 32) {
-        // one warp block per tile: lane = pair, 8 symbols in flight per pass
-        const uint32_t lane = tid & 31, k0 = tid >> 5;
-        uint32_t* out = p.pk + (size_t(blk) * p.n_sym + e0) * 32 + lane;
+    // 32 pairs x 256 symbols leave as runs of (256 * ppw) words, one run per warp block touched by this tile (ppw is a power of two):
+    // word ((wblk * n_sym + e0 + k) << lp) + slot.  A thread keeps its slot and walks k; consecutive threads write consecutive words.
+    const uint32_t lp = 31u - uint32_t(__clz(ppw)), slot = tid & (ppw - 1u), kk = tid >> lp, kstep = uint32_t(INGEST_TILE) >> lp;
+    for (uint32_t wb = 0; wb < (32u >> lp); wb++) {
+        const uint32_t pr = (wb << lp) + slot;               // pair inside the tile
+        const uint16_t* ta = tile + (2u * pr) * RS;
+        uint32_t* outw = p.pk + (((size_t(blk) * (32u >> lp) + wb) * p.n_sym + e0) << lp) + slot;
+        if (n_valid == uint32_t(INGEST_TILE)) {
 #pragma unroll 4
-        for (uint32_t k = k0; k < uint32_t(INGEST_TILE); k += INGEST_TILE / 32) {
-            if (k < n_valid) {
-                const uint32_t a = tile[(2 * lane) * RS + k], b = tile[(2 * lane + 1) * RS + k];
-                out[size_t(k) * 32] = a | (b << 16);
-            }
-        }
-    } else {
-        // 32 pairs x 256 symbols leave as (256 * ppw)-word runs, one run per warp block touched by this tile (ppw is a power of two)
-        const uint32_t lp = 31u - uint32_t(__clz(ppw)), run_shift = 8u + lp;
-#pragma unroll 4
-        for (uint32_t l = tid; l < 32u * INGEST_TILE; l += INGEST_TILE) {
-            const uint32_t wb = l >> run_shift, rem = l & ((1u << run_shift) - 1u), k = rem >> lp, slot = rem & (ppw - 1u);
-            if (k < n_valid) {
-                const uint32_t pr = (wb << lp) + slot;               // pair inside the tile
-                const uint32_t a = tile[(2 * pr) * RS + k], b = tile[(2 * pr + 1) * RS + k];
-                const size_t wblk = size_t(blk) * (32u >> lp) + wb;
-                p.pk[((wblk * p.n_sym + e0 + k) << lp) + slot] = a | (b << 16);
-            }
+            for (uint32_t k = kk; k < uint32_t(INGEST_TILE); k += kstep) outw[size_t(k) << lp] = uint32_t(ta[k]) | (uint32_t(ta[RS + k]) << 16);
+        } else {
+            for (uint32_t k = kk; k < n_valid; k += kstep) outw[size_t(k) << lp] = uint32_t(ta[k]) | (uint32_t(ta[RS + k]) << 16);
         }
     }
 }
