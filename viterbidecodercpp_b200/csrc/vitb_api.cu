@@ -285,24 +285,28 @@ cudaError_t launch_traceback(vitb_decoder* h, const KernelEntry* e, const void* 
         t.total_bits = uint32_t(L); t.state_bits = uint32_t(h->prm.K - 1); t.logt = uint32_t(e->logt); t.end_state = uint32_t(end_state); t.end_states = end_states;
         t.out = d_out; t.out_stride = out_stride;
         // staged kernel: 32 frames per warp; needs the decision buffer padded to whole 64-frame blocks (it is) and PPW <= 16
-        constexpr int ROWS = 8;
+        // two batches of ROWS rows are in flight per warp; with few warps per SM (large frames, small batches) 8 rows leave DRAM
+        // under-subscribed, so 16 are used whenever the shared memory of the 4-warp CTA stays below 160 KB
         const size_t row_words = size_t(16) * (size_t(1) << e->logt) * size_t(e->dec_words);
-        const size_t smem = size_t(4) * 2 * ROWS * row_words * 4;
+        const bool deep = size_t(4) * 2 * 16 * row_words * 4 <= size_t(160) * 1024;
+        const size_t smem = size_t(4) * 2 * (deep ? 16 : 8) * row_words * 4;
         const unsigned grid = unsigned((n_frames + 127) / 128);
         static const bool force_shuffle = getenv("VITB_TRACEBACK_SHUFFLE") != nullptr;
         // the streaming state holds a single warp block (not a padded 64-frame block): only the shuffle kernel stays inside it
         const bool use_shuffle = force_shuffle || dec == h->s_dec.ptr;
+        auto staged = [&](auto kernel) {
+            if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            kernel<<<grid, 128, smem, s>>>(t);
+        };
         if (use_shuffle) {
             const size_t ppw = size_t(32) >> e->logt, n_pairs = (n_frames + 1) / 2, n_wblocks = (n_pairs + ppw - 1) / ppw;
             const unsigned g2 = unsigned((n_wblocks + 3) / 4);
             if (e->dec_words == 1) traceback_group_kernel<1, 16><<<g2, 128, 0, s>>>(t);
             else traceback_group_kernel<2, 16><<<g2, 128, 0, s>>>(t);
         } else if (e->dec_words == 1) {
-            if (smem > 48 * 1024) cudaFuncSetAttribute(traceback_group_staged_kernel<1, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-            traceback_group_staged_kernel<1, ROWS><<<grid, 128, smem, s>>>(t);
+            if (deep) staged(traceback_group_staged_kernel<1, 16>); else staged(traceback_group_staged_kernel<1, 8>);
         } else {
-            if (smem > 48 * 1024) cudaFuncSetAttribute(traceback_group_staged_kernel<2, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-            traceback_group_staged_kernel<2, ROWS><<<grid, 128, smem, s>>>(t);
+            if (deep) staged(traceback_group_staged_kernel<2, 16>); else staged(traceback_group_staged_kernel<2, 8>);
         }
     }
     return cudaGetLastError();
