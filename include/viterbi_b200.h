@@ -151,7 +151,8 @@ int vitb_set_history_kernel(vitb_decoder* h, int enabled);
 /* Traceback of the survivor-history records walks every frame in concurrent segments: each segment warms up over overlap_records
  * records from a guessed state (survivor paths merge) and is verified - and re-walked if it did not merge - against the segment
  * above, so the result is exact.  seg_records = 0 / overlap_records = -1 choose automatically (by batch size / 96 steps); tests use
- * overlap 0 to force the repair path. */
+ * overlap 0 to force the repair path.  Units: history records (8 or 16 steps) for K <= 7, 8 decoded bits / 8 decision rows for the
+ * K = 15 row walk; the lane-group kernels (K = 9) stream whole rows and are not segmented. */
 int vitb_set_traceback_segments(vitb_decoder* h, int seg_records, int overlap_records);
 /* name of the ACS kernel variant selected for this handle, e.g. "acs_pair<K7,R2,u8,scalar-tie>" */
 const char* vitb_kernel_name(const vitb_decoder* h);
