@@ -28,6 +28,17 @@ def test_library_exports_every_declared_symbol():
     assert declared == bound, f"python binding out of sync: {declared ^ bound}"
 
 
+def test_headers_compile_as_c99_and_cpp17(tmp_path):
+    """the drop-in boundary is a C ABI: include/viterbi_b200.h must be plain C; the facade on top of it is header-only C++17"""
+    inc = os.path.join(ROOT, "include")
+    c = tmp_path / "t.c"
+    c.write_text('#include "viterbi_b200.h"\nint main(void) { return VITB_MAX_R > 0 && VITB_END_STATE_BEST != 0 ? 0 : 1; }\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(c)], check=True)
+    cpp = tmp_path / "t.cpp"
+    cpp.write_text('#include "viterbi_cuda/viterbi_decoder_cuda.h"\nint main() { return 0; }\n')
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-fsyntax-only", "-I", inc, str(cpp)], check=True)
+
+
 def test_library_is_built_for_sm_100a():
     out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
