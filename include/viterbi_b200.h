@@ -68,8 +68,8 @@ int vitb_reset(vitb_decoder* h, size_t starting_state);                         
 /* Decoder::update<uint64_t>(base, symbols, N) (scalar.h:28-55): `symbols` is a HOST array of N soft_t, N % R == 0, may be called
  * repeatedly; *accumulated_error receives the sum of renormalisation minima of THIS call. */
 int vitb_update(vitb_decoder* h, const void* symbols, size_t n_symbols, uint64_t* accumulated_error);
-int vitb_get_error(vitb_decoder* h, size_t end_state, uint32_t* error);         /* core.h:195-199 */
-int vitb_chainback(vitb_decoder* h, uint8_t* bytes_out, size_t total_bits, size_t end_state); /* core.h:214-236 */
+int vitb_get_error(vitb_decoder* h, size_t end_state, uint32_t* error);         /* core.h:195-199; VITB_END_STATE_BEST: the minimum */
+int vitb_chainback(vitb_decoder* h, uint8_t* bytes_out, size_t total_bits, size_t end_state); /* core.h:214-236; or VITB_END_STATE_BEST */
 /* public fields of the reference Core, copied out on request */
 int vitb_get_current_decoded_bit(const vitb_decoder* h, size_t* bit);           /* m_current_decoded_bit  core.h:242 */
 int vitb_get_metrics(vitb_decoder* h, uint32_t* metrics_out /* [2^(K-1)] */);   /* m_metrics.get_old()    core.h:240 */

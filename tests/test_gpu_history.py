@@ -224,3 +224,22 @@ def test_best_end_state(cuda_lib, name, decode_type, lanes):
         assert len(set(bests)) > 1
         got = dec.decode_batch(sym, L, end_state=v.VITB_END_STATE_BEST)
         assert_batch_equal(got, (out, acc, fin), f"{name} {decode_type} lanes={lanes} L={L} best end state")
+
+
+@pytest.mark.parametrize("name,decode_type", [("Voyager", "SOFT16"), ("CDMA IS-95A", "HARD8"), ("Cassini", "SOFT16")])
+def test_best_end_state_streaming_calls(cuda_lib, name, decode_type):
+    """get_error / chainback of the streaming API with VITB_END_STATE_BEST (pair, lane-group and K = 15 decision rows)"""
+    code = CODE_BY_NAME[name]
+    dec, dc = make_cuda_decoder(code, decode_type)
+    ora, _ = make_oracle(code, decode_type)
+    L = 203
+    sym = random_symbols(dc, 1, (L + code.K - 1) * code.R, seed=12)[0]
+    for d in (dec, ora):
+        d.set_traceback_length(L)
+        d.reset()
+    assert dec.update(sym) == ora.update(sym)
+    best = int(np.argmin(np.asarray(ora.metrics())))
+    assert best != 0
+    assert dec.get_error(v.VITB_END_STATE_BEST) == ora.get_error(best)
+    assert (dec.chainback(L, v.VITB_END_STATE_BEST) == ora.chainback(L, best)).all()
+    assert (dec.chainback(L, 0) == ora.chainback(L, 0)).all()

@@ -678,10 +678,30 @@ int vitb_update(vitb_decoder* h, const void* symbols, size_t n_symbols, uint64_t
     return VITB_OK;
 }
 
+// best final state of the streaming frame (frame 0 of the streaming block), on the handle's stream
+static int streaming_best_state(vitb_decoder* h, uint32_t* best) {
+    VITB_CUDA(h, h->end_states.reserve(4));
+    h->launches++;
+    best_state_kernel<<<1, 128, 0, h->stream>>>(static_cast<const uint16_t*>(h->s_metrics.ptr), uint32_t(h->n_states), 1u,
+                                                static_cast<uint32_t*>(h->end_states.ptr));
+    VITB_CUDA(h, cudaGetLastError());
+    if (best) {
+        VITB_CUDA(h, cudaMemcpyAsync(best, h->end_states.ptr, 4, cudaMemcpyDeviceToHost, h->stream));
+        VITB_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    return VITB_OK;
+}
+
 int vitb_get_error(vitb_decoder* h, size_t end_state, uint32_t* error) {
     if (!h || !error) return VITB_ERR_ARG;
-    if (end_state >= size_t(h->n_states)) return VITB_ERR_ARG;                              // core.h:196
+    if (end_state >= size_t(h->n_states) && end_state != VITB_END_STATE_BEST) return VITB_ERR_ARG;     // core.h:196
     VITB_CUDA(h, cudaSetDevice(h->prm.device));
+    if (end_state == VITB_END_STATE_BEST) {
+        uint32_t best = 0;
+        const int r = streaming_best_state(h, &best);
+        if (r != VITB_OK) return r;
+        end_state = best;
+    }
     uint16_t v = 0;
     VITB_CUDA(h, cudaMemcpyAsync(&v, static_cast<uint16_t*>(h->s_metrics.ptr) + end_state, 2, cudaMemcpyDeviceToHost, h->stream));
     VITB_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -752,13 +772,20 @@ int vitb_chainback(vitb_decoder* h, uint8_t* bytes_out, size_t total_bits, size_
     if (!h || (!bytes_out && total_bits)) return VITB_ERR_ARG;
     if (h->traceback_length < total_bits) return VITB_ERR_ARG;                              // core.h:216
     if (h->current_decoded_bit < size_t(h->prm.K - 1) + total_bits) return VITB_ERR_STATE;  // core.h:217
-    if (end_state >= size_t(h->n_states)) return VITB_ERR_ARG;                              // core.h:218
+    if (end_state >= size_t(h->n_states) && end_state != VITB_END_STATE_BEST) return VITB_ERR_ARG;     // core.h:218
     if (!total_bits) return VITB_OK;
     VITB_CUDA(h, cudaSetDevice(h->prm.device));
     const size_t nbytes = (total_bits + 7) / 8;
     VITB_CUDA(h, h->s_out.reserve(nbytes));
+    const uint32_t* end_states = nullptr;
+    if (end_state == VITB_END_STATE_BEST) {
+        const int r = streaming_best_state(h, nullptr);
+        if (r != VITB_OK) return r;
+        end_states = static_cast<const uint32_t*>(h->end_states.ptr);
+        end_state = 0;
+    }
     VITB_CUDA(h, launch_traceback(h, h->entry, h->s_dec.ptr, h->traceback_length + size_t(h->prm.K - 1), 1, total_bits, end_state,
-                                  static_cast<uint8_t*>(h->s_out.ptr), nbytes, h->stream));
+                                  static_cast<uint8_t*>(h->s_out.ptr), nbytes, h->stream, end_states));
     VITB_CUDA(h, cudaMemcpyAsync(bytes_out, h->s_out.ptr, nbytes, cudaMemcpyDeviceToHost, h->stream));
     VITB_CUDA(h, cudaStreamSynchronize(h->stream));
     return VITB_OK;
