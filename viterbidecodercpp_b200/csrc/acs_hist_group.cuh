@@ -1,0 +1,251 @@
+// acs_hist_group.cuh -- survivor-history add-compare-select for K = 9 with uint16_t error metrics: ONE FRAME OVER T = 4 LANES.
+//
+// The survivor-history idea of acs_hist.cuh (register = metric << 16 | last <= 16 decisions of the survivor path into that state;
+// a butterfly is 2 adds + 2 fused add-min, no predicates, one record per 16 steps instead of a decision row per step) needs the
+// 32-bit lane format for uint16_t metrics, i.e. one frame per register - and K = 9 has 256 states, too many for one thread.  So the
+// states of a frame are divided among T = 4 lanes exactly like acs_group.cuh divides a frame pair:
+//     position PHI = (q << 2) | t      q = register inside the lane (64 registers), t = lane inside the group
+//     after n steps since the last exchange, logical state s sits at PHI = rotr^n(s)   (8-bit rotation)
+// For n = 0 .. 5 the butterfly partner differs in a register bit (in-place butterflies, no communication); after 6 steps one exchange
+// through shared memory rotates the positions back to PHI = s.  The branch pattern of a butterfly is (compile-time register part) XOR
+// (per-lane part, one value per phase); the lane part is folded into the branch metric table by swapping e_low / e_high.
+//
+// Instruction budget per lane and step: 32 butterflies x 4 + table 16 + exchange 128 / 6 + record 104 / 16 + ~15 = ~185 for 64
+// add-compare-selects of one frame = 2.9 per ACS, against 4.1 for acs_group_kernel<T16> (10 per butterfly of two frames plus its
+// overheads); and traceback reads one halfword per 16 steps instead of streaming every decision row.
+//
+// Records are written in POSITION order (lane t, register q), same layout as acs_hist.cuh with 32 words per lane:
+//     dec = uint32 [n_blocks][n_periods][8][32 lanes][4],  word w of a lane = halfwords [register 2w, register 2w + 1];
+// a block is one warp = 8 frames.  traceback_hist_kernel finds state s of record r at PHI = rotr^m(s), m = (steps done at the end
+// of the record) mod 6.  Whole frames only, symbols fetched directly from 4-byte aligned unpunctured rows (R even).
+#pragma once
+#include <cstdint>
+#include <utility>
+#include <cuda_runtime.h>
+#include "vitb_code.cuh"
+#include "acs_pair.cuh"
+#include "acs_hist.cuh"
+
+namespace vitb {
+
+template <class C>
+struct HistGroupShape {
+    static constexpr int LOGT = 2, T = 4, SB = C::SB, LB = SB - LOGT, NL = 1 << LB, NW = NL / 2, FPW = 32 / T, WARPS = 2;
+    static_assert(SB == 8 && (C::R % 2) == 0, "built for K = 9 codes with an even number of symbols per step");
+    // shared-memory word of position PHI' for frame fw of the warp: rows of 32 words, XOR swizzle so that the 64 writes of a lane
+    // ((t << LB) | q: consecutive q) and its 64 reads ((q << LOGT) | t) both touch 32 distinct banks per warp instruction
+    static __host__ __device__ constexpr uint32_t slot(uint32_t fw, uint32_t phi) {
+        const uint32_t qp = phi >> LOGT, tp = phi & uint32_t(T - 1);
+        return qp * 32u + ((fw * uint32_t(T) + tp) ^ ((qp >> (LB - LOGT)) & uint32_t(T - 1)));
+    }
+};
+
+// one in-place butterfly at compile-time phase PH on registers Q and Q | bit
+template <class C, int PH, bool TIE_SIMD, int Q>
+__device__ __forceinline__ void hg_bfly_at(uint32_t (&x)[HistGroupShape<C>::NL], const uint32_t (&T)[C::NP], const uint32_t (&TT)[C::NP],
+                                           const uint32_t (&V)[C::NP], const uint32_t (&VT)[C::NP]) {
+    using S = HistGroupShape<C>;
+    constexpr int bit = 1 << (S::LB - 1 - PH);
+    if constexpr ((Q & bit) == 0) {
+        constexpr int q0 = Q, q1 = Q | bit;
+        constexpr uint32_t jq = rotl_bits(uint32_t(q0) << S::LOGT, PH, S::SB);   // register-bit part of the old state index
+        constexpr uint32_t pat = bfly_pattern<C>(jq), ipat = (~pat) & uint32_t(C::NP - 1);
+        uint32_t m0, m1;
+        if constexpr (!TIE_SIMD) {
+            const uint32_t b0 = x[q1] + VT[ipat], b1 = x[q1] + TT[pat];        // path 1 tagged                 scalar.h:114,116
+            m0 = __viaddmin_u32(x[q0], T[pat], b0);                             // new state 2j   stays at q0   scalar.h:113,127
+            m1 = __viaddmin_u32(x[q0], V[ipat], b1);                            // new state 2j+1 goes to q1    scalar.h:115,128
+        } else {
+            const uint32_t a0 = x[q0] + TT[pat], a1 = x[q0] + VT[ipat];         // tag on path 0: a tie selects path 1
+            m0 = __viaddmin_u32(x[q1], V[ipat], a0);
+            m1 = __viaddmin_u32(x[q1], T[pat], a1);
+        }
+        x[q0] = m0;
+        x[q1] = m1;
+    }
+}
+
+template <class C, int PH, bool TIE_SIMD, int... Qs>
+__device__ __forceinline__ void hg_bfly_all(uint32_t (&x)[HistGroupShape<C>::NL], const uint32_t (&T)[C::NP], const uint32_t (&TT)[C::NP],
+                                            const uint32_t (&V)[C::NP], const uint32_t (&VT)[C::NP], std::integer_sequence<int, Qs...>) {
+    (hg_bfly_at<C, PH, TIE_SIMD, Qs>(x, T, TT, V, VT), ...);
+}
+
+// one trellis step at phase PH.  fold[i] != 0: the lane part of the branch pattern flips symbol i (e_low and e_high trade places).
+template <class C, int PH, bool TIE_SIMD, bool CONSISTENT>
+__device__ __forceinline__ void hg_step(uint32_t (&x)[HistGroupShape<C>::NL], const uint32_t* sym, const uint32_t fold_bits, const HistConsts& c,
+                                        const uint32_t tag, const uint32_t lane, uint64_t& acc) {
+    using S = HistGroupShape<C>;
+    constexpr int R = C::R, NP = C::NP, NL = S::NL;
+    uint32_t lo[R], hi[R];
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+        const uint32_t l = sym[i] + c.c_low, h = c.c_high - sym[i];        // s - low, high - s  (scalar.h:96-105 for s in [low, high])
+        const bool f = (fold_bits >> (PH * R + i)) & 1u;
+        lo[i] = f ? h : l;
+        hi[i] = f ? l : h;
+    }
+    uint32_t T[NP], TT[NP];
+    HistTable<1, R, R>::run(T, lo, hi);
+#pragma unroll
+    for (int k = 0; k < NP; k++) TT[k] = T[k] + tag;
+    if constexpr (CONSISTENT) {
+        hg_bfly_all<C, PH, TIE_SIMD>(x, T, TT, T, TT, std::make_integer_sequence<int, NL>{});
+    } else {
+        uint32_t V[NP], VT[NP];
+#pragma unroll
+        for (int k = 0; k < NP; k++) { V[k] = T[k] + c.c_inv; VT[k] = TT[k] + c.c_inv; }
+        hg_bfly_all<C, PH, TIE_SIMD>(x, T, TT, V, VT, std::make_integer_sequence<int, NL>{});
+    }
+    // renormalisation (scalar.h:48, 139-153): state 0 sits in register 0 of lane 0 of the group in every phase.  Only those lanes
+    // vote (no shuffle on the per-step critical path); the branch is taken by the whole warp when any of its 8 frames triggers
+    // (about every 12th step), so the shuffles inside are convergent.
+    const bool leader_trig = ((lane & uint32_t(S::T - 1)) == 0u) && (x[0] >= c.thr);
+    if (__any_sync(0xffffffffu, leader_trig)) {
+        const bool trig = __shfl_sync(0xffffffffu, leader_trig ? 1u : 0u, int(lane & ~uint32_t(S::T - 1))) != 0u;
+        uint32_t m = x[0];
+#pragma unroll
+        for (int q = 1; q + 1 < NL; q += 2) m = min(min(m, x[q]), x[q + 1]);
+        m = min(m, x[NL - 1]);
+        m = min(m, __shfl_xor_sync(0xffffffffu, m, 1));
+        m = min(m, __shfl_xor_sync(0xffffffffu, m, 2));
+        const uint32_t sub = trig ? (m & 0xffff0000u) : 0u;
+#pragma unroll
+        for (int q = 0; q < NL; q++) x[q] -= sub;
+        acc += uint64_t(sub >> 16);
+    }
+}
+
+// grid = ceil(n_blocks / WARPS); one warp = 8 frames, lane = 4 * frame + t
+template <class C, bool TIE_SIMD, bool CONSISTENT>
+__global__ void __launch_bounds__(32 * HistGroupShape<C>::WARPS, 7) acs_hist_group_kernel(const AcsParams p) {
+    using S = HistGroupShape<C>;
+    constexpr int R = C::R, NL = S::NL, NW = S::NW, LB = S::LB, LOGT = S::LOGT, T = S::T, SB = S::SB, HB = 16;
+    __shared__ uint32_t xch[S::WARPS][NL * 32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, blk = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (blk >= p.n_blocks) return;
+    const uint32_t fw = lane >> LOGT, t = lane & uint32_t(T - 1);
+    const size_t f = size_t(blk) * S::FPW + fw;
+    const HistConsts c = hist_consts<1>(p);
+    uint32_t* my_xch = xch[warp];
+
+    // lane part of the branch pattern, per phase and symbol: bit (n * R + i)
+    uint32_t fold_bits = 0;
+#pragma unroll
+    for (int n = 0; n < LB; n++) fold_bits |= bfly_pattern_dyn<C>(rotl_bits(t, n, SB)) << (n * R);
+
+    uint32_t x[NL];
+    uint64_t acc = 0;
+    {
+        const uint32_t s0 = p.start_state & uint32_t(C::NS - 1);       // core.h:209-210; phase 0: position = state
+#pragma unroll
+        for (int q = 0; q < NL; q++) x[q] = (((uint32_t(q) << LOGT) | t) == s0) ? c.init_start : c.init_other;
+    }
+
+    const uint32_t n_periods = (p.n_steps + HB - 1) / HB;
+    uint32_t* rec = static_cast<uint32_t*>(p.dec) + size_t(blk) * n_periods * (32 * NW) + lane * 4;
+
+    // symbols: the 4 lanes of a frame read the same row (L1 broadcast).  One exchange period = 6 steps = WPP whole words of the row
+    // (R is even), loaded a period ahead; inside the period every index is a compile-time constant.
+    constexpr int WPP = LB * R / 2;                               // words per period
+    uint32_t cur[WPP], nxt[WPP];
+    const size_t lastf = size_t(p.n_frames) - 1, ld = f < lastf ? f : lastf;      // padding frames re-read the last frame
+    const uint32_t* row = reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(p.sym) + ld * p.sym_row_bytes);
+    const uint32_t maxw = uint32_t((p.sym_total_bytes - ld * p.sym_row_bytes - 4) >> 2);     // loads are clamped to stay inside the array
+#pragma unroll
+    for (int j = 0; j < WPP; j++) nxt[j] = __ldg(row + (uint32_t(j) < maxw ? uint32_t(j) : maxw));
+
+    // exchange after LB phases: the value at (q, t) moves to PHI' = (t << LB) | q, read back as PHI' = (q << LOGT) | t.  With the
+    // swizzle of HistGroupShape::slot both sides reduce to four base addresses per lane plus compile-time offsets:
+    //   write (q, t): row (t << 4) | (q >> 2), column (4 fw + (q & 3)) ^ t      read q: row q, column (4 fw + t) ^ ((q >> 4) & 3)
+    uint32_t* wr_base[4];
+    const uint32_t* rd_base[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        wr_base[k] = my_xch + (t << 4) * 32u + ((fw * 4u + uint32_t(k)) ^ t);
+        rd_base[k] = my_xch + ((fw * 4u + t) ^ uint32_t(k));
+    }
+    auto exchange = [&]() {
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < NL; q++) wr_base[q & 3][(q >> 2) * 32] = x[q];
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < NL; q++) x[q] = rd_base[(q >> 4) & 3][q * 32];
+    };
+
+    uint32_t tag = 1u, pst = 0, r = 0;
+    // history record of the period that just ended (position order), then clear the history fields
+    auto emit_record = [&]() {
+        uint32_t w[NW];
+#pragma unroll
+        for (int i = 0; i < NW; i++) {
+            w[i] = __byte_perm(x[2 * i], x[2 * i + 1], 0x5410u);
+            if constexpr (TIE_SIMD) w[i] = ~w[i] & (0x00010001u * ((1u << pst) - 1u));      // the tag marked path 0: decision = !tag
+        }
+        uint32_t* dst = rec + size_t(r) * (32 * NW);
+#pragma unroll
+        for (int v = 0; v < NW / 4; v++) *reinterpret_cast<uint4*>(dst + v * 128) = make_uint4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
+#pragma unroll
+        for (int q = 0; q < NL; q++) x[q] &= 0xffff0000u;
+        r++;
+        tag = 1u;
+        pst = 0;
+    };
+    // one step at compile-time phase PH of the period that starts at step n0; records fill up (16 steps) only after odd phases
+    auto do_phase = [&](auto ph_tag, uint32_t n0) {
+        constexpr int PH = decltype(ph_tag)::value;
+        if (n0 + uint32_t(PH) >= p.n_steps) return;
+        uint32_t sym[R];
+#pragma unroll
+        for (int i = 0; i < R; i++) {
+            const int e = PH * R + i;
+            sym[i] = (e & 1) ? (cur[e >> 1] & 0xffff0000u) : (cur[e >> 1] << 16);
+        }
+        hg_step<C, PH, TIE_SIMD, CONSISTENT>(x, sym, fold_bits, c, tag, lane, acc);
+        tag <<= 1;
+        pst++;
+        if constexpr (PH == 1 || PH == 3) {         // (after phase 5 the record is cut behind the exchange, see the loop)
+            if (pst == uint32_t(HB)) emit_record();
+        }
+    };
+
+    uint32_t n0 = 0;
+#pragma unroll 1
+    for (; n0 < p.n_steps; n0 += LB) {
+#pragma unroll
+        for (int j = 0; j < WPP; j++) cur[j] = nxt[j];
+        if (n0 + LB < p.n_steps) {
+            const uint32_t w0 = ((n0 / uint32_t(LB)) + 1u) * uint32_t(WPP);
+#pragma unroll
+            for (int j = 0; j < WPP; j++) {
+                const uint32_t w = w0 + uint32_t(j);
+                nxt[j] = __ldg(row + (w < maxw ? w : maxw));
+            }
+        }
+        do_phase(std::integral_constant<int, 0>{}, n0);
+        do_phase(std::integral_constant<int, 1>{}, n0);
+        do_phase(std::integral_constant<int, 2>{}, n0);
+        do_phase(std::integral_constant<int, 3>{}, n0);
+        do_phase(std::integral_constant<int, 4>{}, n0);
+        do_phase(std::integral_constant<int, 5>{}, n0);
+        if (n0 + LB <= p.n_steps) {                 // a full period ran: positions back to PHI = s
+            exchange();
+            if (pst == uint32_t(HB)) emit_record(); // records are cut in the layout the traceback expects: PHI = rotr^(steps mod 6)(s)
+        }
+    }
+    if (pst) emit_record();                         // last, partial record (its pst is still needed for the SIMD tie-break mask)
+    const uint32_t ph = p.n_steps % uint32_t(LB);
+
+    // final metrics in logical order: state s sits at PHI = rotr^ph(s)   (core.h:195-199 reads old_metrics[end_state])
+    uint16_t* m = p.metrics + f * C::NS;
+    switch (ph) {
+#define VITB_HG_WB(PH_) case PH_: _Pragma("unroll") for (int q = 0; q < NL; q++) m[rotl_bits((uint32_t(q) << LOGT) | t, PH_, SB)] = uint16_t(x[q] >> 16); break;
+        VITB_HG_WB(0) VITB_HG_WB(1) VITB_HG_WB(2) VITB_HG_WB(3) VITB_HG_WB(4)
+        default: _Pragma("unroll") for (int q = 0; q < NL; q++) m[rotl_bits((uint32_t(q) << LOGT) | t, 5, SB)] = uint16_t(x[q] >> 16); break;
+#undef VITB_HG_WB
+    }
+    if (t == 0) p.acc[f] = acc;
+}
+
+}  // namespace vitb

@@ -441,6 +441,7 @@ struct TracebackHistParams {
     const uint32_t* end_states;   // nullable: per-frame end states (VITB_END_STATE_BEST), overrides end_state
     uint32_t n_steps;         // S = L + SB
     uint32_t hist_bits;       // HB: 8 (two frames per lane, 64 per block) or 16 (one frame per lane, 32 per block)
+    uint32_t logt;            // acs_hist_group.cuh: a frame spans 2^logt lanes (HB = 16), records in position order; else 0
     uint8_t* out;
     size_t out_stride;
 };
@@ -453,19 +454,21 @@ struct HistFrame {
     const uint8_t* base;      // first record of the frame's warp block
     uint8_t* out;
     size_t rec_bytes;
-    uint32_t lane, half, vw_log, SB, HB, r_last, nv, VS, n_out, end_state;
+    uint32_t lane, half, vw_log, SB, HB, r_last, nv, VS, n_out, end_state, logt, n_steps;
     bool wide;
 };
 
 __device__ __forceinline__ HistFrame hist_frame(const TracebackHistParams& p, uint32_t f) {
     HistFrame c;
     c.SB = p.state_bits; c.HB = p.hist_bits; c.wide = c.HB == 16;
-    const uint32_t NS = 1u << c.SB, nw = NS / 2;
+    c.logt = p.logt; c.n_steps = p.n_steps;
+    const uint32_t NS = 1u << c.SB, nw = (NS >> c.logt) / 2;     // record words per lane
     c.vw_log = nw >= 4 ? 2u : (nw == 2 ? 1u : 0u);
-    c.lane = c.wide ? (f & 31u) : ((f & 63u) >> 1);
+    const uint32_t fpb_log = c.wide ? (5u - c.logt) : 6u;        // frames per warp block: 64, 32, or 32 >> logt
+    c.lane = c.wide ? ((f & ((1u << fpb_log) - 1u)) << c.logt) : ((f & 63u) >> 1);      // first lane of the frame
     c.half = c.wide ? 0u : (f & 1u);
-    c.rec_bytes = size_t(64) * NS;                               // one warp block, one period (both formats)
-    c.base = p.dec + size_t(c.wide ? (f >> 5) : (f >> 6)) * p.n_periods * c.rec_bytes;
+    c.rec_bytes = (size_t(64) * NS) >> c.logt;                   // one warp block, one period
+    c.base = p.dec + size_t(f >> fpb_log) * p.n_periods * c.rec_bytes;
     c.out = p.out + size_t(f) * p.out_stride;
     c.n_out = (p.total_bits + 7) / 8;
     c.r_last = (p.n_steps - 1) / c.HB;
@@ -483,9 +486,18 @@ __device__ __forceinline__ uint32_t hist_walk(const HistFrame& c, int64_t r_hi, 
         const bool last = uint32_t(r) == c.r_last;
         // history of the record above, as far as this record's output needs it
         const uint32_t hnext = last ? ((c.VS >> HB) & hmask) : (SB ? (__brev(state) >> (32 - SB)) : 0u);
-        // word w = state >> 1 of the lane: FMT 0 bytes [A:2w, B:2w, A:2w+1, B:2w+1], FMT 1 halfwords [2w, 2w+1]
-        const uint32_t w = state >> 1;
-        const uint32_t off = ((((w >> c.vw_log) << 5) + c.lane) << (c.vw_log + 2)) + ((w & ((1u << c.vw_log) - 1u)) << 2) + ((state & 1u) << 1) + c.half;
+        // where the history of `state` sits in the record: register `reg` of lane `ln`.  One lane per frame (pair): register = state.
+        // Frame over 2^logt lanes (acs_hist_group.cuh): position PHI = rotr^m(state), m = steps done at the end of the record mod LB.
+        uint32_t reg = state, ln = c.lane;
+        if (c.logt) {
+            const uint32_t done = last ? c.n_steps : HB * (uint32_t(r) + 1u);
+            const uint32_t phi = rotr_rt(state, done % (SB - c.logt), SB);
+            reg = phi >> c.logt;
+            ln = c.lane | (phi & ((1u << c.logt) - 1u));
+        }
+        // word w = reg >> 1 of the lane: FMT 0 bytes [A:2w, B:2w, A:2w+1, B:2w+1], FMT 1 halfwords [2w, 2w+1]
+        const uint32_t w = reg >> 1;
+        const uint32_t off = ((((w >> c.vw_log) << 5) + ln) << (c.vw_log + 2)) + ((w & ((1u << c.vw_log) - 1u)) << 2) + ((reg & 1u) << 1) + c.half;
         const uint8_t* ptr = c.base + size_t(r) * c.rec_bytes + off;
         const uint32_t h = c.wide ? uint32_t(*reinterpret_cast<const uint16_t*>(ptr)) : uint32_t(*ptr);
         uint32_t hext = h;

@@ -32,6 +32,7 @@ static const std::vector<KernelEntry>& registry() {
         register_k9r4_t8(entries); register_k9r4_t16(entries);
         register_k15r6_cta512(entries); register_k15r6_cta1024(entries);
         register_generic(entries);
+        register_k9_hist_group(entries);
     });
     return entries;
 }
@@ -86,6 +87,7 @@ struct vitb_decoder {
     vitb_params prm{};
     std::vector<const KernelEntry*> variants;   // every compiled lanes-per-pair variant of this code/config, ascending logt
     const KernelEntry* entry = nullptr;         // variant used by the single-frame streaming API (fixes its decision layout)
+    const KernelEntry* hg_entry = nullptr;      // frame-over-4-lanes survivor-history kernel (K = 9, uint16_t metrics), batch calls only
     const KernelEntry* last_batch = nullptr;    // variant the last batch call selected
     bool last_batch_hist = false;               // ... and whether it ran as the survivor-history kernel (acs_hist.cuh)
     std::string name_buf;
@@ -137,7 +139,7 @@ std::vector<const KernelEntry*> find_entries(const vitb_params& p) {
     const int consistent = ((p.soft_decision_max_error & mask) == ((span * uint32_t(p.R)) & mask)) ? 1 : 0;
     const uint32_t kmask = (p.K >= 32) ? 0xffffffffu : ((1u << p.K) - 1u);
     for (const KernelEntry& e : registry()) {
-        if (e.generic || e.K != p.K || e.R != p.R || e.sh != sh || e.tie != (p.tie_break ? 1 : 0) || e.consistent != consistent) continue;
+        if (e.generic || e.layout == LAYOUT_HISTGROUP || e.K != p.K || e.R != p.R || e.sh != sh || e.tie != (p.tie_break ? 1 : 0) || e.consistent != consistent) continue;
         bool same = true;
         for (int i = 0; i < p.R; i++) same = same && ((e.G[i] & kmask) == (p.G[i] & kmask));
         if (same) out.push_back(&e);
@@ -148,6 +150,21 @@ std::vector<const KernelEntry*> find_entries(const vitb_params& p) {
     }
     std::sort(out.begin(), out.end(), [](const KernelEntry* a, const KernelEntry* b) { return a->logt < b->logt; });
     return out;
+}
+
+// the frame-over-4-lanes survivor-history kernel of this code, if it has one (K = 9, uint16_t metrics): batch calls only
+const KernelEntry* find_hist_group(const vitb_params& p) {
+    if (p.soft_bytes != 2) return nullptr;
+    const uint32_t span = uint32_t(p.soft_decision_high - p.soft_decision_low);
+    const int consistent = ((p.soft_decision_max_error & 0xffffu) == ((span * uint32_t(p.R)) & 0xffffu)) ? 1 : 0;
+    const uint32_t kmask = (p.K >= 32) ? 0xffffffffu : ((1u << p.K) - 1u);
+    for (const KernelEntry& e : registry()) {
+        if (e.layout != LAYOUT_HISTGROUP || e.K != p.K || e.R != p.R || e.tie != (p.tie_break ? 1 : 0) || e.consistent != consistent) continue;
+        bool same = true;
+        for (int i = 0; i < p.R; i++) same = same && ((e.G[i] & kmask) == (p.G[i] & kmask));
+        if (same) return &e;
+    }
+    return nullptr;
 }
 
 // Variant for a batch of n_frames.  Measured on B200 (profiles/r01_summary.md): fewer lanes per pair = fewer instructions per ACS,
@@ -330,14 +347,23 @@ int decode_chunk_dev(vitb_decoder* h, const KernelEntry* e, const void* d_symbol
     const unsigned n_b64 = unsigned((n_frames + 63) / 64);
     // one-thread-per-pair entries: survivor-history records (acs_hist.cuh) instead of decision rows; same bytes per frame and step.
     // uint8_t metrics: warp block = 64 frames, 8-step records; uint16_t metrics: warp block = 32 frames, 16-step records.
+    // K = 9 with uint16_t metrics: the frame-over-4-lanes history kernel (acs_hist_group.cuh) when the symbols can be fetched directly
+    // and the batch fills the GPU with 8 frames per warp, or when that variant was pinned with vitb_set_variant(h, 4)
+    const size_t row_bytes0 = row_stride * size_t(h->prm.soft_bytes);
+    const bool direct_ok = getenv("VITB_NO_DIRECT") == nullptr && !h->n_depunctured && (row_bytes0 % 4 == 0) && row_bytes0 >= 4 &&
+                           (reinterpret_cast<uintptr_t>(d_symbols) % 4 == 0);
+    const bool hg = h->use_hist && h->hg_entry && direct_ok &&
+                    (h->forced_logt == h->hg_entry->logt || (h->forced_logt < 0 && (n_frames + 7) / 8 >= size_t(h->n_sm) * 2));
+    if (hg) { e = h->hg_entry; h->last_batch = e; }
     const bool hist = h->use_hist && e->launch_hist != nullptr;
     const bool hist_wide = hist && e->sh == 0;
     h->last_batch_hist = hist;
     const size_t hist_bits = hist_wide ? 16 : 8, n_periods = (S + hist_bits - 1) / hist_bits;
     const unsigned ppw = hist_wide ? 16u : unsigned(e->ppw);
-    const unsigned n_wblocks = n_b64 * (32u / ppw);
+    const unsigned n_wblocks = hg ? unsigned((n_frames + 7) / 8) : n_b64 * (32u / ppw);
     VITB_CUDA(h, h->pk.reserve(size_t(n_b64) * n_sym * 32 * 4));
-    VITB_CUDA(h, h->dec.reserve(hist ? size_t(n_wblocks) * n_periods * 64 * size_t(h->n_states) : size_t(n_b64) * dec_bytes_per_block64(e, S)));
+    VITB_CUDA(h, h->dec.reserve(hist ? size_t(n_wblocks) * n_periods * ((64 * size_t(h->n_states)) >> (hg ? e->logt : 0))
+                                     : size_t(n_b64) * dec_bytes_per_block64(e, S)));
     VITB_CUDA(h, h->metrics.reserve(size_t(n_b64) * 64 * h->n_states * 2));
     VITB_CUDA(h, h->acc.reserve(size_t(n_b64) * 64 * 8));
 
@@ -363,7 +389,7 @@ int decode_chunk_dev(vitb_decoder* h, const KernelEntry* e, const void* d_symbol
     a.metrics = static_cast<uint16_t*>(h->metrics.ptr); a.acc = static_cast<uint64_t*>(h->acc.ptr);
     a.n_blocks = n_wblocks; a.n_steps = uint32_t(S); a.dec_rows = uint32_t(S); a.dec_row0 = 0; a.resume = 0; a.start_state = uint32_t(start_state);
     h->launches++;
-    if (hist) VITB_CUDA(h, direct ? e->launch_hist_direct(a, s) : e->launch_hist(a, s));
+    if (hist) VITB_CUDA(h, (direct && !hg) ? e->launch_hist_direct(a, s) : e->launch_hist(a, s));    // the hist-group launcher always fetches directly
     else if (e->generic) VITB_CUDA(h, e->launch_generic(a, h->gcode, s));
     else VITB_CUDA(h, direct ? e->launch_direct(a, s) : e->launch(a, s));
     VITB_CUDA(h, mark(h, s));
@@ -383,7 +409,7 @@ int decode_chunk_dev(vitb_decoder* h, const KernelEntry* e, const void* d_symbol
         TracebackHistParams t{};
         t.dec = static_cast<const uint8_t*>(h->dec.ptr); t.n_periods = uint32_t(n_periods); t.n_frames = uint32_t(n_frames);
         t.total_bits = uint32_t(L); t.state_bits = uint32_t(K - 1); t.end_state = uint32_t(end_state); t.end_states = end_states; t.n_steps = uint32_t(S);
-        t.hist_bits = uint32_t(hist_bits); t.out = d_out; t.out_stride = (L + 7) / 8;
+        t.hist_bits = uint32_t(hist_bits); t.logt = hg ? uint32_t(e->logt) : 0u; t.out = d_out; t.out_stride = (L + 7) / 8;
         // A frame's chain is n_periods dependent memory round trips; small batches cannot hide them, so the chain is cut into
         // segments walked concurrently (warm-up over `overlap` records from a guessed state, verified and repaired afterwards:
         // traceback.cuh).  About 128 K threads saturate DRAM; the warm-up is kept below a quarter of the walk.
@@ -489,6 +515,7 @@ int vitb_create(const vitb_params* p, vitb_decoder** out) {
     h->prm = *p;
     h->variants = found;
     h->entry = e;
+    h->hg_entry = find_hist_group(*p);
     if (const char* f = getenv("VITB_FORCE_LOGT")) h->forced_logt = atoi(f);
     h->n_states = 1 << (p->K - 1);
     h->sh = e->sh;
@@ -540,6 +567,7 @@ int vitb_set_variant(vitb_decoder* h, int lanes_per_pair) {
     for (const KernelEntry* e : h->variants) {
         if ((1 << e->logt) == lanes_per_pair) { h->forced_logt = e->logt; return VITB_OK; }
     }
+    if (h->hg_entry && (1 << h->hg_entry->logt) == lanes_per_pair) { h->forced_logt = h->hg_entry->logt; return VITB_OK; }
     return VITB_ERR_UNSUPPORTED;
 }
 
@@ -559,6 +587,10 @@ int vitb_set_history_kernel(vitb_decoder* h, int enabled) {
 int vitb_get_variants(const vitb_decoder* h, int* lanes_per_pair, int capacity) {
     if (!h) return VITB_ERR_ARG;
     int n = 0;
+    if (h->hg_entry) {          // batch-only variant, listed first (fewest lanes)
+        if (lanes_per_pair && n < capacity) lanes_per_pair[n] = 1 << h->hg_entry->logt;
+        n++;
+    }
     for (const KernelEntry* e : h->variants) {
         if (lanes_per_pair && n < capacity) lanes_per_pair[n] = 1 << e->logt;
         n++;

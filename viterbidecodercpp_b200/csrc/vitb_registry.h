@@ -11,10 +11,11 @@
 #include "acs_group.cuh"
 #include "acs_cta.cuh"
 #include "acs_generic.cuh"
+#include "acs_hist_group.cuh"
 
 namespace vitb {
 
-enum { LAYOUT_PAIR = 0, LAYOUT_GROUP = 1, LAYOUT_CTA = 2 };
+enum { LAYOUT_PAIR = 0, LAYOUT_GROUP = 1, LAYOUT_CTA = 2, LAYOUT_HISTGROUP = 3 };
 
 struct KernelEntry {
     int K, R;
@@ -155,9 +156,36 @@ KernelEntry make_generic_entry(const char* name) {
     VEC.push_back(make_generic_entry<KK, 0, true>("acs_generic<" TAG ",T1,u16,simd-tie>"));                \
     VEC.push_back(make_generic_entry<KK, 8, true>("acs_generic<" TAG ",T1,u8,simd-tie>"));
 
+// survivor-history kernel with a frame over 4 lanes (acs_hist_group.cuh): K = 9, uint16_t metrics, whole-frame batch calls with
+// directly fetchable symbols only - it has no decision-row form, so it is not one of the handle's streaming variants
+template <class C, bool TIE_SIMD, bool CONSISTENT>
+cudaError_t launch_hist_group(const AcsParams& p, cudaStream_t s) {
+    constexpr unsigned W = HistGroupShape<C>::WARPS;
+    acs_hist_group_kernel<C, TIE_SIMD, CONSISTENT><<<(p.n_blocks + W - 1) / W, 32 * W, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+template <class C, bool TIE_SIMD, bool CONSISTENT>
+KernelEntry make_hist_group_entry(const char* name) {
+    KernelEntry e{};
+    e.K = C::K; e.R = C::R;
+    for (int i = 0; i < C::R; i++) e.G[i] = C::G[i];
+    e.sh = 0; e.tie = TIE_SIMD ? 1 : 0; e.consistent = CONSISTENT ? 1 : 0; e.logt = HistGroupShape<C>::LOGT; e.name = name;
+    e.layout = LAYOUT_HISTGROUP; e.ppw = 0; e.dec_words = 0;
+    e.launch_hist = &launch_hist_group<C, TIE_SIMD, CONSISTENT>;
+    return e;
+}
+
+#define VITB_HIST_GROUP_VARIANTS(VEC, CODE, TAG)                                                            \
+    VEC.push_back(make_hist_group_entry<CODE, false, true>("acs<" TAG ",T4,u16,scalar-tie>"));               \
+    VEC.push_back(make_hist_group_entry<CODE, true, true>("acs<" TAG ",T4,u16,simd-tie>"));                  \
+    VEC.push_back(make_hist_group_entry<CODE, false, false>("acs<" TAG ",T4,u16,scalar-tie,cinv>"));         \
+    VEC.push_back(make_hist_group_entry<CODE, true, false>("acs<" TAG ",T4,u16,simd-tie,cinv>"));
+
 // one translation unit per code family and lanes-per-pair setting (parallel compilation)
 void register_small(std::vector<KernelEntry>& v);
 void register_generic(std::vector<KernelEntry>& v);
+void register_k9_hist_group(std::vector<KernelEntry>& v);
 void register_k7r2_t1(std::vector<KernelEntry>& v);
 void register_k7r2_t2(std::vector<KernelEntry>& v);
 void register_k7r2_t4(std::vector<KernelEntry>& v);
