@@ -132,6 +132,40 @@ def test_exchange_swizzle_is_conflict_free():
         assert seen == set(range(NL * 32))
     for SB, g in [(4, 2), (6, 1), (6, 2), (6, 3), (8, 3), (8, 4), (8, 5)]:
         check(SB, g)
+    check(8, 2)       # csrc/acs_hist_group.cuh (HistGroupShape::slot): one frame over 4 lanes, 64 registers per lane
+
+
+def test_hist_group_exchange_base_addresses_match_the_slot_function():
+    """acs_hist_group_kernel addresses its exchange through four base pointers per lane plus compile-time offsets; they must be the
+    slot function above: write (q, t) -> PHI' = (t << 6) | q, read q -> PHI' = (q << 2) | t"""
+    g, LB = 2, 6
+    T = 1 << g
+
+    def slot(fw, phi):
+        qp, tp = phi >> g, phi & (T - 1)
+        return qp * 32 + ((fw * T + tp) ^ ((qp >> (LB - g)) & (T - 1)))
+    for lane in range(32):
+        fw, t = lane >> g, lane & (T - 1)
+        wr_base = [(t << 4) * 32 + ((fw * 4 + k) ^ t) for k in range(4)]
+        rd_base = [((fw * 4 + t) ^ k) for k in range(4)]
+        for q in range(64):
+            assert wr_base[q & 3] + (q >> 2) * 32 == slot(fw, (t << LB) | q)
+            assert rd_base[(q >> 4) & 3] + q * 32 == slot(fw, (q << g) | t)
+
+
+def test_hist_group_record_position_of_a_state():
+    """position algebra shared by acs_hist_group_kernel and traceback_hist_kernel: after n steps since the last exchange logical state s
+    sits at PHI = rotr^n(s) (8-bit rotation); an in-place butterfly at phase n pairs positions that differ in bit 7 - n and leaves new
+    state 2j at the position of old j, 2j + 1 at the position of old j + 128"""
+    SB = 8
+    mask = (1 << SB) - 1
+    rotr = lambda v, r: ((v >> (r % SB)) | (v << (SB - r % SB))) & mask if r % SB else v
+    for n in range(6):
+        for j in range(128):
+            p0, p1 = rotr(j, n), rotr(j + 128, n)
+            assert p0 ^ p1 == 1 << (SB - 1 - n)                      # partners differ in the phase bit
+            assert rotr((2 * j) & mask, n + 1) == p0                 # new state 2j stays where old j was
+            assert rotr((2 * j + 1) & mask, n + 1) == p1             # new state 2j+1 goes where old j+128 was
 
 
 def test_cta_exchange_skew_is_conflict_free():
