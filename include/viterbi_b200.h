@@ -92,7 +92,11 @@ typedef struct vitb_batch_opts {
 /* host pointers: H2D copy, kernels, D2H copy, synchronous */
 int vitb_decode_batch(vitb_decoder* h, const void* symbols, size_t n_frames, size_t total_bits, const vitb_batch_opts* opts,
                       uint8_t* out_bytes, uint64_t* acc_error, uint32_t* final_error);
-/* device pointers on the handle's device, enqueued on `stream` (a cudaStream_t passed as void*; NULL = default stream), asynchronous */
+/* device pointers on the handle's device, enqueued on `stream` (a cudaStream_t passed as void*; NULL = default stream), asynchronous.
+ * All batch calls of ONE handle share its device workspace, so the library orders them on the device: a call enqueued on another
+ * stream first waits (cudaStreamWaitEvent) for the previous batch call of the same handle.  Calls on one handle therefore never
+ * overlap each other, whatever streams they use; to overlap two batches (double buffering) use two handles.  The host side of a
+ * handle stays single-threaded. */
 int vitb_decode_batch_dev(vitb_decoder* h, const void* d_symbols, size_t n_frames, size_t total_bits, const vitb_batch_opts* opts,
                           uint8_t* d_out_bytes, uint64_t* d_acc_error, uint32_t* d_final_error, void* stream);
 

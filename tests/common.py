@@ -36,3 +36,25 @@ def assert_batch_equal(got, want, what=""):
     assert bad.size == 0, f"{what}: decoded bytes differ in {bad.size}/{gb.shape[0]} frames (first {bad[:5]})"
     assert (ga == wa).all(), f"{what}: accumulated error differs in {int((ga != wa).sum())} frames"
     assert (gf == wf).all(), f"{what}: final error differs in {int((gf != wf).sum())} frames"
+
+
+def random_symbols(dc, n_frames, n_sym, seed, pad=0):
+    rng = np.random.default_rng(seed)
+    dt = np.int8 if dc.soft_bytes == 1 else np.int16
+    s = rng.integers(dc.soft_decision_low, dc.soft_decision_high + 1, size=(n_frames, n_sym + pad)).astype(dt)
+    return s
+
+
+def oracle_batch(ora, code, sym, L, start=0, end=0):
+    """the call protocol of run_simple.cpp:76-80 per frame, with explicit start / end states (core.h:195-236)"""
+    n = sym.shape[0]
+    out = np.zeros((n, (L + 7) // 8), dtype=np.uint8)
+    acc = np.zeros(n, dtype=np.uint64)
+    fin = np.zeros(n, dtype=np.uint32)
+    ora.set_traceback_length(L)
+    for f in range(n):
+        ora.reset(start)
+        acc[f] = ora.update(sym[f])
+        fin[f] = ora.get_error(end)
+        out[f] = ora.chainback(L, end)
+    return out, acc, fin

@@ -74,3 +74,21 @@ def test_full_size_noisy_variants_agree_and_sample_matches_oracle(cuda_lib, name
         dep = full
     want = ora.decode_frames(dep, idx.size, L)
     assert_batch_equal((ref[0][idx], ref[1][idx], ref[2][idx]), want, f"{name} sample vs oracle")
+
+
+@pytest.mark.parametrize("ebno", [1.0, 4.0])
+def test_cfg5_full_length_noisy_frames_match_oracle(cuda_lib, ebno):
+    """Cassini K=15 frames at BASELINE.json's FULL length (16384 bits, ~130 renormalisations per frame: the speculation / rollback /
+    replay path of csrc/acs_cta.cuh and the 18-segment traceback) against the scalar oracle, bit for bit; 9 frames so that the last
+    CTA holds a frame pair with one padding frame."""
+    code = CODE_BY_NAME["Cassini"]
+    dec, dc = make_cuda_decoder(code, "SOFT16")
+    ora, _ = make_oracle(code, "SOFT16")
+    F, L = 9, 16384
+    tx, sym = synth.make_frames(code.K, code.R, code.G, F, L, dc.soft_decision_high, dc.soft_decision_low, dc.soft_bytes, ebno, 4242)
+    want = ora.decode_frames(sym, F, L)
+    assert int(want[1].min()) > 0          # every frame renormalised
+    for lanes in dec.variants:
+        dec.set_variant(lanes)
+        got = dec.decode_batch(sym, L)
+        assert_batch_equal(got, want, f"cfg5 full length Eb/N0={ebno} dB variant {lanes}")

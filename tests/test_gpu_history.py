@@ -7,32 +7,10 @@ import numpy as np
 import pytest
 
 import viterbidecodercpp_b200 as v
-from common import CODE_BY_NAME, PAIR_CODES, assert_batch_equal, make_cuda_decoder, make_oracle
+from common import CODE_BY_NAME, PAIR_CODES, assert_batch_equal, make_cuda_decoder, make_oracle, oracle_batch, random_symbols
 from oracle_binding import MODE_SCALAR, MODE_SIMD
 
 pytestmark = pytest.mark.gpu
-
-
-def random_symbols(dc, n_frames, n_sym, seed, pad=0):
-    rng = np.random.default_rng(seed)
-    dt = np.int8 if dc.soft_bytes == 1 else np.int16
-    s = rng.integers(dc.soft_decision_low, dc.soft_decision_high + 1, size=(n_frames, n_sym + pad)).astype(dt)
-    return s
-
-
-def oracle_batch(ora, code, sym, L, start=0, end=0):
-    """the call protocol of run_simple.cpp:76-80 per frame, with explicit start / end states (core.h:195-236)"""
-    n = sym.shape[0]
-    out = np.zeros((n, (L + 7) // 8), dtype=np.uint8)
-    acc = np.zeros(n, dtype=np.uint64)
-    fin = np.zeros(n, dtype=np.uint32)
-    ora.set_traceback_length(L)
-    for f in range(n):
-        ora.reset(start)
-        acc[f] = ora.update(sym[f])
-        fin[f] = ora.get_error(end)
-        out[f] = ora.chainback(L, end)
-    return out, acc, fin
 
 
 @pytest.mark.parametrize("decode_type", ["SOFT16", "SOFT8", "HARD8"])
@@ -51,6 +29,28 @@ def test_history_kernel_every_record_residue(cuda_lib, name, decode_type):
         got = dec.decode_batch(sym, L)
         assert dec.kernel_name.startswith("acs_hist<"), dec.kernel_name
         assert_batch_equal(got, want, f"{name} {decode_type} L={L}")
+
+
+@pytest.mark.parametrize("decode_type", ["SOFT16", "SOFT8", "HARD8"])
+@pytest.mark.parametrize("name", ["Voyager", "LTE", "DAB Radio", "Basic K=3 R=1/2"])
+def test_history_kernel_renormalises_every_step(cuda_lib, name, decode_type):
+    """renormalisation_threshold 0 / 1 / the non-start error: the trigger fires after every step or on the very first steps, and
+    two frames of a register trigger independently (the uint16_t format defers the subtraction into the next step's branch metric
+    table, the uint8_t format subtracts in place); also a renormalisation pending after the LAST step must reach the final metrics"""
+    code = CODE_BY_NAME[name]
+    dc = v.DECODE_TYPES[decode_type](code.R)
+    c = dc.decoder_config
+    for thr in (0, 1, c.initial_non_start_error):
+        cfg = v.ViterbiDecoder_Config(c.soft_decision_max_error, c.initial_start_error, c.initial_non_start_error, thr)
+        dec, _ = make_cuda_decoder(code, decode_type, config_override=cfg)
+        ora, _ = make_oracle(code, decode_type, config_override=cfg)
+        dec.set_variant(1)
+        for L in (3, 16, 47, 300):
+            sym = random_symbols(dc, 70, (L + code.K - 1) * code.R, seed=thr * 7 + L)
+            want = ora.decode_frames(sym, 70, L)
+            got = dec.decode_batch(sym, L)
+            assert dec.kernel_name.startswith("acs_hist<"), dec.kernel_name
+            assert_batch_equal(got, want, f"{name} {decode_type} thr={thr} L={L}")
 
 
 @pytest.mark.parametrize("decode_type", ["SOFT16", "HARD8"])

@@ -149,21 +149,36 @@ struct HistTable<FMT, R, 1> {
     }
 };
 
-// one trellis step x -> y; tag = 2^k in the history field(s), k = step index inside the period
+// one trellis step x -> y; tag = 2^k in the history field(s), k = step index inside the period.
+//
+// LAZY RENORMALISATION: the rare branch only finds the minimum m of the triggered frame(s) and leaves pend = -m in the metric
+// field(s); the NEXT step adds pend to both branch errors of symbol 0, i.e. to every entry of its branch metric table, so its sums
+// are (x + T - m) = ((x - m) + T) modulo 2^8 / 2^16 - bit for bit what the reference computes from the renormalised metrics
+// (scalar.h:139-153), wrap-around included - without the 2^(K-1) subtractions.  A value still pending after the last step is
+// applied when the final metrics are written.  LAZY = false keeps the subtraction inside the branch: measured on the B200, the
+// packed two-frame format behind the direct fetch (config 2) loses 7 % with the lazy form - the table of step k+1 then depends on
+// the trigger of step k and can no longer be built under step k's butterflies - while the 32-bit format gains 0 - 3 %.
+template <int FMT>
+struct HistLazyRenorm { static constexpr bool value = (FMT == 1); };
+
 template <class C, int FMT, bool TIE_SIMD, bool CONSISTENT, bool NEG_BY_NOT>
 __device__ __forceinline__ void hist_step(const uint32_t (&x)[C::NS], uint32_t (&y)[C::NS], const uint32_t* sym, const HistConsts& c,
-                                          const uint32_t tag, uint64_t& accA, uint64_t& accB) {
+                                          const uint32_t tag, uint64_t& accA, uint64_t& accB, uint32_t& pend) {
     using LN = HistLane<FMT>;
     constexpr int R = C::R, NP = C::NP, NS = C::NS;
     uint32_t lo[R], hi[R];
 #pragma unroll
     for (int i = 0; i < R; i++) {
-        lo[i] = LN::add(sym[i], c.c_low);          // s - low
+        constexpr bool LAZY = HistLazyRenorm<FMT>::value;
+        const uint32_t cl = (LAZY && i == 0) ? LN::add(c.c_low, pend) : c.c_low;
+        lo[i] = LN::add(sym[i], cl);               // s - low
         // high - s  (|branch - s| for s in [low, high], scalar.h:30-34, 96-105).  Two equivalent forms; which one ptxas schedules
         // better depends on where the symbols come from (measured on config 2 / 1 / 4: ~s + (c + 1) is 3 % faster behind the direct
         // fetch, where the NOT fuses into the unpacking LOP3; c - s is 5 % faster behind the packed stream)
-        hi[i] = NEG_BY_NOT ? LN::add(~sym[i], c.c_high_n) : LN::sub(c.c_high, sym[i]);
+        if (LAZY && i == 0) hi[i] = NEG_BY_NOT ? LN::add(~sym[i], LN::add(c.c_high_n, pend)) : LN::sub(LN::add(c.c_high, pend), sym[i]);
+        else hi[i] = NEG_BY_NOT ? LN::add(~sym[i], c.c_high_n) : LN::sub(c.c_high, sym[i]);
     }
+    if constexpr (HistLazyRenorm<FMT>::value) pend = 0u;
     uint32_t T[NP], TT[NP];
     HistTable<FMT, R, R>::run(T, lo, hi);
 #pragma unroll
@@ -199,8 +214,12 @@ __device__ __forceinline__ void hist_step(const uint32_t (&x)[C::NS], uint32_t (
             accA += uint64_t(sub >> 16);
         }
         const uint32_t neg = (FMT == 0) ? __vsub2(0u, sub) : (0u - sub);
+        if constexpr (HistLazyRenorm<FMT>::value) {
+            pend = neg;                                            // scalar.h:148-150, applied through the next step's table
+        } else {
 #pragma unroll
-        for (int q = 0; q < NS; q++) y[q] = LN::add(y[q], neg);  // scalar.h:148-150
+            for (int q = 0; q < NS; q++) y[q] = LN::add(y[q], neg);  // scalar.h:148-150
+        }
     }
 }
 
@@ -218,7 +237,7 @@ __global__ void __launch_bounds__(32 * HIST_WARPS) acs_hist_kernel(const AcsPara
     const size_t fA = size_t(blk) * (32 * FPT) + FPT * lane, fB = fA + 1;      // fB only exists for FMT 0
     const HistConsts c = hist_consts<FMT>(p);
 
-    uint32_t x[NS], y[NS];
+    uint32_t x[NS], y[NS], pend = 0u;
     uint64_t accA = 0, accB = 0;
     {
         const uint32_t s = p.start_state & uint32_t(NS - 1);       // core.h:209-210
@@ -256,7 +275,7 @@ __global__ void __launch_bounds__(32 * HIST_WARPS) acs_hist_kernel(const AcsPara
         for (int a = 0; a < NROW; a++) {
             const size_t f = fA + a, ld = f < lastf ? f : lastf;                      // padding lanes re-read the last frame
             row[a] = reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(p.sym) + ld * p.sym_row_bytes);
-            maxw[a] = uint32_t((p.sym_total_bytes - ld * p.sym_row_bytes - 4) >> 2);    // loads are clamped to stay inside the array
+            maxw[a] = clamp_words_left(p.sym_total_bytes, ld * p.sym_row_bytes);    // loads are clamped to stay inside the array
 #pragma unroll
             for (int j = 0; j < WPG; j++) nx[a][j] = __ldg(row[a] + (uint32_t(j) < maxw[a] ? uint32_t(j) : maxw[a]));
         }
@@ -336,8 +355,8 @@ __global__ void __launch_bounds__(32 * HIST_WARPS) acs_hist_kernel(const AcsPara
 #pragma unroll
                     for (int i = 0; i < 2 * R; i++) nxt[i] = (t + 2 + uint32_t(i / R) < p.n_steps) ? __ldg(pk + (size_t(t + 2) * R + i) * SLOTS) : 0u;
                 }
-                hist_step<C, FMT, TIE_SIMD, CONSISTENT, DIRECT>(x, y, &cur[0], c, tag, accA, accB);
-                hist_step<C, FMT, TIE_SIMD, CONSISTENT, DIRECT>(y, x, &cur[R], c, tag << 1, accA, accB);
+                hist_step<C, FMT, TIE_SIMD, CONSISTENT, DIRECT>(x, y, &cur[0], c, tag, accA, accB, pend);
+                hist_step<C, FMT, TIE_SIMD, CONSISTENT, DIRECT>(y, x, &cur[R], c, tag << 1, accA, accB, pend);
                 tag <<= 2;
                 t += 2;
             }
@@ -349,7 +368,7 @@ __global__ void __launch_bounds__(32 * HIST_WARPS) acs_hist_kernel(const AcsPara
 #pragma unroll
                     for (int i = 0; i < 2 * R; i++) cur[i] = unpack_pk(nxt[i]);
                 }
-                hist_step<C, FMT, TIE_SIMD, CONSISTENT, DIRECT>(x, y, &cur[0], c, tag, accA, accB);
+                hist_step<C, FMT, TIE_SIMD, CONSISTENT, DIRECT>(x, y, &cur[0], c, tag, accA, accB, pend);
 #pragma unroll
                 for (int q = 0; q < NS; q++) x[q] = y[q];
                 t += 1;
@@ -376,7 +395,12 @@ __global__ void __launch_bounds__(32 * HIST_WARPS) acs_hist_kernel(const AcsPara
         for (int q = 0; q < NS; q++) x[q] &= LN::METRIC_MASK;
     }
 
-    // final metrics in logical order (core.h:195-199 reads old_metrics[end_state])
+    // final metrics in logical order (core.h:195-199 reads old_metrics[end_state]); a renormalisation triggered by the last step is
+    // still pending
+    if constexpr (HistLazyRenorm<FMT>::value) {
+#pragma unroll
+        for (int q = 0; q < NS; q++) x[q] = LN::add(x[q], pend);
+    }
     uint16_t* mA = p.metrics + fA * NS;
     if constexpr (FMT == 0) {
         uint16_t* mB = p.metrics + fB * NS;

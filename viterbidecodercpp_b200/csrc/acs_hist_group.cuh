@@ -72,19 +72,30 @@ __device__ __forceinline__ void hg_bfly_all(uint32_t (&x)[HistGroupShape<C>::NL]
 }
 
 // one trellis step at phase PH.  fold[i] != 0: the lane part of the branch pattern flips symbol i (e_low and e_high trade places).
+//
+// LAZY RENORMALISATION.  The reference subtracts the minimum from every metric right after the step that triggered
+// (scalar.h:139-153).  Here the rare branch only FINDS the minimum m and leaves `pend = -m` (metric field); the next step adds pend
+// to the two branch errors of symbol 0, i.e. to every entry of its branch metric table, so its sums are (x + T - m) mod 2^16 =
+// ((x - m) + T) mod 2^16: bit for bit what the reference computes from the renormalised metrics, wrap-around included.  The
+// registers x are not written inside the branch, which (a) saves the 64 subtractions and (b) removes the control-flow merge that
+// made ptxas shuffle half of the in-place butterfly results back into canonical registers after every step (34 IMAD.MOV per step
+// in the round-1 build, profiles/r02_ncu_full_acs_hist_group_cfg3.txt).  A pending value left after the last step is applied when
+// the final metrics are written.
 template <class C, int PH, bool TIE_SIMD, bool CONSISTENT>
 __device__ __forceinline__ void hg_step(uint32_t (&x)[HistGroupShape<C>::NL], const uint32_t* sym, const uint32_t fold_bits, const HistConsts& c,
-                                        const uint32_t tag, const uint32_t lane, uint64_t& acc) {
+                                        const uint32_t tag, const uint32_t lane, uint64_t& acc, uint32_t& pend) {
     using S = HistGroupShape<C>;
     constexpr int R = C::R, NP = C::NP, NL = S::NL;
     uint32_t lo[R], hi[R];
 #pragma unroll
     for (int i = 0; i < R; i++) {
-        const uint32_t l = sym[i] + c.c_low, h = c.c_high - sym[i];        // s - low, high - s  (scalar.h:96-105 for s in [low, high])
+        uint32_t l = sym[i] + c.c_low, h = c.c_high - sym[i];              // s - low, high - s  (scalar.h:96-105 for s in [low, high])
+        if (i == 0) { l += pend; h += pend; }                              // pending renormalisation: every table entry holds one of them
         const bool f = (fold_bits >> (PH * R + i)) & 1u;
         lo[i] = f ? h : l;
         hi[i] = f ? l : h;
     }
+    pend = 0u;
     uint32_t T[NP], TT[NP];
     HistTable<1, R, R>::run(T, lo, hi);
 #pragma unroll
@@ -110,8 +121,7 @@ __device__ __forceinline__ void hg_step(uint32_t (&x)[HistGroupShape<C>::NL], co
         m = min(m, __shfl_xor_sync(0xffffffffu, m, 1));
         m = min(m, __shfl_xor_sync(0xffffffffu, m, 2));
         const uint32_t sub = trig ? (m & 0xffff0000u) : 0u;
-#pragma unroll
-        for (int q = 0; q < NL; q++) x[q] -= sub;
+        pend = 0u - sub;                                                    // applied by the next step's table (or the final write-back)
         acc += uint64_t(sub >> 16);
     }
 }
@@ -151,7 +161,7 @@ __global__ void __launch_bounds__(32 * HistGroupShape<C>::WARPS, 7) acs_hist_gro
     uint32_t cur[WPP], nxt[WPP];
     const size_t lastf = size_t(p.n_frames) - 1, ld = f < lastf ? f : lastf;      // padding frames re-read the last frame
     const uint32_t* row = reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(p.sym) + ld * p.sym_row_bytes);
-    const uint32_t maxw = uint32_t((p.sym_total_bytes - ld * p.sym_row_bytes - 4) >> 2);     // loads are clamped to stay inside the array
+    const uint32_t maxw = clamp_words_left(p.sym_total_bytes, ld * p.sym_row_bytes);     // loads are clamped to stay inside the array
 #pragma unroll
     for (int j = 0; j < WPP; j++) nxt[j] = __ldg(row + (uint32_t(j) < maxw ? uint32_t(j) : maxw));
 
@@ -174,7 +184,7 @@ __global__ void __launch_bounds__(32 * HistGroupShape<C>::WARPS, 7) acs_hist_gro
         for (int q = 0; q < NL; q++) x[q] = rd_base[(q >> 4) & 3][q * 32];
     };
 
-    uint32_t tag = 1u, pst = 0, r = 0;
+    uint32_t tag = 1u, pst = 0, r = 0, pend = 0u;
     // history record of the period that just ended (position order), then clear the history fields
     auto emit_record = [&]() {
         uint32_t w[NW];
@@ -192,17 +202,19 @@ __global__ void __launch_bounds__(32 * HistGroupShape<C>::WARPS, 7) acs_hist_gro
         tag = 1u;
         pst = 0;
     };
-    // one step at compile-time phase PH of the period that starts at step n0; records fill up (16 steps) only after odd phases
-    auto do_phase = [&](auto ph_tag, uint32_t n0) {
+    // one step at compile-time phase PH of the period that starts at step n0; records fill up (16 steps) only after odd phases.
+    // GUARD = false: the period is known to be complete (main loop: no per-step bounds test, no control-flow merge per step)
+    auto do_phase = [&](auto ph_tag, auto guard_tag, uint32_t n0) {
         constexpr int PH = decltype(ph_tag)::value;
-        if (n0 + uint32_t(PH) >= p.n_steps) return;
+        constexpr bool GUARD = decltype(guard_tag)::value;
+        if constexpr (GUARD) { if (n0 + uint32_t(PH) >= p.n_steps) return; }
         uint32_t sym[R];
 #pragma unroll
         for (int i = 0; i < R; i++) {
             const int e = PH * R + i;
             sym[i] = (e & 1) ? (cur[e >> 1] & 0xffff0000u) : (cur[e >> 1] << 16);
         }
-        hg_step<C, PH, TIE_SIMD, CONSISTENT>(x, sym, fold_bits, c, tag, lane, acc);
+        hg_step<C, PH, TIE_SIMD, CONSISTENT>(x, sym, fold_bits, c, tag, lane, acc, pend);
         tag <<= 1;
         pst++;
         if constexpr (PH == 1 || PH == 3) {         // (after phase 5 the record is cut behind the exchange, see the loop)
@@ -210,32 +222,40 @@ __global__ void __launch_bounds__(32 * HistGroupShape<C>::WARPS, 7) acs_hist_gro
         }
     };
 
-    uint32_t n0 = 0;
+    using NoGuard = std::false_type;
+    using Guard = std::true_type;
+    uint32_t n0 = 0, w0 = uint32_t(WPP);
 #pragma unroll 1
-    for (; n0 < p.n_steps; n0 += LB) {
+    for (; n0 + LB <= p.n_steps; n0 += LB, w0 += uint32_t(WPP)) {      // complete exchange periods
 #pragma unroll
         for (int j = 0; j < WPP; j++) cur[j] = nxt[j];
-        if (n0 + LB < p.n_steps) {
-            const uint32_t w0 = ((n0 / uint32_t(LB)) + 1u) * uint32_t(WPP);
 #pragma unroll
-            for (int j = 0; j < WPP; j++) {
-                const uint32_t w = w0 + uint32_t(j);
-                nxt[j] = __ldg(row + (w < maxw ? w : maxw));
-            }
+        for (int j = 0; j < WPP; j++) {                                  // words of the next period (clamped: the last period reads ahead)
+            const uint32_t w = w0 + uint32_t(j);
+            nxt[j] = __ldg(row + (w < maxw ? w : maxw));
         }
-        do_phase(std::integral_constant<int, 0>{}, n0);
-        do_phase(std::integral_constant<int, 1>{}, n0);
-        do_phase(std::integral_constant<int, 2>{}, n0);
-        do_phase(std::integral_constant<int, 3>{}, n0);
-        do_phase(std::integral_constant<int, 4>{}, n0);
-        do_phase(std::integral_constant<int, 5>{}, n0);
-        if (n0 + LB <= p.n_steps) {                 // a full period ran: positions back to PHI = s
-            exchange();
-            if (pst == uint32_t(HB)) emit_record(); // records are cut in the layout the traceback expects: PHI = rotr^(steps mod 6)(s)
-        }
+        do_phase(std::integral_constant<int, 0>{}, NoGuard{}, n0);
+        do_phase(std::integral_constant<int, 1>{}, NoGuard{}, n0);
+        do_phase(std::integral_constant<int, 2>{}, NoGuard{}, n0);
+        do_phase(std::integral_constant<int, 3>{}, NoGuard{}, n0);
+        do_phase(std::integral_constant<int, 4>{}, NoGuard{}, n0);
+        do_phase(std::integral_constant<int, 5>{}, NoGuard{}, n0);
+        exchange();                                 // a full period ran: positions back to PHI = s
+        if (pst == uint32_t(HB)) emit_record();     // records are cut in the layout the traceback expects: PHI = rotr^(steps mod 6)(s)
+    }
+    if (n0 < p.n_steps) {                           // the incomplete last period: guarded steps, no exchange
+#pragma unroll
+        for (int j = 0; j < WPP; j++) cur[j] = nxt[j];
+        do_phase(std::integral_constant<int, 0>{}, Guard{}, n0);
+        do_phase(std::integral_constant<int, 1>{}, Guard{}, n0);
+        do_phase(std::integral_constant<int, 2>{}, Guard{}, n0);
+        do_phase(std::integral_constant<int, 3>{}, Guard{}, n0);
+        do_phase(std::integral_constant<int, 4>{}, Guard{}, n0);
     }
     if (pst) emit_record();                         // last, partial record (its pst is still needed for the SIMD tie-break mask)
     const uint32_t ph = p.n_steps % uint32_t(LB);
+#pragma unroll
+    for (int q = 0; q < NL; q++) x[q] += pend;      // renormalisation still pending from the last step (metric field only)
 
     // final metrics in logical order: state s sits at PHI = rotr^ph(s)   (core.h:195-199 reads old_metrics[end_state])
     uint16_t* m = p.metrics + f * C::NS;

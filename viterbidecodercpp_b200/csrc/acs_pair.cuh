@@ -393,8 +393,8 @@ __global__ void __launch_bounds__(32 * PAIR_WARPS) acs_pair_kernel(const AcsPara
         const size_t ldA = fA < lastf ? fA : lastf, ldB = fB < lastf ? fB : lastf;     // padding lanes re-read the last frame
         rowA = reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(p.sym) + ldA * p.sym_row_bytes);
         rowB = reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(p.sym) + ldB * p.sym_row_bytes);
-        maxwA = uint32_t((p.sym_total_bytes - ldA * p.sym_row_bytes - 4) >> 2);
-        maxwB = uint32_t((p.sym_total_bytes - ldB * p.sym_row_bytes - 4) >> 2);
+        maxwA = clamp_words_left(p.sym_total_bytes, ldA * p.sym_row_bytes);
+        maxwB = clamp_words_left(p.sym_total_bytes, ldB * p.sym_row_bytes);
         DF::load(rawA, rowA, 0u, maxwA);
         DF::load(rawB, rowB, 0u, maxwB);
     } else {

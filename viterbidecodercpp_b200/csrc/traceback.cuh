@@ -454,7 +454,7 @@ struct HistFrame {
     const uint8_t* base;      // first record of the frame's warp block
     uint8_t* out;
     size_t rec_bytes;
-    uint32_t lane, half, vw_log, SB, HB, r_last, nv, VS, n_out, end_state, logt, n_steps;
+    uint32_t lane, half, vw_log, row_log, SB, HB, r_last, nv, VS, n_out, end_state, logt, n_steps;
     bool wide;
 };
 
@@ -464,10 +464,13 @@ __device__ __forceinline__ HistFrame hist_frame(const TracebackHistParams& p, ui
     c.logt = p.logt; c.n_steps = p.n_steps;
     const uint32_t NS = 1u << c.SB, nw = (NS >> c.logt) / 2;     // record words per lane
     c.vw_log = nw >= 4 ? 2u : (nw == 2 ? 1u : 0u);
-    const uint32_t fpb_log = c.wide ? (5u - c.logt) : 6u;        // frames per warp block: 64, 32, or 32 >> logt
-    c.lane = c.wide ? ((f & ((1u << fpb_log) - 1u)) << c.logt) : ((f & 63u) >> 1);      // first lane of the frame
+    // logt >= 5 (acs_hist_cta.cuh): a frame IS a block of 2^logt threads; else a block is one warp
+    const bool cta = c.logt >= 5u;
+    const uint32_t fpb_log = cta ? 0u : (c.wide ? (5u - c.logt) : 6u);   // frames per block: 1, or 64, 32, 32 >> logt per warp
+    c.row_log = cta ? c.logt : 5u;                               // threads per row of 16-byte record chunks
+    c.lane = cta ? 0u : (c.wide ? ((f & ((1u << fpb_log) - 1u)) << c.logt) : ((f & 63u) >> 1));      // first lane of the frame
     c.half = c.wide ? 0u : (f & 1u);
-    c.rec_bytes = (size_t(64) * NS) >> c.logt;                   // one warp block, one period
+    c.rec_bytes = cta ? size_t(2) * NS : ((size_t(64) * NS) >> c.logt);   // one block, one period
     c.base = p.dec + size_t(f >> fpb_log) * p.n_periods * c.rec_bytes;
     c.out = p.out + size_t(f) * p.out_stride;
     c.n_out = (p.total_bits + 7) / 8;
@@ -497,7 +500,7 @@ __device__ __forceinline__ uint32_t hist_walk(const HistFrame& c, int64_t r_hi, 
         }
         // word w = reg >> 1 of the lane: FMT 0 bytes [A:2w, B:2w, A:2w+1, B:2w+1], FMT 1 halfwords [2w, 2w+1]
         const uint32_t w = reg >> 1;
-        const uint32_t off = ((((w >> c.vw_log) << 5) + ln) << (c.vw_log + 2)) + ((w & ((1u << c.vw_log) - 1u)) << 2) + ((reg & 1u) << 1) + c.half;
+        const uint32_t off = ((((w >> c.vw_log) << c.row_log) + ln) << (c.vw_log + 2)) + ((w & ((1u << c.vw_log) - 1u)) << 2) + ((reg & 1u) << 1) + c.half;
         const uint8_t* ptr = c.base + size_t(r) * c.rec_bytes + off;
         const uint32_t h = c.wide ? uint32_t(*reinterpret_cast<const uint16_t*>(ptr)) : uint32_t(*ptr);
         uint32_t hext = h;

@@ -33,6 +33,7 @@ static const std::vector<KernelEntry>& registry() {
         register_k15r6_cta512(entries); register_k15r6_cta1024(entries);
         register_generic(entries);
         register_k9_hist_group(entries);
+        register_k15_hist_cta(entries);
     });
     return entries;
 }
@@ -91,7 +92,7 @@ struct vitb_decoder {
     const KernelEntry* last_batch = nullptr;    // variant the last batch call selected
     bool last_batch_hist = false;               // ... and whether it ran as the survivor-history kernel (acs_hist.cuh)
     std::string name_buf;
-    int forced_logt = -1;                       // vitb_set_variant
+    int forced_variant = 0;                     // vitb_set_variant (0 = automatic)
     bool use_hist = getenv("VITB_NO_HIST") == nullptr;   // vitb_set_history_kernel
     int seg_records_forced = 0, seg_overlap_forced = -1;   // vitb_set_traceback_segments (0 / -1 = automatic)
     GenericCode gcode{};                        // branch patterns for the generic kernels (codes outside the compiled catalogue)
@@ -105,6 +106,10 @@ struct vitb_decoder {
     cudaStream_t stream = nullptr;    // owned; used by the host-pointer entry points
     cudaStream_t copy_stream = nullptr;   // owned; host->device copies of the pipelined host-pointer path
     std::vector<cudaEvent_t> copy_ev;     // one per pipeline chunk + fork/join
+    // Every batch call reuses the handle's workspace (pk, dec, metrics, ...), so calls on one handle are ordered on the device even
+    // when they are enqueued on different streams: each call's stream first waits for `batch_done` of the previous call.
+    cudaEvent_t batch_done = nullptr;
+    bool batch_pending = false;
     // batch workspace
     DeviceBuffer pk, dec, metrics, acc, d_in, d_out, d_accout, d_finout, map, tb_spec, tb_fin, end_states;
     size_t n_depunctured = 0, n_received = 0;
@@ -139,7 +144,7 @@ std::vector<const KernelEntry*> find_entries(const vitb_params& p) {
     const int consistent = ((p.soft_decision_max_error & mask) == ((span * uint32_t(p.R)) & mask)) ? 1 : 0;
     const uint32_t kmask = (p.K >= 32) ? 0xffffffffu : ((1u << p.K) - 1u);
     for (const KernelEntry& e : registry()) {
-        if (e.generic || e.layout == LAYOUT_HISTGROUP || e.K != p.K || e.R != p.R || e.sh != sh || e.tie != (p.tie_break ? 1 : 0) || e.consistent != consistent) continue;
+        if (e.generic || e.layout == LAYOUT_HISTGROUP || e.layout == LAYOUT_HISTCTA || e.K != p.K || e.R != p.R || e.sh != sh || e.tie != (p.tie_break ? 1 : 0) || e.consistent != consistent) continue;
         bool same = true;
         for (int i = 0; i < p.R; i++) same = same && ((e.G[i] & kmask) == (p.G[i] & kmask));
         if (same) out.push_back(&e);
@@ -152,14 +157,15 @@ std::vector<const KernelEntry*> find_entries(const vitb_params& p) {
     return out;
 }
 
-// the frame-over-4-lanes survivor-history kernel of this code, if it has one (K = 9, uint16_t metrics): batch calls only
+// the batch-only survivor-history kernel of this code, if it has one: frame over 4 lanes (K = 9) or frame per CTA (K = 15), uint16_t
+// metrics
 const KernelEntry* find_hist_group(const vitb_params& p) {
     if (p.soft_bytes != 2) return nullptr;
     const uint32_t span = uint32_t(p.soft_decision_high - p.soft_decision_low);
     const int consistent = ((p.soft_decision_max_error & 0xffffu) == ((span * uint32_t(p.R)) & 0xffffu)) ? 1 : 0;
     const uint32_t kmask = (p.K >= 32) ? 0xffffffffu : ((1u << p.K) - 1u);
     for (const KernelEntry& e : registry()) {
-        if (e.layout != LAYOUT_HISTGROUP || e.K != p.K || e.R != p.R || e.tie != (p.tie_break ? 1 : 0) || e.consistent != consistent) continue;
+        if ((e.layout != LAYOUT_HISTGROUP && e.layout != LAYOUT_HISTCTA) || e.K != p.K || e.R != p.R || e.tie != (p.tie_break ? 1 : 0) || e.consistent != consistent) continue;
         bool same = true;
         for (int i = 0; i < p.R; i++) same = same && ((e.G[i] & kmask) == (p.G[i] & kmask));
         if (same) return &e;
@@ -172,8 +178,8 @@ const KernelEntry* find_hist_group(const vitb_params& p) {
 // fewest lanes that still give `want` warps per sub-partition (1.5 for the one-thread-per-pair kernel, whose warps carry 32
 // independent butterflies each; 4 for the lane-group kernels), else the most parallel variant.
 const KernelEntry* choose_variant(const vitb_decoder* h, size_t n_frames) {
-    if (h->forced_logt >= 0) {
-        for (const KernelEntry* e : h->variants) if (e->logt == h->forced_logt) return e;
+    if (h->forced_variant > 0) {
+        for (const KernelEntry* e : h->variants) if (entry_variant(e) == h->forced_variant) return e;
     }
     const size_t pairs = (n_frames + 1) / 2, smsp = size_t(h->n_sm) * 4;
     if (h->variants.front()->layout == LAYOUT_CTA) return h->variants.front();  // K = 15: 512 threads x 32 registers measured fastest (56.0 vs 61.1 ms)
@@ -239,9 +245,9 @@ size_t default_ws_limit() {
 }
 
 // workspace bytes per 64 frames for a frame of S steps (identical for every variant: decision rows are 2^(K-1) bits per frame-step)
-size_t block_bytes(const vitb_decoder* h, size_t S) {
+size_t block_bytes(const vitb_decoder* h, size_t S, bool with_packed_stream = true) {
     const size_t n_sym = S * size_t(h->prm.R);
-    return n_sym * 32 * 4                                   // packed symbols
+    return (with_packed_stream ? n_sym * 32 * 4 : 0)        // packed symbols (not needed when the kernel reads the caller's rows itself)
          + S * 64 * (size_t(h->n_states) / 8 < 8 ? 8 : size_t(h->n_states) / 8)   // decision rows
          + size_t(64) * h->n_states * 2                     // metrics
          + 64 * 8;                                          // accumulated error
@@ -274,6 +280,7 @@ cudaError_t launch_traceback(vitb_decoder* h, const KernelEntry* e, const void* 
         const size_t overlap = h->seg_overlap_forced >= 0 ? size_t(h->seg_overlap_forced) * 8 : size_t(16) * size_t(h->prm.K);     // rows
         size_t seg_bits = h->seg_records_forced > 0 ? size_t(h->seg_records_forced) * 8 : ((4 * overlap + 7) / 8 * 8);
         if (seg_bits < 8) seg_bits = 8;
+        if ((L + seg_bits - 1) / seg_bits > 65535) seg_bits = ((L + 65534) / 65535 + 7) / 8 * 8;                    // gridDim.y
         const size_t n_seg = (no_seg || dec == h->s_dec.ptr) ? 1 : (L + seg_bits - 1) / seg_bits;
         if (n_seg <= 1) {
             traceback_cta_kernel<5><<<unsigned((n_frames + 63) / 64), 64, 0, s>>>(t);
@@ -340,6 +347,28 @@ cudaError_t mark(vitb_decoder* h, cudaStream_t s) {
     return cudaEventRecord(h->ev[h->ev_used++], s);
 }
 
+// can the ACS kernel `e` read the caller's rows where they lie (no ingest pass, no packed stream)?
+bool direct_fetch_ok(const vitb_decoder* h, const KernelEntry* e, const void* d_symbols, size_t row_stride) {
+    static const bool no_direct = getenv("VITB_NO_DIRECT") != nullptr;
+    const size_t row_bytes = row_stride * size_t(h->prm.soft_bytes);
+    const bool hist = h->use_hist && e->launch_hist != nullptr;
+    return !no_direct && (hist || e->launch_direct) && !h->n_depunctured && (row_bytes % 4 == 0) && row_bytes >= 4 &&
+           (reinterpret_cast<uintptr_t>(d_symbols) % 4 == 0);
+}
+
+// order this call after the previous batch call of the handle (which may still be running on another stream), and publish its end
+cudaError_t batch_begin(vitb_decoder* h, cudaStream_t s) {
+    if (!h->batch_done) {
+        const cudaError_t e = cudaEventCreateWithFlags(&h->batch_done, cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    return h->batch_pending ? cudaStreamWaitEvent(s, h->batch_done, 0) : cudaSuccess;
+}
+cudaError_t batch_end(vitb_decoder* h, cudaStream_t s) {
+    h->batch_pending = true;
+    return cudaEventRecord(h->batch_done, s);
+}
+
 // One chunk of frames, everything on device, asynchronous on `s`.
 int decode_chunk_dev(vitb_decoder* h, const KernelEntry* e, const void* d_symbols, size_t row_stride, size_t n_frames, size_t L,
                      size_t start_state, size_t end_state, uint8_t* d_out, uint64_t* d_acc, uint32_t* d_final, cudaStream_t s) {
@@ -349,31 +378,40 @@ int decode_chunk_dev(vitb_decoder* h, const KernelEntry* e, const void* d_symbol
     // uint8_t metrics: warp block = 64 frames, 8-step records; uint16_t metrics: warp block = 32 frames, 16-step records.
     // K = 9 with uint16_t metrics: the frame-over-4-lanes history kernel (acs_hist_group.cuh) when the symbols can be fetched directly
     // and the batch fills the GPU with 8 frames per warp, or when that variant was pinned with vitb_set_variant(h, 4)
+    // K = 15 with uint16_t metrics: the frame-per-CTA history kernel (acs_hist_cta.cuh) for unpunctured input (any alignment)
     const size_t row_bytes0 = row_stride * size_t(h->prm.soft_bytes);
-    const bool direct_ok = getenv("VITB_NO_DIRECT") == nullptr && !h->n_depunctured && (row_bytes0 % 4 == 0) && row_bytes0 >= 4 &&
-                           (reinterpret_cast<uintptr_t>(d_symbols) % 4 == 0);
-    const bool hg = h->use_hist && h->hg_entry && direct_ok &&
-                    (h->forced_logt == h->hg_entry->logt || (h->forced_logt < 0 && (n_frames + 7) / 8 >= size_t(h->n_sm) * 2));
-    if (hg) { e = h->hg_entry; h->last_batch = e; }
+    bool hg = false, hc = false;
+    if (h->use_hist && h->hg_entry && getenv("VITB_NO_DIRECT") == nullptr && !h->n_depunctured) {
+        const KernelEntry* a = h->hg_entry;
+        const bool forced = h->forced_variant == entry_variant(a);
+        if (a->layout == LAYOUT_HISTGROUP) {
+            const bool direct_ok = (row_bytes0 % 4 == 0) && row_bytes0 >= 4 && (reinterpret_cast<uintptr_t>(d_symbols) % 4 == 0);
+            hg = direct_ok && (forced || (h->forced_variant == 0 && (n_frames + 7) / 8 >= size_t(h->n_sm) * 2));
+        } else {
+            const bool direct_ok = (row_bytes0 % 2 == 0) && (reinterpret_cast<uintptr_t>(d_symbols) % 2 == 0);
+            hc = direct_ok && (forced || h->forced_variant == 0);
+        }
+        if (hg || hc) { e = a; h->last_batch = e; }
+    }
     const bool hist = h->use_hist && e->launch_hist != nullptr;
     const bool hist_wide = hist && e->sh == 0;
     h->last_batch_hist = hist;
     const size_t hist_bits = hist_wide ? 16 : 8, n_periods = (S + hist_bits - 1) / hist_bits;
     const unsigned ppw = hist_wide ? 16u : unsigned(e->ppw);
-    const unsigned n_wblocks = hg ? unsigned((n_frames + 7) / 8) : n_b64 * (32u / ppw);
-    VITB_CUDA(h, h->pk.reserve(size_t(n_b64) * n_sym * 32 * 4));
-    VITB_CUDA(h, h->dec.reserve(hist ? size_t(n_wblocks) * n_periods * ((64 * size_t(h->n_states)) >> (hg ? e->logt : 0))
-                                     : size_t(n_b64) * dec_bytes_per_block64(e, S)));
+    const unsigned n_wblocks = hc ? unsigned(n_frames) : (hg ? unsigned((n_frames + 7) / 8) : n_b64 * (32u / ppw));
+    // record bytes per block and period: a warp block of the one-lane kernels holds 64 states-bytes x 64 (or 32 x 2) frames, the
+    // lane-group kernel 8 frames, the CTA kernel one frame: always 2^(K-1) bits per frame and step
+    const size_t rec_block_bytes = hc ? size_t(2) * size_t(h->n_states) : ((64 * size_t(h->n_states)) >> (hg ? e->logt : 0));
+    VITB_CUDA(h, h->dec.reserve(hist ? size_t(n_wblocks) * n_periods * rec_block_bytes : size_t(n_b64) * dec_bytes_per_block64(e, S)));
     VITB_CUDA(h, h->metrics.reserve(size_t(n_b64) * 64 * h->n_states * 2));
     VITB_CUDA(h, h->acc.reserve(size_t(n_b64) * 64 * 8));
 
     // one-thread-per-pair kernels can read the caller's rows themselves when they are 4-byte aligned and not punctured
-    static const bool no_direct = getenv("VITB_NO_DIRECT") != nullptr;
     const size_t row_bytes = row_stride * size_t(h->prm.soft_bytes);
-    const bool direct = !no_direct && (hist || e->launch_direct) && !h->n_depunctured && (row_bytes % 4 == 0) &&
-                        (reinterpret_cast<uintptr_t>(d_symbols) % 4 == 0) && row_bytes >= 4;
+    const bool direct = hc || hg || direct_fetch_ok(h, e, d_symbols, row_stride);
     VITB_CUDA(h, mark(h, s));
     if (!direct) {
+        VITB_CUDA(h, h->pk.reserve(size_t(n_b64) * n_sym * 32 * 4));      // packed stream: only the ingest path needs it
         IngestParams ip{};
         ip.symbols = d_symbols; ip.row_stride = row_stride; ip.n_frames = uint32_t(n_frames); ip.n_sym = uint32_t(n_sym);
         ip.depuncture_map = h->n_depunctured ? static_cast<const int32_t*>(h->map.ptr) : nullptr;
@@ -389,7 +427,7 @@ int decode_chunk_dev(vitb_decoder* h, const KernelEntry* e, const void* d_symbol
     a.metrics = static_cast<uint16_t*>(h->metrics.ptr); a.acc = static_cast<uint64_t*>(h->acc.ptr);
     a.n_blocks = n_wblocks; a.n_steps = uint32_t(S); a.dec_rows = uint32_t(S); a.dec_row0 = 0; a.resume = 0; a.start_state = uint32_t(start_state);
     h->launches++;
-    if (hist) VITB_CUDA(h, (direct && !hg) ? e->launch_hist_direct(a, s) : e->launch_hist(a, s));    // the hist-group launcher always fetches directly
+    if (hist) VITB_CUDA(h, (direct && !hg && !hc) ? e->launch_hist_direct(a, s) : e->launch_hist(a, s));    // the hist-group / hist-CTA launchers always fetch directly
     else if (e->generic) VITB_CUDA(h, e->launch_generic(a, h->gcode, s));
     else VITB_CUDA(h, direct ? e->launch_direct(a, s) : e->launch(a, s));
     VITB_CUDA(h, mark(h, s));
@@ -409,18 +447,21 @@ int decode_chunk_dev(vitb_decoder* h, const KernelEntry* e, const void* d_symbol
         TracebackHistParams t{};
         t.dec = static_cast<const uint8_t*>(h->dec.ptr); t.n_periods = uint32_t(n_periods); t.n_frames = uint32_t(n_frames);
         t.total_bits = uint32_t(L); t.state_bits = uint32_t(K - 1); t.end_state = uint32_t(end_state); t.end_states = end_states; t.n_steps = uint32_t(S);
-        t.hist_bits = uint32_t(hist_bits); t.logt = hg ? uint32_t(e->logt) : 0u; t.out = d_out; t.out_stride = (L + 7) / 8;
+        t.hist_bits = uint32_t(hist_bits); t.logt = (hg || hc) ? uint32_t(e->logt) : 0u; t.out = d_out; t.out_stride = (L + 7) / 8;
         // A frame's chain is n_periods dependent memory round trips; small batches cannot hide them, so the chain is cut into
         // segments walked concurrently (warm-up over `overlap` records from a guessed state, verified and repaired afterwards:
         // traceback.cuh).  About 128 K threads saturate DRAM; the warm-up is kept below a quarter of the walk.
         static const bool no_seg = getenv("VITB_NO_SEG_TRACEBACK") != nullptr;
-        const size_t overlap = h->seg_overlap_forced >= 0 ? size_t(h->seg_overlap_forced) : ((hist_bits == 8) ? 12 : 6);   // 96 steps
+        // warm-up: 96 steps for K <= 9, 16 K steps for longer codes (the depth the K = 15 row walk uses)
+        const size_t warm_steps = K <= 9 ? 96 : 16 * K;
+        const size_t overlap = h->seg_overlap_forced >= 0 ? size_t(h->seg_overlap_forced) : (warm_steps + hist_bits - 1) / hist_bits;
         static const size_t seg_target = getenv("VITB_SEG_TARGET") ? size_t(atoll(getenv("VITB_SEG_TARGET"))) : size_t(131072);
         const size_t want_seg = (seg_target + n_frames - 1) / n_frames;
         size_t seg_records = (n_periods + want_seg - 1) / want_seg;
         if (seg_records < 4 * overlap) seg_records = 4 * overlap;
         if (h->seg_records_forced > 0) seg_records = size_t(h->seg_records_forced);
         if (seg_records == 0) seg_records = 1;
+        if ((n_periods + seg_records - 1) / seg_records > 65535) seg_records = (n_periods + 65534) / 65535;      // gridDim.y
         const size_t n_seg = no_seg ? 1 : (n_periods + seg_records - 1) / seg_records;
         if (n_seg <= 1) {
             traceback_hist_kernel<<<unsigned((n_frames + 127) / 128), 128, 0, s>>>(t);
@@ -466,11 +507,12 @@ int check_batch_args(const vitb_decoder* h, size_t n_frames, size_t L, const vit
     return VITB_OK;
 }
 
-size_t chunk_frames_for(const vitb_decoder* h, size_t L) {
+size_t chunk_frames_for(const vitb_decoder* h, size_t L, bool with_packed_stream = true) {
     const size_t S = L + size_t(h->prm.K) - 1;
     const size_t limit = h->ws_limit ? h->ws_limit : h->ws_default;
-    size_t blocks = limit / block_bytes(h, S);
+    size_t blocks = limit / block_bytes(h, S, with_packed_stream);
     if (blocks < 1) blocks = 1;
+    if (blocks > 65535) blocks = 65535;       // the ingest kernel and the segmented tracebacks index 64-frame blocks with gridDim.y
     return blocks * 64;
 }
 
@@ -516,7 +558,7 @@ int vitb_create(const vitb_params* p, vitb_decoder** out) {
     h->variants = found;
     h->entry = e;
     h->hg_entry = find_hist_group(*p);
-    if (const char* f = getenv("VITB_FORCE_LOGT")) h->forced_logt = atoi(f);
+    if (const char* f = getenv("VITB_FORCE_LOGT")) h->forced_variant = 1 << atoi(f);
     h->n_states = 1 << (p->K - 1);
     h->sh = e->sh;
     if (e->generic) {
@@ -526,6 +568,10 @@ int vitb_create(const vitb_params* p, vitb_decoder** out) {
     cudaError_t ce = cudaSetDevice(p->device);
     if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, p->device);
     if (ce == cudaSuccess) h->ws_default = default_ws_limit();
+    if (ce == cudaSuccess) {
+        if (const char* g = getenv("VITB_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, size_t(atoi(g)));   // experiment knob
+        cudaGetLastError();
+    }
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
     if (ce != cudaSuccess) { delete h; return VITB_ERR_CUDA; }
@@ -544,6 +590,7 @@ int vitb_destroy(vitb_decoder* h) {
                             &h->s_pk, &h->s_dec, &h->s_metrics, &h->s_acc, &h->s_in, &h->s_out, &h->g_tx, &h->g_sym, &h->g_cnt}) b->release();
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     for (cudaEvent_t e : h->copy_ev) cudaEventDestroy(e);
+    if (h->batch_done) cudaEventDestroy(h->batch_done);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -563,11 +610,11 @@ const char* vitb_kernel_name(const vitb_decoder* h) {
 
 int vitb_set_variant(vitb_decoder* h, int lanes_per_pair) {
     if (!h) return VITB_ERR_ARG;
-    if (lanes_per_pair <= 0) { h->forced_logt = -1; return VITB_OK; }
+    if (lanes_per_pair <= 0) { h->forced_variant = 0; return VITB_OK; }
     for (const KernelEntry* e : h->variants) {
-        if ((1 << e->logt) == lanes_per_pair) { h->forced_logt = e->logt; return VITB_OK; }
+        if (entry_variant(e) == lanes_per_pair) { h->forced_variant = lanes_per_pair; return VITB_OK; }
     }
-    if (h->hg_entry && (1 << h->hg_entry->logt) == lanes_per_pair) { h->forced_logt = h->hg_entry->logt; return VITB_OK; }
+    if (h->hg_entry && entry_variant(h->hg_entry) == lanes_per_pair) { h->forced_variant = lanes_per_pair; return VITB_OK; }
     return VITB_ERR_UNSUPPORTED;
 }
 
@@ -588,11 +635,11 @@ int vitb_get_variants(const vitb_decoder* h, int* lanes_per_pair, int capacity) 
     if (!h) return VITB_ERR_ARG;
     int n = 0;
     if (h->hg_entry) {          // batch-only variant, listed first (fewest lanes)
-        if (lanes_per_pair && n < capacity) lanes_per_pair[n] = 1 << h->hg_entry->logt;
+        if (lanes_per_pair && n < capacity) lanes_per_pair[n] = entry_variant(h->hg_entry);
         n++;
     }
     for (const KernelEntry* e : h->variants) {
-        if (lanes_per_pair && n < capacity) lanes_per_pair[n] = 1 << e->logt;
+        if (lanes_per_pair && n < capacity) lanes_per_pair[n] = entry_variant(e);
         n++;
     }
     return n;
@@ -629,12 +676,13 @@ int vitb_set_traceback_length(vitb_decoder* h, size_t traceback_length) {
         const size_t row_bytes = dec_row_bytes_unit(h->entry);
         DeviceBuffer nb;
         VITB_CUDA(h, nb.reserve(rows * row_bytes + 16));
-        VITB_CUDA(h, cudaMemsetAsync(nb.ptr, 0, rows * row_bytes + 16, h->stream));
-        if (h->s_dec.ptr) {
+        cudaError_t ce = cudaMemsetAsync(nb.ptr, 0, rows * row_bytes + 16, h->stream);
+        if (ce == cudaSuccess && h->s_dec.ptr) {
             const size_t keep = rows < old_rows ? rows : old_rows;
-            VITB_CUDA(h, cudaMemcpyAsync(nb.ptr, h->s_dec.ptr, keep * row_bytes, cudaMemcpyDeviceToDevice, h->stream));
+            ce = cudaMemcpyAsync(nb.ptr, h->s_dec.ptr, keep * row_bytes, cudaMemcpyDeviceToDevice, h->stream);
         }
-        VITB_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
+        if (ce != cudaSuccess) { nb.release(); return cuda_fail(h, ce); }      // nb is a plain handle: free it on every early return
         h->s_dec.release();
         h->s_dec = nb;
     }
@@ -834,8 +882,12 @@ int vitb_set_puncture_schedule(vitb_decoder* h, const uint8_t* keep, size_t n_de
     std::vector<int32_t> map(n_depunctured);
     int32_t next = 0;
     for (size_t i = 0; i < n_depunctured; i++) map[i] = keep[i] ? next++ : -1;               // puncture_code_helpers.h:29-45
+    // a batch call of this handle may still be reading the old map on a non-blocking stream: order the copy after it
+    VITB_CUDA(h, batch_begin(h, h->stream));
+    VITB_CUDA(h, cudaStreamSynchronize(h->stream));
     VITB_CUDA(h, h->map.reserve(n_depunctured * 4));
-    VITB_CUDA(h, cudaMemcpy(h->map.ptr, map.data(), n_depunctured * 4, cudaMemcpyHostToDevice));
+    VITB_CUDA(h, cudaMemcpyAsync(h->map.ptr, map.data(), n_depunctured * 4, cudaMemcpyHostToDevice, h->stream));
+    VITB_CUDA(h, cudaStreamSynchronize(h->stream));
     h->n_depunctured = n_depunctured;
     h->n_received = size_t(next);
     h->unpunctured_value = unpunctured_value;
@@ -851,9 +903,12 @@ int vitb_decode_batch_dev(vitb_decoder* h, const void* d_symbols, size_t n_frame
     VITB_CUDA(h, cudaSetDevice(h->prm.device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     h->ev_used = 0;
-    const size_t chunk = chunk_frames_for(h, L), out_stride = (L + 7) / 8, sb = size_t(h->prm.soft_bytes);
+    VITB_CUDA(h, batch_begin(h, s));
+    size_t chunk = chunk_frames_for(h, L);
+    const size_t out_stride = (L + 7) / 8, sb = size_t(h->prm.soft_bytes);
     const KernelEntry* e = choose_variant(h, n_frames < chunk ? n_frames : chunk);
     h->last_batch = e;
+    if (n_frames > chunk && direct_fetch_ok(h, e, d_symbols, row_stride)) chunk = chunk_frames_for(h, L, false);   // no packed stream to pay for
     for (size_t f0 = 0; f0 < n_frames; f0 += chunk) {
         const size_t nf = (n_frames - f0 < chunk) ? (n_frames - f0) : chunk;
         const int r = decode_chunk_dev(h, e, static_cast<const uint8_t*>(d_symbols) + f0 * row_stride * sb, row_stride, nf, L, start, end,
@@ -861,6 +916,7 @@ int vitb_decode_batch_dev(vitb_decoder* h, const void* d_symbols, size_t n_frame
                                        d_final ? d_final + f0 : nullptr, s);
         if (r != VITB_OK) return r;
     }
+    VITB_CUDA(h, batch_end(h, s));
     return VITB_OK;
 }
 
@@ -877,6 +933,7 @@ int vitb_decode_batch_async(vitb_decoder* h, const void* symbols, size_t n_frame
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t sb = size_t(h->prm.soft_bytes), out_stride = (L + 7) / 8;
     const size_t row_bytes = row_stride * sb, in_bytes = n_frames * row_bytes;
+    VITB_CUDA(h, batch_begin(h, s));       // also keeps d_in / d_out of a call still in flight on another stream intact
     VITB_CUDA(h, h->d_in.reserve(in_bytes));
     if (out_bytes) VITB_CUDA(h, h->d_out.reserve(n_frames * out_stride));
     if (acc_error) VITB_CUDA(h, h->d_accout.reserve(n_frames * 8));
@@ -923,6 +980,7 @@ int vitb_decode_batch_async(vitb_decoder* h, const void* symbols, size_t n_frame
         if (acc_error) VITB_CUDA(h, cudaMemcpyAsync(acc_error + f0, d_acc, nf * 8, cudaMemcpyDeviceToHost, s));
         if (final_error) VITB_CUDA(h, cudaMemcpyAsync(final_error + f0, d_fin, nf * 4, cudaMemcpyDeviceToHost, s));
     }
+    VITB_CUDA(h, batch_end(h, s));
     return VITB_OK;
 }
 

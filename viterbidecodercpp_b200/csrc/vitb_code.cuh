@@ -53,6 +53,13 @@ __host__ __device__ inline uint32_t bfly_pattern_rt(const uint32_t* G, int R, ui
     return p;
 }
 
+// Direct symbol fetch: largest 32-bit word index of a row that still lies inside the caller's array (loads are clamped to it).
+// Word indices inside a row fit 32 bits; the remaining size of a >= 16 GiB array does not, so it is saturated, not truncated.
+__host__ __device__ inline uint32_t clamp_words_left(size_t total_bytes, size_t row_offset_bytes) {
+    const size_t w = (total_bytes - row_offset_bytes - 4) >> 2;
+    return w > size_t(0xffffffffu) ? 0xffffffffu : uint32_t(w);
+}
+
 // rotate an n-bit index left/right by r
 __host__ __device__ constexpr uint32_t rotl_bits(uint32_t v, int r, int n) {
     r %= n;

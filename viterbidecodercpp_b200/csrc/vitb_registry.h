@@ -12,10 +12,11 @@
 #include "acs_cta.cuh"
 #include "acs_generic.cuh"
 #include "acs_hist_group.cuh"
+#include "acs_hist_cta.cuh"
 
 namespace vitb {
 
-enum { LAYOUT_PAIR = 0, LAYOUT_GROUP = 1, LAYOUT_CTA = 2, LAYOUT_HISTGROUP = 3 };
+enum { LAYOUT_PAIR = 0, LAYOUT_GROUP = 1, LAYOUT_CTA = 2, LAYOUT_HISTGROUP = 3, LAYOUT_HISTCTA = 4 };
 
 struct KernelEntry {
     int K, R;
@@ -39,7 +40,10 @@ struct KernelEntry {
     int generic;
     cudaError_t (*launch_generic)(const AcsParams&, const GenericCode&, cudaStream_t);
     cudaError_t (*launch_hist_direct)(const AcsParams&, cudaStream_t);
+    int variant_id;    // number vitb_set_variant / vitb_get_variants know this entry by; 0 = 1 << logt (lanes per frame pair)
 };
+
+inline int entry_variant(const KernelEntry* e) { return e->variant_id ? e->variant_id : (1 << e->logt); }
 
 // Decision-row kernel of the one-thread-per-pair mapping (streaming calls; batch calls when the history kernel is switched off).
 // A two-register-set (ping-pong) variant of it was measured and dropped: ptxas scheduled all compare-selects ahead of their
@@ -182,10 +186,40 @@ KernelEntry make_hist_group_entry(const char* name) {
     VEC.push_back(make_hist_group_entry<CODE, false, false>("acs<" TAG ",T4,u16,scalar-tie,cinv>"));         \
     VEC.push_back(make_hist_group_entry<CODE, true, false>("acs<" TAG ",T4,u16,simd-tie,cinv>"));
 
+// survivor-history kernel with one frame per 512-thread CTA (acs_hist_cta.cuh): K = 15, uint16_t metrics, whole-frame batch calls
+// with unpunctured input only.  Variant number 256 (threads per frame PAIR would be 1024, which the decision-row kernel
+// acs_cta<T1024> already answers to).
+template <class C, bool TIE_SIMD>
+cudaError_t launch_hist_cta(const AcsParams& p, cudaStream_t s) {
+    using H = HistCtaShape<C>;
+    const cudaError_t e = cudaFuncSetAttribute(acs_hist_cta_kernel<C, TIE_SIMD>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(H::SMEM_BYTES));
+    if (e != cudaSuccess) return e;
+    acs_hist_cta_kernel<C, TIE_SIMD><<<p.n_frames, H::T, H::SMEM_BYTES, s>>>(p);
+    return cudaGetLastError();
+}
+
+template <class C, bool TIE_SIMD>
+KernelEntry make_hist_cta_entry(const char* name, int consistent) {
+    KernelEntry e{};
+    e.K = C::K; e.R = C::R;
+    for (int i = 0; i < C::R; i++) e.G[i] = C::G[i];
+    e.sh = 0; e.tie = TIE_SIMD ? 1 : 0; e.consistent = consistent; e.logt = HistCtaShape<C>::LOGT; e.name = name;
+    e.layout = LAYOUT_HISTCTA; e.ppw = 0; e.dec_words = 0; e.variant_id = 256;
+    e.launch_hist = &launch_hist_cta<C, TIE_SIMD>;
+    return e;
+}
+
+#define VITB_HIST_CTA_VARIANTS(VEC, CODE, TAG)                                                          \
+    for (int cons = 0; cons < 2; cons++) {                                                              \
+        VEC.push_back(make_hist_cta_entry<CODE, false>("acs<" TAG ",T256,u16,scalar-tie>", cons));       \
+        VEC.push_back(make_hist_cta_entry<CODE, true>("acs<" TAG ",T256,u16,simd-tie>", cons));          \
+    }
+
 // one translation unit per code family and lanes-per-pair setting (parallel compilation)
 void register_small(std::vector<KernelEntry>& v);
 void register_generic(std::vector<KernelEntry>& v);
 void register_k9_hist_group(std::vector<KernelEntry>& v);
+void register_k15_hist_cta(std::vector<KernelEntry>& v);
 void register_k7r2_t1(std::vector<KernelEntry>& v);
 void register_k7r2_t2(std::vector<KernelEntry>& v);
 void register_k7r2_t4(std::vector<KernelEntry>& v);
