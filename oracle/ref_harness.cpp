@@ -53,6 +53,7 @@ struct Args {
     uint64_t* decisions;   // optional: [F][L+K-1][words] reference layout
     uint32_t* metrics;     // optional: [F][2^(K-1)] final metrics
     int n_threads; double* seconds;
+    int passes = 1;        // timing runs: every thread decodes its range `passes` times (threads persist; seconds = mean per pass)
 };
 
 template <class Decoder, size_t K, size_t R, typename error_t, typename soft_t>
@@ -104,7 +105,7 @@ int decode_all(const Args& a) {
     const auto t0 = std::chrono::steady_clock::now();
     int rc = 0;
     if (nt == 1) {
-        rc = decode_range<Decoder, K, R, error_t, soft_t>(table, config, a, 0, a.n_frames);
+        for (int pass = 0; pass < a.passes && !rc; pass++) rc = decode_range<Decoder, K, R, error_t, soft_t>(table, config, a, 0, a.n_frames);
     } else {
         // one ViterbiDecoder_Core per thread, contiguous frame ranges, each thread pinned to one allowed logical CPU
         cpu_set_t allowed; CPU_ZERO(&allowed);
@@ -117,15 +118,17 @@ int decode_all(const Args& a) {
             const size_t f0 = a.n_frames * size_t(t) / size_t(nt), f1 = a.n_frames * size_t(t + 1) / size_t(nt);
             threads.emplace_back([&, t, f0, f1]() {
                 if (!cpus.empty()) pin_to_cpu(cpus[size_t(t) % cpus.size()]);
-                const int r = decode_range<Decoder, K, R, error_t, soft_t>(table, config, a, f0, f1);
-                if (r) worst = r;
+                for (int pass = 0; pass < a.passes; pass++) {
+                    const int r = decode_range<Decoder, K, R, error_t, soft_t>(table, config, a, f0, f1);
+                    if (r) { worst = r; break; }
+                }
             });
         }
         for (auto& th : threads) th.join();
         rc = worst;
     }
     const auto t1 = std::chrono::steady_clock::now();
-    if (a.seconds) *a.seconds = std::chrono::duration<double>(t1 - t0).count();
+    if (a.seconds) *a.seconds = std::chrono::duration<double>(t1 - t0).count() / double(a.passes > 0 ? a.passes : 1);
     return rc;
 }
 
@@ -162,6 +165,15 @@ int vitref_decode(int K, int R, const uint32_t* G, int soft_bytes, int high, int
                   uint8_t* out_bytes, uint64_t* acc, uint32_t* final_error, uint64_t* decisions, uint32_t* metrics,
                   int n_threads, double* seconds) {
     Args a{G, high, low, cfg, symbols, n_frames, L, out_bytes, acc, final_error, decisions, metrics, n_threads, seconds};
+    return dispatch(K, R, soft_bytes, impl, a);
+}
+
+// same, `passes` passes over the batch with the worker threads (one pinned Core each) kept alive in between; *seconds = mean per pass
+int vitref_decode_passes(int K, int R, const uint32_t* G, int soft_bytes, int high, int low, const uint64_t cfg[4], int impl,
+                         const void* symbols, size_t n_frames, size_t L, uint8_t* out_bytes, uint64_t* acc, uint32_t* final_error,
+                         int n_threads, int passes, double* seconds) {
+    Args a{G, high, low, cfg, symbols, n_frames, L, out_bytes, acc, final_error, nullptr, nullptr, n_threads, seconds};
+    a.passes = passes > 0 ? passes : 1;
     return dispatch(K, R, soft_bytes, impl, a);
 }
 

@@ -212,7 +212,9 @@ def oracle_encode(K, R, G, data_bytes):
     return out
 
 
-def ref_decode(K, R, G, soft_bytes, high, low, cfg, impl, symbols, n_frames, L, want_decisions=False, want_metrics=False, n_threads=1):
+def ref_decode(K, R, G, soft_bytes, high, low, cfg, impl, symbols, n_frames, L, want_decisions=False, want_metrics=False, n_threads=1,
+               passes=1):
+    """passes > 1: timing run, the pinned worker threads decode their frame ranges `passes` times; seconds = mean per pass"""
     lib = ref_lib()
     s = np.ascontiguousarray(symbols, dtype=soft_dtype(soft_bytes))
     assert s.size == n_frames * (L + K - 1) * R
@@ -223,6 +225,17 @@ def ref_decode(K, R, G, soft_bytes, high, low, cfg, impl, symbols, n_frames, L, 
     dec = np.zeros((n_frames, L + K - 1, words), dtype=np.uint64) if want_decisions else None
     met = np.zeros((n_frames, 1 << (K - 1)), dtype=np.uint32) if want_metrics else None
     secs = C.c_double(0)
+    if passes > 1:
+        assert not want_decisions and not want_metrics
+        lib.vitref_decode_passes.restype = C.c_int
+        lib.vitref_decode_passes.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                             C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        g, c = _u32(G), _u64(cfg)
+        rc = lib.vitref_decode_passes(K, R, C.cast(g, C.c_void_p), soft_bytes, high, low, C.cast(c, C.c_void_p), impl, s.ctypes.data, n_frames, L,
+                                      out.ctypes.data, acc.ctypes.data, fin.ctypes.data, n_threads, passes, C.byref(secs))
+        if rc != 0:
+            raise RuntimeError(f"vitref_decode_passes rc={rc}")
+        return {"bytes": out, "acc": acc, "final": fin, "decisions": None, "metrics": None, "seconds": secs.value}
     rc = lib.vitref_decode(K, R, _u32(G), soft_bytes, high, low, _u64(cfg), impl, s.ctypes.data, n_frames, L,
                            out.ctypes.data, acc.ctypes.data, fin.ctypes.data,
                            dec.ctypes.data if dec is not None else None, met.ctypes.data if met is not None else None,

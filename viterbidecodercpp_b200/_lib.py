@@ -43,6 +43,8 @@ API = [
     ("vitb_get_decisions", C.c_int, [_P, C.c_size_t, C.c_size_t, _P]),
     ("vitb_decode_batch", C.c_int, [_P, _P, C.c_size_t, C.c_size_t, C.POINTER(vitb_batch_opts), _P, _P, _P]),
     ("vitb_decode_batch_dev", C.c_int, [_P, _P, C.c_size_t, C.c_size_t, C.POINTER(vitb_batch_opts), _P, _P, _P, _P]),
+    ("vitb_set_pipelining", C.c_int, [_P, C.c_int]),
+    ("vitb_batch_flush", C.c_int, [_P, _P]),
     ("vitb_decode_batch_async", C.c_int, [_P, _P, C.c_size_t, C.c_size_t, C.POINTER(vitb_batch_opts), _P, _P, _P, _P]),
     ("vitb_set_puncture_schedule", C.c_int, [_P, _P, C.c_size_t, C.c_int32]),
     ("vitb_synth_frames_dev", C.c_int, [_P, C.c_size_t, C.c_size_t, C.c_float, C.c_uint64, _P, _P, C.c_size_t, _P]),

@@ -80,6 +80,15 @@ struct DeviceBuffer {
     void release() { if (ptr) cudaFree(ptr); ptr = nullptr; bytes = 0; }
 };
 
+// Workspace of one chunk of a batch call.  acs_done: recorded on the caller's stream behind the ACS kernel (the traceback on
+// tb_stream waits for it); tb_done: recorded on tb_stream behind the chunk's last kernel / copy (the next ACS that reuses the slot,
+// and whoever wants the results, wait for it).
+struct BatchSlot {
+    DeviceBuffer dec, metrics, acc, tb_spec, tb_fin, end_states;
+    cudaEvent_t acs_done = nullptr, tb_done = nullptr;
+    bool tb_pending = false;
+};
+
 }  // namespace vitb
 
 using namespace vitb;
@@ -110,8 +119,14 @@ struct vitb_decoder {
     // when they are enqueued on different streams: each call's stream first waits for `batch_done` of the previous call.
     cudaEvent_t batch_done = nullptr;
     bool batch_pending = false;
-    // batch workspace
-    DeviceBuffer pk, dec, metrics, acc, d_in, d_out, d_accout, d_finout, map, tb_spec, tb_fin, end_states;
+    // batch workspace.  Everything the traceback / gather of a chunk reads lives in one of two SLOTS, so that the traceback of chunk
+    // c (tb_stream; memory bound) runs next to the add-compare-select of chunk c+1 (caller's stream; issue bound): see BatchSlot
+    DeviceBuffer pk, d_in, d_out, d_accout, d_finout, map, end_states;
+    BatchSlot slots[2];
+    int slot_next = 0;
+    cudaStream_t tb_stream = nullptr;     // owned; traceback, best-state and gather kernels of the batch calls
+    bool pipelined = false;               // vitb_set_pipelining: the join with the last chunk's traceback is deferred to the next call / flush
+    bool overlap_hint = false;            // this chunk's traceback will run next to another chunk's ACS (pipelined call, multi-chunk call)
     size_t n_depunctured = 0, n_received = 0;
     int32_t unpunctured_value = 0;
     // single-frame streaming state (one 64-frame block, frame 0 is the user's)
@@ -245,12 +260,13 @@ size_t default_ws_limit() {
 }
 
 // workspace bytes per 64 frames for a frame of S steps (identical for every variant: decision rows are 2^(K-1) bits per frame-step)
-size_t block_bytes(const vitb_decoder* h, size_t S, bool with_packed_stream = true) {
+size_t block_bytes(const vitb_decoder* h, size_t S, bool with_packed_stream = true, bool two_slots = false) {
     const size_t n_sym = S * size_t(h->prm.R);
+    const size_t slot = S * 64 * (size_t(h->n_states) / 8 < 8 ? 8 : size_t(h->n_states) / 8)   // decision rows
+                      + size_t(64) * h->n_states * 2                                           // metrics
+                      + 64 * 8;                                                                // accumulated error
     return (with_packed_stream ? n_sym * 32 * 4 : 0)        // packed symbols (not needed when the kernel reads the caller's rows itself)
-         + S * 64 * (size_t(h->n_states) / 8 < 8 ? 8 : size_t(h->n_states) / 8)   // decision rows
-         + size_t(64) * h->n_states * 2                     // metrics
-         + 64 * 8;                                          // accumulated error
+         + slot * (two_slots ? 2 : 1);                      // consecutive chunks alternate between two slots (BatchSlot)
 }
 
 size_t dec_bytes_per_block64(const KernelEntry* e, size_t rows) {
@@ -267,7 +283,8 @@ size_t dec_row_bytes_unit(const KernelEntry* e) {
 }
 
 cudaError_t launch_traceback(vitb_decoder* h, const KernelEntry* e, const void* dec, size_t dec_rows, size_t n_frames, size_t L,
-                             size_t end_state, uint8_t* d_out, size_t out_stride, cudaStream_t s, const uint32_t* end_states = nullptr) {
+                             size_t end_state, uint8_t* d_out, size_t out_stride, cudaStream_t s, const uint32_t* end_states = nullptr,
+                             BatchSlot* sl = nullptr) {
     h->launches++;
     if (e->layout == LAYOUT_CTA) {
         TracebackCtaParams t{};
@@ -281,16 +298,16 @@ cudaError_t launch_traceback(vitb_decoder* h, const KernelEntry* e, const void* 
         size_t seg_bits = h->seg_records_forced > 0 ? size_t(h->seg_records_forced) * 8 : ((4 * overlap + 7) / 8 * 8);
         if (seg_bits < 8) seg_bits = 8;
         if ((L + seg_bits - 1) / seg_bits > 65535) seg_bits = ((L + 65534) / 65535 + 7) / 8 * 8;                    // gridDim.y
-        const size_t n_seg = (no_seg || dec == h->s_dec.ptr) ? 1 : (L + seg_bits - 1) / seg_bits;
+        const size_t n_seg = (no_seg || !sl) ? 1 : (L + seg_bits - 1) / seg_bits;      // no slot: the streaming state keeps the plain walk
         if (n_seg <= 1) {
             traceback_cta_kernel<5><<<unsigned((n_frames + 63) / 64), 64, 0, s>>>(t);
         } else {
-            cudaError_t ce = h->tb_spec.reserve(n_seg * n_frames * 4);
-            if (ce == cudaSuccess) ce = h->tb_fin.reserve(n_seg * n_frames * 4);
+            cudaError_t ce = sl->tb_spec.reserve(n_seg * n_frames * 4);
+            if (ce == cudaSuccess) ce = sl->tb_fin.reserve(n_seg * n_frames * 4);
             if (ce != cudaSuccess) return ce;
             TracebackCtaSegParams sp{};
             sp.n_seg = uint32_t(n_seg); sp.seg_bits = uint32_t(seg_bits); sp.overlap = uint32_t(overlap);
-            sp.spec = static_cast<uint32_t*>(h->tb_spec.ptr); sp.fin = static_cast<uint32_t*>(h->tb_fin.ptr);
+            sp.spec = static_cast<uint32_t*>(sl->tb_spec.ptr); sp.fin = static_cast<uint32_t*>(sl->tb_fin.ptr);
             traceback_cta_seg_kernel<5><<<dim3(unsigned((n_frames + 63) / 64), unsigned(n_seg)), 64, 0, s>>>(t, sp);
             ce = cudaGetLastError();
             if (ce != cudaSuccess) return ce;
@@ -369,11 +386,45 @@ cudaError_t batch_end(vitb_decoder* h, cudaStream_t s) {
     return cudaEventRecord(h->batch_done, s);
 }
 
-// One chunk of frames, everything on device, asynchronous on `s`.
+// Slots and streams of the batch calls.  A chunk's ingest and ACS kernels run on the caller's stream `s`; its best-state, traceback,
+// gather kernels (and, for the host-pointer path, its device-to-host copies) run on the handle's tb_stream behind the slot's
+// acs_done event.  The traceback is bound by DRAM round trips and the ACS by instruction issue, so the two overlap almost for free:
+// measured on config 2, a step is 0.83 ms with the stages in sequence and ~0.66 ms with the traceback of batch i next to the ACS of
+// batch i+1 (profiles/r02_summary.md).  join_slots makes `s` wait for the results.
+cudaError_t slot_events(BatchSlot& sl) {
+    if (!sl.acs_done) {
+        cudaError_t e = cudaEventCreateWithFlags(&sl.acs_done, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.tb_done, cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+// `s` waits for the results of every slot (keep_newest: except the slot used last - a pipelined call leaves that one in flight).
+// tb_pending stays set: a later call on ANOTHER stream has to wait again, and waiting for a completed event costs nothing.
+cudaError_t join_slots(vitb_decoder* h, cudaStream_t s, bool keep_newest) {
+    const int newest = h->slot_next ^ 1;
+    for (int i = 0; i < 2; i++) {
+        BatchSlot& sl = h->slots[i];
+        if (!sl.tb_pending || (keep_newest && i == newest)) continue;
+        const cudaError_t e = cudaStreamWaitEvent(s, sl.tb_done, 0);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+// One chunk of frames, everything on device, asynchronous: ACS on `s`, traceback and result gather on h->tb_stream (joined by the
+// caller).  d2h_*: optional host destinations of this chunk's results, copied on tb_stream behind the gather.
 int decode_chunk_dev(vitb_decoder* h, const KernelEntry* e, const void* d_symbols, size_t row_stride, size_t n_frames, size_t L,
-                     size_t start_state, size_t end_state, uint8_t* d_out, uint64_t* d_acc, uint32_t* d_final, cudaStream_t s) {
+                     size_t start_state, size_t end_state, uint8_t* d_out, uint64_t* d_acc, uint32_t* d_final, cudaStream_t s,
+                     uint8_t* h_out = nullptr, uint64_t* h_acc = nullptr, uint32_t* h_final = nullptr) {
     const size_t K = size_t(h->prm.K), R = size_t(h->prm.R), S = L + K - 1, n_sym = S * R;
     const unsigned n_b64 = unsigned((n_frames + 63) / 64);
+    BatchSlot& sl = h->slots[h->slot_next];
+    h->slot_next ^= 1;
+    VITB_CUDA(h, slot_events(sl));
+    if (sl.tb_pending) VITB_CUDA(h, cudaStreamWaitEvent(s, sl.tb_done, 0));     // the slot's buffers are free once its last traceback is done
+    cudaStream_t ts = h->tb_stream;
     // one-thread-per-pair entries: survivor-history records (acs_hist.cuh) instead of decision rows; same bytes per frame and step.
     // uint8_t metrics: warp block = 64 frames, 8-step records; uint16_t metrics: warp block = 32 frames, 16-step records.
     // K = 9 with uint16_t metrics: the frame-over-4-lanes history kernel (acs_hist_group.cuh) when the symbols can be fetched directly
@@ -402,9 +453,9 @@ int decode_chunk_dev(vitb_decoder* h, const KernelEntry* e, const void* d_symbol
     // record bytes per block and period: a warp block of the one-lane kernels holds 64 states-bytes x 64 (or 32 x 2) frames, the
     // lane-group kernel 8 frames, the CTA kernel one frame: always 2^(K-1) bits per frame and step
     const size_t rec_block_bytes = hc ? size_t(2) * size_t(h->n_states) : ((64 * size_t(h->n_states)) >> (hg ? e->logt : 0));
-    VITB_CUDA(h, h->dec.reserve(hist ? size_t(n_wblocks) * n_periods * rec_block_bytes : size_t(n_b64) * dec_bytes_per_block64(e, S)));
-    VITB_CUDA(h, h->metrics.reserve(size_t(n_b64) * 64 * h->n_states * 2));
-    VITB_CUDA(h, h->acc.reserve(size_t(n_b64) * 64 * 8));
+    VITB_CUDA(h, sl.dec.reserve(hist ? size_t(n_wblocks) * n_periods * rec_block_bytes : size_t(n_b64) * dec_bytes_per_block64(e, S)));
+    VITB_CUDA(h, sl.metrics.reserve(size_t(n_b64) * 64 * h->n_states * 2));
+    VITB_CUDA(h, sl.acc.reserve(size_t(n_b64) * 64 * 8));
 
     // one-thread-per-pair kernels can read the caller's rows themselves when they are 4-byte aligned and not punctured
     const size_t row_bytes = row_stride * size_t(h->prm.soft_bytes);
@@ -423,29 +474,31 @@ int decode_chunk_dev(vitb_decoder* h, const KernelEntry* e, const void* d_symbol
     AcsParams a{};
     fill_acs_params(h, a);
     a.sym = d_symbols; a.sym_row_bytes = row_bytes; a.sym_total_bytes = row_bytes * n_frames; a.n_frames = uint32_t(n_frames);
-    a.pk = static_cast<const uint32_t*>(h->pk.ptr); a.dec = h->dec.ptr;
-    a.metrics = static_cast<uint16_t*>(h->metrics.ptr); a.acc = static_cast<uint64_t*>(h->acc.ptr);
+    a.pk = static_cast<const uint32_t*>(h->pk.ptr); a.dec = sl.dec.ptr;
+    a.metrics = static_cast<uint16_t*>(sl.metrics.ptr); a.acc = static_cast<uint64_t*>(sl.acc.ptr);
     a.n_blocks = n_wblocks; a.n_steps = uint32_t(S); a.dec_rows = uint32_t(S); a.dec_row0 = 0; a.resume = 0; a.start_state = uint32_t(start_state);
     h->launches++;
     if (hist) VITB_CUDA(h, (direct && !hg && !hc) ? e->launch_hist_direct(a, s) : e->launch_hist(a, s));    // the hist-group / hist-CTA launchers always fetch directly
     else if (e->generic) VITB_CUDA(h, e->launch_generic(a, h->gcode, s));
     else VITB_CUDA(h, direct ? e->launch_direct(a, s) : e->launch(a, s));
     VITB_CUDA(h, mark(h, s));
+    VITB_CUDA(h, cudaEventRecord(sl.acs_done, s));
+    VITB_CUDA(h, cudaStreamWaitEvent(ts, sl.acs_done, 0));
 
     const uint32_t* end_states = nullptr;
     if (end_state == VITB_END_STATE_BEST) {
-        VITB_CUDA(h, h->end_states.reserve(n_frames * 4));
+        VITB_CUDA(h, sl.end_states.reserve(n_frames * 4));
         h->launches++;
-        best_state_kernel<<<unsigned((n_frames + 3) / 4), 128, 0, s>>>(a.metrics, uint32_t(h->n_states), uint32_t(n_frames),
-                                                                        static_cast<uint32_t*>(h->end_states.ptr));
+        best_state_kernel<<<unsigned((n_frames + 3) / 4), 128, 0, ts>>>(a.metrics, uint32_t(h->n_states), uint32_t(n_frames),
+                                                                         static_cast<uint32_t*>(sl.end_states.ptr));
         VITB_CUDA(h, cudaGetLastError());
-        end_states = static_cast<const uint32_t*>(h->end_states.ptr);
+        end_states = static_cast<const uint32_t*>(sl.end_states.ptr);
         end_state = 0;
     }
     if (d_out && hist) {
         h->launches++;
         TracebackHistParams t{};
-        t.dec = static_cast<const uint8_t*>(h->dec.ptr); t.n_periods = uint32_t(n_periods); t.n_frames = uint32_t(n_frames);
+        t.dec = static_cast<const uint8_t*>(sl.dec.ptr); t.n_periods = uint32_t(n_periods); t.n_frames = uint32_t(n_frames);
         t.total_bits = uint32_t(L); t.state_bits = uint32_t(K - 1); t.end_state = uint32_t(end_state); t.end_states = end_states; t.n_steps = uint32_t(S);
         t.hist_bits = uint32_t(hist_bits); t.logt = (hg || hc) ? uint32_t(e->logt) : 0u; t.out = d_out; t.out_stride = (L + 7) / 8;
         // A frame's chain is n_periods dependent memory round trips; small batches cannot hide them, so the chain is cut into
@@ -456,36 +509,46 @@ int decode_chunk_dev(vitb_decoder* h, const KernelEntry* e, const void* d_symbol
         const size_t warm_steps = K <= 9 ? 96 : 16 * K;
         const size_t overlap = h->seg_overlap_forced >= 0 ? size_t(h->seg_overlap_forced) : (warm_steps + hist_bits - 1) / hist_bits;
         static const size_t seg_target = getenv("VITB_SEG_TARGET") ? size_t(atoll(getenv("VITB_SEG_TARGET"))) : size_t(131072);
-        const size_t want_seg = (seg_target + n_frames - 1) / n_frames;
+        // A traceback that runs NEXT TO the ACS kernel of another chunk only has to finish before that kernel does, and a single chain
+        // per frame always does (n_periods round trips of ~0.63 us against >= 150 clocks per step of the ACS); walking concurrent
+        // segments would only take DRAM bandwidth and latency away from the ACS (config 2, pipelined: 0.749 ms per batch with two
+        // segments per frame, 0.677 ms with one; profiles/r02_summary.md)
+        const size_t want_seg = h->overlap_hint ? 1 : (seg_target + n_frames - 1) / n_frames;
         size_t seg_records = (n_periods + want_seg - 1) / want_seg;
-        if (seg_records < 4 * overlap) seg_records = 4 * overlap;
+        if (seg_records < 4 * overlap && !h->overlap_hint) seg_records = 4 * overlap;
         if (h->seg_records_forced > 0) seg_records = size_t(h->seg_records_forced);
         if (seg_records == 0) seg_records = 1;
         if ((n_periods + seg_records - 1) / seg_records > 65535) seg_records = (n_periods + 65534) / 65535;      // gridDim.y
         const size_t n_seg = no_seg ? 1 : (n_periods + seg_records - 1) / seg_records;
         if (n_seg <= 1) {
-            traceback_hist_kernel<<<unsigned((n_frames + 127) / 128), 128, 0, s>>>(t);
+            traceback_hist_kernel<<<unsigned((n_frames + 127) / 128), 128, 0, ts>>>(t);
         } else {
-            VITB_CUDA(h, h->tb_spec.reserve(n_seg * n_frames * 4));
-            VITB_CUDA(h, h->tb_fin.reserve(n_seg * n_frames * 4));
+            VITB_CUDA(h, sl.tb_spec.reserve(n_seg * n_frames * 4));
+            VITB_CUDA(h, sl.tb_fin.reserve(n_seg * n_frames * 4));
             TracebackSegParams sp{};
             sp.n_seg = uint32_t(n_seg); sp.seg_records = uint32_t(seg_records); sp.overlap = uint32_t(overlap);
-            sp.spec = static_cast<uint32_t*>(h->tb_spec.ptr); sp.fin = static_cast<uint32_t*>(h->tb_fin.ptr);
-            traceback_hist_seg_kernel<<<dim3(unsigned((n_frames + 127) / 128), unsigned(n_seg)), 128, 0, s>>>(t, sp);
+            sp.spec = static_cast<uint32_t*>(sl.tb_spec.ptr); sp.fin = static_cast<uint32_t*>(sl.tb_fin.ptr);
+            traceback_hist_seg_kernel<<<dim3(unsigned((n_frames + 127) / 128), unsigned(n_seg)), 128, 0, ts>>>(t, sp);
             VITB_CUDA(h, cudaGetLastError());
             h->launches++;
-            traceback_hist_fix_kernel<<<unsigned((n_frames + 127) / 128), 128, 0, s>>>(t, sp);
+            traceback_hist_fix_kernel<<<unsigned((n_frames + 127) / 128), 128, 0, ts>>>(t, sp);
         }
         VITB_CUDA(h, cudaGetLastError());
-    } else if (d_out) VITB_CUDA(h, launch_traceback(h, e, h->dec.ptr, S, n_frames, L, end_state, d_out, (L + 7) / 8, s, end_states));
-    VITB_CUDA(h, mark(h, s));
+    } else if (d_out) VITB_CUDA(h, launch_traceback(h, e, sl.dec.ptr, S, n_frames, L, end_state, d_out, (L + 7) / 8, ts, end_states, &sl));
+    VITB_CUDA(h, mark(h, ts));
     if (d_acc || d_final) {
         h->launches++;
-        gather_results_kernel<<<unsigned((n_frames + 255) / 256), 256, 0, s>>>(a.acc, a.metrics, uint32_t(h->n_states), uint32_t(end_state),
-                                                                              end_states, uint32_t(n_frames), d_acc, d_final);
+        gather_results_kernel<<<unsigned((n_frames + 255) / 256), 256, 0, ts>>>(a.acc, a.metrics, uint32_t(h->n_states), uint32_t(end_state),
+                                                                               end_states, uint32_t(n_frames), d_acc, d_final);
         VITB_CUDA(h, cudaGetLastError());
     }
-    VITB_CUDA(h, mark(h, s));
+    VITB_CUDA(h, mark(h, ts));
+    const size_t out_stride = (L + 7) / 8;
+    if (h_out && d_out) VITB_CUDA(h, cudaMemcpyAsync(h_out, d_out, n_frames * out_stride, cudaMemcpyDeviceToHost, ts));
+    if (h_acc && d_acc) VITB_CUDA(h, cudaMemcpyAsync(h_acc, d_acc, n_frames * 8, cudaMemcpyDeviceToHost, ts));
+    if (h_final && d_final) VITB_CUDA(h, cudaMemcpyAsync(h_final, d_final, n_frames * 4, cudaMemcpyDeviceToHost, ts));
+    VITB_CUDA(h, cudaEventRecord(sl.tb_done, ts));
+    sl.tb_pending = true;
     return VITB_OK;
 }
 
@@ -507,10 +570,10 @@ int check_batch_args(const vitb_decoder* h, size_t n_frames, size_t L, const vit
     return VITB_OK;
 }
 
-size_t chunk_frames_for(const vitb_decoder* h, size_t L, bool with_packed_stream = true) {
+size_t chunk_frames_for(const vitb_decoder* h, size_t L, bool with_packed_stream = true, bool two_slots = false) {
     const size_t S = L + size_t(h->prm.K) - 1;
     const size_t limit = h->ws_limit ? h->ws_limit : h->ws_default;
-    size_t blocks = limit / block_bytes(h, S, with_packed_stream);
+    size_t blocks = limit / block_bytes(h, S, with_packed_stream, two_slots);
     if (blocks < 1) blocks = 1;
     if (blocks > 65535) blocks = 65535;       // the ingest kernel and the segmented tracebacks index 64-frame blocks with gridDim.y
     return blocks * 64;
@@ -574,6 +637,7 @@ int vitb_create(const vitb_params* p, vitb_decoder** out) {
     }
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->tb_stream, cudaStreamNonBlocking);
     if (ce != cudaSuccess) { delete h; return VITB_ERR_CUDA; }
     *out = h;
     // core.h:175-176: the constructor leaves the decoder reset with traceback length 0
@@ -586,7 +650,13 @@ int vitb_create(const vitb_params* p, vitb_decoder** out) {
 int vitb_destroy(vitb_decoder* h) {
     if (!h) return VITB_OK;
     cudaSetDevice(h->prm.device);
-    for (DeviceBuffer* b : {&h->pk, &h->dec, &h->metrics, &h->acc, &h->d_in, &h->d_out, &h->d_accout, &h->d_finout, &h->map, &h->tb_spec, &h->tb_fin, &h->end_states,
+    for (BatchSlot& sl : h->slots) {
+        for (DeviceBuffer* b : {&sl.dec, &sl.metrics, &sl.acc, &sl.tb_spec, &sl.tb_fin, &sl.end_states}) b->release();
+        if (sl.acs_done) cudaEventDestroy(sl.acs_done);
+        if (sl.tb_done) cudaEventDestroy(sl.tb_done);
+    }
+    if (h->tb_stream) cudaStreamDestroy(h->tb_stream);
+    for (DeviceBuffer* b : {&h->pk, &h->d_in, &h->d_out, &h->d_accout, &h->d_finout, &h->map, &h->end_states,
                             &h->s_pk, &h->s_dec, &h->s_metrics, &h->s_acc, &h->s_in, &h->s_out, &h->g_tx, &h->g_sym, &h->g_cnt}) b->release();
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     for (cudaEvent_t e : h->copy_ev) cudaEventDestroy(e);
@@ -904,11 +974,15 @@ int vitb_decode_batch_dev(vitb_decoder* h, const void* d_symbols, size_t n_frame
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     h->ev_used = 0;
     VITB_CUDA(h, batch_begin(h, s));
-    size_t chunk = chunk_frames_for(h, L);
+    // a batch that fits the workspace is one chunk in one slot; pipelined calls and multi-chunk batches keep two slots alive
+    size_t chunk = chunk_frames_for(h, L, true, h->pipelined);
     const size_t out_stride = (L + 7) / 8, sb = size_t(h->prm.soft_bytes);
     const KernelEntry* e = choose_variant(h, n_frames < chunk ? n_frames : chunk);
     h->last_batch = e;
-    if (n_frames > chunk && direct_fetch_ok(h, e, d_symbols, row_stride)) chunk = chunk_frames_for(h, L, false);   // no packed stream to pay for
+    const bool no_pk = direct_fetch_ok(h, e, d_symbols, row_stride);                                               // no packed stream to pay for
+    if (n_frames > chunk && no_pk) chunk = chunk_frames_for(h, L, false, h->pipelined);
+    if (n_frames > chunk) chunk = chunk_frames_for(h, L, !no_pk, true);
+    h->overlap_hint = h->pipelined || n_frames > chunk;
     for (size_t f0 = 0; f0 < n_frames; f0 += chunk) {
         const size_t nf = (n_frames - f0 < chunk) ? (n_frames - f0) : chunk;
         const int r = decode_chunk_dev(h, e, static_cast<const uint8_t*>(d_symbols) + f0 * row_stride * sb, row_stride, nf, L, start, end,
@@ -916,7 +990,22 @@ int vitb_decode_batch_dev(vitb_decoder* h, const void* d_symbols, size_t n_frame
                                        d_final ? d_final + f0 : nullptr, s);
         if (r != VITB_OK) return r;
     }
+    // results in stream order at return - or, for pipelined calls, everything but the newest chunk (see vitb_set_pipelining)
+    VITB_CUDA(h, join_slots(h, s, h->pipelined));
     VITB_CUDA(h, batch_end(h, s));
+    return VITB_OK;
+}
+
+int vitb_set_pipelining(vitb_decoder* h, int enabled) {
+    if (!h) return VITB_ERR_ARG;
+    h->pipelined = enabled != 0;
+    return VITB_OK;
+}
+
+int vitb_batch_flush(vitb_decoder* h, void* stream) {
+    if (!h) return VITB_ERR_ARG;
+    VITB_CUDA(h, cudaSetDevice(h->prm.device));
+    VITB_CUDA(h, join_slots(h, static_cast<cudaStream_t>(stream), false));
     return VITB_OK;
 }
 
@@ -944,7 +1033,7 @@ int vitb_decode_batch_async(vitb_decoder* h, const void* symbols, size_t n_frame
     size_t chunk = (n_frames + 3) / 4;
     const size_t min_chunk = (size_t(16) << 20) / (row_bytes ? row_bytes : 1) + 1;
     if (chunk < min_chunk) chunk = min_chunk;
-    const size_t ws_chunk = chunk_frames_for(h, L);
+    const size_t ws_chunk = chunk_frames_for(h, L, true, true);
     if (chunk > ws_chunk) chunk = ws_chunk;
     // one-CTA-per-pair kernels (K = 15) run a few waves of CTAs per batch: splitting only makes the wave quantisation worse
     if (h->variants.front()->layout == LAYOUT_CTA && n_frames < size_t(h->n_sm) * 2 * 16) chunk = ws_chunk;
@@ -967,19 +1056,20 @@ int vitb_decode_batch_async(vitb_decoder* h, const void* symbols, size_t n_frame
     h->ev_used = 0;
     const KernelEntry* e = choose_variant(h, n_frames < chunk ? n_frames : chunk);
     h->last_batch = e;
+    h->overlap_hint = n_chunks > 1;
     for (size_t c = 0; c < n_chunks; c++) {
         const size_t f0 = c * chunk, nf = (n_frames - f0 < chunk) ? (n_frames - f0) : chunk;
         VITB_CUDA(h, cudaStreamWaitEvent(s, h->copy_ev[c], 0));
         uint8_t* d_out = out_bytes ? static_cast<uint8_t*>(h->d_out.ptr) + f0 * out_stride : nullptr;
         uint64_t* d_acc = acc_error ? static_cast<uint64_t*>(h->d_accout.ptr) + f0 : nullptr;
         uint32_t* d_fin = final_error ? static_cast<uint32_t*>(h->d_finout.ptr) + f0 : nullptr;
+        // the chunk's results go back on the traceback stream, behind its gather and next to the ACS of the next chunk
         const int r = decode_chunk_dev(h, e, static_cast<const uint8_t*>(h->d_in.ptr) + f0 * row_bytes, row_stride, nf, L, start, end,
-                                       d_out, d_acc, d_fin, s);
+                                       d_out, d_acc, d_fin, s, out_bytes ? out_bytes + f0 * out_stride : nullptr,
+                                       acc_error ? acc_error + f0 : nullptr, final_error ? final_error + f0 : nullptr);
         if (r != VITB_OK) return r;
-        if (out_bytes) VITB_CUDA(h, cudaMemcpyAsync(out_bytes + f0 * out_stride, d_out, nf * out_stride, cudaMemcpyDeviceToHost, s));
-        if (acc_error) VITB_CUDA(h, cudaMemcpyAsync(acc_error + f0, d_acc, nf * 8, cudaMemcpyDeviceToHost, s));
-        if (final_error) VITB_CUDA(h, cudaMemcpyAsync(final_error + f0, d_fin, nf * 4, cudaMemcpyDeviceToHost, s));
     }
+    VITB_CUDA(h, join_slots(h, s, false));
     VITB_CUDA(h, batch_end(h, s));
     return VITB_OK;
 }
@@ -1121,6 +1211,7 @@ int vitb_ber_trial(vitb_decoder* h, size_t n_frames, size_t total_bits, float Eb
     vitb_batch_opts o{}; o.row_stride = row;
     r = vitb_decode_batch_dev(h, h->g_sym.ptr, n_frames, total_bits, &o, static_cast<uint8_t*>(h->d_out.ptr), nullptr, nullptr, h->stream);
     if (r != VITB_OK) return r;
+    VITB_CUDA(h, join_slots(h, h->stream, false));
     h->launches++;
     bit_errors_kernel<<<296, 256, 0, h->stream>>>(static_cast<const uint8_t*>(h->g_tx.ptr), static_cast<const uint8_t*>(h->d_out.ptr), nb,
                                                   static_cast<unsigned long long*>(h->g_cnt.ptr));

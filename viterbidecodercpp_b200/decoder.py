@@ -198,6 +198,13 @@ class ViterbiDecoder_CUDA:
         _check(self._L.vitb_decode_batch_async(self._h, h_symbols, n_frames, total_bits, C.byref(o), h_out, h_acc, h_final, stream),
                "decode_batch_async")
 
+    def set_pipelining(self, enabled=True):
+        """vitb_set_pipelining: results of a decode_batch_dev call are complete (in stream order) after the NEXT call or batch_flush"""
+        _check(self._L.vitb_set_pipelining(self._h, 1 if enabled else 0))
+
+    def batch_flush(self, stream=0):
+        _check(self._L.vitb_batch_flush(self._h, C.c_void_p(stream)))
+
     def set_profiling(self, enabled=True):
         _check(self._L.vitb_set_profiling(self._h, 1 if enabled else 0))
 
@@ -217,6 +224,11 @@ class ViterbiDecoder_CUDA:
         e = float("nan") if EbNo_dB is None else float(EbNo_dB)
         _check(self._L.vitb_synth_frames(self._h, n_frames, total_bits, e, seed, tx.ctypes.data, sym.ctypes.data, row), "synth_frames")
         return tx, sym
+
+    def synth_frames_dev(self, n_frames, total_bits, d_tx, d_symbols, EbNo_dB=None, seed=1, row_stride=0, stream=0):
+        """device pointers (ints): [F][L/8] transmitted bytes and [F][row_stride] soft symbols are generated in place on `stream`"""
+        e = float("nan") if EbNo_dB is None else float(EbNo_dB)
+        _check(self._L.vitb_synth_frames_dev(self._h, n_frames, total_bits, e, seed, d_tx, d_symbols, row_stride, stream), "synth_frames_dev")
 
     def quantise(self, x, scale, mean):
         x = np.ascontiguousarray(x, dtype=np.float32)
