@@ -114,7 +114,7 @@ def test_default_mode_results_are_in_stream_order_at_return(cuda_lib):
     code = CODE_BY_NAME["Voyager"]
     dec, dc = make_cuda_decoder(code, "HARD8")
     ora, _ = make_oracle(code, "HARD8")
-    n_frames, L = 5000, 700
+    n_frames, L = 5000, 704
     s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
     for k, s in enumerate([s1, s2, s1, s2]):          # consecutive calls of one handle on two different streams
         tx, sym = frames(code, dc, n_frames, L, 2.0, seed=70 + k)

@@ -163,6 +163,9 @@ __global__ void __launch_bounds__(CtaShape<C, LT>::T, 1) acs_cta_kernel(const Ac
 
     const uint32_t t = threadIdx.x, pair = blockIdx.x;
     const size_t fA = size_t(pair) * 2, fB = fA + 1;
+    // the grid covers whole 64-frame blocks of the packed stream: pairs behind the last frame have nothing to decode (they used to
+    // decode padding: 888 frames ran 448 CTAs, one more wave than 444 on 148 SMs)
+    if (fA >= size_t(p.n_frames)) return;
     uint16_t* mA = p.metrics + fA * C::NS;
     uint16_t* mB = p.metrics + fB * C::NS;
 

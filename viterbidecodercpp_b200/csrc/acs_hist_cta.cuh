@@ -49,7 +49,8 @@ __host__ __device__ constexpr uint32_t rotl_rt(uint32_t v, uint32_t r, uint32_t 
 }
 
 template <class C, int PH, bool TIE_SIMD, int Q>
-__device__ __forceinline__ void hc_bfly_at(uint32_t (&x)[HistCtaShape<C>::NL], const uint2* tbl_ph, const uint32_t pt, const uint32_t tag) {
+__device__ __forceinline__ void hc_bfly_at(uint32_t (&x)[HistCtaShape<C>::NL], const uint2* tbl_ph, const uint32_t pt, const uint32_t tag,
+                                           const uint32_t one) {
     using H = HistCtaShape<C>;
     constexpr int bit = 1 << (H::LB - 1 - PH);
     if constexpr ((Q & bit) == 0) {
@@ -58,12 +59,17 @@ __device__ __forceinline__ void hc_bfly_at(uint32_t (&x)[HistCtaShape<C>::NL], c
         constexpr uint32_t pq = bfly_pattern<C>(jq);
         const uint2 e = tbl_ph[pq ^ pt];                // {total_error, inverted_error} << 16 of pattern pq ^ pt (scalar.h:66-73, 107)
         uint32_t m0, m1;
+        // The tag is added to the path-1 register ONCE (x1t), with a multiply-add by a run-time 1 so that ptxas cannot fold it back
+        // into two three-input IADD3: IADD3 issues on the same pipe as VIADDMNMX and LOP3 (6 of 6 instructions per butterfly on one
+        // pipe: the kernel ran at 1360 clocks per step); IMAD and the two-input adds (IMAD.IADD) go to the other pipe.
         if constexpr (!TIE_SIMD) {
-            const uint32_t b0 = x[q1] + e.y + tag, b1 = x[q1] + e.x + tag;      // path 1 tagged                 scalar.h:114,116
+            const uint32_t x1t = tag * one + x[q1];                             // path 1 tagged
+            const uint32_t b0 = x1t + e.y, b1 = x1t + e.x;                      //                               scalar.h:114,116
             m0 = __viaddmin_u32(x[q0], e.x, b0);                                // new state 2j   stays at q0   scalar.h:113,127
             m1 = __viaddmin_u32(x[q0], e.y, b1);                                // new state 2j+1 goes to q1    scalar.h:115,128
         } else {
-            const uint32_t a0 = x[q0] + e.x + tag, a1 = x[q0] + e.y + tag;      // tag on path 0: a tie selects path 1
+            const uint32_t x0t = tag * one + x[q0];                             // tag on path 0: a tie selects path 1
+            const uint32_t a0 = x0t + e.x, a1 = x0t + e.y;
             m0 = __viaddmin_u32(x[q1], e.y, a0);
             m1 = __viaddmin_u32(x[q1], e.x, a1);
         }
@@ -74,13 +80,14 @@ __device__ __forceinline__ void hc_bfly_at(uint32_t (&x)[HistCtaShape<C>::NL], c
 
 template <class C, int PH, bool TIE_SIMD, int... Qs>
 __device__ __forceinline__ void hc_bfly_all(uint32_t (&x)[HistCtaShape<C>::NL], const uint2* tbl_ph, const uint32_t pt, const uint32_t tag,
-                                            std::integer_sequence<int, Qs...>) {
-    (hc_bfly_at<C, PH, TIE_SIMD, Qs>(x, tbl_ph, pt, tag), ...);
+                                            const uint32_t one, std::integer_sequence<int, Qs...>) {
+    (hc_bfly_at<C, PH, TIE_SIMD, Qs>(x, tbl_ph, pt, tag, one), ...);
 }
 
 // grid = number of frames, block = 512, dynamic shared memory = HistCtaShape::SMEM_BYTES.  Whole frames only (no resume).
-template <class C, bool TIE_SIMD>
-__global__ void __launch_bounds__(HistCtaShape<C>::T, 1) acs_hist_cta_kernel(const AcsParams p) {
+// MINB: CTAs per SM the register allocation is made for (1: 128 registers per thread; 2: 64 registers - measured slower, it spills)
+template <class C, bool TIE_SIMD, int MINB>
+__global__ void __launch_bounds__(HistCtaShape<C>::T, MINB) acs_hist_cta_kernel(const AcsParams p) {
     using H = HistCtaShape<C>;
     using S = typename H::S;
     constexpr int LB = H::LB, NL = H::NL, NW = H::NW, R = C::R, NP = H::NP, SB = H::SB, LOGT = H::LOGT, HB = H::HB;
@@ -93,6 +100,7 @@ __global__ void __launch_bounds__(HistCtaShape<C>::T, 1) acs_hist_cta_kernel(con
     const uint32_t t = threadIdx.x;
     const size_t f = blockIdx.x;
     const HistConsts c = hist_consts<1>(p);
+    const uint32_t one = p.resume + 1u;                               // whole frames only: resume is 0.  A 1 the compiler cannot see (hc_bfly_at)
 
     uint32_t pt[LB];                                                  // thread part of the branch pattern per phase
 #pragma unroll
@@ -180,7 +188,7 @@ __global__ void __launch_bounds__(HistCtaShape<C>::T, 1) acs_hist_cta_kernel(con
             constexpr int PH = decltype(PHc)::value;
             constexpr bool GUARD = decltype(guard_tag)::value;
             if constexpr (GUARD) { if (uint32_t(PH) >= span) return; }
-            hc_bfly_all<C, PH, TIE_SIMD>(x, tbl + PH * NP, pt[PH], tag, std::make_integer_sequence<int, NL>{});
+            hc_bfly_all<C, PH, TIE_SIMD>(x, tbl + PH * NP, pt[PH], tag, one, std::make_integer_sequence<int, NL>{});
             mx = max(mx, x[0]);
             tag <<= 1;
             pst++;
@@ -210,7 +218,7 @@ __global__ void __launch_bounds__(HistCtaShape<C>::T, 1) acs_hist_cta_kernel(con
             auto replay_phase = [&](auto PHc) {
                 constexpr int PH = decltype(PHc)::value;
                 if (uint32_t(PH) < span) {
-                    hc_bfly_all<C, PH, TIE_SIMD>(x, tbl + PH * NP, pt[PH], tag, std::make_integer_sequence<int, NL>{});
+                    hc_bfly_all<C, PH, TIE_SIMD>(x, tbl + PH * NP, pt[PH], tag, one, std::make_integer_sequence<int, NL>{});
                     tag <<= 1;
                     pst++;
                     if (t == 0) flag[1] = x[0];

@@ -100,7 +100,7 @@ struct vitb_decoder {
     const KernelEntry* hg_entry = nullptr;      // frame-over-4-lanes survivor-history kernel (K = 9, uint16_t metrics), batch calls only
     const KernelEntry* last_batch = nullptr;    // variant the last batch call selected
     bool last_batch_hist = false;               // ... and whether it ran as the survivor-history kernel (acs_hist.cuh)
-    std::string name_buf;
+    std::string name_buf, name_override;        // name_override: a batch call that used two kernels (cta_wave_split)
     int forced_variant = 0;                     // vitb_set_variant (0 = automatic)
     bool use_hist = getenv("VITB_NO_HIST") == nullptr;   // vitb_set_history_kernel
     int seg_records_forced = 0, seg_overlap_forced = -1;   // vitb_set_traceback_segments (0 / -1 = automatic)
@@ -439,8 +439,11 @@ int decode_chunk_dev(vitb_decoder* h, const KernelEntry* e, const void* d_symbol
             const bool direct_ok = (row_bytes0 % 4 == 0) && row_bytes0 >= 4 && (reinterpret_cast<uintptr_t>(d_symbols) % 4 == 0);
             hg = direct_ok && (forced || (h->forced_variant == 0 && (n_frames + 7) / 8 >= size_t(h->n_sm) * 2));
         } else {
+            // One frame per CTA: 1.5 times the instructions per frame of the packed decision-row kernel (acs_cta.cuh, a frame PAIR per
+            // CTA: 14.0 ms per wave of 148 pairs against 10.4 ms per wave of 148 frames, config 5), but half the granularity: it takes
+            // the batches (and, see cta_wave_split, the last partial wave of a large batch) that fit one wave of single-frame CTAs
             const bool direct_ok = (row_bytes0 % 2 == 0) && (reinterpret_cast<uintptr_t>(d_symbols) % 2 == 0);
-            hc = direct_ok && (forced || h->forced_variant == 0);
+            hc = direct_ok && (forced || (h->forced_variant == 0 && n_frames <= size_t(h->n_sm)));
         }
         if (hg || hc) { e = a; h->last_batch = e; }
     }
@@ -550,6 +553,15 @@ int decode_chunk_dev(vitb_decoder* h, const KernelEntry* e, const void* d_symbol
     VITB_CUDA(h, cudaEventRecord(sl.tb_done, ts));
     sl.tb_pending = true;
     return VITB_OK;
+}
+
+// K = 15: frames of a batch that go to the decision-row kernel (whole waves of n_sm frame pairs); the rest, if it fits one wave of
+// single-frame CTAs, is decoded as a second chunk by the history kernel (1024 frames on 148 SMs: 3 waves of pairs + 136 single
+// frames = 3 x 14.0 + 10.4 ms instead of 4 x 14.0 ms).  Returns n_frames when there is nothing to split.
+size_t cta_wave_split(const vitb_decoder* h, size_t n_frames) {
+    if (!h->hg_entry || h->hg_entry->layout != LAYOUT_HISTCTA || h->forced_variant != 0 || !h->use_hist || h->n_depunctured) return n_frames;
+    const size_t wave = size_t(h->n_sm) * 2, first = n_frames / wave * wave, rem = n_frames - first;
+    return (first && rem && rem <= size_t(h->n_sm)) ? first : n_frames;
 }
 
 int check_batch_args(const vitb_decoder* h, size_t n_frames, size_t L, const vitb_batch_opts* o, size_t* row_stride, size_t* start, size_t* end) {
@@ -670,6 +682,7 @@ int vitb_destroy(vitb_decoder* h) {
 int vitb_last_cuda_error(const vitb_decoder* h) { return h ? h->last_cuda : 0; }
 const char* vitb_kernel_name(const vitb_decoder* h) {
     if (!h) return "";
+    if (!h->name_override.empty()) return h->name_override.c_str();
     if (h->last_batch && h->last_batch_hist) {      // "acs<...>" -> "acs_hist<...>"
         vitb_decoder* m = const_cast<vitb_decoder*>(h);
         m->name_buf = std::string("acs_hist") + (h->last_batch->name + 3);
@@ -815,6 +828,7 @@ int vitb_update(vitb_decoder* h, const void* symbols, size_t n_symbols, uint64_t
     a.pk = static_cast<const uint32_t*>(h->s_pk.ptr); a.dec = h->s_dec.ptr;
     a.metrics = static_cast<uint16_t*>(h->s_metrics.ptr); a.acc = static_cast<uint64_t*>(h->s_acc.ptr);
     a.n_blocks = 1;      // warp block 0 holds the user's frame (frame 0); its other frames decode zeros and are ignored
+    a.n_frames = 1;
     a.n_steps = uint32_t(steps); a.dec_rows = uint32_t(rows); a.dec_row0 = uint32_t(h->current_decoded_bit);
     a.resume = 1; a.start_state = 0;
     h->launches++;
@@ -983,6 +997,10 @@ int vitb_decode_batch_dev(vitb_decoder* h, const void* d_symbols, size_t n_frame
     if (n_frames > chunk && no_pk) chunk = chunk_frames_for(h, L, false, h->pipelined);
     if (n_frames > chunk) chunk = chunk_frames_for(h, L, !no_pk, true);
     h->overlap_hint = h->pipelined || n_frames > chunk;
+    const size_t split = (n_frames <= chunk) ? cta_wave_split(h, n_frames) : n_frames;
+    if (split < n_frames) chunk = split;                  // K = 15: whole waves of frame pairs, then the rest one frame per CTA
+    if (!h->pipelined && n_frames <= chunk) h->slot_next = 0;      // isolated single-chunk calls stay in one slot (half the workspace)
+    h->name_override.clear();
     for (size_t f0 = 0; f0 < n_frames; f0 += chunk) {
         const size_t nf = (n_frames - f0 < chunk) ? (n_frames - f0) : chunk;
         const int r = decode_chunk_dev(h, e, static_cast<const uint8_t*>(d_symbols) + f0 * row_stride * sb, row_stride, nf, L, start, end,
@@ -990,6 +1008,7 @@ int vitb_decode_batch_dev(vitb_decoder* h, const void* d_symbols, size_t n_frame
                                        d_final ? d_final + f0 : nullptr, s);
         if (r != VITB_OK) return r;
     }
+    if (split < n_frames) h->name_override = std::string(e->name) + " for " + std::to_string(split) + " frames + acs_hist" + (h->hg_entry->name + 3) + " for the rest";
     // results in stream order at return - or, for pipelined calls, everything but the newest chunk (see vitb_set_pipelining)
     VITB_CUDA(h, join_slots(h, s, h->pipelined));
     VITB_CUDA(h, batch_end(h, s));
@@ -1057,6 +1076,7 @@ int vitb_decode_batch_async(vitb_decoder* h, const void* symbols, size_t n_frame
     const KernelEntry* e = choose_variant(h, n_frames < chunk ? n_frames : chunk);
     h->last_batch = e;
     h->overlap_hint = n_chunks > 1;
+    h->name_override.clear();
     for (size_t c = 0; c < n_chunks; c++) {
         const size_t f0 = c * chunk, nf = (n_frames - f0 < chunk) ? (n_frames - f0) : chunk;
         VITB_CUDA(h, cudaStreamWaitEvent(s, h->copy_ev[c], 0));
