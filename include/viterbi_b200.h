@@ -75,6 +75,11 @@ int vitb_get_current_decoded_bit(const vitb_decoder* h, size_t* bit);           
 int vitb_get_metrics(vitb_decoder* h, uint32_t* metrics_out /* [2^(K-1)] */);   /* m_metrics.get_old()    core.h:240 */
 /* m_decisions[first_row .. first_row+n_rows) in the reference layout: max(2^(K-1)/64,1) uint64 per row, bit s%64 of word s/64 (core.h:49-83) */
 int vitb_get_decisions(vitb_decoder* h, size_t first_row, size_t n_rows, uint64_t* rows_out);
+/* m_metrics and m_current_decoded_bit are public members of the reference's core (core.h:238-242), so a caller may also ASSIGN
+ * them; the adapter that lets the reference's own programs drive this backend (include/viterbi_cuda/viterbi_decoder_cuda_ref.h)
+ * keeps the decoder state in the reference object and hands it to the GPU around every update.  metrics_in: [2^(K-1)] values. */
+int vitb_set_metrics(vitb_decoder* h, const uint32_t* metrics_in);
+int vitb_set_current_decoded_bit(vitb_decoder* h, size_t bit);
 
 /* ---- batched API: n_frames independent frames per call, each decoded as reset(start) + update(all) + get_error(end) +
  *      chainback(L, end).  symbols: [n_frames][row_stride] soft_t with (L+K-1)*R symbols used per frame (or the punctured

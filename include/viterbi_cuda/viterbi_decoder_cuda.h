@@ -21,6 +21,8 @@
 #include <stdexcept>
 #include <string>
 #include <type_traits>
+#include <utility>
+#include <vector>
 #include "../viterbi_b200.h"
 
 namespace viterbi_cuda {
@@ -35,6 +37,14 @@ struct ViterbiDecoder_Config {            // viterbi_decoder_config.h:11-18
     error_t initial_start_error;
     error_t initial_non_start_error;
     error_t renormalisation_threshold;
+    ViterbiDecoder_Config() = default;
+    ViterbiDecoder_Config(error_t max_error, error_t start, error_t non_start, error_t threshold)
+        : soft_decision_max_error(max_error), initial_start_error(start), initial_non_start_error(non_start), renormalisation_threshold(threshold) {}
+    // from the reference's own ::ViterbiDecoder_Config<error_t> (any type with the same four fields)
+    template <class RefConfig, typename = decltype(std::declval<const RefConfig&>().renormalisation_threshold)>
+    ViterbiDecoder_Config(const RefConfig& c)
+        : soft_decision_max_error(c.soft_decision_max_error), initial_start_error(c.initial_start_error),
+          initial_non_start_error(c.initial_non_start_error), renormalisation_threshold(c.renormalisation_threshold) {}
 };
 
 // On the GPU the table is folded into the kernels at compile time; this object only carries what the reference constructor takes.
@@ -49,18 +59,50 @@ public:
         : soft_decision_high(_soft_decision_high), soft_decision_low(_soft_decision_low) {
         static_assert(K > 1u && R > 1u && R <= VITB_MAX_R, "unsupported code");
         for (size_t i = 0; i < R; i++) m_G[i] = uint32_t(G[i]);
+        fill();
     }
-    // BT[i][j] = parity((j << 1) & G[i]) ? high : low   (viterbi_branch_table.h:45-54), computed on demand
-    soft_t at(size_t index, size_t state) const {
-        uint32_t v = (uint32_t(state) << 1) & m_G[index];
-        v ^= v >> 16; v ^= v >> 8; v ^= v >> 4; v ^= v >> 2; v ^= v >> 1;
-        return (v & 1u) ? soft_decision_high : soft_decision_low;
+    // From the reference's own ::ViterbiBranchTable<K,R,soft_t> (any type with its operator[]: table[i][j], j < 2^(K-2)).  The table
+    // holds bits 1 .. K-2 of every polynomial; bit 0 (input tap) and bit K-1 (oldest bit) never enter it - the decoder assumes both
+    // set.  Entry [i][0] is always the low soft level (parity of 0), any other value the high one (both are private in the reference).
+    template <class RefTable, typename = decltype(std::declval<const RefTable&>()[0][0]), typename = typename std::enable_if<!std::is_pointer<RefTable>::value>::type>
+    explicit ViterbiBranchTable(const RefTable& ref) : soft_decision_high(high_of(ref)), soft_decision_low(ref[0][0]) {
+        for (size_t i = 0; i < R; i++) {
+            uint32_t g = 1u | (1u << (K - 1));
+            for (size_t b = 1; b + 1 < K; b++)
+                if (ref[i][size_t(1) << (b - 1)] != soft_decision_low) g |= 1u << b;
+            m_G[i] = g;
+        }
+        fill();
     }
+    // BT[i][j] = parity((j << 1) & G[i]) ? high : low   (viterbi_branch_table.h:45-54)
+    soft_t at(size_t index, size_t state) const { return m_table[index * NUMSTATES + state]; }
+    const soft_t* operator[](size_t index) const { return &m_table[index * NUMSTATES]; }        // viterbi_branch_table.h:59-62
+    const soft_t* data() const { return m_table.data(); }                                       // viterbi_branch_table.h:64-66 (rows are contiguous here)
     const uint32_t* polynomials() const { return m_G; }
     const soft_t soft_decision_high;
     const soft_t soft_decision_low;
 private:
+    template <class RefTable>
+    static soft_t high_of(const RefTable& ref) {
+        const soft_t lo = ref[0][0];
+        soft_t hi = lo;
+        for (size_t i = 0; i < R; i++)
+            for (size_t j = 0; j < NUMSTATES; j++)
+                if (ref[i][j] != lo) hi = ref[i][j];
+        return hi;
+    }
+    void fill() {
+        m_table.resize(R * NUMSTATES);
+        for (size_t i = 0; i < R; i++) {
+            for (size_t state = 0; state < NUMSTATES; state++) {
+                uint32_t v = (uint32_t(state) << 1) & m_G[i];
+                v ^= v >> 16; v ^= v >> 8; v ^= v >> 4; v ^= v >> 2; v ^= v >> 1;
+                m_table[i * NUMSTATES + state] = (v & 1u) ? soft_decision_high : soft_decision_low;
+            }
+        }
+    }
     uint32_t m_G[VITB_MAX_R] = {};
+    std::vector<soft_t> m_table;       // host copy for callers that index the table; the kernels fold G into their code
 };
 
 template <size_t constraint_length, size_t code_rate, typename error_t, typename soft_t>
@@ -105,6 +147,25 @@ public:
         check(vitb_chainback(m_handle, bytes_out, total_bits, end_state), "chainback");
     }
     size_t current_decoded_bit() const { size_t n = 0; check(vitb_get_current_decoded_bit(m_handle, &n), "current_decoded_bit"); return n; }
+    // The reference's public data members (core.h:238-242) live on the device here; these read them out / assign them.
+    size_t m_current_decoded_bit() const { return current_decoded_bit(); }
+    void set_current_decoded_bit(size_t bit) { check(vitb_set_current_decoded_bit(m_handle, bit), "set_current_decoded_bit"); }
+    std::vector<error_t> m_metrics() {                                          // m_metrics.get_old()[0 .. NUMSTATES)
+        std::vector<uint32_t> raw(NUMSTATES);
+        check(vitb_get_metrics(m_handle, raw.data()), "get_metrics");
+        return std::vector<error_t>(raw.begin(), raw.end());
+    }
+    void set_metrics(const error_t* metrics) {
+        std::vector<uint32_t> raw(metrics, metrics + NUMSTATES);
+        check(vitb_set_metrics(m_handle, raw.data()), "set_metrics");
+    }
+    // m_decisions[first_row .. first_row + n_rows) in the reference layout: max(NUMSTATES/64, 1) uint64 per row (core.h:49-83)
+    static constexpr size_t DECISION_WORDS = (NUMSTATES + 63) / 64;
+    std::vector<uint64_t> m_decisions(size_t first_row, size_t n_rows) {
+        std::vector<uint64_t> rows(n_rows * DECISION_WORDS);
+        if (n_rows) check(vitb_get_decisions(m_handle, first_row, n_rows, rows.data()), "get_decisions");
+        return rows;
+    }
     vitb_decoder* handle() { return m_handle; }
     const Config m_config;
 private:

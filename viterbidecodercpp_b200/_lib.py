@@ -40,6 +40,8 @@ API = [
     ("vitb_chainback", C.c_int, [_P, _P, C.c_size_t, C.c_size_t]),
     ("vitb_get_current_decoded_bit", C.c_int, [_P, C.POINTER(C.c_size_t)]),
     ("vitb_get_metrics", C.c_int, [_P, _P]),
+    ("vitb_set_metrics", C.c_int, [_P, _P]),
+    ("vitb_set_current_decoded_bit", C.c_int, [_P, C.c_size_t]),
     ("vitb_get_decisions", C.c_int, [_P, C.c_size_t, C.c_size_t, _P]),
     ("vitb_decode_batch", C.c_int, [_P, _P, C.c_size_t, C.c_size_t, C.POINTER(vitb_batch_opts), _P, _P, _P]),
     ("vitb_decode_batch_dev", C.c_int, [_P, _P, C.c_size_t, C.c_size_t, C.POINTER(vitb_batch_opts), _P, _P, _P, _P]),

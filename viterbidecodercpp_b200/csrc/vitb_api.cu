@@ -883,6 +883,26 @@ int vitb_get_metrics(vitb_decoder* h, uint32_t* metrics_out) {
     return VITB_OK;
 }
 
+// the reference's m_metrics and m_current_decoded_bit are public members (core.h:238-242): callers may assign them
+int vitb_set_metrics(vitb_decoder* h, const uint32_t* metrics_in) {
+    if (!h || !metrics_in) return VITB_ERR_ARG;
+    VITB_CUDA(h, cudaSetDevice(h->prm.device));
+    if (!h->s_metrics.ptr) return VITB_ERR_STATE;
+    const uint32_t emask = (h->prm.soft_bytes == 1) ? 0xffu : 0xffffu;
+    std::vector<uint16_t> m(size_t(h->n_states));
+    for (size_t i = 0; i < m.size(); i++) m[i] = uint16_t(metrics_in[i] & emask);
+    VITB_CUDA(h, cudaMemcpyAsync(h->s_metrics.ptr, m.data(), m.size() * 2, cudaMemcpyHostToDevice, h->stream));      // frame 0 of the streaming block
+    VITB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return VITB_OK;
+}
+
+int vitb_set_current_decoded_bit(vitb_decoder* h, size_t bit) {
+    if (!h) return VITB_ERR_ARG;
+    if (bit > h->traceback_length + size_t(h->prm.K - 1)) return VITB_ERR_ARG;       // core.h:183-185 keeps it inside the decision rows
+    h->current_decoded_bit = bit;
+    return VITB_OK;
+}
+
 int vitb_get_decisions(vitb_decoder* h, size_t first_row, size_t n_rows, uint64_t* rows_out) {
     if (!h || (!rows_out && n_rows)) return VITB_ERR_ARG;
     const size_t rows = h->traceback_length + size_t(h->prm.K - 1);
