@@ -276,6 +276,39 @@ def strong_cfg5(torch, dist, v, world, rank, local_rank, dev, steps=3, warmup=1)
             "byte_errors": byte_errors, "kernel": name, "data": "device-generated BPSK/AWGN at 4 dB (Philox), inputs resident in HBM"}
 
 
+def multi_in_process(torch, v, world, w, steps=3, warmup=1):
+    """the north star's "per-GPU streams and a host scatter" inside ONE process: vitb_decode_batch_multi with one handle per device,
+    each device decoding a full batch of the workload from one pinned host array (weak scaling, like the torchrun leg).  The call is
+    synchronous (it returns when every device has finished), so it is timed with the host clock around it."""
+    code, dc = w["code_obj"], w["dc"]
+    F, L = w["sym"].shape[0], w["bits"]
+    bt = v.ViterbiBranchTable(code.K, code.R, code.G, dc.soft_decision_high, dc.soft_decision_low, dc.soft_bytes)
+    decs = [v.ViterbiDecoder_CUDA(bt, dc.decoder_config, device=d) for d in range(world)]
+    for d in decs:
+        if w["keep"] is not None:
+            d.set_puncture_schedule(w["keep"].astype(np.uint8), 0)
+    h_sym = torch.from_numpy(np.concatenate([w["sym"]] * world)).pin_memory()
+    n = F * world
+    h_out = torch.zeros((n, (L + 7) // 8), dtype=torch.uint8).pin_memory()
+    h_acc = torch.zeros(n, dtype=torch.int64).pin_memory()
+    h_fin = torch.zeros(n, dtype=torch.int32).pin_memory()
+
+    def step():
+        v.decode_batch_multi_raw(decs, h_sym.data_ptr(), n, L, h_out.data_ptr(), h_acc.data_ptr(), h_fin.data_ptr(), row_stride=w["sym"].shape[1])
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    ms = (time.perf_counter() - t0) / steps * 1e3
+    ber = float(np.unpackbits(h_out.numpy()[-F:] ^ w["tx"]).mean())
+    for d in decs:
+        d.close()
+    return {"call": "vitb_decode_batch_multi, one handle per device, pinned host memory, one host thread", "n_devices": world,
+            "frames_total": n, "steps": steps, "ms_per_step": ms, "value": n * L / (ms * 1e-3) / 1e6, "unit": "Mbit/s",
+            "timing": "host clock around the synchronous call", "ber_last_device": ber}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -429,6 +462,21 @@ def main():
     ms_copy = timed(step_copy, e2e_steps)
 
     strong = None if args.no_strong else strong_cfg5(torch, dist, v, world, rank, local_rank, dev)
+    multi = None
+    if world > 1 and not args.no_strong:
+        # rank 0 drives every device from one process; the other ranks wait ON THE HOST (a key in the rendezvous store): a NCCL
+        # barrier would park a spinning kernel on their GPUs for the whole leg
+        barrier()
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            try:
+                multi = multi_in_process(torch, v, world, w)
+            except Exception as e:
+                multi = {"failed": str(e)}
+            store.set("multi_in_process_done", "1")
+        else:
+            store.wait(["multi_in_process_done"])
+        barrier()
 
     if rank != 0:
         if world > 1:
@@ -490,6 +538,8 @@ def main():
     }
     if strong is not None:
         line["strong_cfg5"] = strong
+    if multi is not None:
+        line["multi_in_process"] = multi
 
     if world == 1 and not args.no_cpu_baseline:
         try:

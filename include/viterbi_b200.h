@@ -141,7 +141,9 @@ int vitb_quantise(vitb_decoder* h, const float* x, size_t n, float scale, float 
 int vitb_ber_trial(vitb_decoder* h, size_t n_frames, size_t total_bits, float EbNo_dB, uint64_t seed, uint64_t* bit_errors);
 
 /* ---- multi-GPU: frames are independent, so the batch is split into contiguous ranges, one per handle (each created on its own
- *      device), decoded concurrently from host memory; no collective.  ---- */
+ *      device), decoded concurrently from host memory; no collective.  With pinned host buffers (cudaHostAlloc / cudaHostRegister)
+ *      one host thread enqueues every device's copies and kernels on that device's streams and then waits for all of them; with
+ *      pageable buffers (whose asynchronous copies block) one host thread per device is used.  Synchronous.  ---- */
 int vitb_decode_batch_multi(vitb_decoder* const* handles, int n_handles, const void* symbols, size_t n_frames, size_t total_bits,
                             const vitb_batch_opts* opts, uint8_t* out_bytes, uint64_t* acc_error, uint32_t* final_error);
 

@@ -1272,18 +1272,39 @@ int vitb_decode_batch_multi(vitb_decoder* const* handles, int n_handles, const v
     if (rc != VITB_OK || n_frames == 0) return rc;
     const size_t sb = size_t(handles[0]->prm.soft_bytes), out_stride = (L + 7) / 8;
     vitb_batch_opts o{}; o.row_stride = row_stride; o.starting_state = start; o.end_state = end;
+    // contiguous range of frames per device, no exchange between devices
+    auto range = [&](int i, size_t& f0, size_t& f1) { f0 = n_frames * size_t(i) / size_t(n_handles); f1 = n_frames * size_t(i + 1) / size_t(n_handles); };
+    auto call = [&](int i, bool async) -> int {
+        size_t f0, f1;
+        range(i, f0, f1);
+        if (f1 == f0) return VITB_OK;
+        const void* in = static_cast<const uint8_t*>(symbols) + f0 * row_stride * sb;
+        uint8_t* ob = out_bytes ? out_bytes + f0 * out_stride : nullptr;
+        uint64_t* oa = acc_error ? acc_error + f0 : nullptr;
+        uint32_t* of = final_error ? final_error + f0 : nullptr;
+        return async ? vitb_decode_batch_async(handles[i], in, f1 - f0, L, &o, ob, oa, of, handles[i]->stream)
+                     : vitb_decode_batch(handles[i], in, f1 - f0, L, &o, ob, oa, of);
+    };
+    // Pinned host memory: every copy is asynchronous, so ONE host thread enqueues the whole pipeline (copies in, kernels, copies out)
+    // of every device on that device's streams and then waits for them: the devices run concurrently with no thread per call.
+    // Pageable memory makes cudaMemcpyAsync block the calling thread, so there the ranges are decoded by one host thread per device.
+    cudaPointerAttributes pa{};
+    const bool pinned = cudaPointerGetAttributes(&pa, symbols) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
+                        (!out_bytes || (cudaPointerGetAttributes(&pa, out_bytes) == cudaSuccess && pa.type == cudaMemoryTypeHost));
+    cudaGetLastError();
+    if (pinned) {
+        int rc2 = VITB_OK;
+        for (int i = 0; i < n_handles && rc2 == VITB_OK; i++) rc2 = call(i, true);
+        for (int i = 0; i < n_handles; i++) {           // join every device, also after an error
+            if (cudaSetDevice(handles[i]->prm.device) != cudaSuccess || cudaStreamSynchronize(handles[i]->stream) != cudaSuccess) {
+                if (rc2 == VITB_OK) rc2 = cuda_fail(handles[i], cudaGetLastError());
+            }
+        }
+        return rc2;
+    }
     std::vector<int> results(size_t(n_handles), VITB_OK);
     std::vector<std::thread> threads;
-    for (int i = 0; i < n_handles; i++) {
-        // contiguous range of frames per device, no exchange between devices
-        const size_t f0 = n_frames * size_t(i) / size_t(n_handles), f1 = n_frames * size_t(i + 1) / size_t(n_handles);
-        if (f1 == f0) continue;
-        threads.emplace_back([&, i, f0, f1] {
-            results[size_t(i)] = vitb_decode_batch(handles[i], static_cast<const uint8_t*>(symbols) + f0 * row_stride * sb, f1 - f0, L, &o,
-                                                   out_bytes ? out_bytes + f0 * out_stride : nullptr, acc_error ? acc_error + f0 : nullptr,
-                                                   final_error ? final_error + f0 : nullptr);
-        });
-    }
+    for (int i = 0; i < n_handles; i++) threads.emplace_back([&, i] { results[size_t(i)] = call(i, false); });
     for (auto& t : threads) t.join();
     for (int r : results) if (r != VITB_OK) return r;
     return VITB_OK;

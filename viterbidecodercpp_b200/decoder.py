@@ -296,3 +296,12 @@ def decode_batch_multi(decoders, symbols, total_bits, starting_state=0, end_stat
     _check(L.vitb_decode_batch_multi(hs, len(decoders), s.ctypes.data, F, total_bits, C.byref(o), out.ctypes.data, acc.ctypes.data,
                                      fin.ctypes.data), "decode_batch_multi")
     return out, acc, fin
+
+
+def decode_batch_multi_raw(decoders, h_symbols, n_frames, total_bits, h_out, h_acc, h_final, row_stride=0, starting_state=0, end_state=0):
+    """vitb_decode_batch_multi on raw HOST pointers (ints; pinned memory lets one host thread drive every device asynchronously)"""
+    L = _lib.load()
+    hs = (C.c_void_p * len(decoders))(*[d._h.value for d in decoders])
+    o = vitb_batch_opts()
+    o.row_stride, o.starting_state, o.end_state = row_stride, starting_state, end_state
+    _check(L.vitb_decode_batch_multi(hs, len(decoders), h_symbols, n_frames, total_bits, C.byref(o), h_out, h_acc, h_final), "decode_batch_multi")
