@@ -319,6 +319,7 @@ def main():
     ap.add_argument("--frames", type=int, default=0, help="override the number of frames (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lanes", type=int, default=0, help="pin the lanes-per-frame-pair kernel variant (0 = automatic)")
+    ap.add_argument("--window", type=int, default=0, help="K=15: sliding-window traceback with this many bits per window (0 = exact mode)")
     ap.add_argument("--no-strong", action="store_true", help="skip the config-5 strong-scaling leg (1024 Cassini frames over all GPUs)")
     ap.add_argument("--no-pipelining", action="store_true", help="time the device-resident leg with the stages of a batch in sequence")
     args = ap.parse_args()
@@ -352,6 +353,8 @@ def main():
         dec.set_puncture_schedule(w["keep"].astype(np.uint8), 0)
     if args.lanes:
         dec.set_variant(args.lanes)
+    if args.window:
+        dec.set_traceback_window(args.window)
 
     out_stride = (L + 7) // 8
     # pinned host buffers of the end-to-end leg: allocated (first touch) while this thread sits on the NUMA node of its GPU, so that
@@ -513,7 +516,7 @@ def main():
                    "l2": "inputs larger than L2 (no flush)" if w["sym"].nbytes > 130e6 else "inputs smaller than L2; decision buffer larger than L2",
                    "kernel": kernel_name, "parallelism": f"frames sharded over {world} GPU(s), no collective",
                    "pipelining": "traceback of batch i next to the ACS of batch i+1 (vitb_set_pipelining), flush inside the timed region" if pipelined else "off",
-                   "host_numa_node": numa_node},
+                   "host_numa_node": numa_node, "traceback_window_bits": args.window, "workspace_bytes": dec.workspace_bytes(F, L)},
         "ms_per_step_serial": ms_serial,
         "acs_gops": world * F * ab["acs_ops"] / (ms_step * 1e-3) / 1e9,
         "ber": ber,

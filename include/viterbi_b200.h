@@ -174,6 +174,17 @@ int vitb_set_history_kernel(vitb_decoder* h, int enabled);
  * overlap 0 to force the repair path.  Units: history records (8 or 16 steps) for K <= 7, 8 decoded bits / 8 decision rows for the
  * K = 15 row walk; the lane-group kernels (K = 9) stream whole rows and are not segmented. */
 int vitb_set_traceback_segments(vitb_decoder* h, int seg_records, int overlap_records);
+/* Sliding-window traceback (K = 15, whose decision rows are 2 KB per frame and step: 34.4 GB for 1024 frames of 16384 bits).  The
+ * reference keeps every row of a frame until chainback (core.h:180-186); with a window the library keeps a ring of 2 x window_bits
+ * rows per frame: the ACS kernel runs one window per launch and the decoded bits of a window are walked out as soon as the next
+ * window is in, starting window_bits - (K-1) rows above them from state 0 (survivor paths merge within a few constraint lengths;
+ * the last window starts from the true end state).  Path metrics and errors are not affected.  The decoded bytes equal the exact
+ * result whenever every warm-up merged, and the library COUNTS the window boundaries where it did not:
+ * vitb_get_window_mismatches (of the last batch call; synchronises the device) == 0 certifies the bytes.  window_bits is rounded
+ * up to a multiple of 40; 0 = keep every row (exact, verified and repaired: the default).  vitb_workspace_bytes reflects the
+ * setting (config 5: 34.4 GB -> 1.7 GB at window_bits = 400).  VITB_ERR_UNSUPPORTED for K <= 9 (rows are small there). */
+int vitb_set_traceback_window(vitb_decoder* h, size_t window_bits);
+int vitb_get_window_mismatches(vitb_decoder* h, uint64_t* count);
 /* name of the ACS kernel variant selected for this handle, e.g. "acs_pair<K7,R2,u8,scalar-tie>" */
 const char* vitb_kernel_name(const vitb_decoder* h);
 int vitb_last_cuda_error(const vitb_decoder* h);

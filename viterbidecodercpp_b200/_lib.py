@@ -45,6 +45,8 @@ API = [
     ("vitb_get_decisions", C.c_int, [_P, C.c_size_t, C.c_size_t, _P]),
     ("vitb_decode_batch", C.c_int, [_P, _P, C.c_size_t, C.c_size_t, C.POINTER(vitb_batch_opts), _P, _P, _P]),
     ("vitb_decode_batch_dev", C.c_int, [_P, _P, C.c_size_t, C.c_size_t, C.POINTER(vitb_batch_opts), _P, _P, _P, _P]),
+    ("vitb_set_traceback_window", C.c_int, [_P, C.c_size_t]),
+    ("vitb_get_window_mismatches", C.c_int, [_P, C.POINTER(C.c_uint64)]),
     ("vitb_set_pipelining", C.c_int, [_P, C.c_int]),
     ("vitb_batch_flush", C.c_int, [_P, _P]),
     ("vitb_decode_batch_async", C.c_int, [_P, _P, C.c_size_t, C.c_size_t, C.POINTER(vitb_batch_opts), _P, _P, _P, _P]),

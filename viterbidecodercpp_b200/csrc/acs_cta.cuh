@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(CtaShape<C, LT>::T, 1) acs_cta_kernel(const Ac
         }
     }
 
-    const uint32_t* pk = p.pk + size_t(pair) * p.n_steps * R;                                    // [n_steps][R]
+    const uint32_t* pk = p.pk + (size_t(pair) * (p.pk_steps ? p.pk_steps : p.n_steps) + p.pk_step0) * R;   // [steps][R], this launch's first step
     constexpr int W = Kn::W;
     uint32_t* dec = static_cast<uint32_t*>(p.dec) + ((size_t(pair) * p.dec_rows + p.dec_row0) * S::T + t) * W;
 

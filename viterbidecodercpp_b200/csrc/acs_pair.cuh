@@ -51,6 +51,9 @@ struct AcsParams {
     uint64_t sym_row_bytes;
     uint64_t sym_total_bytes;   // n_frames * sym_row_bytes (loads are clamped to stay inside)
     uint32_t n_frames;
+    // acs_cta.cuh, sliding-window calls: the launch covers steps pk_step0 .. pk_step0 + n_steps - 1 of frames whose packed stream
+    // holds pk_steps steps per pair (0 = the launch covers the whole stream: n_steps steps from step 0)
+    uint32_t pk_steps, pk_step0;
 };
 
 template <class C>

@@ -303,6 +303,7 @@ struct TracebackCtaParams {
     const uint32_t* end_states;   // nullable: per-frame end states (VITB_END_STATE_BEST), overrides end_state
     uint8_t* out;
     size_t out_stride;
+    uint32_t ring_rows;       // sliding-window calls: row r lives at r % ring_rows (a multiple of the exchange period); 0 = every row is kept
 };
 
 // Walk decision rows r_hi .. r_lo (downwards) of one frame from `state` (the state after row r_hi); returns the state after row
@@ -321,7 +322,10 @@ __device__ __forceinline__ uint32_t cta_walk(const TracebackCtaParams& p, const 
         const uint32_t t = rotr_rt(state, n + 1, SB) & (T - 1);
         uint32_t w[MAXLB];
 #pragma unroll
-        for (int k = 0; k < MAXLB; k++) w[k] = (uint32_t(k) < cnt) ? __ldcs(d + (size_t(r - k) * T + t) * W) : 0u;
+        for (int k = 0; k < MAXLB; k++) {
+            const size_t row = p.ring_rows ? size_t(uint64_t(r - k) % p.ring_rows) : size_t(r - k);
+            w[k] = (uint32_t(k) < cnt) ? __ldcs(d + (row * T + t) * W) : 0u;
+        }
 #pragma unroll
         for (int k = 0; k < MAXLB; k++) {
             if (uint32_t(k) < cnt) {
@@ -373,12 +377,13 @@ struct TracebackCtaSegParams {
     uint32_t n_seg, seg_bits, overlap;
     uint32_t* spec;           // [n_seg][n_frames]
     uint32_t* fin;            // [n_seg][n_frames]
+    uint32_t seg0;            // first segment of this launch (grid.y counts from it): sliding-window calls walk one segment per launch
 };
 
 // grid = (ceil(n_frames / 64), n_seg)
 template <int MAXLB>
 __global__ void __launch_bounds__(64) traceback_cta_seg_kernel(const TracebackCtaParams p, const TracebackCtaSegParams sp) {
-    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x, g = blockIdx.y;
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x, g = blockIdx.y + sp.seg0;
     if (f >= p.n_frames) return;
     const uint32_t SB = p.state_bits, T = 1u << p.logt, L = p.total_bits, half = f & 1u, W = p.words;
     const uint32_t* d = p.dec + size_t(f >> 1) * p.dec_rows * T * W + (W == 2 ? half : 0u);
@@ -401,6 +406,18 @@ __global__ void __launch_bounds__(64) traceback_cta_seg_kernel(const TracebackCt
         sp.spec[size_t(g) * p.n_frames + f] = state;
     }
     sp.fin[size_t(g) * p.n_frames + f] = cta_walk<MAXLB, true>(p, d, out, bit_base, r_hi, r_lo, state, byte);
+}
+
+// Sliding-window calls cannot repair (the rows of a segment are overwritten before the segment above has been walked): they count,
+// per call, the segment boundaries at which the warm-up from state 0 did NOT arrive in the state the segment above ended in - 0
+// means the windowed result is the exact one.
+__global__ void __launch_bounds__(128) traceback_seg_count_mismatch_kernel(const uint32_t* spec, const uint32_t* fin, uint32_t n_seg,
+                                                                             uint32_t n_frames, unsigned long long* count) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_frames) return;
+    uint32_t bad = 0;
+    for (uint32_t g = 0; g + 1 < n_seg; g++) bad += spec[size_t(g) * n_frames + f] != fin[size_t(g + 1) * n_frames + f];
+    if (bad) atomicAdd(count, (unsigned long long)bad);
 }
 
 // one thread per frame: top-down check of the segment boundaries, re-walk on mismatch

@@ -126,6 +126,8 @@ struct vitb_decoder {
     int slot_next = 0;
     cudaStream_t tb_stream = nullptr;     // owned; traceback, best-state and gather kernels of the batch calls
     bool pipelined = false;               // vitb_set_pipelining: the join with the last chunk's traceback is deferred to the next call / flush
+    size_t window_bits = 0;               // vitb_set_traceback_window (K = 15): decision rows kept per frame = 2 windows; 0 = all
+    DeviceBuffer win_count;               // mismatch counter of the sliding-window calls
     bool overlap_hint = false;            // this chunk's traceback will run next to another chunk's ACS (pipelined call, multi-chunk call)
     size_t n_depunctured = 0, n_received = 0;
     int32_t unpunctured_value = 0;
@@ -262,7 +264,10 @@ size_t default_ws_limit() {
 // workspace bytes per 64 frames for a frame of S steps (identical for every variant: decision rows are 2^(K-1) bits per frame-step)
 size_t block_bytes(const vitb_decoder* h, size_t S, bool with_packed_stream = true, bool two_slots = false) {
     const size_t n_sym = S * size_t(h->prm.R);
-    const size_t slot = S * 64 * (size_t(h->n_states) / 8 < 8 ? 8 : size_t(h->n_states) / 8)   // decision rows
+    const bool windowed = h->window_bits && h->variants.front()->layout == LAYOUT_CTA && S > 2 * h->window_bits;
+    if (windowed) two_slots = false;                         // sliding-window calls use one slot
+    const size_t rows = windowed ? 2 * h->window_bits : S;   // sliding window: a ring of two windows of decision rows
+    const size_t slot = rows * 64 * (size_t(h->n_states) / 8 < 8 ? 8 : size_t(h->n_states) / 8)   // decision rows
                       + size_t(64) * h->n_states * 2                                           // metrics
                       + 64 * 8;                                                                // accumulated error
     return (with_packed_stream ? n_sym * 32 * 4 : 0)        // packed symbols (not needed when the kernel reads the caller's rows itself)
@@ -555,6 +560,108 @@ int decode_chunk_dev(vitb_decoder* h, const KernelEntry* e, const void* d_symbol
     return VITB_OK;
 }
 
+// Sliding-window decode of one chunk of frames (K = 15, decision-row kernel; vitb_set_traceback_window).  The reference keeps every
+// decision row of a frame until chainback (core.h:180-186: 2 KB per step, 33.6 MB per config-5 frame).  Here the frame is cut
+// into windows of W = window_bits steps; the ACS kernel runs one window per launch (resuming from the saved metrics, acs_cta.cuh) into
+// a ring of 2 W rows, and as soon as window c+1 is in, the decoded bits of window c are walked out: the walk starts W - (K-1) rows
+// above them from state 0, and survivor paths merge long before they reach the bits that are written (the same warm-up as the
+// segmented walk of the exact mode, which additionally verifies and repairs; here the rows are gone by then, so mismatches are only
+// COUNTED: vitb_get_window_mismatches == 0 certifies that the windowed bytes are the exact ones).  The last window starts from the
+// true end state.  Metrics, accumulated errors and final errors are unaffected by the window.  Everything runs on `s`.
+int decode_chunk_window(vitb_decoder* h, const KernelEntry* e, const void* d_symbols, size_t row_stride, size_t n_frames, size_t L,
+                        size_t start_state, size_t end_state, uint8_t* d_out, uint64_t* d_acc, uint32_t* d_final, cudaStream_t s) {
+    const size_t K = size_t(h->prm.K), R = size_t(h->prm.R), SB = K - 1, S = L + SB, n_sym = S * R, W = h->window_bits, ring = 2 * W;
+    const unsigned n_b64 = unsigned((n_frames + 63) / 64);
+    BatchSlot& sl = h->slots[0];
+    h->slot_next = 1;
+    VITB_CUDA(h, slot_events(sl));
+    if (sl.tb_pending) VITB_CUDA(h, cudaStreamWaitEvent(s, sl.tb_done, 0));
+    h->last_batch = e;
+    h->last_batch_hist = false;
+    VITB_CUDA(h, sl.dec.reserve(size_t(n_b64) * dec_bytes_per_block64(e, ring)));
+    VITB_CUDA(h, sl.metrics.reserve(size_t(n_b64) * 64 * h->n_states * 2));
+    VITB_CUDA(h, sl.acc.reserve(size_t(n_b64) * 64 * 8));
+    VITB_CUDA(h, h->pk.reserve(size_t(n_b64) * n_sym * 32 * 4));
+    VITB_CUDA(h, h->win_count.reserve(8));
+    VITB_CUDA(h, mark(h, s));
+    IngestParams ip{};
+    ip.symbols = d_symbols; ip.row_stride = row_stride; ip.n_frames = uint32_t(n_frames); ip.n_sym = uint32_t(n_sym);
+    ip.depuncture_map = h->n_depunctured ? static_cast<const int32_t*>(h->map.ptr) : nullptr;
+    ip.fill_value = h->unpunctured_value; ip.pk = static_cast<uint32_t*>(h->pk.ptr); ip.ppw = unsigned(e->ppw);
+    VITB_CUDA(h, run_ingest(h, ip, n_b64, s));
+    VITB_CUDA(h, mark(h, s));
+
+    const size_t n_seg = (L + W - 1) / W, n_win = (S + W - 1) / W;
+    if (d_out) {
+        VITB_CUDA(h, sl.tb_spec.reserve(n_seg * n_frames * 4));
+        VITB_CUDA(h, sl.tb_fin.reserve(n_seg * n_frames * 4));
+    }
+    TracebackCtaParams t{};
+    t.dec = static_cast<const uint32_t*>(sl.dec.ptr); t.dec_rows = uint32_t(ring); t.ring_rows = uint32_t(ring); t.n_frames = uint32_t(n_frames);
+    t.total_bits = uint32_t(L); t.state_bits = uint32_t(SB); t.logt = uint32_t(e->logt); t.end_state = uint32_t(end_state == VITB_END_STATE_BEST ? 0 : end_state);
+    t.end_states = nullptr; t.out = d_out; t.out_stride = (L + 7) / 8; t.words = uint32_t(e->dec_words);
+    TracebackCtaSegParams sp{};
+    sp.n_seg = uint32_t(n_seg); sp.seg_bits = uint32_t(W); sp.overlap = uint32_t(W - SB);
+    sp.spec = static_cast<uint32_t*>(sl.tb_spec.ptr); sp.fin = static_cast<uint32_t*>(sl.tb_fin.ptr);
+    auto walk_segment = [&](size_t j) -> cudaError_t {
+        sp.seg0 = uint32_t(j);
+        h->launches++;
+        traceback_cta_seg_kernel<5><<<dim3(unsigned((n_frames + 63) / 64), 1), 64, 0, s>>>(t, sp);
+        return cudaGetLastError();
+    };
+
+    AcsParams a{};
+    fill_acs_params(h, a);
+    a.sym = d_symbols; a.n_frames = uint32_t(n_frames);
+    a.pk = static_cast<const uint32_t*>(h->pk.ptr); a.dec = sl.dec.ptr;
+    a.metrics = static_cast<uint16_t*>(sl.metrics.ptr); a.acc = static_cast<uint64_t*>(sl.acc.ptr);
+    a.n_blocks = n_b64 * (32u / unsigned(e->ppw)); a.dec_rows = uint32_t(ring); a.start_state = uint32_t(start_state);
+    a.pk_steps = uint32_t(S);
+    size_t next_seg = 0;
+    for (size_t c = 0; c < n_win; c++) {
+        const size_t step0 = c * W, nst = (S - step0 < W) ? (S - step0) : W;
+        a.n_steps = uint32_t(nst); a.pk_step0 = uint32_t(step0); a.dec_row0 = uint32_t((c & 1) * W); a.resume = c ? 1u : 0u;
+        h->launches++;
+        VITB_CUDA(h, e->launch(a, s));
+        // window c-1 can be walked once rows up to (c+1) W - 1 exist (its warm-up ends there); the windows whose warm-up would
+        // reach the end of the frame wait for the end state
+        if (d_out && c >= 1 && next_seg == c - 1 && next_seg + 1 < n_seg && (c + 1) * W <= S) {
+            VITB_CUDA(h, walk_segment(next_seg));
+            next_seg++;
+        }
+    }
+    VITB_CUDA(h, mark(h, s));
+    const uint32_t* end_states = nullptr;
+    if (end_state == VITB_END_STATE_BEST) {
+        VITB_CUDA(h, sl.end_states.reserve(n_frames * 4));
+        h->launches++;
+        best_state_kernel<<<unsigned((n_frames + 3) / 4), 128, 0, s>>>(a.metrics, uint32_t(h->n_states), uint32_t(n_frames),
+                                                                        static_cast<uint32_t*>(sl.end_states.ptr));
+        VITB_CUDA(h, cudaGetLastError());
+        end_states = static_cast<const uint32_t*>(sl.end_states.ptr);
+        t.end_states = end_states;
+        end_state = 0;
+    }
+    if (d_out) {
+        for (; next_seg < n_seg; next_seg++) VITB_CUDA(h, walk_segment(next_seg));
+        h->launches++;
+        traceback_seg_count_mismatch_kernel<<<unsigned((n_frames + 127) / 128), 128, 0, s>>>(sp.spec, sp.fin, uint32_t(n_seg), uint32_t(n_frames),
+                                                                                            static_cast<unsigned long long*>(h->win_count.ptr));
+        VITB_CUDA(h, cudaGetLastError());
+    }
+    VITB_CUDA(h, mark(h, s));
+    if (d_acc || d_final) {
+        h->launches++;
+        gather_results_kernel<<<unsigned((n_frames + 255) / 256), 256, 0, s>>>(a.acc, a.metrics, uint32_t(h->n_states), uint32_t(end_state),
+                                                                              end_states, uint32_t(n_frames), d_acc, d_final);
+        VITB_CUDA(h, cudaGetLastError());
+    }
+    VITB_CUDA(h, mark(h, s));
+    VITB_CUDA(h, cudaEventRecord(sl.tb_done, s));
+    sl.tb_pending = true;
+    return VITB_OK;
+}
+
 // K = 15: frames of a batch that go to the decision-row kernel (whole waves of n_sm frame pairs); the rest, if it fits one wave of
 // single-frame CTAs, is decoded as a second chunk by the history kernel (1024 frames on 148 SMs: 3 waves of pairs + 136 single
 // frames = 3 x 14.0 + 10.4 ms instead of 4 x 14.0 ms).  Returns n_frames when there is nothing to split.
@@ -668,7 +775,7 @@ int vitb_destroy(vitb_decoder* h) {
         if (sl.tb_done) cudaEventDestroy(sl.tb_done);
     }
     if (h->tb_stream) cudaStreamDestroy(h->tb_stream);
-    for (DeviceBuffer* b : {&h->pk, &h->d_in, &h->d_out, &h->d_accout, &h->d_finout, &h->map, &h->end_states,
+    for (DeviceBuffer* b : {&h->pk, &h->d_in, &h->d_out, &h->d_accout, &h->d_finout, &h->map, &h->end_states, &h->win_count,
                             &h->s_pk, &h->s_dec, &h->s_metrics, &h->s_acc, &h->s_in, &h->s_out, &h->g_tx, &h->g_sym, &h->g_cnt}) b->release();
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     for (cudaEvent_t e : h->copy_ev) cudaEventDestroy(e);
@@ -1017,6 +1124,21 @@ int vitb_decode_batch_dev(vitb_decoder* h, const void* d_symbols, size_t n_frame
     if (n_frames > chunk && no_pk) chunk = chunk_frames_for(h, L, false, h->pipelined);
     if (n_frames > chunk) chunk = chunk_frames_for(h, L, !no_pk, true);
     h->overlap_hint = h->pipelined || n_frames > chunk;
+    const bool windowed = h->window_bits && e->layout == LAYOUT_CTA && !e->generic && L + size_t(h->prm.K) - 1 > 2 * h->window_bits;
+    if (windowed) {
+        VITB_CUDA(h, h->win_count.reserve(8));
+        VITB_CUDA(h, cudaMemsetAsync(h->win_count.ptr, 0, 8, s));
+        h->name_override.clear();
+        for (size_t f0 = 0; f0 < n_frames; f0 += chunk) {
+            const size_t nf = (n_frames - f0 < chunk) ? (n_frames - f0) : chunk;
+            const int r = decode_chunk_window(h, e, static_cast<const uint8_t*>(d_symbols) + f0 * row_stride * sb, row_stride, nf, L, start, end,
+                                              d_out ? d_out + f0 * out_stride : nullptr, d_acc ? d_acc + f0 : nullptr,
+                                              d_final ? d_final + f0 : nullptr, s);
+            if (r != VITB_OK) return r;
+        }
+        VITB_CUDA(h, batch_end(h, s));
+        return VITB_OK;
+    }
     const size_t split = (n_frames <= chunk) ? cta_wave_split(h, n_frames) : n_frames;
     if (split < n_frames) chunk = split;                  // K = 15: whole waves of frame pairs, then the rest one frame per CTA
     if (!h->pipelined && n_frames <= chunk) h->slot_next = 0;      // isolated single-chunk calls stay in one slot (half the workspace)
@@ -1032,6 +1154,30 @@ int vitb_decode_batch_dev(vitb_decoder* h, const void* d_symbols, size_t n_frame
     // results in stream order at return - or, for pipelined calls, everything but the newest chunk (see vitb_set_pipelining)
     VITB_CUDA(h, join_slots(h, s, h->pipelined));
     VITB_CUDA(h, batch_end(h, s));
+    return VITB_OK;
+}
+
+int vitb_set_traceback_window(vitb_decoder* h, size_t window_bits) {
+    if (!h) return VITB_ERR_ARG;
+    if (window_bits == 0) { h->window_bits = 0; return VITB_OK; }
+    if (h->variants.front()->layout != LAYOUT_CTA) return VITB_ERR_UNSUPPORTED;      // K <= 9 keeps every row: a frame's rows are small there
+    // whole bytes of output and whole exchange periods of the kernel per window; the warm-up (window - (K-1) rows) must be positive
+    const size_t unit = 8 * (size_t(h->prm.K) - 1 - size_t(h->variants.front()->logt));
+    size_t w = (window_bits + unit - 1) / unit * unit;
+    if (w < 2 * unit) w = 2 * unit;
+    h->window_bits = w;
+    return VITB_OK;
+}
+
+int vitb_get_window_mismatches(vitb_decoder* h, uint64_t* count) {
+    if (!h || !count) return VITB_ERR_ARG;
+    *count = 0;
+    if (!h->win_count.ptr) return VITB_OK;
+    VITB_CUDA(h, cudaSetDevice(h->prm.device));
+    VITB_CUDA(h, cudaDeviceSynchronize());
+    unsigned long long c = 0;
+    VITB_CUDA(h, cudaMemcpy(&c, h->win_count.ptr, 8, cudaMemcpyDeviceToHost));
+    *count = c;
     return VITB_OK;
 }
 
@@ -1066,6 +1212,20 @@ int vitb_decode_batch_async(vitb_decoder* h, const void* symbols, size_t n_frame
     if (out_bytes) VITB_CUDA(h, h->d_out.reserve(n_frames * out_stride));
     if (acc_error) VITB_CUDA(h, h->d_accout.reserve(n_frames * 8));
     if (final_error) VITB_CUDA(h, h->d_finout.reserve(n_frames * 4));
+    if (h->window_bits && h->variants.front()->layout == LAYOUT_CTA && L + size_t(h->prm.K) - 1 > 2 * h->window_bits) {
+        // sliding-window mode: copy in, the device-pointer call, copy out, all on `s`
+        VITB_CUDA(h, cudaMemcpyAsync(h->d_in.ptr, symbols, in_bytes, cudaMemcpyHostToDevice, s));
+        vitb_batch_opts o{}; o.row_stride = row_stride; o.starting_state = start; o.end_state = end;
+        const int r = vitb_decode_batch_dev(h, h->d_in.ptr, n_frames, L, &o, out_bytes ? static_cast<uint8_t*>(h->d_out.ptr) : nullptr,
+                                            acc_error ? static_cast<uint64_t*>(h->d_accout.ptr) : nullptr,
+                                            final_error ? static_cast<uint32_t*>(h->d_finout.ptr) : nullptr, s);
+        if (r != VITB_OK) return r;
+        if (out_bytes) VITB_CUDA(h, cudaMemcpyAsync(out_bytes, h->d_out.ptr, n_frames * out_stride, cudaMemcpyDeviceToHost, s));
+        if (acc_error) VITB_CUDA(h, cudaMemcpyAsync(acc_error, h->d_accout.ptr, n_frames * 8, cudaMemcpyDeviceToHost, s));
+        if (final_error) VITB_CUDA(h, cudaMemcpyAsync(final_error, h->d_finout.ptr, n_frames * 4, cudaMemcpyDeviceToHost, s));
+        VITB_CUDA(h, batch_end(h, s));
+        return VITB_OK;
+    }
 
     // pipeline chunks: at least ~16 MB of input each (PCIe efficiency), at most 8 chunks, whole 64-frame blocks, and never larger
     // than what the workspace allows

@@ -198,6 +198,16 @@ class ViterbiDecoder_CUDA:
         _check(self._L.vitb_decode_batch_async(self._h, h_symbols, n_frames, total_bits, C.byref(o), h_out, h_acc, h_final, stream),
                "decode_batch_async")
 
+    def set_traceback_window(self, window_bits=0):
+        """vitb_set_traceback_window: K = 15 only; 0 = keep every decision row (exact mode)"""
+        _check(self._L.vitb_set_traceback_window(self._h, window_bits), "set_traceback_window")
+
+    @property
+    def window_mismatches(self):
+        n = C.c_uint64(0)
+        _check(self._L.vitb_get_window_mismatches(self._h, C.byref(n)))
+        return int(n.value)
+
     def set_pipelining(self, enabled=True):
         """vitb_set_pipelining: results of a decode_batch_dev call are complete (in stream order) after the NEXT call or batch_flush"""
         _check(self._L.vitb_set_pipelining(self._h, 1 if enabled else 0))
