@@ -40,9 +40,11 @@ WORKLOADS = {
 
 
 def read_traffic(kernel_name, frames):
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/r01_traffic.json), scaled
-    to this run's frame count; None when no capture exists for this kernel variant"""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` captures (profiles/r02_traffic.json), scaled
+    to this run's frame count; None when no capture exists for this kernel variant.  A call that used two kernels (K = 15 wave
+    split) is looked up by the first, which decodes most of the frames."""
+    kernel_name = kernel_name.split(" for ")[0]
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if not os.path.exists(p):
         return None
     with open(p) as f:

@@ -21,6 +21,7 @@ struct vo_decoder {
     size_t rows;                /* traceback_length + K-1             viterbi_decoder_core.h:180-186 */
     size_t decoded_bit;         /* m_current_decoded_bit                                            */
     uint32_t max_seen;
+    uint32_t max_seen_all;   /* like max_seen, but kept across reset(): the largest metric of a whole batch */
 };
 
 /* include/viterbi/parity_table.h:46-54 : parity of all bits of x */
@@ -150,6 +151,7 @@ static void step(vo_decoder* d, const int32_t* sym, uint64_t* row, const uint32_
         nw[2 * j + 1] = d1 ? e11 : e01;
         if (nw[2 * j] > d->max_seen) d->max_seen = nw[2 * j];
         if (nw[2 * j + 1] > d->max_seen) d->max_seen = nw[2 * j + 1];
+        if (d->max_seen > d->max_seen_all) d->max_seen_all = d->max_seen;
         const size_t s0 = 2 * j;                                          /* scalar.h:131-134 */
         row[s0 / 64] |= ((uint64_t)(d0 | (d1 << 1))) << (s0 % 64);
     }
@@ -217,6 +219,8 @@ const uint64_t* vo_decision_row(const vo_decoder* d, size_t t) { return d->decis
 size_t vo_decision_words_per_row(const vo_decoder* d) { return d->words_per_row; }
 const uint32_t* vo_metrics(const vo_decoder* d) { return d->metric[d->cur]; }
 uint32_t vo_max_metric_seen(const vo_decoder* d) { return d->max_seen; }
+/* largest metric since the decoder was created or the value was last cleared (clear != 0) */
+uint32_t vo_max_metric_seen_all(vo_decoder* d, int clear) { const uint32_t v = d->max_seen_all; if (clear) d->max_seen_all = 0; return v; }
 
 /* The call protocol of examples/run_simple.cpp:76-80 applied to each frame of a batch */
 int vo_decode_frames(vo_decoder* d, const void* symbols, size_t n_frames, size_t L,

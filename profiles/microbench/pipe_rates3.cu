@@ -11,10 +11,10 @@
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e_), __LINE__); exit(1);} } while (0)
 
 constexpr int NR = 32, ITER = 4096;
-enum { ADD2, MIN2, ADDMIN2, LOP, PRM, IADD, IMADK, MIN3, ADD2I, NONE };
+enum { ADD2, MIN2, ADDMIN2, LOP, PRM, IADD, IMADK, MIN3, ADD2I, NONE, ADD2R, ADDMIN2R, MIN2R };
 
 template <int OP>
-__device__ __forceinline__ uint32_t op(uint32_t a, uint32_t b, uint32_t c) {
+__device__ __forceinline__ uint32_t op(uint32_t a, uint32_t b, uint32_t c, uint32_t g_t0 = 0, uint32_t g_t1 = 0, uint32_t g_t2 = 0) {
     if (OP == ADD2) return __vadd2(a, b);
     if (OP == MIN2) return __vminu2(a, b);
     if (OP == ADDMIN2) return __viaddmin_u16x2(a, b, c);
@@ -24,6 +24,11 @@ __device__ __forceinline__ uint32_t op(uint32_t a, uint32_t b, uint32_t c) {
     if (OP == IMADK) return a * 3u + b;
     if (OP == MIN3) return __vimin3_u16x2(a, b, c);
     if (OP == ADD2I) return __vadd2(a, 0x01000100u);
+    // "R" forms: every operand but the first is the SAME register in every instruction of the stream (operand reuse cache: one
+    // register-file read per instruction)
+    if (OP == ADD2R) return __vadd2(a, g_t0);
+    if (OP == ADDMIN2R) return __viaddmin_u16x2(a, g_t1, g_t2);
+    if (OP == MIN2R) return __vminu2(a, g_t1);
     return a;
 }
 
@@ -40,14 +45,14 @@ __global__ void __launch_bounds__(128) mix(uint32_t* out, const uint32_t* in) {
 #pragma unroll
         for (int i = 0; i < NR; i++) {
             const int k = i % (NA + NB);
-            if (k < NA) x[i] = op<A>(x[i], T[i & 3], y[i]);
-            else x[i] = op<B>(x[i], T[i & 3], y[i]);
+            if (k < NA) x[i] = op<A>(x[i], T[i & 3], y[i], T[0], T[1], T[2]);
+            else x[i] = op<B>(x[i], T[i & 3], y[i], T[0], T[1], T[2]);
         }
 #pragma unroll
         for (int i = 0; i < NR; i++) {
             const int k = i % (NA + NB);
-            if (k < NA) y[i] = op<A>(y[i], T[(i + 1) & 3], x[(i + 5) & 31]);
-            else y[i] = op<B>(y[i], T[(i + 1) & 3], x[(i + 5) & 31]);
+            if (k < NA) y[i] = op<A>(y[i], T[(i + 1) & 3], x[(i + 5) & 31], T[0], T[1], T[2]);
+            else y[i] = op<B>(y[i], T[(i + 1) & 3], x[(i + 5) & 31], T[0], T[1], T[2]);
         }
     }
     uint32_t acc = 0;
@@ -106,5 +111,10 @@ int main() {
     run<PRM, 1, ADDMIN2, 1>("PRMT : VIADDMNMX.U16x2 = 1:1", nsm, din, clk_hz);
     run<MIN3, 1, ADD2, 1>("VIMNMX3.U16x2 : VIADD.16x2 = 1:1", nsm, din, clk_hz);
     run<MIN3, 1, ADD2, 2>("VIMNMX3.U16x2 : VIADD.16x2 = 1:2", nsm, din, clk_hz);
+    printf("-- one register-file read per instruction (all other operands repeat: operand reuse cache) --\n");
+    run<ADD2R, 1, MIN2R, 1>("VIADD.16x2 : VIMNMX.U16x2 = 1:1, 1 read each", nsm, din, clk_hz);
+    run<ADD2R, 1, ADDMIN2R, 1>("VIADD.16x2 : VIADDMNMX.U16x2 = 1:1, 1 read each", nsm, din, clk_hz);
+    run<ADD2R, 1, NONE, 0>("VIADD.16x2, 1 read", nsm, din, clk_hz);
+    run<ADDMIN2R, 1, NONE, 0>("VIADDMNMX.U16x2, 1 read", nsm, din, clk_hz);
     return 0;
 }

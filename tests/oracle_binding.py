@@ -81,6 +81,8 @@ def oracle_lib():
         L.vo_metrics.argtypes = [C.c_void_p]
         L.vo_max_metric_seen.restype = C.c_uint32
         L.vo_max_metric_seen.argtypes = [C.c_void_p]
+        L.vo_max_metric_seen_all.restype = C.c_uint32
+        L.vo_max_metric_seen_all.argtypes = [C.c_void_p, C.c_int]
         L.vo_decode_frames.restype = C.c_int
         L.vo_decode_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
         L.vo_update_punctured.restype = C.c_size_t
@@ -182,6 +184,10 @@ class OracleDecoder:
 
     def max_metric_seen(self):
         return int(self.L.vo_max_metric_seen(self.h))
+
+    def max_metric_seen_all(self, clear=True):
+        """largest metric since creation / the last clearing call (a whole batch, where max_metric_seen covers the last frame)"""
+        return int(self.L.vo_max_metric_seen_all(self.h, 1 if clear else 0))
 
     def decode_frames(self, symbols, n_frames, L):
         s = np.ascontiguousarray(symbols, dtype=soft_dtype(self.soft_bytes))

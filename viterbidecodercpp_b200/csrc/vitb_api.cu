@@ -521,9 +521,12 @@ int decode_chunk_dev(vitb_decoder* h, const KernelEntry* e, const void* d_symbol
         // per frame always does (n_periods round trips of ~0.63 us against >= 150 clocks per step of the ACS); walking concurrent
         // segments would only take DRAM bandwidth and latency away from the ACS (config 2, pipelined: 0.749 ms per batch with two
         // segments per frame, 0.677 ms with one; profiles/r02_summary.md)
-        const size_t want_seg = h->overlap_hint ? 1 : (seg_target + n_frames - 1) / n_frames;
+        // (Only behind the one-lane kernels, whose few CTAs leave room on every SM: the K = 9 kernel fills the register files, the
+        // traceback then runs in its tail anyway and is better off segmented - config 3 pipelined: 4.83 ms single chain, 4.64 segmented.)
+        const bool gentle = h->overlap_hint && !hg && !hc;
+        const size_t want_seg = gentle ? 1 : (seg_target + n_frames - 1) / n_frames;
         size_t seg_records = (n_periods + want_seg - 1) / want_seg;
-        if (seg_records < 4 * overlap && !h->overlap_hint) seg_records = 4 * overlap;
+        if (seg_records < 4 * overlap && !gentle) seg_records = 4 * overlap;
         if (h->seg_records_forced > 0) seg_records = size_t(h->seg_records_forced);
         if (seg_records == 0) seg_records = 1;
         if ((n_periods + seg_records - 1) / seg_records > 65535) seg_records = (n_periods + 65534) / 65535;      // gridDim.y
