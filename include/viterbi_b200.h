@@ -35,6 +35,13 @@ typedef enum vitb_status {
 /* tie-break of the compare-select */
 #define VITB_TIE_SCALAR 0   /* decision = path0 >  path1  (viterbi_decoder_scalar.h:123-124) -- the parity oracle            */
 #define VITB_TIE_SIMD   1   /* decision = path0 >= path1  (x86/viterbi_decoder_avx_u16.h:112-115, SSE/NEON alike)            */
+/* VITB_TIE_SIMD keeps the scalar decoder's wrapping arithmetic and only breaks ties the SIMD way: equal to the SIMD decoders as
+ * long as no metric saturates there (true for the stock presets except uint8_t metrics of the long codes).  VITB_TIE_SIMD_SAT
+ * reproduces them exactly: saturating metric adds (avx_u16.h:107-110 adds_epu16 / avx_u8.h adds_epu8), inverted error formed as
+ * max_error -sat total (:106), saturating sum of the branch errors (:95-97), ties - saturated candidates included - to path 1.
+ * It runs on the decision-row kernels (the survivor-history kernels keep their decisions where a saturated metric would clobber
+ * them), so batch calls are about half as fast as with the other two flavours.  Catalogue codes only. */
+#define VITB_TIE_SIMD_SAT 2
 
 /* Everything the reference passes to ViterbiBranchTable<K,R,soft_t>(G, high, low) (viterbi_branch_table.h:33-35) and
  * ViterbiDecoder_Core<K,R,error_t,soft_t>(branch_table, config) (viterbi_decoder_core.h:170), flattened. */
@@ -49,7 +56,7 @@ typedef struct vitb_params {
     uint32_t initial_start_error;       /* viterbi_decoder_config.h:15                                           */
     uint32_t initial_non_start_error;   /* viterbi_decoder_config.h:16                                           */
     uint32_t renormalisation_threshold; /* viterbi_decoder_config.h:17                                           */
-    int32_t tie_break;                  /* VITB_TIE_SCALAR (default) or VITB_TIE_SIMD                            */
+    int32_t tie_break;                  /* VITB_TIE_SCALAR (default), VITB_TIE_SIMD or VITB_TIE_SIMD_SAT         */
     int32_t device;                     /* CUDA device ordinal                                                   */
 } vitb_params;
 

@@ -21,6 +21,7 @@ struct vo_decoder {
     size_t rows;                /* traceback_length + K-1             viterbi_decoder_core.h:180-186 */
     size_t decoded_bit;         /* m_current_decoded_bit                                            */
     uint32_t max_seen;
+    uint64_t n_clipped;      /* see addu / subu */
     uint32_t max_seen_all;   /* like max_seen, but kept across reset(): the largest metric of a whole batch */
 };
 
@@ -44,16 +45,18 @@ static int32_t sat_soft(const vo_decoder* d, int32_t v) {
     return v > hi ? hi : (v < lo ? lo : v);
 }
 
+/* n_clipped counts the additions / subtractions whose exact result left the range of error_t: where the SIMD mode saturated, or the
+ * scalar mode wrapped (test instrumentation: 0 certifies that wrapping and saturating arithmetic cannot have differed) */
 static uint32_t addu(const vo_decoder* d, uint32_t a, uint32_t b) {
     const uint32_t m = err_mask(d);
-    if (d->mode == VO_MODE_SIMD) {          /* _mm256_adds_epu16: x86/viterbi_decoder_avx_u16.h:107-110 */
-        uint64_t s = (uint64_t)a + b;
-        return s > m ? m : (uint32_t)s;
-    }
+    const uint64_t s = (uint64_t)a + b;
+    if (s > m) ((vo_decoder*)d)->n_clipped++;
+    if (d->mode == VO_MODE_SIMD) return s > m ? m : (uint32_t)s;   /* _mm256_adds_epu16: x86/viterbi_decoder_avx_u16.h:107-110 */
     return (a + b) & m;                      /* plain error_t '+': viterbi_decoder_scalar.h:113-116 */
 }
 
 static uint32_t subu(const vo_decoder* d, uint32_t a, uint32_t b) {
+    if (b > a) ((vo_decoder*)d)->n_clipped++;
     if (d->mode == VO_MODE_SIMD) return a > b ? a - b : 0u;   /* _mm256_subs_epu16: avx_u16.h:106,165 */
     return (a - b) & err_mask(d);                             /* scalar.h:107,149 */
 }
@@ -219,6 +222,8 @@ const uint64_t* vo_decision_row(const vo_decoder* d, size_t t) { return d->decis
 size_t vo_decision_words_per_row(const vo_decoder* d) { return d->words_per_row; }
 const uint32_t* vo_metrics(const vo_decoder* d) { return d->metric[d->cur]; }
 uint32_t vo_max_metric_seen(const vo_decoder* d) { return d->max_seen; }
+/* number of additions / subtractions that saturated (SIMD mode) or wrapped (scalar mode) since creation / the last clearing call */
+uint64_t vo_clipped(vo_decoder* d, int clear) { const uint64_t v = d->n_clipped; if (clear) d->n_clipped = 0; return v; }
 /* largest metric since the decoder was created or the value was last cleared (clear != 0) */
 uint32_t vo_max_metric_seen_all(vo_decoder* d, int clear) { const uint32_t v = d->max_seen_all; if (clear) d->max_seen_all = 0; return v; }
 

@@ -54,6 +54,7 @@ size_t vo_decision_words_per_row(const vo_decoder* d);
 const uint32_t* vo_metrics(const vo_decoder* d);
 uint32_t vo_max_metric_seen(const vo_decoder* d);
 uint32_t vo_max_metric_seen_all(vo_decoder* d, int clear);
+uint64_t vo_clipped(vo_decoder* d, int clear);
 
 /* whole-frame convenience: reset(0) + update(all) + get_error(0) + chainback(L, 0) over n_frames frames laid out [frame][(L+K-1)*R] */
 int vo_decode_frames(vo_decoder* d, const void* symbols, size_t n_frames, size_t L,

@@ -83,6 +83,8 @@ def oracle_lib():
         L.vo_max_metric_seen.argtypes = [C.c_void_p]
         L.vo_max_metric_seen_all.restype = C.c_uint32
         L.vo_max_metric_seen_all.argtypes = [C.c_void_p, C.c_int]
+        L.vo_clipped.restype = C.c_uint64
+        L.vo_clipped.argtypes = [C.c_void_p, C.c_int]
         L.vo_decode_frames.restype = C.c_int
         L.vo_decode_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
         L.vo_update_punctured.restype = C.c_size_t
@@ -184,6 +186,10 @@ class OracleDecoder:
 
     def max_metric_seen(self):
         return int(self.L.vo_max_metric_seen(self.h))
+
+    def clipped(self, clear=True):
+        """additions / subtractions that saturated (SIMD mode) or wrapped (scalar mode) since creation / the last clearing call"""
+        return int(self.L.vo_clipped(self.h, 1 if clear else 0))
 
     def max_metric_seen_all(self, clear=True):
         """largest metric since creation / the last clearing call (a whole batch, where max_metric_seen covers the last frame)"""

@@ -67,25 +67,24 @@ def adversarial_batches(dc, n_frames, n_sym, seed):
 def test_tag_kernels_on_tie_storms(cuda_lib, name, decode_type, variant, prefix, n_frames, L, tie):
     """stock configuration, both tie-break flavours (the SIMD flavour tags the other path and inverts the record).  VITB_TIE_SIMD
     reproduces the SIMD decoders' tie-break, not their saturating adds (include/viterbi_b200.h), and the oracle's SIMD mode
-    saturates: a batch whose metrics reach the top of their type in the oracle is outside what that flavour promises and is only
-    checked in the scalar flavour."""
+    saturates: a batch in which any addition of the oracle saturated is outside what that flavour promises (the saturating flavour,
+    VITB_TIE_SIMD_SAT, is covered by tests/test_gpu_simd_sat.py) and is only checked in the scalar flavour."""
     code = CODE_BY_NAME[name]
     dec, dc = make_cuda_decoder(code, decode_type, tie_break=tie)
     ora, _ = make_oracle(code, decode_type, mode=tie)
     dec.set_variant(variant)
     n_sym = (L + code.K - 1) * code.R
-    top = 255 if dc.soft_bytes == 1 else 65535
     checked = 0
     for what, sym in adversarial_batches(dc, n_frames, n_sym, seed=L).items():
-        ora.max_metric_seen_all(clear=True)
+        ora.clipped(clear=True)
         want = oracle_batch(ora, code, sym, L) if code.K >= 15 else ora.decode_frames(sym, n_frames, L)
-        if tie == 1 and ora.max_metric_seen_all() >= top:
+        if tie == 1 and ora.clipped() > 0:
             continue
         got = dec.decode_batch(sym, L)
         assert dec.kernel_name.startswith(prefix), dec.kernel_name
         assert_batch_equal(got, want, f"{name} {decode_type} tie={tie} {what}")
         checked += 1
-    assert checked >= 3
+    assert checked >= (3 if tie == 0 else 1)
     dec.close()
 
 

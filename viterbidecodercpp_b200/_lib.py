@@ -9,7 +9,7 @@ VITB_MAX_R = 16
 
 VITB_END_STATE_BEST = 2 ** 64 - 1     # (size_t)-1
 VITB_OK, VITB_ERR_ARG, VITB_ERR_UNSUPPORTED, VITB_ERR_CUDA, VITB_ERR_STATE, VITB_ERR_NOMEM = 0, -1, -2, -3, -4, -5
-VITB_TIE_SCALAR, VITB_TIE_SIMD = 0, 1
+VITB_TIE_SCALAR, VITB_TIE_SIMD, VITB_TIE_SIMD_SAT = 0, 1, 2
 
 
 class vitb_params(C.Structure):

@@ -53,7 +53,7 @@ template <int NL> struct CtaAcc { static constexpr int value = NL >= 32 ? 4 : (N
 #endif
 constexpr int CTA_CHAINS = VITB_CTA_CHAINS;          // chains per decision byte (1, 2 or 4)
 
-template <class C, int LT, int PH, bool TIE_SIMD, int Q>
+template <class C, int LT, int PH, int TIE_SIMD, int Q>
 __device__ __forceinline__ void cta_bfly_at(uint32_t (&x)[CtaShape<C, LT>::NL], const uint2* tbl_ph, const uint32_t pt, float (&fa)[2][CtaAcc<CtaShape<C, LT>::NL>::value][CTA_CHAINS]) {
     using S = CtaShape<C, LT>;
     constexpr int bit = 1 << (S::LB - 1 - PH);
@@ -61,9 +61,10 @@ __device__ __forceinline__ void cta_bfly_at(uint32_t (&x)[CtaShape<C, LT>::NL], 
         constexpr int q0 = Q, q1 = Q | bit;
         constexpr uint32_t jq = rotl_bits(uint32_t(q0) << S::LOGT, PH, S::SB);
         constexpr uint32_t pq = bfly_pattern<C>(jq);
+        constexpr bool SAT = Sat<TIE_SIMD>::value;  // saturating flavour, see acs_pair.cuh
         const uint2 e = tbl_ph[pq ^ pt];            // {total_error, inverted_error} of pattern pq ^ pt   (scalar.h:66-73, 107)
-        const uint32_t a0 = __vadd2(x[q0], e.x), b0 = __vadd2(x[q1], e.y);     // scalar.h:113-114
-        const uint32_t a1 = __vadd2(x[q0], e.y), b1 = __vadd2(x[q1], e.x);     // scalar.h:115-116
+        const uint32_t a0 = metric_add<SAT>(x[q0], e.x), b0 = metric_add<SAT>(x[q1], e.y);     // scalar.h:113-114
+        const uint32_t a1 = metric_add<SAT>(x[q0], e.y), b1 = metric_add<SAT>(x[q1], e.x);     // scalar.h:115-116
         bool h0, l0, h1, l1, dA0, dB0, dA1, dB1;
         if constexpr (!TIE_SIMD) {
             x[q0] = __vibmin_u16x2(a0, b0, &h0, &l0);
@@ -84,13 +85,13 @@ __device__ __forceinline__ void cta_bfly_at(uint32_t (&x)[CtaShape<C, LT>::NL], 
     }
 }
 
-template <class C, int LT, int PH, bool TIE_SIMD, int... Qs>
+template <class C, int LT, int PH, int TIE_SIMD, int... Qs>
 __device__ __forceinline__ void cta_bfly_all(uint32_t (&x)[CtaShape<C, LT>::NL], const uint2* tbl_ph, const uint32_t pt, float (&fa)[2][CtaAcc<CtaShape<C, LT>::NL>::value][CTA_CHAINS],
                                              std::integer_sequence<int, Qs...>) {
     (cta_bfly_at<C, LT, PH, TIE_SIMD, Qs>(x, tbl_ph, pt, fa), ...);
 }
 
-template <class C, int LT, int SH, bool TIE_SIMD>
+template <class C, int LT, int SH, int TIE_SIMD>
 struct CtaKernel {
     using S = CtaShape<C, LT>;
     static constexpr int LB = S::LB, NL = S::NL, R = C::R, NP = C::NP, T = S::T, SB = S::SB;
@@ -150,7 +151,7 @@ struct CtaKernel {
 };
 
 // grid = number of frame pairs, block = 512, dynamic shared memory = CtaShape::SMEM_BYTES
-template <class C, int LT, int SH, bool TIE_SIMD>
+template <class C, int LT, int SH, int TIE_SIMD>
 __global__ void __launch_bounds__(CtaShape<C, LT>::T, 1) acs_cta_kernel(const AcsParams p) {
     using S = CtaShape<C, LT>;
     using Kn = CtaKernel<C, LT, SH, TIE_SIMD>;
@@ -193,6 +194,9 @@ __global__ void __launch_bounds__(CtaShape<C, LT>::T, 1) acs_cta_kernel(const Ac
         }
     }
 
+#pragma unroll
+    for (int q = 0; q < NL; q++) x[q] = metric_ones<Sat<TIE_SIMD>::value, SH>(x[q]);       // saturating flavour: low byte 0xFF (acs_pair.cuh)
+
     const uint32_t* pk = p.pk + (size_t(pair) * (p.pk_steps ? p.pk_steps : p.n_steps) + p.pk_step0) * R;   // [steps][R], this launch's first step
     constexpr int W = Kn::W;
     uint32_t* dec = static_cast<uint32_t*>(p.dec) + ((size_t(pair) * p.dec_rows + p.dec_row0) * S::T + t) * W;
@@ -211,9 +215,14 @@ __global__ void __launch_bounds__(CtaShape<C, LT>::T, 1) acs_cta_kernel(const Ac
                     const uint32_t sv = __ldg(sy + i);
                     const uint32_t lo = __vadd2(sv, p.c_low2), hi = __vadd2(~sv, p.c_high2);
                     const bool bb = (pat >> i) & 1u;
-                    tot = __vadd2(tot, bb ? hi : lo);          // viterbi_branch_table.h:52 + scalar.h:66-73
-                    inv = __vadd2(inv, bb ? lo : hi);          // scalar.h:107 (max_error - total), complementary pattern + c_inv
+                    if constexpr (Sat<TIE_SIMD>::value) {
+                        tot = metric_field<true, SH>(__vaddus2(tot, bb ? hi : lo));       // avx_u16.h:95-97: saturating sum of the errors
+                    } else {
+                        tot = __vadd2(tot, bb ? hi : lo);      // viterbi_branch_table.h:52 + scalar.h:66-73
+                        inv = __vadd2(inv, bb ? lo : hi);      // scalar.h:107 (max_error - total), complementary pattern + c_inv
+                    }
                 }
+                if constexpr (Sat<TIE_SIMD>::value) inv = __vsubus2(p.max_err2, tot);     // avx_u16.h:106: max_error -sat total
                 tbl[tph * NP + pat] = make_uint2(tot, inv);
             }
         }
@@ -284,7 +293,7 @@ __global__ void __launch_bounds__(CtaShape<C, LT>::T, 1) acs_cta_kernel(const Ac
                     bool tb, ta;
                     (void)__vibmin_u16x2(p.thr2, x00, &tb, &ta);
                     if (ta || tb) {                                    // uniform across the CTA
-                        const uint32_t m = Kn::cta_min(x, red);
+                        const uint32_t m = metric_field<Sat<TIE_SIMD>::value, SH>(Kn::cta_min(x, red));
                         const uint32_t mAv = m & 0xffffu, mBv = m >> 16;
                         const uint32_t sub = (ta ? mAv : 0u) | ((tb ? mBv : 0u) << 16);
                         const uint32_t neg = __vsub2(0u, sub);

@@ -32,7 +32,7 @@ struct GenericCode {
     uint8_t pat[32];          // branch pattern of butterfly j (old state with leading bit 0), j < 2^(K-2)
 };
 
-template <int K, bool TIE_SIMD, int J>
+template <int K, int TIE_SIMD, int J>
 __device__ __forceinline__ void gen_bfly_at(const uint32_t (&x)[1 << (K - 1)], uint32_t (&y)[1 << (K - 1)], const uint32_t* Tcol,
                                             const GenericCode& gc, const uint32_t np_mask, const uint32_t c_inv2,
                                             float (&fa)[2][(1 << (K - 1)) >= 16 ? (1 << (K - 1)) / 16 : 1]) {
@@ -61,7 +61,7 @@ __device__ __forceinline__ void gen_bfly_at(const uint32_t (&x)[1 << (K - 1)], u
     if (dB1) fa[1][acc1] += w1;
 }
 
-template <int K, bool TIE_SIMD, int... Js>
+template <int K, int TIE_SIMD, int... Js>
 __device__ __forceinline__ void gen_bfly_all(const uint32_t (&x)[1 << (K - 1)], uint32_t (&y)[1 << (K - 1)], const uint32_t* Tcol,
                                              const GenericCode& gc, const uint32_t np_mask, const uint32_t c_inv2,
                                              float (&fa)[2][(1 << (K - 1)) >= 16 ? (1 << (K - 1)) / 16 : 1], std::integer_sequence<int, Js...>) {
@@ -69,7 +69,7 @@ __device__ __forceinline__ void gen_bfly_all(const uint32_t (&x)[1 << (K - 1)], 
 }
 
 // one trellis step x -> y; sym = this step's R packed symbol words
-template <int K, int SH, bool TIE_SIMD>
+template <int K, int SH, int TIE_SIMD>
 __device__ __forceinline__ void gen_step(const uint32_t (&x)[1 << (K - 1)], uint32_t (&y)[1 << (K - 1)], const uint32_t* sym, uint32_t* Tcol,
                                          const AcsParams& p, const GenericCode& gc, uint64_t* dec_row, uint64_t& accA, uint64_t& accB) {
     constexpr int NS = 1 << (K - 1), NACC = NS >= 16 ? NS / 16 : 1;
@@ -124,7 +124,7 @@ __device__ __forceinline__ void gen_step(const uint32_t (&x)[1 << (K - 1)], uint
 }
 
 // grid = ceil(n_blocks / 2), block = 64 threads (2 warps, one 64-frame block each); packed symbol stream in the 32-pairs-per-warp layout
-template <int K, int SH, bool TIE_SIMD>
+template <int K, int SH, int TIE_SIMD>
 __global__ void __launch_bounds__(GENERIC_THREADS) acs_generic_kernel(const AcsParams p, const GenericCode gc) {
     constexpr int NS = 1 << (K - 1);
     __shared__ uint32_t Tsm[(1 << GENERIC_MAX_R) * GENERIC_THREADS];

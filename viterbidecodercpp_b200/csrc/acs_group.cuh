@@ -50,10 +50,12 @@ struct GroupShape {
     }
 };
 
-template <class C, int LOGT, int PH, bool TIE_SIMD, int Q>
+template <class C, int LOGT, int PH, int TIE_SIMD, int Q>
 __device__ __forceinline__ void group_bfly_at(uint32_t (&x)[GroupShape<C, LOGT>::NL], const uint32_t (&T)[C::NP],
-                                              float (&fa)[2][GroupShape<C, LOGT>::NACC], const uint32_t c_inv2, const bool consistent) {
+                                              float (&fa)[2][GroupShape<C, LOGT>::NACC], const uint32_t c_inv2, const bool consistent,
+                                              const uint32_t max_err2) {
     using S = GroupShape<C, LOGT>;
+    constexpr bool SAT = Sat<TIE_SIMD>::value;          // saturating flavour, see acs_pair.cuh
     constexpr int bit = 1 << (S::LB - 1 - PH);
     if constexpr ((Q & bit) == 0) {
         constexpr int q0 = Q, q1 = Q | bit;
@@ -61,9 +63,9 @@ __device__ __forceinline__ void group_bfly_at(uint32_t (&x)[GroupShape<C, LOGT>:
         constexpr uint32_t pat = bfly_pattern<C>(jq);                          // ... and of its branch pattern
         constexpr uint32_t ipat = (~pat) & uint32_t(C::NP - 1);
         const uint32_t tot = T[pat];
-        const uint32_t inv = consistent ? T[ipat] : __vadd2(T[ipat], c_inv2);
-        const uint32_t a0 = __vadd2(x[q0], tot), b0 = __vadd2(x[q1], inv);     // scalar.h:113-114
-        const uint32_t a1 = __vadd2(x[q0], inv), b1 = __vadd2(x[q1], tot);     // scalar.h:115-116
+        const uint32_t inv = consistent ? T[ipat] : (SAT ? __vsubus2(max_err2, tot) : __vadd2(T[ipat], c_inv2));
+        const uint32_t a0 = metric_add<SAT>(x[q0], tot), b0 = metric_add<SAT>(x[q1], inv);     // scalar.h:113-114
+        const uint32_t a1 = metric_add<SAT>(x[q0], inv), b1 = metric_add<SAT>(x[q1], tot);     // scalar.h:115-116
         bool h0, l0, h1, l1, dA0, dB0, dA1, dB1;
         if constexpr (!TIE_SIMD) {
             x[q0] = __vibmin_u16x2(a0, b0, &h0, &l0);
@@ -83,11 +85,11 @@ __device__ __forceinline__ void group_bfly_at(uint32_t (&x)[GroupShape<C, LOGT>:
     }
 }
 
-template <class C, int LOGT, int PH, bool TIE_SIMD, int... Qs>
+template <class C, int LOGT, int PH, int TIE_SIMD, int... Qs>
 __device__ __forceinline__ void group_bfly_all(uint32_t (&x)[GroupShape<C, LOGT>::NL], const uint32_t (&T)[C::NP],
                                                float (&fa)[2][GroupShape<C, LOGT>::NACC], const uint32_t c_inv2, const bool consistent,
-                                               std::integer_sequence<int, Qs...>) {
-    (group_bfly_at<C, LOGT, PH, TIE_SIMD, Qs>(x, T, fa, c_inv2, consistent), ...);
+                                               const uint32_t max_err2, std::integer_sequence<int, Qs...>) {
+    (group_bfly_at<C, LOGT, PH, TIE_SIMD, Qs>(x, T, fa, c_inv2, consistent, max_err2), ...);
 }
 
 // per-lane, per-phase constants that fold the lane part of the branch pattern into the table
@@ -97,7 +99,7 @@ struct LaneConsts {
     uint32_t m[S::LB][C::R];      // 0 or ~0: x = sym ^ m;  e(folded bit 0) = x + (m ? c_high : c_low),  e(folded bit 1) = ~x + (m ? c_low : c_high)
 };
 
-template <class C, int LOGT, int SH, bool TIE_SIMD, bool CONSISTENT>
+template <class C, int LOGT, int SH, int TIE_SIMD, bool CONSISTENT>
 struct GroupKernel {
     using S = GroupShape<C, LOGT>;
     static constexpr int LB = S::LB, NL = S::NL, R = C::R, NP = C::NP, T = S::T, SB = S::SB;
@@ -113,12 +115,14 @@ struct GroupKernel {
             lo[i] = __vadd2(xs, p.c_low2 ^ (mk & cd));      // constants swap when the lane part of the pattern flips this symbol
             hi[i] = __vadd2(~xs, p.c_high2 ^ (mk & cd));
         }
+        constexpr bool SAT = Sat<TIE_SIMD>::value;
         uint32_t Tt[NP];
-        TableBuild<R, R>::run(Tt, lo, hi);
+        if constexpr (SAT) table_build_sat<R, SH>(Tt, lo, hi);
+        else TableBuild<R, R>::run(Tt, lo, hi);
         float fa[2][S::NACC];
 #pragma unroll
         for (int a = 0; a < S::NACC; a++) { fa[0][a] = 8388608.f; fa[1][a] = 8388608.f; }
-        group_bfly_all<C, LOGT, PH, TIE_SIMD>(x, Tt, fa, p.c_inv2, CONSISTENT, std::make_integer_sequence<int, NL>{});
+        group_bfly_all<C, LOGT, PH, TIE_SIMD>(x, Tt, fa, p.c_inv2, CONSISTENT, p.max_err2, std::make_integer_sequence<int, NL>{});
 
         if constexpr (S::W == 1) {
             dec_lane_row[0] = __byte_perm(__float_as_uint(fa[0][0]), __float_as_uint(fa[1][0]), 0x5410);   // A bits | B bits << 16
@@ -136,6 +140,7 @@ struct GroupKernel {
             uint32_t m = packed_min<NL>(x);
 #pragma unroll
             for (int d = 1; d < T; d <<= 1) m = __vminu2(m, __shfl_xor_sync(pair_mask, m, d));
+            m = metric_field<SAT, SH>(m);
             const uint32_t mA = m & 0xffffu, mB = m >> 16;
             const uint32_t sub = (trigA ? mA : 0u) | ((trigB ? mB : 0u) << 16);
             const uint32_t neg = __vsub2(0u, sub);
@@ -174,7 +179,7 @@ struct GroupKernel {
 };
 
 // grid = ceil(n_wblocks / WARPS), block = 32 * WARPS
-template <class C, int LOGT, int SH, bool TIE_SIMD, bool CONSISTENT>
+template <class C, int LOGT, int SH, int TIE_SIMD, bool CONSISTENT>
 __global__ void __launch_bounds__(32 * GroupShape<C, LOGT>::WARPS, GroupShape<C, LOGT>::MIN_CTAS) acs_group_kernel(const AcsParams p) {
     using S = GroupShape<C, LOGT>;
     using Kn = GroupKernel<C, LOGT, SH, TIE_SIMD, CONSISTENT>;
@@ -221,6 +226,9 @@ __global__ void __launch_bounds__(32 * GroupShape<C, LOGT>::WARPS, GroupShape<C,
             x[q] = (s == s0) ? p.init_start2 : p.init_other2;
         }
     }
+
+#pragma unroll
+    for (int q = 0; q < NL; q++) x[q] = metric_ones<Sat<TIE_SIMD>::value, SH>(x[q]);       // saturating flavour: low byte 0xFF (acs_pair.cuh)
 
     const uint32_t* pk = p.pk + size_t(wblk) * p.n_steps * R * PPW + pw;
     uint32_t* dec_lane = static_cast<uint32_t*>(p.dec) + ((size_t(wblk) * p.dec_rows + p.dec_row0) * 32 + lane) * S::W;

@@ -99,7 +99,7 @@ struct HistShape {
     static constexpr int VW = NW < 4 ? NW : 4;           // words per vector store
 };
 
-template <class C, int FMT, bool TIE_SIMD, int J>
+template <class C, int FMT, int TIE_SIMD, int J>
 __device__ __forceinline__ void hist_bfly_at(const uint32_t (&x)[C::NS], uint32_t (&y)[C::NS], const uint32_t (&T)[C::NP],
                                              const uint32_t (&TT)[C::NP], const uint32_t (&V)[C::NP], const uint32_t (&VT)[C::NP]) {
     using LN = HistLane<FMT>;
@@ -119,7 +119,7 @@ __device__ __forceinline__ void hist_bfly_at(const uint32_t (&x)[C::NS], uint32_
     }
 }
 
-template <class C, int FMT, bool TIE_SIMD, int... Js>
+template <class C, int FMT, int TIE_SIMD, int... Js>
 __device__ __forceinline__ void hist_bfly_all(const uint32_t (&x)[C::NS], uint32_t (&y)[C::NS], const uint32_t (&T)[C::NP],
                                               const uint32_t (&TT)[C::NP], const uint32_t (&V)[C::NP], const uint32_t (&VT)[C::NP],
                                               std::integer_sequence<int, Js...>) {
@@ -161,7 +161,7 @@ struct HistTable<FMT, R, 1> {
 template <int FMT>
 struct HistLazyRenorm { static constexpr bool value = (FMT == 1); };
 
-template <class C, int FMT, bool TIE_SIMD, bool CONSISTENT, bool NEG_BY_NOT>
+template <class C, int FMT, int TIE_SIMD, bool CONSISTENT, bool NEG_BY_NOT>
 __device__ __forceinline__ void hist_step(const uint32_t (&x)[C::NS], uint32_t (&y)[C::NS], const uint32_t* sym, const HistConsts& c,
                                           const uint32_t tag, uint64_t& accA, uint64_t& accB, uint32_t& pend) {
     using LN = HistLane<FMT>;
@@ -228,7 +228,7 @@ constexpr int HIST_WARPS = 4;
 // grid = ceil(n_blocks / warps per CTA), at most HIST_WARPS warps per CTA; one warp per block of 64 (FMT 0) / 32 (FMT 1) frames.
 // Whole frames only: p.resume must be 0 and p.dec_row0 must be 0 (the streaming API keeps using acs_pair_kernel / acs_group_kernel).
 // FMT 1 reads the packed stream in the 16-pairs-per-warp-block layout (ingest with ppw = 16).
-template <class C, int FMT, bool TIE_SIMD, bool CONSISTENT, bool DIRECT>
+template <class C, int FMT, int TIE_SIMD, bool CONSISTENT, bool DIRECT>
 __global__ void __launch_bounds__(32 * HIST_WARPS) acs_hist_kernel(const AcsParams p) {
     using LN = HistLane<FMT>;
     constexpr int R = C::R, NS = C::NS, NW = HistShape<C>::NW, VW = HistShape<C>::VW, HB = LN::HB, FPT = LN::FPT;

@@ -48,7 +48,7 @@ __host__ __device__ constexpr uint32_t rotl_rt(uint32_t v, uint32_t r, uint32_t 
     return r == 0 ? v : (((v << r) | (v >> (n - r))) & ((1u << n) - 1u));
 }
 
-template <class C, int PH, bool TIE_SIMD, int Q>
+template <class C, int PH, int TIE_SIMD, int Q>
 __device__ __forceinline__ void hc_bfly_at(uint32_t (&x)[HistCtaShape<C>::NL], const uint2* tbl_ph, const uint32_t pt, const uint32_t tag,
                                            const uint32_t one) {
     using H = HistCtaShape<C>;
@@ -78,7 +78,7 @@ __device__ __forceinline__ void hc_bfly_at(uint32_t (&x)[HistCtaShape<C>::NL], c
     }
 }
 
-template <class C, int PH, bool TIE_SIMD, int... Qs>
+template <class C, int PH, int TIE_SIMD, int... Qs>
 __device__ __forceinline__ void hc_bfly_all(uint32_t (&x)[HistCtaShape<C>::NL], const uint2* tbl_ph, const uint32_t pt, const uint32_t tag,
                                             const uint32_t one, std::integer_sequence<int, Qs...>) {
     (hc_bfly_at<C, PH, TIE_SIMD, Qs>(x, tbl_ph, pt, tag, one), ...);
@@ -86,7 +86,7 @@ __device__ __forceinline__ void hc_bfly_all(uint32_t (&x)[HistCtaShape<C>::NL], 
 
 // grid = number of frames, block = 512, dynamic shared memory = HistCtaShape::SMEM_BYTES.  Whole frames only (no resume).
 // MINB: CTAs per SM the register allocation is made for (1: 128 registers per thread; 2: 64 registers - measured slower, it spills)
-template <class C, bool TIE_SIMD, int MINB>
+template <class C, int TIE_SIMD, int MINB>
 __global__ void __launch_bounds__(HistCtaShape<C>::T, MINB) acs_hist_cta_kernel(const AcsParams p) {
     using H = HistCtaShape<C>;
     using S = typename H::S;

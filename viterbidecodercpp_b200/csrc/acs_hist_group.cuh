@@ -41,7 +41,7 @@ struct HistGroupShape {
 };
 
 // one in-place butterfly at compile-time phase PH on registers Q and Q | bit
-template <class C, int PH, bool TIE_SIMD, int Q>
+template <class C, int PH, int TIE_SIMD, int Q>
 __device__ __forceinline__ void hg_bfly_at(uint32_t (&x)[HistGroupShape<C>::NL], const uint32_t (&T)[C::NP], const uint32_t (&TT)[C::NP],
                                            const uint32_t (&V)[C::NP], const uint32_t (&VT)[C::NP]) {
     using S = HistGroupShape<C>;
@@ -65,7 +65,7 @@ __device__ __forceinline__ void hg_bfly_at(uint32_t (&x)[HistGroupShape<C>::NL],
     }
 }
 
-template <class C, int PH, bool TIE_SIMD, int... Qs>
+template <class C, int PH, int TIE_SIMD, int... Qs>
 __device__ __forceinline__ void hg_bfly_all(uint32_t (&x)[HistGroupShape<C>::NL], const uint32_t (&T)[C::NP], const uint32_t (&TT)[C::NP],
                                             const uint32_t (&V)[C::NP], const uint32_t (&VT)[C::NP], std::integer_sequence<int, Qs...>) {
     (hg_bfly_at<C, PH, TIE_SIMD, Qs>(x, T, TT, V, VT), ...);
@@ -81,7 +81,7 @@ __device__ __forceinline__ void hg_bfly_all(uint32_t (&x)[HistGroupShape<C>::NL]
 // made ptxas shuffle half of the in-place butterfly results back into canonical registers after every step (34 IMAD.MOV per step
 // in the round-1 build, profiles/r02_ncu_full_acs_hist_group_cfg3.txt).  A pending value left after the last step is applied when
 // the final metrics are written.
-template <class C, int PH, bool TIE_SIMD, bool CONSISTENT>
+template <class C, int PH, int TIE_SIMD, bool CONSISTENT>
 __device__ __forceinline__ void hg_step(uint32_t (&x)[HistGroupShape<C>::NL], const uint32_t* sym, const uint32_t fold_bits, const HistConsts& c,
                                         const uint32_t tag, const uint32_t lane, uint64_t& acc, uint32_t& pend) {
     using S = HistGroupShape<C>;
@@ -127,7 +127,7 @@ __device__ __forceinline__ void hg_step(uint32_t (&x)[HistGroupShape<C>::NL], co
 }
 
 // grid = ceil(n_blocks / WARPS); one warp = 8 frames, lane = 4 * frame + t
-template <class C, bool TIE_SIMD, bool CONSISTENT>
+template <class C, int TIE_SIMD, bool CONSISTENT>
 __global__ void __launch_bounds__(32 * HistGroupShape<C>::WARPS, 7) acs_hist_group_kernel(const AcsParams p) {
     using S = HistGroupShape<C>;
     constexpr int R = C::R, NL = S::NL, NW = S::NW, LB = S::LB, LOGT = S::LOGT, T = S::T, SB = S::SB, HB = 16;

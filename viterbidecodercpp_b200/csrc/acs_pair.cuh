@@ -54,6 +54,7 @@ struct AcsParams {
     // acs_cta.cuh, sliding-window calls: the launch covers steps pk_step0 .. pk_step0 + n_steps - 1 of frames whose packed stream
     // holds pk_steps steps per pair (0 = the launch covers the whole stream: n_steps steps from step 0)
     uint32_t pk_steps, pk_step0;
+    uint32_t max_err2;      // per half: soft_decision_max_error << SH (the saturating flavour forms inverted = max_error -sat total)
 };
 
 template <class C>
@@ -89,11 +90,44 @@ struct TableBuild<R, 1> {
     }
 };
 
+// ---- saturating flavour (VITB_TIE_SIMD_SAT, template value TIE_SIMD == 2) ------------------------------------------------------------
+// The reference's SSE / AVX / NEON decoders add path metrics with saturating instructions (x86/viterbi_decoder_avx_u16.h:107-110
+// adds_epu16, avx_u8.h:107-110 adds_epu8), form inverted_error = max_error -sat total_error (:106) and accumulate the branch errors with
+// saturating adds too (:97); a tie - including two saturated candidates - selects path 1 (:112-115).  This flavour reproduces all of
+// that in the decision-row kernels.  uint16_t metrics: __vaddus2 on the native halves.  uint8_t metrics are held as metric << 8; in
+// this flavour the LOW BYTE OF EVERY METRIC IS 0xFF, so that a 16-bit saturating add of (m << 8 | 0xFF) + (e << 8) saturates to
+// 0xFFFF = (0xFF << 8 | 0xFF) exactly when m + e >= 256: the representation is closed under add, min and the subtraction of a
+// minimum whose low byte was cleared.  Branch errors keep a zero low byte.
+template <int TIE_SIMD>
+struct Sat { static constexpr bool value = (TIE_SIMD == 2); };
+template <bool SAT>
+__device__ __forceinline__ uint32_t metric_add(uint32_t a, uint32_t b) { return SAT ? __vaddus2(a, b) : __vadd2(a, b); }
+template <bool SAT, int SH>
+__device__ __forceinline__ uint32_t metric_ones(uint32_t x) { return (SAT && SH == 8) ? (x | 0x00ff00ffu) : x; }      // metric representation
+template <bool SAT, int SH>
+__device__ __forceinline__ uint32_t metric_field(uint32_t x) { return (SAT && SH == 8) ? (x & 0xff00ff00u) : x; }     // value with a zero low byte
+
+// branch metric table with saturating accumulation of the R errors (avx_u16.h:95-97); entries keep a zero low byte
+template <int R, int SH, int NP>
+__device__ __forceinline__ void table_build_sat(uint32_t (&T)[NP], const uint32_t (&lo)[R], const uint32_t (&hi)[R]) {
+#pragma unroll
+    for (int pat = 0; pat < NP; pat++) {
+        uint32_t acc = 0u;
+#pragma unroll
+        for (int i = 0; i < R; i++) {
+            acc = __vaddus2(acc, ((pat >> i) & 1) ? hi[i] : lo[i]);
+            if (SH == 8) acc &= 0xff00ff00u;
+        }
+        T[pat] = acc;
+    }
+}
+
 // ---- one butterfly, everything about its position known at compile time ----------------------------------------------
-template <class C, int PH, bool TIE_SIMD, int Q>
+template <class C, int PH, int TIE_SIMD, int Q>
 __device__ __forceinline__ void bfly_at(uint32_t (&x)[C::NS], const uint32_t (&T)[C::NP], float (&fa)[2][PairShape<C>::NACC],
-                                        const uint32_t c_inv2, const bool consistent) {
+                                        const uint32_t c_inv2, const bool consistent, const uint32_t max_err2) {
     constexpr int SB = C::SB;
+    constexpr bool SAT = Sat<TIE_SIMD>::value;
     constexpr int bit = 1 << (SB - 1 - PH);
     if constexpr ((Q & bit) == 0) {
         constexpr int q0 = Q, q1 = Q | bit;
@@ -104,11 +138,11 @@ __device__ __forceinline__ void bfly_at(uint32_t (&x)[C::NS], const uint32_t (&T
         constexpr uint32_t s0 = 2 * j, s1 = 2 * j + 1;              // logical new states -> decision bit positions
         const uint32_t tot = T[pat];
         // inverted_error = max_error - total_error (scalar.h:107) = T[~pat] + c_inv2
-        const uint32_t inv = consistent ? T[ipat] : __vadd2(T[ipat], c_inv2);
-        const uint32_t a0 = __vadd2(x[q0], tot);   // (0|X) -> (X|0)   scalar.h:113
-        const uint32_t b0 = __vadd2(x[q1], inv);   // (1|X) -> (X|0)   scalar.h:114
-        const uint32_t a1 = __vadd2(x[q0], inv);   // (0|X) -> (X|1)   scalar.h:115
-        const uint32_t b1 = __vadd2(x[q1], tot);   // (1|X) -> (X|1)   scalar.h:116
+        const uint32_t inv = consistent ? T[ipat] : (SAT ? __vsubus2(max_err2, tot) : __vadd2(T[ipat], c_inv2));
+        const uint32_t a0 = metric_add<SAT>(x[q0], tot);   // (0|X) -> (X|0)   scalar.h:113
+        const uint32_t b0 = metric_add<SAT>(x[q1], inv);   // (1|X) -> (X|0)   scalar.h:114
+        const uint32_t a1 = metric_add<SAT>(x[q0], inv);   // (0|X) -> (X|1)   scalar.h:115
+        const uint32_t b1 = metric_add<SAT>(x[q1], tot);   // (1|X) -> (X|1)   scalar.h:116
         bool h0, l0, h1, l1;
         bool dA0, dB0, dA1, dB1;
         if constexpr (!TIE_SIMD) {
@@ -129,10 +163,11 @@ __device__ __forceinline__ void bfly_at(uint32_t (&x)[C::NS], const uint32_t (&T
     }
 }
 
-template <class C, int PH, bool TIE_SIMD, int... Qs>
+template <class C, int PH, int TIE_SIMD, int... Qs>
 __device__ __forceinline__ void bfly_all(uint32_t (&x)[C::NS], const uint32_t (&T)[C::NP], float (&fa)[2][PairShape<C>::NACC],
-                                         const uint32_t c_inv2, const bool consistent, std::integer_sequence<int, Qs...>) {
-    (bfly_at<C, PH, TIE_SIMD, Qs>(x, T, fa, c_inv2, consistent), ...);
+                                         const uint32_t c_inv2, const bool consistent, const uint32_t max_err2,
+                                         std::integer_sequence<int, Qs...>) {
+    (bfly_at<C, PH, TIE_SIMD, Qs>(x, T, fa, c_inv2, consistent, max_err2), ...);
 }
 
 // ---- tagged butterfly (uint8_t metrics only) --------------------------------------------------------------------------
@@ -145,7 +180,7 @@ __device__ __forceinline__ void bfly_all(uint32_t (&x)[C::NS], const uint32_t (&
 // TIE_SIMD puts the tag on path 0 instead and the collected bits are inverted at the end.
 // T = total error by pattern, V = inverted error by pattern's complement index (V[k] = T[k] + c_inv), TT / VT = the same with the
 // tag byte set.  For consistent configurations V aliases T and VT aliases TT.
-template <class C, int PH, bool TIE_SIMD, int J>
+template <class C, int PH, int TIE_SIMD, int J>
 __device__ __forceinline__ void tag_bfly_at(uint32_t (&x)[C::NS], const uint32_t (&T)[C::NP], const uint32_t (&TT)[C::NP],
                                             const uint32_t (&V)[C::NP], const uint32_t (&VT)[C::NP],
                                             uint32_t (&dacc)[(C::NS / 2 + 7) / 8]) {
@@ -173,7 +208,7 @@ __device__ __forceinline__ void tag_bfly_at(uint32_t (&x)[C::NS], const uint32_t
     x[q1] = m1 & 0xff00ff00u;
 }
 
-template <class C, int PH, bool TIE_SIMD, int... Js>
+template <class C, int PH, int TIE_SIMD, int... Js>
 __device__ __forceinline__ void tag_bfly_all(uint32_t (&x)[C::NS], const uint32_t (&T)[C::NP], const uint32_t (&TT)[C::NP],
                                              const uint32_t (&V)[C::NP], const uint32_t (&VT)[C::NP],
                                              uint32_t (&dacc)[(C::NS / 2 + 7) / 8], std::integer_sequence<int, Js...>) {
@@ -191,7 +226,7 @@ __device__ __forceinline__ uint32_t packed_min(const uint32_t (&x)[NS]) {
 }
 
 // ---- one trellis step at compile-time phase PH ---------------------------------------------------------------------
-template <class C, int SH, bool TIE_SIMD, bool CONSISTENT, int PH, bool TAG = (SH == 8)>
+template <class C, int SH, int TIE_SIMD, bool CONSISTENT, int PH, bool TAG = (SH == 8 && TIE_SIMD != 2)>
 __device__ __forceinline__ void acs_pair_step(uint32_t (&x)[C::NS], const uint32_t* sym /* R packed words */, const AcsParams& p,
                                               uint64_t* dec_row /* this lane's 16 bytes of the row */, uint64_t& accA, uint64_t& accB) {
     constexpr int R = C::R, NP = C::NP, NS = C::NS, NACC = PairShape<C>::NACC;
@@ -203,8 +238,10 @@ __device__ __forceinline__ void acs_pair_step(uint32_t (&x)[C::NS], const uint32
         lo[i] = __vadd2(sym[i], p.c_low2);
         hi[i] = __vadd2(~sym[i], p.c_high2);
     }
+    constexpr bool SAT = Sat<TIE_SIMD>::value;
     uint32_t T[NP];
-    TableBuild<R, R>::run(T, lo, hi);
+    if constexpr (SAT) table_build_sat<R, SH>(T, lo, hi);
+    else TableBuild<R, R>::run(T, lo, hi);
 
     uint32_t wA0, wA1 = 0, wB0, wB1 = 0;
     if constexpr (TAG) {
@@ -245,7 +282,7 @@ __device__ __forceinline__ void acs_pair_step(uint32_t (&x)[C::NS], const uint32
 #pragma unroll
     for (int a = 0; a < NACC; a++) { fa[0][a] = 8388608.f; fa[1][a] = 8388608.f; }
 
-    bfly_all<C, PH, TIE_SIMD>(x, T, fa, p.c_inv2, CONSISTENT, std::make_integer_sequence<int, NS>{});
+    bfly_all<C, PH, TIE_SIMD>(x, T, fa, p.c_inv2, CONSISTENT, p.max_err2, std::make_integer_sequence<int, NS>{});
 
     // decision row: bit s of the 64-bit word = decision of logical state s (same bit order as core.h:49-83 / scalar.h:131-134)
     if constexpr (NACC == 4) {
@@ -267,7 +304,7 @@ __device__ __forceinline__ void acs_pair_step(uint32_t (&x)[C::NS], const uint32
     bool trigB, trigA;
     (void)__vibmin_u16x2(p.thr2, x[0], &trigB, &trigA);      // pred = thr <= x0
     if (trigA || trigB) {
-        const uint32_t m = packed_min<NS>(x);                   // scalar.h:140-146
+        const uint32_t m = metric_field<SAT, SH>(packed_min<NS>(x));   // scalar.h:140-146
         const uint32_t mA = m & 0xffffu, mB = m >> 16;
         const uint32_t sub = (trigA ? mA : 0u) | ((trigB ? mB : 0u) << 16);
         const uint32_t neg = __vsub2(0u, sub);
@@ -285,7 +322,7 @@ __device__ __forceinline__ void acs_pair_step(uint32_t (&x)[C::NS], const uint32
 template <class C>
 struct PairPeriod { static constexpr int value = (C::SB == 6) ? 3 : C::SB; };
 
-template <class C, int SH, bool TIE_SIMD, bool CONSISTENT, int PERIOD = PairPeriod<C>::value>
+template <class C, int SH, int TIE_SIMD, bool CONSISTENT, int PERIOD = PairPeriod<C>::value>
 struct PairRunner {
     static constexpr int P = PERIOD, R = C::R, NS = C::NS;
 
@@ -358,7 +395,7 @@ struct DirectFetch {
     }
 };
 
-template <class C, int SH, bool TIE_SIMD, bool CONSISTENT, int PERIOD = PairPeriod<C>::value, bool DIRECT = false>
+template <class C, int SH, int TIE_SIMD, bool CONSISTENT, int PERIOD = PairPeriod<C>::value, bool DIRECT = false>
 __global__ void __launch_bounds__(32 * PAIR_WARPS) acs_pair_kernel(const AcsParams p) {
     constexpr int P = PERIOD, R = C::R, NS = C::NS, SB = C::SB;
     using Run = PairRunner<C, SH, TIE_SIMD, CONSISTENT, PERIOD>;
@@ -381,6 +418,8 @@ __global__ void __launch_bounds__(32 * PAIR_WARPS) acs_pair_kernel(const AcsPara
 #pragma unroll
         for (int q = 0; q < NS; q++) x[q] = (uint32_t(q) == s) ? p.init_start2 : p.init_other2;
     }
+#pragma unroll
+    for (int q = 0; q < NS; q++) x[q] = metric_ones<Sat<TIE_SIMD>::value, SH>(x[q]);
 
     const uint32_t* pk = p.pk + size_t(blk) * p.n_steps * R * 32 + lane;
     uint64_t* dec_lane = static_cast<uint64_t*>(p.dec) + (size_t(blk) * p.dec_rows + p.dec_row0) * 64 + 2 * lane;

@@ -161,14 +161,14 @@ std::vector<const KernelEntry*> find_entries(const vitb_params& p) {
     const int consistent = ((p.soft_decision_max_error & mask) == ((span * uint32_t(p.R)) & mask)) ? 1 : 0;
     const uint32_t kmask = (p.K >= 32) ? 0xffffffffu : ((1u << p.K) - 1u);
     for (const KernelEntry& e : registry()) {
-        if (e.generic || e.layout == LAYOUT_HISTGROUP || e.layout == LAYOUT_HISTCTA || e.K != p.K || e.R != p.R || e.sh != sh || e.tie != (p.tie_break ? 1 : 0) || e.consistent != consistent) continue;
+        if (e.generic || e.layout == LAYOUT_HISTGROUP || e.layout == LAYOUT_HISTCTA || e.K != p.K || e.R != p.R || e.sh != sh || e.tie != p.tie_break || e.consistent != consistent) continue;
         bool same = true;
         for (int i = 0; i < p.R; i++) same = same && ((e.G[i] & kmask) == (p.G[i] & kmask));
         if (same) out.push_back(&e);
     }
     if (out.empty() && p.R <= GENERIC_MAX_R) {      // not in the compiled catalogue: the generic kernel of this K, if there is one
         for (const KernelEntry& e : registry())
-            if (e.generic && e.K == p.K && e.sh == sh && e.tie == (p.tie_break ? 1 : 0)) out.push_back(&e);
+            if (e.generic && e.K == p.K && e.sh == sh && e.tie == p.tie_break) out.push_back(&e);
     }
     std::sort(out.begin(), out.end(), [](const KernelEntry* a, const KernelEntry* b) { return a->logt < b->logt; });
     return out;
@@ -182,7 +182,7 @@ const KernelEntry* find_hist_group(const vitb_params& p) {
     const int consistent = ((p.soft_decision_max_error & 0xffffu) == ((span * uint32_t(p.R)) & 0xffffu)) ? 1 : 0;
     const uint32_t kmask = (p.K >= 32) ? 0xffffffffu : ((1u << p.K) - 1u);
     for (const KernelEntry& e : registry()) {
-        if ((e.layout != LAYOUT_HISTGROUP && e.layout != LAYOUT_HISTCTA) || e.K != p.K || e.R != p.R || e.tie != (p.tie_break ? 1 : 0) || e.consistent != consistent) continue;
+        if ((e.layout != LAYOUT_HISTGROUP && e.layout != LAYOUT_HISTCTA) || e.K != p.K || e.R != p.R || e.tie != p.tie_break || e.consistent != consistent) continue;
         bool same = true;
         for (int i = 0; i < p.R; i++) same = same && ((e.G[i] & kmask) == (p.G[i] & kmask));
         if (same) return &e;
@@ -220,6 +220,7 @@ bool params_valid(const vitb_params& p) {
     if (p.K < 2 || p.K > 24 || p.R < 1 || p.R > VITB_MAX_R) return false;
     if (p.soft_bytes != 1 && p.soft_bytes != 2) return false;
     if (p.soft_decision_high <= p.soft_decision_low) return false;        // viterbi_branch_table.h:43
+    if (p.tie_break < VITB_TIE_SCALAR || p.tie_break > VITB_TIE_SIMD_SAT) return false;
     const int lim = (p.soft_bytes == 1) ? 127 : 32767;
     if (p.soft_decision_high > lim || p.soft_decision_low < -lim - 1) return false;
     return true;
@@ -233,6 +234,7 @@ void fill_acs_params(const vitb_decoder* h, AcsParams& a) {
     a.c_high2 = pack2((uint32_t(p.soft_decision_high) << sh) + 1u);
     const uint32_t span = uint32_t(p.soft_decision_high - p.soft_decision_low);
     a.c_inv2 = pack2(((p.soft_decision_max_error - span * uint32_t(p.R)) & emask) << sh);
+    a.max_err2 = pack2((p.soft_decision_max_error & emask) << sh);
     a.thr2 = pack2((p.renormalisation_threshold & emask) << sh);
     a.init_start2 = pack2((p.initial_start_error & emask) << sh);
     a.init_other2 = pack2((p.initial_non_start_error & emask) << sh);
@@ -323,7 +325,7 @@ cudaError_t launch_traceback(vitb_decoder* h, const KernelEntry* e, const void* 
         TracebackParams t{};
         t.dec = static_cast<const uint64_t*>(dec); t.dec_rows = uint32_t(dec_rows); t.n_frames = uint32_t(n_frames);
         t.total_bits = uint32_t(L); t.state_bits = uint32_t(h->prm.K - 1); t.end_state = uint32_t(end_state); t.end_states = end_states;
-        t.out = d_out; t.out_stride = out_stride; t.tag_layout = (e->sh == 8 && !e->generic) ? 1u : 0u;     // uint8_t catalogue pair kernels use the tagged butterfly
+        t.out = d_out; t.out_stride = out_stride; t.tag_layout = e->tagged_rows ? 1u : 0u;     // uint8_t catalogue pair kernels use the tagged butterfly
         traceback_u64_kernel<32><<<unsigned((n_frames + 127) / 128), 128, 0, s>>>(t);
     } else {
         TracebackGroupParams t{};
@@ -1025,7 +1027,7 @@ int vitb_get_decisions(vitb_decoder* h, size_t first_row, size_t n_rows, uint64_
         VITB_CUDA(h, cudaMemcpy2DAsync(rows_out, 8, static_cast<uint64_t*>(h->s_dec.ptr) + first_row * 64, 64 * 8, 8, n_rows,
                                        cudaMemcpyDeviceToHost, h->stream));
         VITB_CUDA(h, cudaStreamSynchronize(h->stream));
-        if (e->sh == 8 && !e->generic) {      // tagged row layout -> reference bit order
+        if (e->tagged_rows) {      // tagged row layout -> reference bit order
             for (size_t r = 0; r < n_rows; r++) {
                 const uint64_t w = rows_out[r];
                 uint64_t o = 0;

@@ -41,6 +41,7 @@ struct KernelEntry {
     cudaError_t (*launch_generic)(const AcsParams&, const GenericCode&, cudaStream_t);
     cudaError_t (*launch_hist_direct)(const AcsParams&, cudaStream_t);
     int variant_id;    // number vitb_set_variant / vitb_get_variants know this entry by; 0 = 1 << logt (lanes per frame pair)
+    int tagged_rows;   // LAYOUT_PAIR: decision rows in the tagged-butterfly bit order (uint8_t metrics, not the saturating flavour)
 };
 
 inline int entry_variant(const KernelEntry* e) { return e->variant_id ? e->variant_id : (1 << e->logt); }
@@ -48,21 +49,21 @@ inline int entry_variant(const KernelEntry* e) { return e->variant_id ? e->varia
 // Decision-row kernel of the one-thread-per-pair mapping (streaming calls; batch calls when the history kernel is switched off).
 // A two-register-set (ping-pong) variant of it was measured and dropped: ptxas scheduled all compare-selects ahead of their
 // predicated FADDs, ran out of predicate registers and spilled them (2.14 ms vs 1.42 ms on config 2, profiles/r01_summary.md).
-template <class C, int SH, bool TIE_SIMD, bool CONSISTENT>
+template <class C, int SH, int TIE_SIMD, bool CONSISTENT>
 cudaError_t launch_pair(const AcsParams& p, cudaStream_t s) {
     const unsigned grid = (p.n_blocks + PAIR_WARPS - 1) / PAIR_WARPS;
     acs_pair_kernel<C, SH, TIE_SIMD, CONSISTENT><<<grid, 32 * PAIR_WARPS, 0, s>>>(p);
     return cudaGetLastError();
 }
 
-template <class C, int SH, bool TIE_SIMD, bool CONSISTENT>
+template <class C, int SH, int TIE_SIMD, bool CONSISTENT>
 cudaError_t launch_pair_direct(const AcsParams& p, cudaStream_t s) {
     const unsigned grid = (p.n_blocks + PAIR_WARPS - 1) / PAIR_WARPS;
     acs_pair_kernel<C, SH, TIE_SIMD, CONSISTENT, PairPeriod<C>::value, true><<<grid, 32 * PAIR_WARPS, 0, s>>>(p);
     return cudaGetLastError();
 }
 
-template <class C, int FMT, bool TIE_SIMD, bool CONSISTENT, bool DIRECT>
+template <class C, int FMT, int TIE_SIMD, bool CONSISTENT, bool DIRECT>
 cudaError_t launch_hist(const AcsParams& p, cudaStream_t s) {
     static const unsigned warps = getenv("VITB_HIST_WARPS") ? unsigned(atoi(getenv("VITB_HIST_WARPS"))) : unsigned(HIST_WARPS);
     const unsigned w = (warps >= 1 && warps <= unsigned(HIST_WARPS)) ? warps : unsigned(HIST_WARPS);
@@ -71,7 +72,7 @@ cudaError_t launch_hist(const AcsParams& p, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-template <class C, int LOGT, int SH, bool TIE_SIMD, bool CONSISTENT>
+template <class C, int LOGT, int SH, int TIE_SIMD, bool CONSISTENT>
 cudaError_t launch_group(const AcsParams& p, cudaStream_t s) {
     constexpr int WARPS = GroupShape<C, LOGT>::WARPS;
     acs_group_kernel<C, LOGT, SH, TIE_SIMD, CONSISTENT><<<(p.n_blocks + WARPS - 1) / WARPS, 32 * WARPS, 0, s>>>(p);
@@ -79,7 +80,7 @@ cudaError_t launch_group(const AcsParams& p, cudaStream_t s) {
 }
 
 // CONSISTENT is irrelevant for the CTA kernel (c_inv is folded into the shared-memory table)
-template <class C, int LT, int SH, bool TIE_SIMD>
+template <class C, int LT, int SH, int TIE_SIMD>
 cudaError_t launch_cta(const AcsParams& p, cudaStream_t s) {
     using S = CtaShape<C, LT>;
     // the attribute is per device: set it on every launch (cheap) so that handles on different GPUs all get it
@@ -89,12 +90,12 @@ cudaError_t launch_cta(const AcsParams& p, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-template <class C, int LT, int SH, bool TIE_SIMD>
+template <class C, int LT, int SH, int TIE_SIMD>
 KernelEntry make_cta_entry(const char* name, int consistent) {
     KernelEntry e{};
     e.K = C::K; e.R = C::R;
     for (int i = 0; i < C::R; i++) e.G[i] = C::G[i];
-    e.sh = SH; e.tie = TIE_SIMD ? 1 : 0; e.consistent = consistent; e.logt = LT; e.name = name;
+    e.sh = SH; e.tie = TIE_SIMD; e.consistent = consistent; e.logt = LT; e.name = name;
     e.layout = LAYOUT_CTA; e.ppw = 1; e.dec_words = CtaKernel<C, LT, SH, TIE_SIMD>::W;
     e.launch = &launch_cta<C, LT, SH, TIE_SIMD>;
     return e;
@@ -106,20 +107,25 @@ KernelEntry make_cta_entry(const char* name, int consistent) {
         VEC.push_back(make_cta_entry<CODE, LT, 8, false>("acs_cta<" TAG ",u8,scalar-tie>", cons));  \
         VEC.push_back(make_cta_entry<CODE, LT, 0, true>("acs_cta<" TAG ",u16,simd-tie>", cons));    \
         VEC.push_back(make_cta_entry<CODE, LT, 8, true>("acs_cta<" TAG ",u8,simd-tie>", cons));     \
+        VEC.push_back(make_cta_entry<CODE, LT, 0, 2>("acs_cta<" TAG ",u16,simd-sat>", cons));       \
+        VEC.push_back(make_cta_entry<CODE, LT, 8, 2>("acs_cta<" TAG ",u8,simd-sat>", cons));        \
     }
 
-template <class C, int LOGT, int SH, bool TIE_SIMD, bool CONSISTENT>
+template <class C, int LOGT, int SH, int TIE_SIMD, bool CONSISTENT>
 KernelEntry make_entry(const char* name) {
     KernelEntry e{};
     e.K = C::K; e.R = C::R;
     for (int i = 0; i < C::R; i++) e.G[i] = C::G[i];
-    e.sh = SH; e.tie = TIE_SIMD ? 1 : 0; e.consistent = CONSISTENT ? 1 : 0; e.logt = LOGT; e.name = name;
+    e.sh = SH; e.tie = TIE_SIMD; e.consistent = CONSISTENT ? 1 : 0; e.logt = LOGT; e.name = name;
     if constexpr (LOGT == 0) {
         e.layout = LAYOUT_PAIR; e.ppw = 32; e.dec_words = 0;
+        e.tagged_rows = (SH == 8 && TIE_SIMD != 2) ? 1 : 0;
         e.launch = &launch_pair<C, SH, TIE_SIMD, CONSISTENT>;
         if constexpr (DirectFetch<C, SH, PairPeriod<C>::value>::supported) e.launch_direct = &launch_pair_direct<C, SH, TIE_SIMD, CONSISTENT>;
-        e.launch_hist = &launch_hist<C, SH == 8 ? 0 : 1, TIE_SIMD, CONSISTENT, false>;
-        e.launch_hist_direct = &launch_hist<C, SH == 8 ? 0 : 1, TIE_SIMD, CONSISTENT, true>;
+        if constexpr (TIE_SIMD != 2) {      // the saturating flavour exists in the decision-row kernels only (acs_pair.cuh)
+            e.launch_hist = &launch_hist<C, SH == 8 ? 0 : 1, TIE_SIMD, CONSISTENT, false>;
+            e.launch_hist_direct = &launch_hist<C, SH == 8 ? 0 : 1, TIE_SIMD, CONSISTENT, true>;
+        }
     } else {
         e.layout = LAYOUT_GROUP; e.ppw = GroupShape<C, LOGT>::PPW; e.dec_words = GroupShape<C, LOGT>::W;
         e.launch = &launch_group<C, LOGT, SH, TIE_SIMD, CONSISTENT>;
@@ -136,19 +142,23 @@ KernelEntry make_entry(const char* name) {
     VEC.push_back(make_entry<CODE, LOGT, 0, false, false>("acs<" TAG ",u16,scalar-tie,cinv>"));     \
     VEC.push_back(make_entry<CODE, LOGT, 8, false, false>("acs<" TAG ",u8,scalar-tie,cinv>"));      \
     VEC.push_back(make_entry<CODE, LOGT, 0, true, false>("acs<" TAG ",u16,simd-tie,cinv>"));        \
-    VEC.push_back(make_entry<CODE, LOGT, 8, true, false>("acs<" TAG ",u8,simd-tie,cinv>"));
+    VEC.push_back(make_entry<CODE, LOGT, 8, true, false>("acs<" TAG ",u8,simd-tie,cinv>"));         \
+    VEC.push_back(make_entry<CODE, LOGT, 0, 2, true>("acs<" TAG ",u16,simd-sat>"));                 \
+    VEC.push_back(make_entry<CODE, LOGT, 8, 2, true>("acs<" TAG ",u8,simd-sat>"));                  \
+    VEC.push_back(make_entry<CODE, LOGT, 0, 2, false>("acs<" TAG ",u16,simd-sat,cinv>"));           \
+    VEC.push_back(make_entry<CODE, LOGT, 8, 2, false>("acs<" TAG ",u8,simd-sat,cinv>"));
 
-template <int K, int SH, bool TIE_SIMD>
+template <int K, int SH, int TIE_SIMD>
 cudaError_t launch_generic(const AcsParams& p, const GenericCode& gc, cudaStream_t s) {
     constexpr unsigned W = GENERIC_THREADS / 32;
     acs_generic_kernel<K, SH, TIE_SIMD><<<(p.n_blocks + W - 1) / W, GENERIC_THREADS, 0, s>>>(p, gc);
     return cudaGetLastError();
 }
 
-template <int K, int SH, bool TIE_SIMD>
+template <int K, int SH, int TIE_SIMD>
 KernelEntry make_generic_entry(const char* name) {
     KernelEntry e{};
-    e.K = K; e.R = 0; e.sh = SH; e.tie = TIE_SIMD ? 1 : 0; e.consistent = -1; e.logt = 0; e.name = name;
+    e.K = K; e.R = 0; e.sh = SH; e.tie = TIE_SIMD; e.consistent = -1; e.logt = 0; e.name = name;
     e.layout = LAYOUT_PAIR; e.ppw = 32; e.dec_words = 0; e.generic = 1;
     e.launch_generic = &launch_generic<K, SH, TIE_SIMD>;
     return e;
@@ -162,19 +172,19 @@ KernelEntry make_generic_entry(const char* name) {
 
 // survivor-history kernel with a frame over 4 lanes (acs_hist_group.cuh): K = 9, uint16_t metrics, whole-frame batch calls with
 // directly fetchable symbols only - it has no decision-row form, so it is not one of the handle's streaming variants
-template <class C, bool TIE_SIMD, bool CONSISTENT>
+template <class C, int TIE_SIMD, bool CONSISTENT>
 cudaError_t launch_hist_group(const AcsParams& p, cudaStream_t s) {
     constexpr unsigned W = HistGroupShape<C>::WARPS;
     acs_hist_group_kernel<C, TIE_SIMD, CONSISTENT><<<(p.n_blocks + W - 1) / W, 32 * W, 0, s>>>(p);
     return cudaGetLastError();
 }
 
-template <class C, bool TIE_SIMD, bool CONSISTENT>
+template <class C, int TIE_SIMD, bool CONSISTENT>
 KernelEntry make_hist_group_entry(const char* name) {
     KernelEntry e{};
     e.K = C::K; e.R = C::R;
     for (int i = 0; i < C::R; i++) e.G[i] = C::G[i];
-    e.sh = 0; e.tie = TIE_SIMD ? 1 : 0; e.consistent = CONSISTENT ? 1 : 0; e.logt = HistGroupShape<C>::LOGT; e.name = name;
+    e.sh = 0; e.tie = TIE_SIMD; e.consistent = CONSISTENT ? 1 : 0; e.logt = HistGroupShape<C>::LOGT; e.name = name;
     e.layout = LAYOUT_HISTGROUP; e.ppw = 0; e.dec_words = 0;
     e.launch_hist = &launch_hist_group<C, TIE_SIMD, CONSISTENT>;
     return e;
@@ -189,7 +199,7 @@ KernelEntry make_hist_group_entry(const char* name) {
 // survivor-history kernel with one frame per 512-thread CTA (acs_hist_cta.cuh): K = 15, uint16_t metrics, whole-frame batch calls
 // with unpunctured input only.  Variant number 256 (threads per frame PAIR would be 1024, which the decision-row kernel
 // acs_cta<T1024> already answers to).
-template <class C, bool TIE_SIMD>
+template <class C, int TIE_SIMD>
 cudaError_t launch_hist_cta(const AcsParams& p, cudaStream_t s) {
     using H = HistCtaShape<C>;
     static const int minb = getenv("VITB_HC_MINB") ? atoi(getenv("VITB_HC_MINB")) : 1;      // experiment knob: CTAs per SM
@@ -205,12 +215,12 @@ cudaError_t launch_hist_cta(const AcsParams& p, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-template <class C, bool TIE_SIMD>
+template <class C, int TIE_SIMD>
 KernelEntry make_hist_cta_entry(const char* name, int consistent) {
     KernelEntry e{};
     e.K = C::K; e.R = C::R;
     for (int i = 0; i < C::R; i++) e.G[i] = C::G[i];
-    e.sh = 0; e.tie = TIE_SIMD ? 1 : 0; e.consistent = consistent; e.logt = HistCtaShape<C>::LOGT; e.name = name;
+    e.sh = 0; e.tie = TIE_SIMD; e.consistent = consistent; e.logt = HistCtaShape<C>::LOGT; e.name = name;
     e.layout = LAYOUT_HISTCTA; e.ppw = 0; e.dec_words = 0; e.variant_id = 256;
     e.launch_hist = &launch_hist_cta<C, TIE_SIMD>;
     return e;
