@@ -117,7 +117,10 @@ int vitb_decode_batch_dev(vitb_decoder* h, const void* d_symbols, size_t n_frame
  * in stream order as documented above.  With pipelining enabled that wait is DEFERRED by one call: when call i+1 returns, the
  * results of call i are complete in the order of call i+1's stream, while the traceback of call i+1 is still free to run next to the
  * ACS of call i+2 (config 2: 0.83 -> ~0.66 ms per batch of 65 536 frames).  vitb_batch_flush(h, stream) makes `stream` wait for
- * everything outstanding.  Output buffers of consecutive calls may be the same (tracebacks run in call order).  Twice the workspace. */
+ * everything outstanding.  Output buffers of consecutive calls may be the same (tracebacks run in call order).  Twice the workspace.
+ * Pipelined calls also run their ACS kernel on a handle-owned stream (so that the caller's stream can already run the next call's
+ * ingest pass: a three-stage pipeline ingest | ACS | traceback), which means the INPUT buffer of call i is still being read after the
+ * call returned: like its outputs, it must be left alone until call i+1 has returned (stream order) or the flush. */
 int vitb_set_pipelining(vitb_decoder* h, int enabled);
 int vitb_batch_flush(vitb_decoder* h, void* stream);
 
