@@ -466,6 +466,33 @@ def main():
     step_copy()
     ms_copy = timed(step_copy, e2e_steps)
 
+    # single-frame streaming calls (the reference's own call protocol; run_punctured_decoder calls update once per trellis step):
+    # host time per vitb_update of one step, and of one whole frame in one call
+    streaming = None
+    if rank == 0:
+        one = np.ascontiguousarray(w["sym"][0] if w["keep"] is None else reference_inputs(w)[0])
+        dec.set_traceback_length(L)
+        dec.reset()
+        R_ = code.R
+        n_small = min(200, one.size // R_)
+        dec.update(one[:R_])
+        dec.reset()
+        t0 = time.perf_counter()
+        for k in range(n_small):
+            dec.update(one[k * R_:(k + 1) * R_])
+        t_small = (time.perf_counter() - t0) / n_small
+        dec.reset()
+        dec.update(one)
+        dec.reset()
+        t0 = time.perf_counter()
+        dec.update(one)
+        err = dec.get_error()
+        out1 = dec.chainback(L)
+        t_frame = time.perf_counter() - t0
+        assert (out1 == d_out[0].cpu().numpy()).all(), "streaming calls and batch call disagree on frame 0"
+        streaming = {"update_one_step_us": t_small * 1e6, "whole_frame_update_get_error_chainback_ms": t_frame * 1e3,
+                     "note": "host clock, synchronous calls through the C ABI (H2D of the symbols, ingest, ACS kernel, D2H of the result per call)"}
+
     strong = None if args.no_strong else strong_cfg5(torch, dist, v, world, rank, local_rank, dev)
     multi = None
     if world > 1 and not args.no_strong:
@@ -541,6 +568,8 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    if streaming is not None:
+        line["streaming"] = streaming
     if strong is not None:
         line["strong_cfg5"] = strong
     if multi is not None:

@@ -1245,9 +1245,10 @@ int vitb_decode_batch_async(vitb_decoder* h, const void* symbols, size_t n_frame
         return VITB_OK;
     }
 
-    // pipeline chunks: at least ~16 MB of input each (PCIe efficiency), at most 8 chunks, whole 64-frame blocks, and never larger
-    // than what the workspace allows
-    size_t chunk = (n_frames + 3) / 4;
+    // pipeline chunks: at least ~16 MB of input each (PCIe efficiency), 4 chunks (measured, VITB_E2E_CHUNKS = 4 / 8 / 16: config 2
+    // 5.54 / 5.55 / 8.03 ms, config 3 11.5 / 13.5 ms - smaller chunks underfill the GPU), whole 64-frame blocks, and never larger than what the workspace allows
+    static const size_t want_chunks = getenv("VITB_E2E_CHUNKS") ? size_t(atoi(getenv("VITB_E2E_CHUNKS"))) : size_t(4);
+    size_t chunk = (n_frames + want_chunks - 1) / (want_chunks ? want_chunks : 1);
     const size_t min_chunk = (size_t(16) << 20) / (row_bytes ? row_bytes : 1) + 1;
     if (chunk < min_chunk) chunk = min_chunk;
     const size_t ws_chunk = chunk_frames_for(h, L, true, true);
