@@ -220,8 +220,9 @@ def strong_cfg5(torch, dist, v, world, rank, local_rank, dev, steps=3, warmup=1)
     Timed like the main leg: CUDA events around `steps` device-resident batch calls, barrier on both sides, max over ranks."""
     code = {c.name: c for c in v.COMMON_CODES}["Cassini"]
     dc = v.DECODE_TYPES["SOFT16"](code.R)
+    from viterbidecodercpp_b200 import sharding
     total, L = 1024, 16384
-    f0, f1 = total * rank // world, total * (rank + 1) // world
+    f0, f1 = sharding.frame_range(rank, world, total)          # the split tests/test_host_cpu.py checks under gloo
     F = f1 - f0
     row = (L + code.K - 1) * code.R
     bt = v.ViterbiBranchTable(code.K, code.R, code.G, dc.soft_decision_high, dc.soft_decision_low, dc.soft_bytes)
@@ -258,15 +259,9 @@ def strong_cfg5(torch, dist, v, world, rank, local_rank, dev, steps=3, warmup=1)
     torch.cuda.synchronize()
     st = dec.stage_ms()
     dec.set_profiling(False)
-    t = torch.tensor([ms, st["acs"], float(byte_errors)], dtype=torch.float64, device=dev)
-    if world > 1:
-        mx = t.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = t.clone()
-        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        ms, acs_ms, byte_errors = float(mx[0].item()), float(mx[1].item()), int(sm[2].item())
-    else:
-        acs_ms = st["acs"]
+    ms = sharding.max_over_ranks(ms, dev)                       # slowest rank
+    acs_ms = sharding.max_over_ranks(st["acs"], dev)
+    byte_errors = int(sharding.sum_over_ranks(byte_errors, dev))
     name = dec.kernel_name
     dec.close()
     del d_sym, d_tx, d_out
@@ -338,6 +333,7 @@ def main():
     import torch
     import torch.distributed as dist
     import viterbidecodercpp_b200 as v
+    from viterbidecodercpp_b200 import sharding
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
@@ -403,12 +399,7 @@ def main():
             after()
         e1.record(stream)
         barrier()
-        total_ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)       # max over ranks
-            total_ms = float(t.item())
-        return total_ms / steps
+        return sharding.max_over_ranks(e0.elapsed_time(e1), dev) / steps       # max over ranks
 
     def stage_breakdown(steps):
         """average device time of each pipeline stage over `steps` more steps (CUDA events recorded by the library on the same stream)"""
