@@ -221,3 +221,36 @@ def test_two_rank_gloo_sharding(tmp_path):
                         "--master-port", "29533", str(script), ROOT], capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "OK 1001 11.0" in r.stdout
+
+
+def test_tie_break_flavours_are_checked_without_a_gpu():
+    """VITB_TIE_SIMD_SAT exists for the catalogue codes only (decision-row kernels); unknown flavours are rejected"""
+    lib = v.load_library()
+    p = _lib.vitb_params()
+    p.K, p.R, p.soft_bytes, p.soft_decision_high, p.soft_decision_low = 7, 2, 1, 3, -3
+    p.G[0], p.G[1] = 109, 79
+    p.soft_decision_max_error, p.initial_non_start_error, p.renormalisation_threshold = 12, 36, 200
+    for tie, want in ((_lib.VITB_TIE_SCALAR, 1), (_lib.VITB_TIE_SIMD, 1), (_lib.VITB_TIE_SIMD_SAT, 1), (3, 0), (-1, 0)):
+        p.tie_break = tie
+        assert lib.vitb_is_supported(C.byref(p)) == want, tie
+    p.G[1] = 0o165                       # uncatalogued polynomials: generic kernel, which has no saturating flavour
+    for tie, want in ((_lib.VITB_TIE_SCALAR, 1), (_lib.VITB_TIE_SIMD, 1), (_lib.VITB_TIE_SIMD_SAT, 0)):
+        p.tie_break = tie
+        assert lib.vitb_is_supported(C.byref(p)) == want, tie
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/include/viterbi"), reason="needs the reference headers (build container only)")
+def test_reference_adapter_and_cuda_slot_compile_against_the_reference_headers(tmp_path):
+    """include/viterbi_cuda/viterbi_decoder_cuda_ref.h (decoder class on the reference's own Core) and the test-only SIMD_CUDA slot
+    (oracle/ref_programs/cuda_slot.h) against the unmodified reference tree; the facade's converting constructors too"""
+    inc = os.path.join(ROOT, "include")
+    cpp = tmp_path / "t.cpp"
+    cpp.write_text('#include <stddef.h>\n#include <stdint.h>\n#include "cuda_slot.h"\n#include "viterbi_cuda/viterbi_decoder_cuda.h"\n'
+                   'using D = viterbi_cuda::ViterbiDecoder_CUDA_Ref<7, 2, uint16_t, int16_t>;\n'
+                   'static_assert(D::is_valid, "u16/s16 is a supported type pair");\n'
+                   'static_assert(!viterbi_cuda::ViterbiDecoder_CUDA_Ref<7, 2, uint32_t, int16_t>::is_valid, "other pairs are not");\n'
+                   'uint64_t f(D::Base& b, const int16_t* s, size_t n) { return D::update<uint64_t>(b, s, n); }\n'
+                   'viterbi_cuda::ViterbiBranchTable<7, 2, int16_t> g(const ::ViterbiBranchTable<7, 2, int16_t>& t) { return viterbi_cuda::ViterbiBranchTable<7, 2, int16_t>(t); }\n'
+                   'int main() { return simd_type_list_with_cuda().back() == SIMD_CUDA ? 0 : 1; }\n')
+    subprocess.run(["g++", "-std=c++17", "-mavx2", "-msse4.2", "-Wall", "-fsyntax-only", "-I", inc, "-I", "/root/reference/include", "-I", "/root/reference/examples",
+                    "-I", os.path.join(ROOT, "oracle", "ref_programs"), str(cpp)], check=True)
