@@ -331,10 +331,16 @@ __global__ void __launch_bounds__(32 * HIST_WARPS) acs_hist_kernel(const AcsPara
                     const uint32_t w0 = ((t >> 3) + 1u) * uint32_t(WPG);
 #pragma unroll
                     for (int a = 0; a < NROW; a++) {
+                        if (w0 + uint32_t(WPG - 1) <= maxw[a]) {            // the whole group lies inside the array: one base, constant offsets
+                            const uint32_t* q = row[a] + w0;
 #pragma unroll
-                        for (int j = 0; j < WPG; j++) {
-                            const uint32_t w = w0 + uint32_t(j);
-                            nx[a][j] = __ldg(row[a] + (w < maxw[a] ? w : maxw[a]));
+                            for (int j = 0; j < WPG; j++) nx[a][j] = __ldg(q + j);
+                        } else {                                             // last rows of the array: clamp every word
+#pragma unroll
+                            for (int j = 0; j < WPG; j++) {
+                                const uint32_t w = w0 + uint32_t(j);
+                                nx[a][j] = __ldg(row[a] + (w < maxw[a] ? w : maxw[a]));
+                            }
                         }
                     }
                 }
