@@ -99,14 +99,19 @@ struct HistShape {
     static constexpr int VW = NW < 4 ? NW : 4;           // words per vector store
 };
 
-template <class C, int FMT, int TIE_SIMD, int J>
+template <class C, int FMT, int TIE_SIMD, int J, bool FLIP = false>
 __device__ __forceinline__ void hist_bfly_at(const uint32_t (&x)[C::NS], uint32_t (&y)[C::NS], const uint32_t (&T)[C::NP],
                                              const uint32_t (&TT)[C::NP], const uint32_t (&V)[C::NP], const uint32_t (&VT)[C::NP]) {
     using LN = HistLane<FMT>;
     constexpr int H = C::NS / 2;
     constexpr uint32_t pat = bfly_pattern<C>(uint32_t(J));
     constexpr uint32_t ipat = (~pat) & uint32_t(C::NP - 1);
-    if constexpr (!TIE_SIMD) {
+    if constexpr (!TIE_SIMD && FLIP) {          // same butterfly, the (0|X)-side results first (source order only: VITB_HIST_FLIP)
+        const uint32_t b1 = LN::add(x[J + H], TT[pat]);
+        const uint32_t b0 = LN::add(x[J + H], VT[ipat]);
+        y[2 * J + 1] = LN::addmin(x[J], V[ipat], b1);
+        y[2 * J] = LN::addmin(x[J], T[pat], b0);
+    } else if constexpr (!TIE_SIMD) {
         const uint32_t b0 = LN::add(x[J + H], VT[ipat]);                    // (1|X) + inverted, tagged    scalar.h:114
         const uint32_t b1 = LN::add(x[J + H], TT[pat]);                     // (1|X) + total,    tagged    scalar.h:116
         y[2 * J] = LN::addmin(x[J], T[pat], b0);                            // min((0|X) + total, b0)      scalar.h:113,127
@@ -119,11 +124,57 @@ __device__ __forceinline__ void hist_bfly_at(const uint32_t (&x)[C::NS], uint32_
     }
 }
 
+// Source order of the butterflies of a step (VITB_HIST_ORDER; profiles/microbench/hist_kernel_variants.cu times the config-2 kernel
+// for each on the bench's own frames): 0 = ascending (the default), 1 = descending, 2 = the two halves of the state space interleaved,
+// 3 = grouped by branch pattern pair {p, ~p}, 4 = grouped by pattern, 6 = 3 descending inside the groups.  The butterfly is bound by
+// register-file reads (profiles/r02_summary.md) and ptxas keeps much of the source order, so grouping the butterflies of a pattern
+// lets consecutive instructions take their table operand from the operand reuse cache - but the register allocation that comes with
+// each order matters as much: config 2 on real frames, B200: 0.635 ms (0, 136 registers), 0.674 (1, 128 + spills), 0.649 (3, 133),
+// 0.656 (4, 127 + spills), 0.646 (6, 134); 3 with __launch_bounds__(128, 1): 0.635 (149 registers).  No order beats the plain one.
+#ifndef VITB_HIST_ORDER
+#define VITB_HIST_ORDER 0
+#endif
+template <class C>
+__host__ __device__ constexpr int hist_bfly_order(int i) {
+    constexpr int H = C::NS / 2;
+    if (VITB_HIST_ORDER == 1) return H - 1 - i;
+    if (VITB_HIST_ORDER == 2) return (i & 1) ? (H / 2 + i / 2) : (i / 2);
+    if (VITB_HIST_ORDER == 3 || VITB_HIST_ORDER == 5 || VITB_HIST_ORDER == 6) {      // stable sort by min(pattern, ~pattern)
+        int n = 0;
+        for (uint32_t g = 0; g < uint32_t(C::NP); g++)
+            for (int jj = 0; jj < H; jj++) {
+                const int j = (VITB_HIST_ORDER == 6) ? (H - 1 - jj) : jj;
+                const uint32_t p = bfly_pattern<C>(uint32_t(j)), q = (~p) & uint32_t(C::NP - 1), key = p < q ? p : q;
+                if (key == g) { if (n == i) return j; n++; }
+            }
+    }
+    if (VITB_HIST_ORDER == 4) {      // stable sort by pattern
+        int n = 0;
+        for (uint32_t g = 0; g < uint32_t(C::NP); g++)
+            for (int j = 0; j < H; j++)
+                if (bfly_pattern<C>(uint32_t(j)) == g) { if (n == i) return j; n++; }
+    }
+    return i;
+}
+// VITB_HIST_FLIP: 1 = every second butterfly (in source order) computes its two results in the opposite order; 2 = butterflies whose
+// pattern is the larger of {p, ~p} do (so that consecutive butterflies of a group start with the same table operand)
+#ifndef VITB_HIST_FLIP
+#define VITB_HIST_FLIP 0
+#endif
+template <class C>
+__host__ __device__ constexpr bool hist_bfly_flip(int i) {
+    if (VITB_HIST_FLIP == 1) return (i & 1) != 0;
+    if (VITB_HIST_FLIP == 2) {
+        const uint32_t p = bfly_pattern<C>(uint32_t(hist_bfly_order<C>(i))), q = (~p) & uint32_t(C::NP - 1);
+        return p > q;
+    }
+    return false;
+}
 template <class C, int FMT, int TIE_SIMD, int... Js>
 __device__ __forceinline__ void hist_bfly_all(const uint32_t (&x)[C::NS], uint32_t (&y)[C::NS], const uint32_t (&T)[C::NP],
                                               const uint32_t (&TT)[C::NP], const uint32_t (&V)[C::NP], const uint32_t (&VT)[C::NP],
                                               std::integer_sequence<int, Js...>) {
-    (hist_bfly_at<C, FMT, TIE_SIMD, Js>(x, y, T, TT, V, VT), ...);
+    (hist_bfly_at<C, FMT, TIE_SIMD, hist_bfly_order<C>(Js), hist_bfly_flip<C>(Js)>(x, y, T, TT, V, VT), ...);
 }
 
 // branch metric table in the lane format: T[p] = sum_i (bit_i(p) ? e_high_i : e_low_i)
@@ -228,8 +279,17 @@ constexpr int HIST_WARPS = 4;
 // grid = ceil(n_blocks / warps per CTA), at most HIST_WARPS warps per CTA; one warp per block of 64 (FMT 0) / 32 (FMT 1) frames.
 // Whole frames only: p.resume must be 0 and p.dec_row0 must be 0 (the streaming API keeps using acs_pair_kernel / acs_group_kernel).
 // FMT 1 reads the packed stream in the 16-pairs-per-warp-block layout (ingest with ppw = 16).
+// VITB_HIST_MINB (experiment knob): CTAs per SM the register allocation is made for.  Not giving the second argument at all is NOT the
+// same as giving 1: ptxas then allocates 137 instead of 150 registers for the config-2 kernel, and that build is 5 % faster on real
+// frames (0.637 vs 0.669 ms; profiles/microbench/hist_kernel_variants.cu).
+#ifdef VITB_HIST_MINB
+#define VITB_HIST_BOUNDS __launch_bounds__(32 * HIST_WARPS, VITB_HIST_MINB)
+#else
+#define VITB_HIST_MINB 0
+#define VITB_HIST_BOUNDS __launch_bounds__(32 * HIST_WARPS)
+#endif
 template <class C, int FMT, int TIE_SIMD, bool CONSISTENT, bool DIRECT>
-__global__ void __launch_bounds__(32 * HIST_WARPS) acs_hist_kernel(const AcsParams p) {
+__global__ void VITB_HIST_BOUNDS acs_hist_kernel(const AcsParams p) {
     using LN = HistLane<FMT>;
     constexpr int R = C::R, NS = C::NS, NW = HistShape<C>::NW, VW = HistShape<C>::VW, HB = LN::HB, FPT = LN::FPT;
     const uint32_t lane = threadIdx.x & 31, blk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
