@@ -13,8 +13,10 @@
 // (core.h:238-242).  update() hands the current metrics and row counter to a GPU handle (vitb_set_metrics,
 // vitb_set_current_decoded_bit), runs vitb_update, and copies the new metrics and the new decision rows (reference bit order,
 // vitb_get_decisions) back into the object; get_error and chainback then run as the reference wrote them.  One GPU handle per
-// (code, soft levels, config) is created on first use and shared by every Core of that type (the handle holds no state between
-// calls).  It is a compatibility path (one host round trip per update call); batches go through viterbi_decoder_cuda.h.
+// (code, soft levels, config) AND PER HOST THREAD is created on first use and shared by every Core of that type the thread decodes
+// (the handle holds no state between calls; per thread because the reference's programs decode from a thread pool,
+// examples/run_snr_ber.cpp:260-264, and a handle is single-threaded).  It is a compatibility path (one host round trip per update
+// call); batches go through viterbi_decoder_cuda.h.
 //
 // Needs the reference headers on the include path (<viterbi/viterbi_decoder_core.h>); nothing of them is copied here.
 #pragma once
@@ -98,13 +100,13 @@ private:
     static void ok(int status, const char* what) {
         if (status != VITB_OK) throw std::runtime_error(std::string("ViterbiDecoder_CUDA_Ref: ") + what + ": " + vitb_status_string(status));
     }
-    // one handle per (polynomials, soft levels, config); created on first use, destroyed at exit
+    // one handle per (polynomials, soft levels, config) and host thread; created on first use, destroyed when the thread ends
     struct Cache {
         std::map<std::vector<uint32_t>, vitb_decoder*> handles;
         ~Cache() { for (auto& kv : handles) vitb_destroy(kv.second); }
     };
     static vitb_decoder* handle_for(const Base& base) {
-        static Cache cache;
+        static thread_local Cache cache;
         vitb_params p{};
         p.K = int32_t(K); p.R = int32_t(R);
         polynomials_of<K, R, soft_t>(base.m_branch_table, p.G, p.soft_decision_high, p.soft_decision_low);

@@ -67,3 +67,31 @@ def test_facade_accepts_the_reference_objects(cuda_lib):
     rc, out = run_program("facade_from_reference_cuda")
     assert rc == 0, out[-3000:]
     assert out.count("PASS") == 5
+
+
+def _json_entries(text):
+    import json
+    start = text.index("[")
+    return json.loads(text[start:text.rindex("]") + 1])
+
+
+def test_reference_run_snr_ber_with_the_cuda_decoder(cuda_lib):
+    """run_snr_ber.cpp:255-275 from its thread pool (4 threads, one GPU handle per thread): with the same seed the SIMD_CUDA curve
+    must equal the SCALAR curve point for point (same generated frames, bit-exact decoder)"""
+    rc, out = run_program("run_snr_ber_cuda", "-c", "2", "-d", "soft16", "-s", "scalar", "-s", "simd_cuda", "-t", "4", "-n", "300", "-D", "4",
+                          "-L", "256", "-S", "7", "-k", "0.2")
+    assert rc == 0, out[-3000:]
+    entries = {e["simd_type"]: e for e in _json_entries(out)}
+    assert set(entries) == {"SCALAR", "SIMD_CUDA"}, list(entries)
+    a, b = entries["SCALAR"], entries["SIMD_CUDA"]
+    assert len(a["ber"]) == len(b["ber"]) > 0
+    assert a["EbNo_dB"] == b["EbNo_dB"]
+    assert a["total_bit_errors"] == b["total_bit_errors"] if "total_bit_errors" in a else a["ber"] == b["ber"]
+
+
+def test_reference_run_benchmark_with_the_cuda_decoder(cuda_lib):
+    """run_benchmark.cpp:188-245 timing the streaming calls of the CUDA decoder class (reported, not judged: compatibility path)"""
+    rc, out = run_program("run_benchmark_cuda", "-c", "2", "-d", "hard8", "-s", "simd_cuda", "-T", "0.3")      # (-M is listed in its usage but not parsed)
+    assert rc == 0, out[-3000:]
+    entries = _json_entries(out)
+    assert len(entries) == 1 and entries[0]["simd_type"] == "SIMD_CUDA", entries
