@@ -43,6 +43,114 @@ struct CtaShape {
     static __host__ __device__ constexpr uint32_t slot(uint32_t phi) { return phi + (phi >> 5); }
 };
 
+// TABLE FETCH BY BUTTERFLY PAIRS.  The entry of a butterfly is T[pq ^ pt] (pq: pattern of the register bits, a compile-time constant;
+// pt: pattern of the thread bits).  Two butterflies whose registers differ in one bit (the "pairing bit") have patterns that differ by
+// a constant v, so in slot coordinates M with M(v) = 1 (M linear and invertible) their entries sit at idx and idx ^ 1.  The table
+// stores every entry twice - slot idx = {T[idx], T[idx ^ 1]}, 16 bytes - so that ONE LDS.128 at slot M(pq) ^ M(pt) fetches the entries
+// of both butterflies, in butterfly order whatever the thread's M(pt) is: 8 LDS.128 per step instead of 16 LDS.64 for the same bytes,
+// and few enough addresses that ptxas keeps them in registers for the whole kernel (no XOR per fetch).  The three low rows of M are
+// chosen so that the 8 lanes of a quarter warp read 8 different 16-byte bank groups (profiles/microbench/lds128_merge.cu: an LDS.128
+// is served a quarter warp at a time, lanes of different quarters never share a wavefront).
+// Used by acs_hist_cta.cuh (8.85 instead of 10.4 ms per wave of 148 frames).  The frame-pair kernel below keeps one LDS.64 per
+// butterfly: with the paired fetch ptxas spills the 40 slot addresses it then wants to keep (48 bytes of stack, 27 LDL in the loop)
+// and a wave of 148 pairs takes 14.55 instead of 14.05 ms (B200, config 5).
+// Slot coordinates of the table of one phase: index bit i of pattern p = parity(p & row[i]); pb = the pairing register bit.
+struct PairMap {
+    uint32_t row[8];
+    int pb;
+};
+__host__ __device__ constexpr uint32_t pair_apply(const PairMap& m, int R, uint32_t p) {
+    uint32_t idx = 0;
+    for (int i = 0; i < R; i++) idx |= parity32(p & m.row[i]) << i;
+    return idx;
+}
+// insert r into an XOR basis kept in echelon form by leading bit; false if r depends on the basis
+__host__ __device__ constexpr bool pair_basis_add(uint32_t (&lead)[8], uint32_t r) {
+    for (int b = 7; b >= 0; b--) {
+        if (!((r >> b) & 1u)) continue;
+        if (lead[b] == 0) { lead[b] = r; return true; }
+        r ^= lead[b];
+    }
+    return false;
+}
+// EXCL_NEXT: the pairing bit must not be the bit that says "path-1 operand of the next step" either (acs_hist_cta.cuh)
+template <class C, int LOGT, bool EXCL_NEXT>
+__host__ __device__ constexpr PairMap pair_map(int PH) {
+    constexpr int SB = C::SB, LB = SB - LOGT, R = C::R;
+    static_assert(R >= 3 && R <= 8, "the slot map is built for 8 <= 2^R <= 256 patterns");
+    PairMap m{};
+    // pairing bit: not the butterfly bit (LB-1-PH), not the bit that says "path-1 operand of the next step" (LB-2-PH), pattern != 0
+    uint32_t v = 0;
+    m.pb = -1;
+    for (int b = 0; b < LB && m.pb < 0; b++) {
+        if (b == LB - 1 - PH || (EXCL_NEXT && b == LB - 2 - PH)) continue;
+        const uint32_t pv = bfly_pattern<C>(rotl_bits((1u << b) << LOGT, PH, SB));
+        if (pv != 0) { m.pb = b; v = pv; }
+    }
+    // patterns of the three lane bits that vary inside a quarter warp
+    uint32_t pl[3] = {};
+    for (int k = 0; k < 3; k++) pl[k] = bfly_pattern<C>(rotl_bits(1u << k, PH, SB));
+    auto rho = [&](uint32_t r) { return parity32(r & pl[0]) | (parity32(r & pl[1]) << 1) | (parity32(r & pl[2]) << 2); };
+    uint32_t lead[8] = {}, lead_rho[8] = {};
+    const uint32_t NPAT = 1u << R;
+    // rows 1, 2: vanish on v, restrictions to the lane patterns independent; row 0: 1 on v, restriction independent of rows 1, 2
+    int have = 0;
+    uint32_t rows12[2] = {};
+    for (int pass = 0; pass < 2 && have < 2; pass++)                 // pass 0 insists on an independent restriction, pass 1 takes any
+        for (uint32_t r = 1; r < NPAT && have < 2; r++) {
+            if (parity32(r & v)) continue;
+            uint32_t t1[8] = {}, t2[8] = {};
+            for (int i = 0; i < 8; i++) { t1[i] = lead[i]; t2[i] = lead_rho[i]; }
+            if (!pair_basis_add(t1, r)) continue;
+            if (pass == 0 && !pair_basis_add(t2, rho(r))) continue;
+            for (int i = 0; i < 8; i++) { lead[i] = t1[i]; if (pass == 0) lead_rho[i] = t2[i]; }
+            rows12[have++] = r;
+        }
+    uint32_t row0 = 0;
+    for (int pass = 0; pass < 2 && row0 == 0; pass++)
+        for (uint32_t r = 1; r < NPAT && row0 == 0; r++) {
+            if (!parity32(r & v)) continue;
+            uint32_t t1[8] = {}, t2[8] = {};
+            for (int i = 0; i < 8; i++) { t1[i] = lead[i]; t2[i] = lead_rho[i]; }
+            if (!pair_basis_add(t1, r)) continue;
+            if (pass == 0 && !pair_basis_add(t2, rho(r))) continue;
+            for (int i = 0; i < 8; i++) lead[i] = t1[i];
+            row0 = r;
+        }
+    m.row[0] = row0; m.row[1] = rows12[0]; m.row[2] = rows12[1];
+    // Every other row must vanish on v too (M(v) = 1 exactly), and complete the map to an invertible one
+    int n = 3;
+    for (uint32_t r = 1; r < NPAT && n < R; r++) {
+        if (parity32(r & v)) continue;
+        if (pair_basis_add(lead, r)) m.row[n++] = r;
+    }
+    return m;
+}
+template <class C, int LOGT, bool EXCL_NEXT, int PH, int... Is>
+__device__ __forceinline__ uint32_t pair_apply_dyn_impl(uint32_t p, std::integer_sequence<int, Is...>) {
+    constexpr PairMap M = pair_map<C, LOGT, EXCL_NEXT>(PH);
+    uint32_t idx = 0;
+    ((idx |= (uint32_t(__popc(p & std::integral_constant<uint32_t, M.row[Is]>::value)) & 1u) << Is), ...);
+    return idx;
+}
+template <class C, int LOGT, bool EXCL_NEXT, int PH>
+__device__ __forceinline__ uint32_t pair_apply_dyn(uint32_t p) {
+    return pair_apply_dyn_impl<C, LOGT, EXCL_NEXT, PH>(p, std::make_integer_sequence<int, C::R>{});
+}
+// same for a run-time phase (table build)
+template <class C, int LOGT, bool EXCL_NEXT, int... PHs>
+__device__ __forceinline__ uint32_t pair_apply_phase(uint32_t ph, uint32_t p, std::integer_sequence<int, PHs...>) {
+    uint32_t idx = 0;
+    ((idx = (ph == uint32_t(PHs)) ? pair_apply_dyn<C, LOGT, EXCL_NEXT, PHs>(p) : idx), ...);
+    return idx;
+}
+// slot part of thread t for every phase
+template <class C, int LOGT, bool EXCL_NEXT, int... PHs>
+__device__ __forceinline__ void pair_thread_slots(uint32_t (&mpt)[sizeof...(PHs)], uint32_t t, std::integer_sequence<int, PHs...>) {
+    ((mpt[PHs] = pair_apply_dyn<C, LOGT, EXCL_NEXT, PHs>(bfly_pattern_dyn<C>(rotl_bits(t, PHs, C::SB)))), ...);
+}
+
+
 // float accumulators per frame: one per 8 decision bits, each split into two chains of 4 predicated FADDs (low nibble starts at 2^23,
 // high nibble at 0, summed exactly at the end).  Short chains let ptxas consume the VIMNMX predicates quickly: with chains of 8 it
 // ran out of predicate registers and spilled them through pairs of LOP3 bit-mask updates (36 LOP3 of 171 instructions per step in

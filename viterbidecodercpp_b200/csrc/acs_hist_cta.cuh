@@ -4,7 +4,7 @@
 // Replaces ViterbiDecoder_Scalar::update / bfly / renormalise (include/viterbi/viterbi_decoder_scalar.h:28-153) for whole-frame
 // batch calls, like acs_cta.cuh, but with the survivor-history formulation of acs_hist.cuh / acs_hist_group.cuh:
 //     register = metric << 16 | last <= 16 decisions of the survivor path into that state
-//     butterfly = 1 LDS.64 (branch metric table entry {total, inverted}) + 2 three-input adds (x + metric + tag) + 2 fused add-min
+//     butterfly = half an LDS.128 (the branch metric table entries {total, inverted} of TWO butterflies) + 2 adds + 2 fused add-min
 // instead of acs_cta.cuh's 4 packed adds + 2 packed min + 4 predicated FADDs + decision-byte assembly + a 4 KB decision row per
 // step.  One frame per register (no packing: uint16_t metrics leave no spare bits in a 16-bit half), so a CTA holds ONE frame:
 //   * 1024 config-5 frames are 1024 CTAs = 6.92 rounds on 148 SMs (acs_cta.cuh: 512 CTAs = 3.46 rounds, the last one half empty),
@@ -15,6 +15,14 @@
 // LB = 5 register-only steps, then the CTA exchanges through 64 KB of shared memory (skewed, conflict-free) under two
 // __syncthreads.  The branch metric table of a whole group ({total, inverted} x 64 patterns x 5 steps, metric field format) is built
 // cooperatively from the caller's int16_t row (read where it lies: unpunctured input only, any alignment) at each exchange.
+//
+// TABLE FETCH: by butterfly pairs, one LDS.128 per pair (acs_cta.cuh, PairMap).
+//
+// TAGS.  The path-1 register of a butterfly must carry the tag 2^k of step k (acs_hist.cuh).  Instead of adding it to 16 registers
+// per step, the butterflies of step k-1 whose results become path-1 operands of step k (a register bit, or for the step before an
+// exchange a thread bit: either way a constant slot offset) fetch their entries from a second copy of the table that has 2^k added to
+// both members - both paths of the compare move by the same amount, the result carries the tag.  The first step of a period finds
+// its tag set by the record cut that clears the history fields (and the first step of the frame by the initial metrics).
 //
 // Renormalisation (scalar.h:48, 139-153) is the speculation / rollback / replay scheme of acs_cta.cuh: a group runs without it
 // while thread 0 (state 0 sits in its register 0 in every phase) tracks the trigger; if it fired, the CTA restores the metrics AND
@@ -40,7 +48,8 @@ struct HistCtaShape {
     using S = CtaShape<C, 9>;
     static constexpr int LOGT = 9, T = 512, SB = C::SB, LB = S::LB, NL = S::NL, NW = NL / 2, NP = C::NP, HB = 16, WARPS = T / 32;
     static_assert(SB == 14 && LB == 5 && NL == 32, "built for K = 15");
-    static constexpr size_t XCH_WORDS = S::XCH_WORDS, TBL_WORDS = S::TBL_WORDS;
+    static constexpr size_t XCH_WORDS = (S::XCH_WORDS + 3) / 4 * 4;                 // the table behind it holds 16-byte slots
+    static constexpr size_t TBL_WORDS = size_t(LB) * 2 * NP * 4;                    // [LB][plain, next tag added][NP] x {own, partner} x {total, inverted}
     static constexpr size_t SMEM_BYTES = (XCH_WORDS + TBL_WORDS + 64) * 4;
 };
 
@@ -48,40 +57,63 @@ __host__ __device__ constexpr uint32_t rotl_rt(uint32_t v, uint32_t r, uint32_t 
     return r == 0 ? v : (((v << r) | (v >> (n - r))) & ((1u << n) - 1u));
 }
 
+// one butterfly on registers (q0, q1) with table entry {ex, ey} = {total, inverted}; the tag of this step is already in the path-1
+// (TIE_SIMD: path-0) register, the tag of the next step comes with the entry where it is due
+template <int TIE_SIMD>
+__device__ __forceinline__ void hc_bfly(uint32_t& x0, uint32_t& x1, const uint32_t ex, const uint32_t ey) {
+    uint32_t m0, m1;
+    if constexpr (!TIE_SIMD) {
+        const uint32_t b0 = x1 + ey, b1 = x1 + ex;                              //                               scalar.h:114,116
+        m0 = __viaddmin_u32(x0, ex, b0);                                        // new state 2j   stays at q0   scalar.h:113,127
+        m1 = __viaddmin_u32(x0, ey, b1);                                        // new state 2j+1 goes to q1    scalar.h:115,128
+    } else {
+        const uint32_t a0 = x0 + ex, a1 = x0 + ey;                              // tag on path 0: a tie selects path 1
+        m0 = __viaddmin_u32(x1, ey, a0);
+        m1 = __viaddmin_u32(x1, ex, a1);
+    }
+    x0 = m0;
+    x1 = m1;
+}
+
+// does register q hold a tagged operand in the step whose "path-1 half" is register bit NEXTBIT?
+template <int TIE_SIMD>
+__host__ __device__ constexpr bool hc_tagged(int q, int nextbit) { return (((q >> nextbit) & 1) != 0) != (TIE_SIMD != 0); }
+
 template <class C, int PH, int TIE_SIMD, int Q>
-__device__ __forceinline__ void hc_bfly_at(uint32_t (&x)[HistCtaShape<C>::NL], const uint2* tbl_ph, const uint32_t pt, const uint32_t tag,
-                                           const uint32_t one) {
+__device__ __forceinline__ void hc_bfly_pair_at(uint32_t (&x)[HistCtaShape<C>::NL], const uint4* tbl_ph, const uint32_t mpt) {
     using H = HistCtaShape<C>;
-    constexpr int bit = 1 << (H::LB - 1 - PH);
-    if constexpr ((Q & bit) == 0) {
-        constexpr int q0 = Q, q1 = Q | bit;
-        constexpr uint32_t jq = rotl_bits(uint32_t(q0) << H::LOGT, PH, H::SB);   // register-bit part of the old state index
-        constexpr uint32_t pq = bfly_pattern<C>(jq);
-        const uint2 e = tbl_ph[pq ^ pt];                // {total_error, inverted_error} << 16 of pattern pq ^ pt (scalar.h:66-73, 107)
-        uint32_t m0, m1;
-        // The tag is added to the path-1 register ONCE (x1t), with a multiply-add by a run-time 1 so that ptxas cannot fold it back
-        // into two three-input IADD3: IADD3 issues on the same pipe as VIADDMNMX and LOP3 (6 of 6 instructions per butterfly on one
-        // pipe: the kernel ran at 1360 clocks per step); IMAD and the two-input adds (IMAD.IADD) go to the other pipe.
-        if constexpr (!TIE_SIMD) {
-            const uint32_t x1t = tag * one + x[q1];                             // path 1 tagged
-            const uint32_t b0 = x1t + e.y, b1 = x1t + e.x;                      //                               scalar.h:114,116
-            m0 = __viaddmin_u32(x[q0], e.x, b0);                                // new state 2j   stays at q0   scalar.h:113,127
-            m1 = __viaddmin_u32(x[q0], e.y, b1);                                // new state 2j+1 goes to q1    scalar.h:115,128
-        } else {
-            const uint32_t x0t = tag * one + x[q0];                             // tag on path 0: a tie selects path 1
-            const uint32_t a0 = x0t + e.x, a1 = x0t + e.y;
-            m0 = __viaddmin_u32(x[q1], e.y, a0);
-            m1 = __viaddmin_u32(x[q1], e.x, a1);
-        }
-        x[q0] = m0;
-        x[q1] = m1;
+    constexpr PairMap M = pair_map<C, H::LOGT, true>(PH);
+    static_assert(M.pb >= 0, "no pairing bit with a non-zero pattern");
+    constexpr int bit = 1 << (H::LB - 1 - PH), pbit = 1 << M.pb;
+    if constexpr ((Q & bit) == 0 && (Q & pbit) == 0) {
+        constexpr int a0 = Q, a1 = Q | bit, b0 = Q | pbit, b1 = Q | pbit | bit;
+        constexpr uint32_t pa = bfly_pattern<C>(rotl_bits(uint32_t(a0) << H::LOGT, PH, H::SB));   // register-bit part of the old state index
+        constexpr uint32_t pb = bfly_pattern<C>(rotl_bits(uint32_t(b0) << H::LOGT, PH, H::SB));
+        constexpr uint32_t ia = pair_apply(M, C::R, pa);
+        static_assert(pair_apply(M, C::R, pb) == (ia ^ 1u), "paired butterflies must sit in one table slot");
+        // entries with the next step's tag added: both results of a butterfly land in the same half of the next step's butterflies.
+        // Before an exchange that half is a thread bit: mpt carries the offset then.
+        constexpr bool pre = (PH < H::LB - 1) && hc_tagged<TIE_SIMD>(Q, H::LB - 2 - PH);
+        const uint4 e = tbl_ph[(ia ^ mpt) + (pre ? uint32_t(H::NP) : 0u)];   // {total, inverted} of a, of b   (scalar.h:66-73, 107)
+        hc_bfly<TIE_SIMD>(x[a0], x[a1], e.x, e.y);
+        hc_bfly<TIE_SIMD>(x[b0], x[b1], e.z, e.w);
     }
 }
 
 template <class C, int PH, int TIE_SIMD, int... Qs>
-__device__ __forceinline__ void hc_bfly_all(uint32_t (&x)[HistCtaShape<C>::NL], const uint2* tbl_ph, const uint32_t pt, const uint32_t tag,
-                                            const uint32_t one, std::integer_sequence<int, Qs...>) {
-    (hc_bfly_at<C, PH, TIE_SIMD, Qs>(x, tbl_ph, pt, tag, one), ...);
+__device__ __forceinline__ void hc_bfly_all(uint32_t (&x)[HistCtaShape<C>::NL], const uint4* tbl_ph, const uint32_t mpt,
+                                            std::integer_sequence<int, Qs...>) {
+    (hc_bfly_pair_at<C, PH, TIE_SIMD, Qs>(x, tbl_ph, mpt), ...);
+}
+
+// slot part of thread t per phase; the phase before an exchange adds the offset of the tagged copy for the threads whose registers
+// become path-1 (TIE_SIMD: path-0) operands of the step behind the exchange: position bit LOGT - 1 -> register bit LB - 1
+template <class C, int TIE_SIMD, int... PHs>
+__device__ __forceinline__ void hc_thread_slots(uint32_t (&mpt)[sizeof...(PHs)], uint32_t t, std::integer_sequence<int, PHs...>) {
+    using H = HistCtaShape<C>;
+    pair_thread_slots<C, H::LOGT, true>(mpt, t, std::integer_sequence<int, PHs...>{});
+    const bool top = ((t >> (H::LOGT - 1)) & 1u) != 0u;
+    if (top != (TIE_SIMD != 0)) mpt[H::LB - 1] += uint32_t(H::NP);
 }
 
 // grid = number of frames, block = 512, dynamic shared memory = HistCtaShape::SMEM_BYTES.  Whole frames only (no resume).
@@ -93,32 +125,32 @@ __global__ void __launch_bounds__(HistCtaShape<C>::T, MINB) acs_hist_cta_kernel(
     constexpr int LB = H::LB, NL = H::NL, NW = H::NW, R = C::R, NP = H::NP, SB = H::SB, LOGT = H::LOGT, HB = H::HB;
     extern __shared__ uint32_t smem[];
     uint32_t* xch = smem;                                             // [NS] exchange buffer = registers at the start of the group
-    uint2* tbl = reinterpret_cast<uint2*>(smem + H::XCH_WORDS);       // [LB][NP] {total, inverted}
+    uint4* tbl = reinterpret_cast<uint4*>(smem + H::XCH_WORDS);       // [LB][2][NP] {total, inverted} of slot idx, of slot idx ^ 1
     uint32_t* red = smem + H::XCH_WORDS + H::TBL_WORDS;               // [WARPS] reduction scratch
     uint32_t* flag = red + H::WARPS;                                  // [2] trigger flags
 
     const uint32_t t = threadIdx.x;
     const size_t f = blockIdx.x;
     const HistConsts c = hist_consts<1>(p);
-    const uint32_t one = p.resume + 1u;                               // whole frames only: resume is 0.  A 1 the compiler cannot see (hc_bfly_at)
 
-    uint32_t pt[LB];                                                  // thread part of the branch pattern per phase
-#pragma unroll
-    for (int n = 0; n < LB; n++) pt[n] = bfly_pattern_dyn<C>(rotl_bits(t, n, SB));
+    uint32_t mpt[LB];                                                 // thread part of the table slot per phase
+    hc_thread_slots<C, TIE_SIMD>(mpt, t, std::make_integer_sequence<int, LB>{});
 
     uint32_t x[NL];
     uint64_t acc = 0;
     {
         const uint32_t s0 = p.start_state & uint32_t(C::NS - 1);      // core.h:209-210; phase 0: position = state
 #pragma unroll
-        for (int q = 0; q < NL; q++) x[q] = (((uint32_t(q) << LOGT) | t) == s0) ? c.init_start : c.init_other;
+        for (int q = 0; q < NL; q++)                                  // + the tag of step 0 where step 0 expects it
+            x[q] = ((((uint32_t(q) << LOGT) | t) == s0) ? c.init_start : c.init_other) | (hc_tagged<TIE_SIMD>(q, LB - 1) ? 1u : 0u);
     }
 
     const uint32_t n_periods = (p.n_steps + HB - 1) / HB;
     uint32_t* rec = static_cast<uint32_t*>(p.dec) + f * size_t(n_periods) * (size_t(C::NS) / 2) + t * 4;
     const int16_t* row = reinterpret_cast<const int16_t*>(static_cast<const uint8_t*>(p.sym) + f * p.sym_row_bytes);
 
-    // branch metric tables of the n steps of the group that starts at first_step, one entry per thread (320 of the 512)
+    // branch metric tables of the n steps of the group that starts at first_step, one pattern per thread (320 of the 512), each stored
+    // as "own" member of its slot and "partner" member of the neighbouring slot, plain and with the next step's tag added
     auto build_tables = [&](uint32_t first_step, uint32_t n) {
         if (t < uint32_t(LB * NP)) {
             const uint32_t tph = t / NP, pat = t % NP;
@@ -133,14 +165,24 @@ __global__ void __launch_bounds__(HistCtaShape<C>::T, MINB) acs_hist_cta_kernel(
                     tot += bb ? hi : lo;                    // viterbi_branch_table.h:52 + scalar.h:66-73
                     inv += bb ? lo : hi;                    // scalar.h:107 (max_error - total): complementary pattern + c_inv
                 }
-                tbl[tph * NP + pat] = make_uint2(tot, inv);
+                const uint32_t step = first_step + tph, k = step % uint32_t(HB);
+                // no tag for the step after a record cut (the cut sets it) and none after the last step
+                const uint32_t nxt = (k == uint32_t(HB - 1) || step + 1u == p.n_steps) ? 0u : (2u << k);
+                const uint32_t idx = pair_apply_phase<C, LOGT, true>(tph, pat, std::make_integer_sequence<int, LB>{});
+                uint2* t2 = reinterpret_cast<uint2*>(tbl + size_t(tph) * 2 * NP);
+                t2[2 * idx] = make_uint2(tot, inv);
+                t2[2 * (idx ^ 1u) + 1] = make_uint2(tot, inv);
+                t2[2 * (NP + idx)] = make_uint2(tot + nxt, inv + nxt);
+                t2[2 * (NP + (idx ^ 1u)) + 1] = make_uint2(tot + nxt, inv + nxt);
             }
         }
     };
 
-    uint32_t tag = 1u, pst = 0, r = 0;
-    // history record of the period that just ended (position order), then clear the history fields
-    auto emit_record = [&]() {
+    uint32_t pst = 0, r = 0;
+    // history record of the period that just ended (position order), then clear the history fields and set the tag of the next
+    // period's first step, whose path-1 operands are the registers with bit NEXTBIT set
+    auto emit_record = [&](auto nextbit) {
+        constexpr int NEXTBIT = decltype(nextbit)::value;
         uint32_t w[NW];
 #pragma unroll
         for (int i = 0; i < NW; i++) {
@@ -151,9 +193,8 @@ __global__ void __launch_bounds__(HistCtaShape<C>::T, MINB) acs_hist_cta_kernel(
 #pragma unroll
         for (int v = 0; v < NW / 4; v++) *reinterpret_cast<uint4*>(dst + size_t(v) * (H::T * 4)) = make_uint4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
 #pragma unroll
-        for (int q = 0; q < NL; q++) x[q] &= 0xffff0000u;
+        for (int q = 0; q < NL; q++) x[q] = (x[q] & 0xffff0000u) | (hc_tagged<TIE_SIMD>(q, NEXTBIT) ? 1u : 0u);
         r++;
-        tag = 1u;
         pst = 0;
     };
     auto cta_min = [&]() -> uint32_t {                   // the metric field of the smallest register is the smallest metric
@@ -180,7 +221,7 @@ __global__ void __launch_bounds__(HistCtaShape<C>::T, MINB) acs_hist_cta_kernel(
 
     while (done < p.n_steps) {
         const uint32_t left = p.n_steps - done, span = left < uint32_t(LB) ? left : uint32_t(LB);
-        const uint32_t tag0 = tag, pst0 = pst, r0 = r;
+        const uint32_t pst0 = pst, r0 = r;
 
         // ---- speculative run of the group (no renormalisation); thread 0 keeps the running maximum of state 0's register
         uint32_t mx = 0u;
@@ -188,11 +229,10 @@ __global__ void __launch_bounds__(HistCtaShape<C>::T, MINB) acs_hist_cta_kernel(
             constexpr int PH = decltype(PHc)::value;
             constexpr bool GUARD = decltype(guard_tag)::value;
             if constexpr (GUARD) { if (uint32_t(PH) >= span) return; }
-            hc_bfly_all<C, PH, TIE_SIMD>(x, tbl + PH * NP, pt[PH], tag, one, std::make_integer_sequence<int, NL>{});
+            hc_bfly_all<C, PH, TIE_SIMD>(x, tbl + PH * 2 * NP, mpt[PH], std::make_integer_sequence<int, NL>{});
             mx = max(mx, x[0]);
-            tag <<= 1;
             pst++;
-            if constexpr (PH != LB - 1) { if (pst == uint32_t(HB)) emit_record(); }     // after the last phase: behind the exchange
+            if constexpr (PH != LB - 1) { if (pst == uint32_t(HB)) emit_record(std::integral_constant<int, LB - 2 - PH>{}); }     // after the last phase: behind the exchange
         };
         if (span == uint32_t(LB)) {
             spec_phase(std::integral_constant<int, 0>{}, std::false_type{});
@@ -214,12 +254,11 @@ __global__ void __launch_bounds__(HistCtaShape<C>::T, MINB) acs_hist_cta_kernel(
             // ---- roll back (registers and record bookkeeping) and replay step by step with the reference's renormalisation
 #pragma unroll
             for (int q = 0; q < NL; q++) x[q] = xch[S::slot((uint32_t(q) << LOGT) | t)];
-            tag = tag0; pst = pst0; r = r0;
+            pst = pst0; r = r0;
             auto replay_phase = [&](auto PHc) {
                 constexpr int PH = decltype(PHc)::value;
                 if (uint32_t(PH) < span) {
-                    hc_bfly_all<C, PH, TIE_SIMD>(x, tbl + PH * NP, pt[PH], tag, one, std::make_integer_sequence<int, NL>{});
-                    tag <<= 1;
+                    hc_bfly_all<C, PH, TIE_SIMD>(x, tbl + PH * 2 * NP, mpt[PH], std::make_integer_sequence<int, NL>{});
                     pst++;
                     if (t == 0) flag[1] = x[0];
                     __syncthreads();
@@ -232,7 +271,7 @@ __global__ void __launch_bounds__(HistCtaShape<C>::T, MINB) acs_hist_cta_kernel(
                     } else {
                         __syncthreads();                                   // flag[1] may be rewritten by the next phase
                     }
-                    if constexpr (PH != LB - 1) { if (pst == uint32_t(HB)) emit_record(); }
+                    if constexpr (PH != LB - 1) { if (pst == uint32_t(HB)) emit_record(std::integral_constant<int, LB - 2 - PH>{}); }
                 }
             };
             replay_phase(std::integral_constant<int, 0>{});
@@ -261,7 +300,7 @@ __global__ void __launch_bounds__(HistCtaShape<C>::T, MINB) acs_hist_cta_kernel(
             // no barrier needed here: the buffer is next written after B1 of the next group, which every thread reaches only
             // after these loads; until then it doubles as the rollback copy of the group's starting registers
             if (pst == uint32_t(HB)) {
-                emit_record();                               // records are cut in the layout the traceback expects: PHI = rotr^(steps mod 5)(s)
+                emit_record(std::integral_constant<int, LB - 1>{});   // records are cut in the layout the traceback expects: PHI = rotr^(steps mod 5)(s)
                 // the rollback copy must match the registers the next group starts from (history fields cleared); every thread
                 // rewrites exactly the words it has just read and will read back on a rollback: no barrier needed
 #pragma unroll
@@ -269,7 +308,7 @@ __global__ void __launch_bounds__(HistCtaShape<C>::T, MINB) acs_hist_cta_kernel(
             }
         }
     }
-    if (pst) emit_record();                                  // last, partial record (its pst is still needed for the SIMD tie-break mask)
+    if (pst) emit_record(std::integral_constant<int, 0>{});  // last, partial record (its pst is still needed for the SIMD tie-break mask)
 
     // final metrics in logical order: state s sits at PHI = rotr^ph(s)   (core.h:195-199 reads old_metrics[end_state])
     const uint32_t ph = p.n_steps % uint32_t(LB);
