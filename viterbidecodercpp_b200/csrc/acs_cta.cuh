@@ -43,7 +43,7 @@ struct CtaShape {
     static __host__ __device__ constexpr uint32_t slot(uint32_t phi) { return phi + (phi >> 5); }
 };
 
-// TABLE FETCH BY BUTTERFLY PAIRS.  The entry of a butterfly is T[pq ^ pt] (pq: pattern of the register bits, a compile-time constant;
+// TABLE FETCH BY BUTTERFLY PAIRS (OR QUADS).  The entry of a butterfly is T[pq ^ pt] (pq: pattern of the register bits, a compile-time constant;
 // pt: pattern of the thread bits).  Two butterflies whose registers differ in one bit (the "pairing bit") have patterns that differ by
 // a constant v, so in slot coordinates M with M(v) = 1 (M linear and invertible) their entries sit at idx and idx ^ 1.  The table
 // stores every entry twice - slot idx = {T[idx], T[idx ^ 1]}, 16 bytes - so that ONE LDS.128 at slot M(pq) ^ M(pt) fetches the entries
@@ -57,7 +57,7 @@ struct CtaShape {
 // Slot coordinates of the table of one phase: index bit i of pattern p = parity(p & row[i]); pb = the pairing register bit.
 struct PairMap {
     uint32_t row[8];
-    int pb;
+    int pb[2];
 };
 __host__ __device__ constexpr uint32_t pair_apply(const PairMap& m, int R, uint32_t p) {
     uint32_t idx = 0;
@@ -73,19 +73,21 @@ __host__ __device__ constexpr bool pair_basis_add(uint32_t (&lead)[8], uint32_t 
     }
     return false;
 }
-// EXCL_NEXT: the pairing bit must not be the bit that says "path-1 operand of the next step" either (acs_hist_cta.cuh)
-template <class C, int LOGT, bool EXCL_NEXT>
+// NV pairing bits (1: pairs, 2: quads of butterflies per slot; slot idx then holds the entries idx, idx ^ 1, idx ^ 2, idx ^ 3).
+// EXCL_NEXT: a pairing bit must not be the bit that says "path-1 operand of the next step" either (acs_hist_cta.cuh)
+template <class C, int LOGT, bool EXCL_NEXT, int NV>
 __host__ __device__ constexpr PairMap pair_map(int PH) {
     constexpr int SB = C::SB, LB = SB - LOGT, R = C::R;
-    static_assert(R >= 3 && R <= 8, "the slot map is built for 8 <= 2^R <= 256 patterns");
+    static_assert(R >= 3 && R <= 8 && NV >= 1 && NV <= 2, "the slot map is built for 8 <= 2^R <= 256 patterns and pairs or quads");
     PairMap m{};
-    // pairing bit: not the butterfly bit (LB-1-PH), not the bit that says "path-1 operand of the next step" (LB-2-PH), pattern != 0
-    uint32_t v = 0;
-    m.pb = -1;
-    for (int b = 0; b < LB && m.pb < 0; b++) {
+    // pairing bits: not the butterfly bit (LB-1-PH), not the next step's (LB-2-PH), patterns independent
+    uint32_t v[2] = {}, vlead[8] = {};
+    int nv = 0;
+    m.pb[0] = m.pb[1] = -1;
+    for (int b = 0; b < LB && nv < NV; b++) {
         if (b == LB - 1 - PH || (EXCL_NEXT && b == LB - 2 - PH)) continue;
         const uint32_t pv = bfly_pattern<C>(rotl_bits((1u << b) << LOGT, PH, SB));
-        if (pv != 0) { m.pb = b; v = pv; }
+        if (pair_basis_add(vlead, pv)) { m.pb[nv] = b; v[nv++] = pv; }
     }
     // patterns of the three lane bits that vary inside a quarter warp
     uint32_t pl[3] = {};
@@ -93,61 +95,61 @@ __host__ __device__ constexpr PairMap pair_map(int PH) {
     auto rho = [&](uint32_t r) { return parity32(r & pl[0]) | (parity32(r & pl[1]) << 1) | (parity32(r & pl[2]) << 2); };
     uint32_t lead[8] = {}, lead_rho[8] = {};
     const uint32_t NPAT = 1u << R;
-    // rows 1, 2: vanish on v, restrictions to the lane patterns independent; row 0: 1 on v, restriction independent of rows 1, 2
-    int have = 0;
-    uint32_t rows12[2] = {};
-    for (int pass = 0; pass < 2 && have < 2; pass++)                 // pass 0 insists on an independent restriction, pass 1 takes any
-        for (uint32_t r = 1; r < NPAT && have < 2; r++) {
-            if (parity32(r & v)) continue;
-            uint32_t t1[8] = {}, t2[8] = {};
-            for (int i = 0; i < 8; i++) { t1[i] = lead[i]; t2[i] = lead_rho[i]; }
-            if (!pair_basis_add(t1, r)) continue;
-            if (pass == 0 && !pair_basis_add(t2, rho(r))) continue;
-            for (int i = 0; i < 8; i++) { lead[i] = t1[i]; if (pass == 0) lead_rho[i] = t2[i]; }
-            rows12[have++] = r;
-        }
-    uint32_t row0 = 0;
-    for (int pass = 0; pass < 2 && row0 == 0; pass++)
-        for (uint32_t r = 1; r < NPAT && row0 == 0; r++) {
-            if (!parity32(r & v)) continue;
-            uint32_t t1[8] = {}, t2[8] = {};
-            for (int i = 0; i < 8; i++) { t1[i] = lead[i]; t2[i] = lead_rho[i]; }
-            if (!pair_basis_add(t1, r)) continue;
-            if (pass == 0 && !pair_basis_add(t2, rho(r))) continue;
-            for (int i = 0; i < 8; i++) lead[i] = t1[i];
-            row0 = r;
-        }
-    m.row[0] = row0; m.row[1] = rows12[0]; m.row[2] = rows12[1];
-    // Every other row must vanish on v too (M(v) = 1 exactly), and complete the map to an invertible one
-    int n = 3;
-    for (uint32_t r = 1; r < NPAT && n < R; r++) {
-        if (parity32(r & v)) continue;
-        if (pair_basis_add(lead, r)) m.row[n++] = r;
-    }
+    // row i < NV is 1 on v[i] and 0 on the other pairing pattern; every other row vanishes on all of them (M(v[i]) = 2^i exactly).
+    // The three low rows additionally get independent restrictions to the lane patterns where that is possible (pass 0); the rows
+    // with the fewest candidates left are not the problem here, so the free ones go first.
+    auto pick = [&](int want0, int want1, bool need_rho) -> uint32_t {
+        for (int pass = need_rho ? 0 : 1; pass < 2; pass++)
+            for (uint32_t r = 1; r < NPAT; r++) {
+                if (int(parity32(r & v[0])) != want0) continue;
+                if (NV > 1 && int(parity32(r & v[1])) != want1) continue;
+                uint32_t t1[8] = {}, t2[8] = {};
+                for (int i = 0; i < 8; i++) { t1[i] = lead[i]; t2[i] = lead_rho[i]; }
+                if (!pair_basis_add(t1, r)) continue;
+                if (pass == 0 && !pair_basis_add(t2, rho(r))) continue;
+                for (int i = 0; i < 8; i++) { lead[i] = t1[i]; if (pass == 0) lead_rho[i] = t2[i]; }
+                return r;
+            }
+        return 0u;
+    };
+    for (int i = NV; i < 3; i++) m.row[i] = pick(0, 0, true);
+    for (int i = NV - 1; i >= 0; i--) m.row[i] = pick(i == 0 ? 1 : 0, i == 1 ? 1 : 0, true);
+    for (int i = 3; i < R; i++) m.row[i] = pick(0, 0, false);
     return m;
 }
-template <class C, int LOGT, bool EXCL_NEXT, int PH, int... Is>
+// do the 8 lanes of a quarter warp read 8 different 16-byte bank groups (or the same slot)?
+template <class C, int LOGT, bool EXCL_NEXT, int NV>
+__host__ __device__ constexpr bool pair_map_conflict_free(int PH) {
+    const PairMap m = pair_map<C, LOGT, EXCL_NEXT, NV>(PH);
+    uint32_t idx[8] = {};
+    for (uint32_t l = 0; l < 8; l++) idx[l] = pair_apply(m, C::R, bfly_pattern<C>(rotl_bits(l, PH, C::SB)));
+    for (int a = 0; a < 8; a++)
+        for (int b = a + 1; b < 8; b++)
+            if (idx[a] != idx[b] && (idx[a] & 7u) == (idx[b] & 7u)) return false;
+    return true;
+}
+template <class C, int LOGT, bool EXCL_NEXT, int NV, int PH, int... Is>
 __device__ __forceinline__ uint32_t pair_apply_dyn_impl(uint32_t p, std::integer_sequence<int, Is...>) {
-    constexpr PairMap M = pair_map<C, LOGT, EXCL_NEXT>(PH);
+    constexpr PairMap M = pair_map<C, LOGT, EXCL_NEXT, NV>(PH);
     uint32_t idx = 0;
     ((idx |= (uint32_t(__popc(p & std::integral_constant<uint32_t, M.row[Is]>::value)) & 1u) << Is), ...);
     return idx;
 }
-template <class C, int LOGT, bool EXCL_NEXT, int PH>
+template <class C, int LOGT, bool EXCL_NEXT, int NV, int PH>
 __device__ __forceinline__ uint32_t pair_apply_dyn(uint32_t p) {
-    return pair_apply_dyn_impl<C, LOGT, EXCL_NEXT, PH>(p, std::make_integer_sequence<int, C::R>{});
+    return pair_apply_dyn_impl<C, LOGT, EXCL_NEXT, NV, PH>(p, std::make_integer_sequence<int, C::R>{});
 }
 // same for a run-time phase (table build)
-template <class C, int LOGT, bool EXCL_NEXT, int... PHs>
+template <class C, int LOGT, bool EXCL_NEXT, int NV, int... PHs>
 __device__ __forceinline__ uint32_t pair_apply_phase(uint32_t ph, uint32_t p, std::integer_sequence<int, PHs...>) {
     uint32_t idx = 0;
-    ((idx = (ph == uint32_t(PHs)) ? pair_apply_dyn<C, LOGT, EXCL_NEXT, PHs>(p) : idx), ...);
+    ((idx = (ph == uint32_t(PHs)) ? pair_apply_dyn<C, LOGT, EXCL_NEXT, NV, PHs>(p) : idx), ...);
     return idx;
 }
 // slot part of thread t for every phase
-template <class C, int LOGT, bool EXCL_NEXT, int... PHs>
+template <class C, int LOGT, bool EXCL_NEXT, int NV, int... PHs>
 __device__ __forceinline__ void pair_thread_slots(uint32_t (&mpt)[sizeof...(PHs)], uint32_t t, std::integer_sequence<int, PHs...>) {
-    ((mpt[PHs] = pair_apply_dyn<C, LOGT, EXCL_NEXT, PHs>(bfly_pattern_dyn<C>(rotl_bits(t, PHs, C::SB)))), ...);
+    ((mpt[PHs] = pair_apply_dyn<C, LOGT, EXCL_NEXT, NV, PHs>(bfly_pattern_dyn<C>(rotl_bits(t, PHs, C::SB)))), ...);
 }
 
 

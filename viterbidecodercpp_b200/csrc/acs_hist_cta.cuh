@@ -4,7 +4,7 @@
 // Replaces ViterbiDecoder_Scalar::update / bfly / renormalise (include/viterbi/viterbi_decoder_scalar.h:28-153) for whole-frame
 // batch calls, like acs_cta.cuh, but with the survivor-history formulation of acs_hist.cuh / acs_hist_group.cuh:
 //     register = metric << 16 | last <= 16 decisions of the survivor path into that state
-//     butterfly = half an LDS.128 (the branch metric table entries {total, inverted} of TWO butterflies) + 2 adds + 2 fused add-min
+//     butterfly = a quarter of an LDS.128 (the total errors of FOUR butterflies) + 3 adds + 2 fused add-min
 // instead of acs_cta.cuh's 4 packed adds + 2 packed min + 4 predicated FADDs + decision-byte assembly + a 4 KB decision row per
 // step.  One frame per register (no packing: uint16_t metrics leave no spare bits in a 16-bit half), so a CTA holds ONE frame:
 //   * 1024 config-5 frames are 1024 CTAs = 6.92 rounds on 148 SMs (acs_cta.cuh: 512 CTAs = 3.46 rounds, the last one half empty),
@@ -16,12 +16,16 @@
 // __syncthreads.  The branch metric table of a whole group ({total, inverted} x 64 patterns x 5 steps, metric field format) is built
 // cooperatively from the caller's int16_t row (read where it lies: unpunctured input only, any alignment) at each exchange.
 //
-// TABLE FETCH: by butterfly pairs, one LDS.128 per pair (acs_cta.cuh, PairMap).
+// TABLE FETCH: the kernel is bound by shared-memory wavefronts (table fetch + exchange), not by issue slots, so the table holds
+// only the total error of a pattern (4 bytes; the inverted error is max_error - total, one more add per butterfly) and is fetched
+// by butterfly QUADS: one LDS.128 for the four butterflies that differ in two register bits (acs_cta.cuh, PairMap with NV = 2).
+// 16 bytes per butterfly and lane and step became 4: 33 -> 16 wavefronts per warp and step.
 //
 // TAGS.  The path-1 register of a butterfly must carry the tag 2^k of step k (acs_hist.cuh).  Instead of adding it to 16 registers
 // per step, the butterflies of step k-1 whose results become path-1 operands of step k (a register bit, or for the step before an
-// exchange a thread bit: either way a constant slot offset) fetch their entries from a second copy of the table that has 2^k added to
-// both members - both paths of the compare move by the same amount, the result carries the tag.  The first step of a period finds
+// exchange a thread bit: either way a constant slot offset) fetch their entries from a second copy of the table that has 2^k added
+// (and use max_error + 2 * 2^k, so that the inverted error carries it too) - both paths of the compare move by the same amount, the
+// result carries the tag.  The first step of a period finds
 // its tag set by the record cut that clears the history fields (and the first step of the frame by the initial metrics).
 //
 // Renormalisation (scalar.h:48, 139-153) is the speculation / rollback / replay scheme of acs_cta.cuh: a group runs without it
@@ -49,7 +53,7 @@ struct HistCtaShape {
     static constexpr int LOGT = 9, T = 512, SB = C::SB, LB = S::LB, NL = S::NL, NW = NL / 2, NP = C::NP, HB = 16, WARPS = T / 32;
     static_assert(SB == 14 && LB == 5 && NL == 32, "built for K = 15");
     static constexpr size_t XCH_WORDS = (S::XCH_WORDS + 3) / 4 * 4;                 // the table behind it holds 16-byte slots
-    static constexpr size_t TBL_WORDS = size_t(LB) * 2 * NP * 4;                    // [LB][plain, next tag added][NP] x {own, partner} x {total, inverted}
+    static constexpr size_t TBL_WORDS = size_t(LB) * 2 * NP * 4;                    // [LB][plain, next tag added][NP] x 4 total errors
     static constexpr size_t SMEM_BYTES = (XCH_WORDS + TBL_WORDS + 64) * 4;
 };
 
@@ -57,20 +61,15 @@ __host__ __device__ constexpr uint32_t rotl_rt(uint32_t v, uint32_t r, uint32_t 
     return r == 0 ? v : (((v << r) | (v >> (n - r))) & ((1u << n) - 1u));
 }
 
-// one butterfly on registers (q0, q1) with table entry {ex, ey} = {total, inverted}; the tag of this step is already in the path-1
-// (TIE_SIMD: path-0) register, the tag of the next step comes with the entry where it is due
-template <int TIE_SIMD>
-__device__ __forceinline__ void hc_bfly(uint32_t& x0, uint32_t& x1, const uint32_t ex, const uint32_t ey) {
-    uint32_t m0, m1;
-    if constexpr (!TIE_SIMD) {
-        const uint32_t b0 = x1 + ey, b1 = x1 + ex;                              //                               scalar.h:114,116
-        m0 = __viaddmin_u32(x0, ex, b0);                                        // new state 2j   stays at q0   scalar.h:113,127
-        m1 = __viaddmin_u32(x0, ey, b1);                                        // new state 2j+1 goes to q1    scalar.h:115,128
-    } else {
-        const uint32_t a0 = x0 + ex, a1 = x0 + ey;                              // tag on path 0: a tie selects path 1
-        m0 = __viaddmin_u32(x1, ey, a0);
-        m1 = __viaddmin_u32(x1, ex, a1);
-    }
+// one butterfly on registers (x0, x1) = states (j, j + NS/2) with the branch error ex = total_error << 16 of its pattern and
+// cq = max_error << 16: the inverted error is cq - ex (scalar.h:107).  The tag of this step is already in the path-1 (TIE_SIMD:
+// path-0) register - which is also all the two tie-break flavours differ in -, the tag of the next step comes with ex AND cq (twice,
+// so that cq - ex carries it once) where it is due.
+__device__ __forceinline__ void hc_bfly(uint32_t& x0, uint32_t& x1, const uint32_t ex, const uint32_t cq) {
+    const uint32_t ey = cq - ex;
+    const uint32_t b0 = x1 + ey, a1 = x0 + ey;                                  // scalar.h:114,115
+    const uint32_t m0 = __viaddmin_u32(x0, ex, b0);                             // new state 2j   stays at q0   scalar.h:113,127
+    const uint32_t m1 = __viaddmin_u32(x1, ex, a1);                             // new state 2j+1 goes to q1    scalar.h:116,128
     x0 = m0;
     x1 = m1;
 }
@@ -79,31 +78,36 @@ __device__ __forceinline__ void hc_bfly(uint32_t& x0, uint32_t& x1, const uint32
 template <int TIE_SIMD>
 __host__ __device__ constexpr bool hc_tagged(int q, int nextbit) { return (((q >> nextbit) & 1) != 0) != (TIE_SIMD != 0); }
 
+// the four butterflies whose lower registers are Q, Q | p1, Q | p2, Q | p1 | p2 (p1, p2: the pairing bits): one table fetch
 template <class C, int PH, int TIE_SIMD, int Q>
-__device__ __forceinline__ void hc_bfly_pair_at(uint32_t (&x)[HistCtaShape<C>::NL], const uint4* tbl_ph, const uint32_t mpt) {
+__device__ __forceinline__ void hc_bfly_quad_at(uint32_t (&x)[HistCtaShape<C>::NL], const uint4* tbl_ph, const uint32_t mpt, const uint32_t cplain,
+                                                const uint32_t cpre) {
     using H = HistCtaShape<C>;
-    constexpr PairMap M = pair_map<C, H::LOGT, true>(PH);
-    static_assert(M.pb >= 0, "no pairing bit with a non-zero pattern");
-    constexpr int bit = 1 << (H::LB - 1 - PH), pbit = 1 << M.pb;
-    if constexpr ((Q & bit) == 0 && (Q & pbit) == 0) {
-        constexpr int a0 = Q, a1 = Q | bit, b0 = Q | pbit, b1 = Q | pbit | bit;
-        constexpr uint32_t pa = bfly_pattern<C>(rotl_bits(uint32_t(a0) << H::LOGT, PH, H::SB));   // register-bit part of the old state index
-        constexpr uint32_t pb = bfly_pattern<C>(rotl_bits(uint32_t(b0) << H::LOGT, PH, H::SB));
-        constexpr uint32_t ia = pair_apply(M, C::R, pa);
-        static_assert(pair_apply(M, C::R, pb) == (ia ^ 1u), "paired butterflies must sit in one table slot");
+    constexpr PairMap M = pair_map<C, H::LOGT, true, 2>(PH);
+    static_assert(M.pb[0] >= 0 && M.pb[1] >= 0, "no two pairing bits with independent patterns");
+    static_assert(pair_map_conflict_free<C, H::LOGT, true, 2>(PH), "table fetch with shared-memory bank conflicts inside a quarter warp");
+    constexpr int bit = 1 << (H::LB - 1 - PH), p1 = 1 << M.pb[0], p2 = 1 << M.pb[1];
+    if constexpr ((Q & (bit | p1 | p2)) == 0) {
+        constexpr uint32_t ia = pair_apply(M, C::R, bfly_pattern<C>(rotl_bits(uint32_t(Q) << H::LOGT, PH, H::SB)));   // register-bit part of the old state index
+        static_assert(pair_apply(M, C::R, bfly_pattern<C>(rotl_bits(uint32_t(Q | p1) << H::LOGT, PH, H::SB))) == (ia ^ 1u) &&
+                      pair_apply(M, C::R, bfly_pattern<C>(rotl_bits(uint32_t(Q | p2) << H::LOGT, PH, H::SB))) == (ia ^ 2u),
+                      "the butterflies of a quad must sit in one table slot");
         // entries with the next step's tag added: both results of a butterfly land in the same half of the next step's butterflies.
-        // Before an exchange that half is a thread bit: mpt carries the offset then.
+        // Before an exchange that half is a thread bit: mpt and cplain = cpre carry the choice then.
         constexpr bool pre = (PH < H::LB - 1) && hc_tagged<TIE_SIMD>(Q, H::LB - 2 - PH);
-        const uint4 e = tbl_ph[(ia ^ mpt) + (pre ? uint32_t(H::NP) : 0u)];   // {total, inverted} of a, of b   (scalar.h:66-73, 107)
-        hc_bfly<TIE_SIMD>(x[a0], x[a1], e.x, e.y);
-        hc_bfly<TIE_SIMD>(x[b0], x[b1], e.z, e.w);
+        const uint4 e = tbl_ph[(ia ^ mpt) + (pre ? uint32_t(H::NP) : 0u)];   // total_error of the four patterns   (scalar.h:66-73)
+        const uint32_t cq = pre ? cpre : cplain;
+        hc_bfly(x[Q], x[Q | bit], e.x, cq);
+        hc_bfly(x[Q | p1], x[Q | p1 | bit], e.y, cq);
+        hc_bfly(x[Q | p2], x[Q | p2 | bit], e.z, cq);
+        hc_bfly(x[Q | p1 | p2], x[Q | p1 | p2 | bit], e.w, cq);
     }
 }
 
 template <class C, int PH, int TIE_SIMD, int... Qs>
-__device__ __forceinline__ void hc_bfly_all(uint32_t (&x)[HistCtaShape<C>::NL], const uint4* tbl_ph, const uint32_t mpt,
-                                            std::integer_sequence<int, Qs...>) {
-    (hc_bfly_pair_at<C, PH, TIE_SIMD, Qs>(x, tbl_ph, mpt), ...);
+__device__ __forceinline__ void hc_bfly_all(uint32_t (&x)[HistCtaShape<C>::NL], const uint4* tbl_ph, const uint32_t mpt, const uint32_t cplain,
+                                            const uint32_t cpre, std::integer_sequence<int, Qs...>) {
+    (hc_bfly_quad_at<C, PH, TIE_SIMD, Qs>(x, tbl_ph, mpt, cplain, cpre), ...);
 }
 
 // slot part of thread t per phase; the phase before an exchange adds the offset of the tagged copy for the threads whose registers
@@ -111,7 +115,7 @@ __device__ __forceinline__ void hc_bfly_all(uint32_t (&x)[HistCtaShape<C>::NL], 
 template <class C, int TIE_SIMD, int... PHs>
 __device__ __forceinline__ void hc_thread_slots(uint32_t (&mpt)[sizeof...(PHs)], uint32_t t, std::integer_sequence<int, PHs...>) {
     using H = HistCtaShape<C>;
-    pair_thread_slots<C, H::LOGT, true>(mpt, t, std::integer_sequence<int, PHs...>{});
+    pair_thread_slots<C, H::LOGT, true, 2>(mpt, t, std::integer_sequence<int, PHs...>{});
     const bool top = ((t >> (H::LOGT - 1)) & 1u) != 0u;
     if (top != (TIE_SIMD != 0)) mpt[H::LB - 1] += uint32_t(H::NP);
 }
@@ -125,7 +129,7 @@ __global__ void __launch_bounds__(HistCtaShape<C>::T, MINB) acs_hist_cta_kernel(
     constexpr int LB = H::LB, NL = H::NL, NW = H::NW, R = C::R, NP = H::NP, SB = H::SB, LOGT = H::LOGT, HB = H::HB;
     extern __shared__ uint32_t smem[];
     uint32_t* xch = smem;                                             // [NS] exchange buffer = registers at the start of the group
-    uint4* tbl = reinterpret_cast<uint4*>(smem + H::XCH_WORDS);       // [LB][2][NP] {total, inverted} of slot idx, of slot idx ^ 1
+    uint4* tbl = reinterpret_cast<uint4*>(smem + H::XCH_WORDS);       // [LB][plain, tagged][NP] total errors of slots idx, idx ^ 1, idx ^ 2, idx ^ 3
     uint32_t* red = smem + H::XCH_WORDS + H::TBL_WORDS;               // [WARPS] reduction scratch
     uint32_t* flag = red + H::WARPS;                                  // [2] trigger flags
 
@@ -149,31 +153,29 @@ __global__ void __launch_bounds__(HistCtaShape<C>::T, MINB) acs_hist_cta_kernel(
     uint32_t* rec = static_cast<uint32_t*>(p.dec) + f * size_t(n_periods) * (size_t(C::NS) / 2) + t * 4;
     const int16_t* row = reinterpret_cast<const int16_t*>(static_cast<const uint8_t*>(p.sym) + f * p.sym_row_bytes);
 
-    // branch metric tables of the n steps of the group that starts at first_step, one pattern per thread (320 of the 512), each stored
-    // as "own" member of its slot and "partner" member of the neighbouring slot, plain and with the next step's tag added
+    // branch metric tables of the n steps of the group that starts at first_step, one pattern per thread (320 of the 512), stored as
+    // a member of the four slots that use it, plain and with the next step's tag added
     auto build_tables = [&](uint32_t first_step, uint32_t n) {
         if (t < uint32_t(LB * NP)) {
             const uint32_t tph = t / NP, pat = t % NP;
             if (tph < n) {
                 const int16_t* sy = row + size_t(first_step + tph) * R;
-                uint32_t tot = 0, inv = c.c_inv;
+                uint32_t tot = 0;
 #pragma unroll
                 for (int i = 0; i < R; i++) {
                     const uint32_t sv = uint32_t(uint16_t(__ldg(sy + i))) << 16;
                     const uint32_t lo = sv + c.c_low, hi = c.c_high - sv;       // s - low, high - s  (scalar.h:96-105 for s in [low, high])
-                    const bool bb = (pat >> i) & 1u;
-                    tot += bb ? hi : lo;                    // viterbi_branch_table.h:52 + scalar.h:66-73
-                    inv += bb ? lo : hi;                    // scalar.h:107 (max_error - total): complementary pattern + c_inv
+                    tot += ((pat >> i) & 1u) ? hi : lo;     // viterbi_branch_table.h:52 + scalar.h:66-73
                 }
-                const uint32_t step = first_step + tph, k = step % uint32_t(HB);
-                // no tag for the step after a record cut (the cut sets it) and none after the last step
-                const uint32_t nxt = (k == uint32_t(HB - 1) || step + 1u == p.n_steps) ? 0u : (2u << k);
-                const uint32_t idx = pair_apply_phase<C, LOGT, true>(tph, pat, std::make_integer_sequence<int, LB>{});
-                uint2* t2 = reinterpret_cast<uint2*>(tbl + size_t(tph) * 2 * NP);
-                t2[2 * idx] = make_uint2(tot, inv);
-                t2[2 * (idx ^ 1u) + 1] = make_uint2(tot, inv);
-                t2[2 * (NP + idx)] = make_uint2(tot + nxt, inv + nxt);
-                t2[2 * (NP + (idx ^ 1u)) + 1] = make_uint2(tot + nxt, inv + nxt);
+                // the tag of the next step; none behind a record cut (the cut sets it)
+                const uint32_t nxt = (2u << ((first_step + tph) % uint32_t(HB))) & 0xffffu;
+                const uint32_t idx = pair_apply_phase<C, LOGT, true, 2>(tph, pat, std::make_integer_sequence<int, LB>{});
+                uint32_t* tw = reinterpret_cast<uint32_t*>(tbl + size_t(tph) * 2 * NP);
+#pragma unroll
+                for (uint32_t j = 0; j < 4; j++) {                              // member j of slot idx ^ j
+                    tw[(idx ^ j) * 4 + j] = tot;
+                    tw[(NP + (idx ^ j)) * 4 + j] = tot + nxt;
+                }
             }
         }
     };
@@ -182,18 +184,19 @@ __global__ void __launch_bounds__(HistCtaShape<C>::T, MINB) acs_hist_cta_kernel(
     // history record of the period that just ended (position order), then clear the history fields and set the tag of the next
     // period's first step, whose path-1 operands are the registers with bit NEXTBIT set
     auto emit_record = [&](auto nextbit) {
-        constexpr int NEXTBIT = decltype(nextbit)::value;
+        constexpr int NEXTBIT = decltype(nextbit)::value;         // -1: the last, partial record of the frame
         uint32_t w[NW];
 #pragma unroll
         for (int i = 0; i < NW; i++) {
             w[i] = __byte_perm(x[2 * i], x[2 * i + 1], 0x5410u);
-            if constexpr (TIE_SIMD) w[i] = ~w[i] & (0x00010001u * ((1u << pst) - 1u));      // the tag marked path 0: decision = !tag
+            if constexpr (TIE_SIMD) w[i] = ~w[i];                                          // the tag marked path 0: decision = !tag
+            if constexpr (TIE_SIMD || NEXTBIT < 0) w[i] &= 0x00010001u * ((1u << pst) - 1u);   // bits of steps not taken (and the last step's tag for a step that never comes)
         }
         uint32_t* dst = rec + size_t(r) * (size_t(C::NS) / 2);
 #pragma unroll
         for (int v = 0; v < NW / 4; v++) *reinterpret_cast<uint4*>(dst + size_t(v) * (H::T * 4)) = make_uint4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
 #pragma unroll
-        for (int q = 0; q < NL; q++) x[q] = (x[q] & 0xffff0000u) | (hc_tagged<TIE_SIMD>(q, NEXTBIT) ? 1u : 0u);
+        for (int q = 0; q < NL; q++) x[q] = (x[q] & 0xffff0000u) | ((NEXTBIT >= 0 && hc_tagged<TIE_SIMD>(q, NEXTBIT)) ? 1u : 0u);
         r++;
         pst = 0;
     };
@@ -210,6 +213,20 @@ __global__ void __launch_bounds__(HistCtaShape<C>::T, MINB) acs_hist_cta_kernel(
         for (int w = 1; w < H::WARPS; w++) rr = min(rr, red[w]);
         __syncthreads();
         return rr;
+    };
+
+    // max_error << 16 = total + inverted error of any pattern (scalar.h:107); with twice the next step's tag for the tagged entries
+    const uint32_t cplain = c.c_inv + uint32_t(R) * (c.c_low + c.c_high);
+    const bool tag_behind_exchange = (((t >> (LOGT - 1)) & 1u) != 0u) != (TIE_SIMD != 0);
+    auto run_bfly = [&](auto PHc) {
+        constexpr int PH = decltype(PHc)::value;
+        const uint32_t cpre = cplain + ((4u << pst) & 0x1fffeu);
+        if constexpr (PH == LB - 1) {
+            const uint32_t cl = tag_behind_exchange ? cpre : cplain;
+            hc_bfly_all<C, PH, TIE_SIMD>(x, tbl + PH * 2 * NP, mpt[PH], cl, cl, std::make_integer_sequence<int, NL>{});
+        } else {
+            hc_bfly_all<C, PH, TIE_SIMD>(x, tbl + PH * 2 * NP, mpt[PH], cplain, cpre, std::make_integer_sequence<int, NL>{});
+        }
     };
 
     uint32_t done = 0;
@@ -229,7 +246,7 @@ __global__ void __launch_bounds__(HistCtaShape<C>::T, MINB) acs_hist_cta_kernel(
             constexpr int PH = decltype(PHc)::value;
             constexpr bool GUARD = decltype(guard_tag)::value;
             if constexpr (GUARD) { if (uint32_t(PH) >= span) return; }
-            hc_bfly_all<C, PH, TIE_SIMD>(x, tbl + PH * 2 * NP, mpt[PH], std::make_integer_sequence<int, NL>{});
+            run_bfly(PHc);
             mx = max(mx, x[0]);
             pst++;
             if constexpr (PH != LB - 1) { if (pst == uint32_t(HB)) emit_record(std::integral_constant<int, LB - 2 - PH>{}); }     // after the last phase: behind the exchange
@@ -258,7 +275,7 @@ __global__ void __launch_bounds__(HistCtaShape<C>::T, MINB) acs_hist_cta_kernel(
             auto replay_phase = [&](auto PHc) {
                 constexpr int PH = decltype(PHc)::value;
                 if (uint32_t(PH) < span) {
-                    hc_bfly_all<C, PH, TIE_SIMD>(x, tbl + PH * 2 * NP, mpt[PH], std::make_integer_sequence<int, NL>{});
+                    run_bfly(PHc);
                     pst++;
                     if (t == 0) flag[1] = x[0];
                     __syncthreads();
@@ -308,7 +325,7 @@ __global__ void __launch_bounds__(HistCtaShape<C>::T, MINB) acs_hist_cta_kernel(
             }
         }
     }
-    if (pst) emit_record(std::integral_constant<int, 0>{});  // last, partial record (its pst is still needed for the SIMD tie-break mask)
+    if (pst) emit_record(std::integral_constant<int, -1>{}); // last, partial record (its pst is still needed for the SIMD tie-break mask)
 
     // final metrics in logical order: state s sits at PHI = rotr^ph(s)   (core.h:195-199 reads old_metrics[end_state])
     const uint32_t ph = p.n_steps % uint32_t(LB);
