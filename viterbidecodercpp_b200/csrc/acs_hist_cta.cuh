@@ -12,8 +12,10 @@
 //   * traceback reads one halfword per 16 steps and frame instead of one word per step.
 //
 // Position algebra of acs_cta.cuh with LOGT = 9: PHI = (q << 9) | t; n steps after an exchange state s sits at PHI = rotr^n(s);
-// LB = 5 register-only steps, then the CTA exchanges through 64 KB of shared memory (skewed, conflict-free) under two
-// __syncthreads.  The branch metric table of a whole group ({total, inverted} x 64 patterns x 5 steps, metric field format) is built
+// LB = 5 register-only steps, then the CTA exchanges through 64 KB of shared memory (skewed, conflict-free).  Exchange buffer
+// and tables are double-buffered: the last step of a group stores its results into the other buffer as they are produced, the
+// tables of the next group are built (from symbols prefetched a group earlier) while the current one runs, and ONE __syncthreads
+// per group separates the stores from the loads.  The branch metric table of a whole group ({total, inverted} x 64 patterns x 5 steps, metric field format) is built
 // cooperatively from the caller's int16_t row (read where it lies: unpunctured input only, any alignment) at each exchange.
 //
 // TABLE FETCH: the kernel is bound by shared-memory wavefronts (table fetch + exchange), not by issue slots, so the table holds
@@ -54,7 +56,7 @@ struct HistCtaShape {
     static_assert(SB == 14 && LB == 5 && NL == 32, "built for K = 15");
     static constexpr size_t XCH_WORDS = (S::XCH_WORDS + 3) / 4 * 4;                 // the table behind it holds 16-byte slots
     static constexpr size_t TBL_WORDS = size_t(LB) * 2 * NP * 4;                    // [LB][plain, next tag added][NP] x 4 total errors
-    static constexpr size_t SMEM_BYTES = (XCH_WORDS + TBL_WORDS + 64) * 4;
+    static constexpr size_t SMEM_BYTES = (2 * XCH_WORDS + 2 * TBL_WORDS + 64) * 4;  // both double-buffered (156 KB: one CTA per SM)
 };
 
 __host__ __device__ constexpr uint32_t rotl_rt(uint32_t v, uint32_t r, uint32_t n) {
@@ -79,9 +81,11 @@ template <int TIE_SIMD>
 __host__ __device__ constexpr bool hc_tagged(int q, int nextbit) { return (((q >> nextbit) & 1) != 0) != (TIE_SIMD != 0); }
 
 // the four butterflies whose lower registers are Q, Q | p1, Q | p2, Q | p1 | p2 (p1, p2: the pairing bits): one table fetch
-template <class C, int PH, int TIE_SIMD, int Q>
+// xout != nullptr (last phase of a full group): the eight results go straight to the other exchange buffer, position (t << LB) | q,
+// so that the stores of the exchange run under the butterflies of the phase instead of behind a barrier
+template <class C, int PH, int TIE_SIMD, bool STORE, int Q>
 __device__ __forceinline__ void hc_bfly_quad_at(uint32_t (&x)[HistCtaShape<C>::NL], const uint4* tbl_ph, const uint32_t mpt, const uint32_t cplain,
-                                                const uint32_t cpre) {
+                                                const uint32_t cpre, uint32_t* xout) {
     using H = HistCtaShape<C>;
     constexpr PairMap M = pair_map<C, H::LOGT, true, 2>(PH);
     static_assert(M.pb[0] >= 0 && M.pb[1] >= 0, "no two pairing bits with independent patterns");
@@ -101,13 +105,20 @@ __device__ __forceinline__ void hc_bfly_quad_at(uint32_t (&x)[HistCtaShape<C>::N
         hc_bfly(x[Q | p1], x[Q | p1 | bit], e.y, cq);
         hc_bfly(x[Q | p2], x[Q | p2 | bit], e.z, cq);
         hc_bfly(x[Q | p1 | p2], x[Q | p1 | p2 | bit], e.w, cq);
+        if constexpr (STORE) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                constexpr int qs[8] = {Q, Q | bit, Q | p1, Q | p1 | bit, Q | p2, Q | p2 | bit, Q | p1 | p2, Q | p1 | p2 | bit};
+                xout[qs[k]] = x[qs[k]];                      // xout = buffer + slot(t << LB): slot((t << LB) | q) = slot(t << LB) + q
+            }
+        }
     }
 }
 
-template <class C, int PH, int TIE_SIMD, int... Qs>
+template <class C, int PH, int TIE_SIMD, bool STORE, int... Qs>
 __device__ __forceinline__ void hc_bfly_all(uint32_t (&x)[HistCtaShape<C>::NL], const uint4* tbl_ph, const uint32_t mpt, const uint32_t cplain,
-                                            const uint32_t cpre, std::integer_sequence<int, Qs...>) {
-    (hc_bfly_quad_at<C, PH, TIE_SIMD, Qs>(x, tbl_ph, mpt, cplain, cpre), ...);
+                                            const uint32_t cpre, uint32_t* xout, std::integer_sequence<int, Qs...>) {
+    (hc_bfly_quad_at<C, PH, TIE_SIMD, STORE, Qs>(x, tbl_ph, mpt, cplain, cpre, xout), ...);
 }
 
 // slot part of thread t per phase; the phase before an exchange adds the offset of the tagged copy for the threads whose registers
@@ -128,10 +139,13 @@ __global__ void __launch_bounds__(HistCtaShape<C>::T, MINB) acs_hist_cta_kernel(
     using S = typename H::S;
     constexpr int LB = H::LB, NL = H::NL, NW = H::NW, R = C::R, NP = H::NP, SB = H::SB, LOGT = H::LOGT, HB = H::HB;
     extern __shared__ uint32_t smem[];
-    uint32_t* xch = smem;                                             // [NS] exchange buffer = registers at the start of the group
-    uint4* tbl = reinterpret_cast<uint4*>(smem + H::XCH_WORDS);       // [LB][plain, tagged][NP] total errors of slots idx, idx ^ 1, idx ^ 2, idx ^ 3
-    uint32_t* red = smem + H::XCH_WORDS + H::TBL_WORDS;               // [WARPS] reduction scratch
-    uint32_t* flag = red + H::WARPS;                                  // [2] trigger flags
+    // Two exchange buffers and two table sets, used in turn (cur): buffer cur = the registers at the start of the current group
+    // (read back by the exchange, kept for the rollback), the other one takes the results of the group while it still runs.
+    uint32_t* xch0 = smem;                                            // [2][NS (skewed)]
+    uint4* tbl0 = reinterpret_cast<uint4*>(smem + 2 * H::XCH_WORDS);  // [2][LB][plain, tagged][NP] total errors of slots idx, idx ^ 1, idx ^ 2, idx ^ 3
+    uint32_t* red = smem + 2 * H::XCH_WORDS + 2 * H::TBL_WORDS;       // [WARPS] reduction scratch
+    uint32_t* flag = red + H::WARPS;                                  // [0..1] trigger flag of the groups in turn, [2] replay scratch
+    static_assert(H::WARPS + 3 <= 64, "scratch words");
 
     const uint32_t t = threadIdx.x;
     const size_t f = blockIdx.x;
@@ -155,7 +169,7 @@ __global__ void __launch_bounds__(HistCtaShape<C>::T, MINB) acs_hist_cta_kernel(
 
     // branch metric tables of the n steps of the group that starts at first_step, one pattern per thread (320 of the 512), stored as
     // a member of the four slots that use it, plain and with the next step's tag added
-    auto build_tables = [&](uint32_t first_step, uint32_t n) {
+    auto build_tables = [&](uint4* tbl, uint32_t first_step, uint32_t n) {
         if (t < uint32_t(LB * NP)) {
             const uint32_t tph = t / NP, pat = t % NP;
             if (tph < n) {
@@ -218,40 +232,63 @@ __global__ void __launch_bounds__(HistCtaShape<C>::T, MINB) acs_hist_cta_kernel(
     // max_error << 16 = total + inverted error of any pattern (scalar.h:107); with twice the next step's tag for the tagged entries
     const uint32_t cplain = c.c_inv + uint32_t(R) * (c.c_low + c.c_high);
     const bool tag_behind_exchange = (((t >> (LOGT - 1)) & 1u) != 0u) != (TIE_SIMD != 0);
-    auto run_bfly = [&](auto PHc) {
+    auto run_bfly = [&](auto PHc, auto store_tag, const uint4* tbl, uint32_t* xout) {
         constexpr int PH = decltype(PHc)::value;
+        constexpr bool STORE = decltype(store_tag)::value;
         const uint32_t cpre = cplain + ((4u << pst) & 0x1fffeu);
         if constexpr (PH == LB - 1) {
             const uint32_t cl = tag_behind_exchange ? cpre : cplain;
-            hc_bfly_all<C, PH, TIE_SIMD>(x, tbl + PH * 2 * NP, mpt[PH], cl, cl, std::make_integer_sequence<int, NL>{});
+            hc_bfly_all<C, PH, TIE_SIMD, STORE>(x, tbl + PH * 2 * NP, mpt[PH], cl, cl, xout, std::make_integer_sequence<int, NL>{});
         } else {
-            hc_bfly_all<C, PH, TIE_SIMD>(x, tbl + PH * 2 * NP, mpt[PH], cplain, cpre, std::make_integer_sequence<int, NL>{});
+            hc_bfly_all<C, PH, TIE_SIMD, false>(x, tbl + PH * 2 * NP, mpt[PH], cplain, cpre, xout, std::make_integer_sequence<int, NL>{});
+        }
+    };
+    // the symbols of a group are pulled into L1 one group ahead of the table build that reads them
+    auto prefetch_symbols = [&](uint32_t first_step) {
+        if (t < uint32_t(LB)) {
+            const uint32_t st = first_step + t;
+            if (st < p.n_steps) asm volatile("prefetch.global.L1 [%0];" ::"l"(row + size_t(st) * R));
         }
     };
 
-    uint32_t done = 0;
-    // prologue: the exchange buffer always holds the registers at the start of the current group (for the rollback)
+    uint32_t done = 0, cur = 0;
+    // prologue: buffer 0 holds the registers at the start of group 0, table set 0 its tables
 #pragma unroll
-    for (int q = 0; q < NL; q++) xch[S::slot((uint32_t(q) << LOGT) | t)] = x[q];
-    if (p.n_steps) build_tables(0u, p.n_steps < uint32_t(LB) ? p.n_steps : uint32_t(LB));
+    for (int q = 0; q < NL; q++) xch0[S::slot((uint32_t(q) << LOGT) | t)] = x[q];
+    if (p.n_steps) build_tables(tbl0, 0u, p.n_steps < uint32_t(LB) ? p.n_steps : uint32_t(LB));
+    prefetch_symbols(uint32_t(LB));
     __syncthreads();
 
     while (done < p.n_steps) {
         const uint32_t left = p.n_steps - done, span = left < uint32_t(LB) ? left : uint32_t(LB);
         const uint32_t pst0 = pst, r0 = r;
+        const bool full = span == uint32_t(LB);
+        uint32_t* xcur = xch0 + size_t(cur) * H::XCH_WORDS;
+        uint32_t* xnew = xch0 + size_t(cur ^ 1u) * H::XCH_WORDS;
+        const uint4* tcur = tbl0 + size_t(cur) * (H::TBL_WORDS / 4);
+        uint4* tnew = tbl0 + size_t(cur ^ 1u) * (H::TBL_WORDS / 4);
 
-        // ---- speculative run of the group (no renormalisation); thread 0 keeps the running maximum of state 0's register
+        // ---- tables of the NEXT group into the other set (every thread left that set at the barrier of the previous group, or at
+        //      the one behind its replay), symbols of the group after that on their way
+        if (full && done + uint32_t(LB) < p.n_steps) {
+            const uint32_t nleft = p.n_steps - done - uint32_t(LB);
+            build_tables(tnew, done + uint32_t(LB), nleft < uint32_t(LB) ? nleft : uint32_t(LB));
+            prefetch_symbols(done + 2u * uint32_t(LB));
+        }
+
+        // ---- speculative run of the group (no renormalisation); thread 0 keeps the running maximum of state 0's register.
+        //      The last phase of a full group stores its results into the other exchange buffer as they are produced.
         uint32_t mx = 0u;
         auto spec_phase = [&](auto PHc, auto guard_tag) {
             constexpr int PH = decltype(PHc)::value;
             constexpr bool GUARD = decltype(guard_tag)::value;
             if constexpr (GUARD) { if (uint32_t(PH) >= span) return; }
-            run_bfly(PHc);
+            run_bfly(PHc, std::integral_constant<bool, !GUARD>{}, tcur, xnew + S::slot(t << LB));
             mx = max(mx, x[0]);
             pst++;
             if constexpr (PH != LB - 1) { if (pst == uint32_t(HB)) emit_record(std::integral_constant<int, LB - 2 - PH>{}); }     // after the last phase: behind the exchange
         };
-        if (span == uint32_t(LB)) {
+        if (full) {
             spec_phase(std::integral_constant<int, 0>{}, std::false_type{});
             spec_phase(std::integral_constant<int, 1>{}, std::false_type{});
             spec_phase(std::integral_constant<int, 2>{}, std::false_type{});
@@ -263,30 +300,30 @@ __global__ void __launch_bounds__(HistCtaShape<C>::T, MINB) acs_hist_cta_kernel(
             spec_phase(std::integral_constant<int, 2>{}, std::true_type{});
             spec_phase(std::integral_constant<int, 3>{}, std::true_type{});
         }
-        if (t == 0) flag[0] = (mx >= c.thr) ? 1u : 0u;       // metric >= threshold  <=>  register >= threshold << 16
-        __syncthreads();                                     // B1: all steps done, tables and exchange buffer free again
-        const uint32_t any_trig = flag[0];
+        if (t == 0) flag[cur] = (mx >= c.thr) ? 1u : 0u;     // metric >= threshold  <=>  register >= threshold << 16
+        __syncthreads();                                     // the ONE barrier of a group: steps done, results and next tables in place
+        const uint32_t any_trig = flag[cur];                 // (the flag word of the next group is the other one)
 
         if (any_trig) {
             // ---- roll back (registers and record bookkeeping) and replay step by step with the reference's renormalisation
 #pragma unroll
-            for (int q = 0; q < NL; q++) x[q] = xch[S::slot((uint32_t(q) << LOGT) | t)];
+            for (int q = 0; q < NL; q++) x[q] = xcur[S::slot((uint32_t(q) << LOGT) | t)];
             pst = pst0; r = r0;
             auto replay_phase = [&](auto PHc) {
                 constexpr int PH = decltype(PHc)::value;
                 if (uint32_t(PH) < span) {
-                    run_bfly(PHc);
+                    run_bfly(PHc, std::false_type{}, tcur, xnew);
                     pst++;
-                    if (t == 0) flag[1] = x[0];
+                    if (t == 0) flag[2] = x[0];
                     __syncthreads();
-                    const uint32_t x00 = flag[1];
+                    const uint32_t x00 = flag[2];
                     if (x00 >= c.thr) {                                    // uniform across the CTA (scalar.h:48)
                         const uint32_t sub = cta_min() & 0xffff0000u;      // scalar.h:140-146
 #pragma unroll
                         for (int q = 0; q < NL; q++) x[q] -= sub;          // scalar.h:148-150
                         acc += uint64_t(sub >> 16);                        // scalar.h:49, 152 (only thread 0's copy is stored)
                     } else {
-                        __syncthreads();                                   // flag[1] may be rewritten by the next phase
+                        __syncthreads();                                   // flag[2] may be rewritten by the next phase
                     }
                     if constexpr (PH != LB - 1) { if (pst == uint32_t(HB)) emit_record(std::integral_constant<int, LB - 2 - PH>{}); }
                 }
@@ -296,32 +333,27 @@ __global__ void __launch_bounds__(HistCtaShape<C>::T, MINB) acs_hist_cta_kernel(
             replay_phase(std::integral_constant<int, 2>{});
             replay_phase(std::integral_constant<int, 3>{});
             replay_phase(std::integral_constant<int, 4>{});
+            if (full) {
+                // the exchange of the replayed group: value at (q, t) moves to PHI' = (t << LB) | q
+#pragma unroll
+                for (int q = 0; q < NL; q++) xnew[S::slot((t << LB) | uint32_t(q))] = x[q];
+            }
             __syncthreads();
         }
 
         done += span;
-        const bool full = span == uint32_t(LB);
         if (full) {
-            // ---- exchange: value at (q, t) moves to PHI' = (t << LB) | q, bringing the layout back to PHI = s
+            // ---- exchange, read side: positions back to PHI = s.  The buffer just read is the rollback copy of the next group; the
+            //      other one is written again only in the last phase of the next group, behind every thread's loads.
 #pragma unroll
-            for (int q = 0; q < NL; q++) xch[S::slot((t << LB) | uint32_t(q))] = x[q];
-        }
-        if (done < p.n_steps) {
-            const uint32_t nleft = p.n_steps - done;
-            build_tables(done, nleft < uint32_t(LB) ? nleft : uint32_t(LB));
-        }
-        __syncthreads();                                     // B2: exchange data and the next group's tables are in place
-        if (full) {
-#pragma unroll
-            for (int q = 0; q < NL; q++) x[q] = xch[S::slot((uint32_t(q) << LOGT) | t)];
-            // no barrier needed here: the buffer is next written after B1 of the next group, which every thread reaches only
-            // after these loads; until then it doubles as the rollback copy of the group's starting registers
+            for (int q = 0; q < NL; q++) x[q] = xnew[S::slot((uint32_t(q) << LOGT) | t)];
+            cur ^= 1u;
             if (pst == uint32_t(HB)) {
                 emit_record(std::integral_constant<int, LB - 1>{});   // records are cut in the layout the traceback expects: PHI = rotr^(steps mod 5)(s)
                 // the rollback copy must match the registers the next group starts from (history fields cleared); every thread
                 // rewrites exactly the words it has just read and will read back on a rollback: no barrier needed
 #pragma unroll
-                for (int q = 0; q < NL; q++) xch[S::slot((uint32_t(q) << LOGT) | t)] = x[q];
+                for (int q = 0; q < NL; q++) xnew[S::slot((uint32_t(q) << LOGT) | t)] = x[q];
             }
         }
     }
