@@ -36,7 +36,7 @@ struct CtaShape {
     static constexpr int WARPS = T / 32;
     static constexpr size_t XCH_WORDS = size_t(C::NS) + size_t(C::NS) / 32 + 32;   // skewed by one word per 32
     static constexpr size_t TBL_WORDS = size_t(LB) * NP * 2;
-    static constexpr size_t SMEM_BYTES = (XCH_WORDS + TBL_WORDS + 64) * 4;
+    static constexpr size_t SMEM_BYTES = (2 * XCH_WORDS + 2 * TBL_WORDS + 64) * 4;   // exchange buffer and tables are double-buffered
     // Skew instead of XOR so that every access is (per-thread base) + (compile-time offset): the exchange writes position
     // (t << LB) | q -> word 33t + q (LB = 5) and reads (q << LOGT) | t -> word q * (T + T/32) + t + (t >> 5); both hit 32 distinct
     // banks per warp (tests/test_host_cpu.py::test_cta_exchange_skew_is_conflict_free).
@@ -163,8 +163,11 @@ template <int NL> struct CtaAcc { static constexpr int value = NL >= 32 ? 4 : (N
 #endif
 constexpr int CTA_CHAINS = VITB_CTA_CHAINS;          // chains per decision byte (1, 2 or 4)
 
-template <class C, int LT, int PH, int TIE_SIMD, int Q>
-__device__ __forceinline__ void cta_bfly_at(uint32_t (&x)[CtaShape<C, LT>::NL], const uint2* tbl_ph, const uint32_t pt, float (&fa)[2][CtaAcc<CtaShape<C, LT>::NL>::value][CTA_CHAINS]) {
+// STORE (last phase of a full group): both results go straight to the other exchange buffer, xout = buffer + slot(t << LB), so that
+// the stores of the exchange run under the butterflies of the phase instead of behind a barrier
+template <class C, int LT, int PH, int TIE_SIMD, bool STORE, int Q>
+__device__ __forceinline__ void cta_bfly_at(uint32_t (&x)[CtaShape<C, LT>::NL], const uint2* tbl_ph, const uint32_t pt, float (&fa)[2][CtaAcc<CtaShape<C, LT>::NL>::value][CTA_CHAINS],
+                                            uint32_t* xout) {
     using S = CtaShape<C, LT>;
     constexpr int bit = 1 << (S::LB - 1 - PH);
     if constexpr ((Q & bit) == 0) {
@@ -192,13 +195,14 @@ __device__ __forceinline__ void cta_bfly_at(uint32_t (&x)[CtaShape<C, LT>::NL], 
         if (dB0) fa[1][acc0][n0] += w0;
         if (dA1) fa[0][acc1][n1] += w1;
         if (dB1) fa[1][acc1][n1] += w1;
+        if constexpr (STORE) { xout[q0] = x[q0]; xout[q1] = x[q1]; }      // slot((t << LB) | q) = slot(t << LB) + q
     }
 }
 
-template <class C, int LT, int PH, int TIE_SIMD, int... Qs>
+template <class C, int LT, int PH, int TIE_SIMD, bool STORE, int... Qs>
 __device__ __forceinline__ void cta_bfly_all(uint32_t (&x)[CtaShape<C, LT>::NL], const uint2* tbl_ph, const uint32_t pt, float (&fa)[2][CtaAcc<CtaShape<C, LT>::NL>::value][CTA_CHAINS],
-                                             std::integer_sequence<int, Qs...>) {
-    (cta_bfly_at<C, LT, PH, TIE_SIMD, Qs>(x, tbl_ph, pt, fa), ...);
+                                             uint32_t* xout, std::integer_sequence<int, Qs...>) {
+    (cta_bfly_at<C, LT, PH, TIE_SIMD, STORE, Qs>(x, tbl_ph, pt, fa, xout), ...);
 }
 
 template <class C, int LT, int SH, int TIE_SIMD>
@@ -209,8 +213,8 @@ struct CtaKernel {
     // one trellis step at compile-time phase PH; decisions to dec_row (this thread's uint2 of the row)
     static constexpr int W = NL > 16 ? 2 : 1;     // 32-bit decision words per thread and step
     // dec_row: this thread's W words of the row.  NL = 32: {A word, B word}; NL = 16: one word, A bits | B bits << 16
-    template <int PH>
-    static __device__ __forceinline__ void step(uint32_t (&x)[NL], const uint2* tbl, const uint32_t (&pt)[LB], uint32_t* dec_row) {
+    template <int PH, bool STORE = false>
+    static __device__ __forceinline__ void step(uint32_t (&x)[NL], const uint2* tbl, const uint32_t (&pt)[LB], uint32_t* dec_row, uint32_t* xout = nullptr) {
         constexpr int NACC = CtaAcc<NL>::value;
         float fn[2][NACC][CTA_CHAINS];
 #pragma unroll
@@ -218,7 +222,7 @@ struct CtaKernel {
 #pragma unroll
             for (int c = 0; c < CTA_CHAINS; c++) { fn[0][a][c] = c ? 0.f : 8388608.f; fn[1][a][c] = c ? 0.f : 8388608.f; }
         }
-        cta_bfly_all<C, LT, PH, TIE_SIMD>(x, tbl + PH * NP, pt[PH], fn, std::make_integer_sequence<int, NL>{});
+        cta_bfly_all<C, LT, PH, TIE_SIMD, STORE>(x, tbl + PH * NP, pt[PH], fn, xout, std::make_integer_sequence<int, NL>{});
         float fa[2][NACC];
 #pragma unroll
         for (int a = 0; a < NACC; a++) {
@@ -267,10 +271,13 @@ __global__ void __launch_bounds__(CtaShape<C, LT>::T, 1) acs_cta_kernel(const Ac
     using Kn = CtaKernel<C, LT, SH, TIE_SIMD>;
     constexpr int LB = S::LB, NL = S::NL, R = C::R, NP = C::NP, SB = S::SB, LOGT = S::LOGT;
     extern __shared__ uint32_t smem[];
-    uint32_t* xch = smem;                                             // [NS] exchange buffer = metrics at the start of the group
-    uint2* tbl = reinterpret_cast<uint2*>(smem + S::XCH_WORDS);       // [LB][NP] {total, inverted}
-    uint32_t* red = smem + S::XCH_WORDS + S::TBL_WORDS;               // [WARPS] reduction scratch
-    uint32_t* flag = red + S::WARPS;                                  // [2] trigger flags
+    // Two exchange buffers and two table sets, used in turn (cur): buffer cur = the metrics at the start of the current group (read
+    // back by the exchange, kept for the rollback), the other one takes the results of the group while it still runs.
+    uint32_t* xch0 = smem;                                            // [2][NS (skewed)]
+    uint2* tbl0 = reinterpret_cast<uint2*>(smem + 2 * S::XCH_WORDS);  // [2][LB][NP] {total, inverted}
+    uint32_t* red = smem + 2 * S::XCH_WORDS + 2 * S::TBL_WORDS;       // [WARPS] reduction scratch
+    uint32_t* flag = red + S::WARPS;                                  // [0..1] trigger flag of the groups in turn, [2] replay scratch
+    static_assert(S::WARPS + 3 <= 64, "scratch words");
 
     const uint32_t t = threadIdx.x, pair = blockIdx.x;
     const size_t fA = size_t(pair) * 2, fB = fA + 1;
@@ -312,7 +319,7 @@ __global__ void __launch_bounds__(CtaShape<C, LT>::T, 1) acs_cta_kernel(const Ac
     uint32_t* dec = static_cast<uint32_t*>(p.dec) + ((size_t(pair) * p.dec_rows + p.dec_row0) * S::T + t) * W;
 
     // branch metric tables {total, inverted} of the steps of one group, built by the first LB*NP threads (one entry each)
-    auto build_tables = [&](uint32_t first_step, int first_phase, uint32_t n) {
+    auto build_tables = [&](uint2* tbl, uint32_t first_step, int first_phase, uint32_t n) {
         if (t < uint32_t(LB * NP)) {
             const int tph = int(t) / NP;
             const uint32_t pat = t % NP;
@@ -342,24 +349,48 @@ __global__ void __launch_bounds__(CtaShape<C, LT>::T, 1) acs_cta_kernel(const Ac
         return uint32_t(LB - ph_) < left ? uint32_t(LB - ph_) : left;
     };
 
-    uint32_t done = 0;
-    // prologue: the exchange buffer always holds the metrics at the start of the current group (for the rollback)
+    // the packed symbols of a group are pulled into L1 one group ahead of the table build that reads them
+    auto prefetch_symbols = [&](uint32_t first_step) {
+        if (t < uint32_t(LB)) {
+            const uint32_t st = first_step + t;
+            if (st < p.n_steps) asm volatile("prefetch.global.L1 [%0];" ::"l"(pk + size_t(st) * R));
+        }
+    };
+
+    uint32_t done = 0, cur = 0;
+    // prologue: buffer 0 holds the metrics at the start of the first group, table set 0 its tables
 #pragma unroll
-    for (int q = 0; q < NL; q++) xch[S::slot((uint32_t(q) << LOGT) | t)] = x[q];
-    if (p.n_steps) build_tables(0u, ph, group_span(0u, ph));
+    for (int q = 0; q < NL; q++) xch0[S::slot((uint32_t(q) << LOGT) | t)] = x[q];
+    if (p.n_steps) {
+        build_tables(tbl0, 0u, ph, group_span(0u, ph));
+        prefetch_symbols(group_span(0u, ph));
+    }
     __syncthreads();
 
     while (done < p.n_steps) {
         const uint32_t span = group_span(done, ph);        // steps in this group: phases ph .. ph+span-1
+        const bool full = uint32_t(ph) + span == uint32_t(LB);
         uint32_t* drow = dec + size_t(done) * S::T * W;
+        uint32_t* xcur = xch0 + size_t(cur) * S::XCH_WORDS;
+        uint32_t* xnew = xch0 + size_t(cur ^ 1u) * S::XCH_WORDS;
+        const uint2* tcur = tbl0 + size_t(cur) * (S::TBL_WORDS / 2);
+        uint2* tnew = tbl0 + size_t(cur ^ 1u) * (S::TBL_WORDS / 2);
+
+        // ---- tables of the NEXT group (it starts at phase 0) into the other set - every thread left that set at the barrier of the
+        //      previous group, or at the one behind its replay -, symbols of the group after that on their way
+        if (full && done + span < p.n_steps) {
+            build_tables(tnew, done + span, 0, group_span(done + span, 0));
+            prefetch_symbols(done + span + uint32_t(LB));
+        }
 
         // ---- speculative run of the group (no renormalisation).  The running maximum of register 0 is all the trigger test
         //      needs (thread 0 holds state 0 there): if it never reached the threshold, no step of the group renormalised.
+        //      The last phase of a complete group stores its results into the other exchange buffer as they are produced.
         uint32_t mx = 0u;
         if (ph == 0 && span == uint32_t(LB)) {
             auto fast_phase = [&](auto PHc) {
                 constexpr int PH = decltype(PHc)::value;
-                Kn::template step<PH>(x, tbl, pt, drow + size_t(PH) * S::T * W);
+                Kn::template step<PH, PH == LB - 1>(x, tcur, pt, drow + size_t(PH) * S::T * W, xnew + S::slot(t << LB));
                 mx = __vmaxu2(mx, x[0]);
             };
             fast_phase(std::integral_constant<int, 0>{});
@@ -371,7 +402,7 @@ __global__ void __launch_bounds__(CtaShape<C, LT>::T, 1) acs_cta_kernel(const Ac
             auto run_phase = [&](auto PHc) {
                 constexpr int PH = decltype(PHc)::value;
                 if (PH >= ph && uint32_t(PH - ph) < span) {
-                    Kn::template step<PH>(x, tbl, pt, drow + size_t(PH - ph) * S::T * W);
+                    Kn::template step<PH>(x, tcur, pt, drow + size_t(PH - ph) * S::T * W);
                     mx = __vmaxu2(mx, x[0]);
                 }
             };
@@ -380,26 +411,30 @@ __global__ void __launch_bounds__(CtaShape<C, LT>::T, 1) acs_cta_kernel(const Ac
             if constexpr (LB > 2) run_phase(std::integral_constant<int, 2>{});
             if constexpr (LB > 3) run_phase(std::integral_constant<int, 3>{});
             if constexpr (LB > 4) run_phase(std::integral_constant<int, 4>{});
+            if (full) {                                      // a group that started inside an exchange period (streaming API)
+#pragma unroll
+                for (int q = 0; q < NL; q++) xnew[S::slot((t << LB) | uint32_t(q))] = x[q];
+            }
         }
         if (t == 0) {
             bool tb, ta;
             (void)__vibmin_u16x2(p.thr2, mx, &tb, &ta);     // thr <= max over the group of state 0's metric
-            flag[0] = (ta || tb) ? 1u : 0u;
+            flag[cur] = (ta || tb) ? 1u : 0u;
         }
-        __syncthreads();                                     // B1: all steps done, tables and exchange buffer free again
-        const uint32_t any_trig = flag[0];
+        __syncthreads();                                     // the ONE barrier of a group: steps done, results and next tables in place
+        const uint32_t any_trig = flag[cur];                 // (the flag word of the next group is the other one)
 
         if (any_trig) {
             // ---- roll back and replay step by step with the reference's renormalisation (scalar.h:48-50, 139-153)
 #pragma unroll
-            for (int q = 0; q < NL; q++) x[q] = xch[S::slot((uint32_t(q) << LOGT) | t)];
+            for (int q = 0; q < NL; q++) x[q] = xcur[S::slot((uint32_t(q) << LOGT) | t)];
             auto replay_phase = [&](auto PHc) {
                 constexpr int PH = decltype(PHc)::value;
                 if (PH >= ph && uint32_t(PH - ph) < span) {
-                    Kn::template step<PH>(x, tbl, pt, drow + size_t(PH - ph) * S::T * W);
-                    if (t == 0) flag[1] = x[0];
+                    Kn::template step<PH>(x, tcur, pt, drow + size_t(PH - ph) * S::T * W);
+                    if (t == 0) flag[2] = x[0];
                     __syncthreads();
-                    const uint32_t x00 = flag[1];
+                    const uint32_t x00 = flag[2];
                     bool tb, ta;
                     (void)__vibmin_u16x2(p.thr2, x00, &tb, &ta);
                     if (ta || tb) {                                    // uniform across the CTA
@@ -412,7 +447,7 @@ __global__ void __launch_bounds__(CtaShape<C, LT>::T, 1) acs_cta_kernel(const Ac
                         if (ta) accA += uint64_t(mAv >> SH);
                         if (tb) accB += uint64_t(mBv >> SH);
                     } else {
-                        __syncthreads();                               // flag[1] may be rewritten by the next phase
+                        __syncthreads();                               // flag[2] may be rewritten by the next phase
                     }
                 }
             };
@@ -421,26 +456,24 @@ __global__ void __launch_bounds__(CtaShape<C, LT>::T, 1) acs_cta_kernel(const Ac
             if constexpr (LB > 2) replay_phase(std::integral_constant<int, 2>{});
             if constexpr (LB > 3) replay_phase(std::integral_constant<int, 3>{});
             if constexpr (LB > 4) replay_phase(std::integral_constant<int, 4>{});
+            if (full) {
+                // the exchange of the replayed group: value at (q, t) moves to PHI' = (t << LB) | q
+#pragma unroll
+                for (int q = 0; q < NL; q++) xnew[S::slot((t << LB) | uint32_t(q))] = x[q];
+            }
             __syncthreads();
         }
 
         done += span;
-        const bool full = uint32_t(ph) + span == uint32_t(LB);
         if (full) {
-            // ---- exchange: value at (q, t) moves to PHI' = (t << LB) | q, bringing the layout back to PHI = s
+            // ---- exchange, read side: the layout is back to PHI = s.  The buffer just read is the rollback copy of the next group;
+            //      the other one is written again only at the end of the next group, behind every thread's loads.
 #pragma unroll
-            for (int q = 0; q < NL; q++) xch[S::slot((t << LB) | uint32_t(q))] = x[q];
+            for (int q = 0; q < NL; q++) x[q] = xnew[S::slot((uint32_t(q) << LOGT) | t)];
+            cur ^= 1u;
             ph = 0;
         } else {
             ph += int(span);                                 // the call ends inside an exchange period (streaming API)
-        }
-        if (done < p.n_steps) build_tables(done, ph, group_span(done, ph));
-        __syncthreads();                                     // B2: exchange data and the next group's tables are in place
-        if (full) {
-#pragma unroll
-            for (int q = 0; q < NL; q++) x[q] = xch[S::slot((uint32_t(q) << LOGT) | t)];
-            // no barrier needed here: the buffer is next written after B1 of the next group, which every thread reaches only
-            // after these loads; until then it doubles as the rollback copy of the group's starting metrics
         }
     }
 
