@@ -36,7 +36,11 @@ struct CtaShape {
     static constexpr int WARPS = T / 32;
     static constexpr size_t XCH_WORDS = size_t(C::NS) + size_t(C::NS) / 32 + 32;   // skewed by one word per 32
     static constexpr size_t TBL_WORDS = size_t(LB) * NP * 2;
-    static constexpr size_t SMEM_BYTES = (2 * XCH_WORDS + 2 * TBL_WORDS + 64) * 4;   // exchange buffer and tables are double-buffered
+    // Exchange buffer and tables are double-buffered.  The two table sets lie a power of two apart, so that "which set" is one bit of
+    // the per-thread byte offset a fetch XORs its pattern into - the base stays a constant the load takes as immediate.
+    static constexpr uint32_t TBL_SET_BYTES = 4096;
+    static_assert(TBL_WORDS * 4 <= TBL_SET_BYTES, "a table set must fit its slot");
+    static constexpr size_t SMEM_BYTES = (2 * XCH_WORDS + 64) * 4 + 2 * TBL_SET_BYTES;
     // Skew instead of XOR so that every access is (per-thread base) + (compile-time offset): the exchange writes position
     // (t << LB) | q -> word 33t + q (LB = 5) and reads (q << LOGT) | t -> word q * (T + T/32) + t + (t >> 5); both hit 32 distinct
     // banks per warp (tests/test_host_cpu.py::test_cta_exchange_skew_is_conflict_free).
@@ -163,6 +167,52 @@ template <int NL> struct CtaAcc { static constexpr int value = NL >= 32 ? 4 : (N
 #endif
 constexpr int CTA_CHAINS = VITB_CTA_CHAINS;          // chains per decision byte (1, 2 or 4)
 
+// ARITHMETIC DECISIONS (the wrapping flavours).  The predicate form below pays ~1.4 instructions per decision bit on top of its
+// 4 adds + 2 min per butterfly (predicated FADD / FSEL + FADD, 89 of 290 instructions per step, and the kernel is issue bound).
+// Here the min is fused with one of the adds and the decision is read off the result:
+//     a = x0 + ex;  m = min(x1 + ey, a)  [VIADDMNMX.U16x2];  a - m != 0  <=>  path 1 strictly better: the reference's decision
+//     d = min(a - m, 1) per half (a plain 32-bit subtraction: m <= a in both halves);  word += d << q                          (scalar.h:113-128; A bits in the low half, B in the high)
+// 5 instructions per new state for both frames instead of 5.9.  The SIMD tie-break (a tie selects path 1) uses the path-1 sum as
+// the explicit one and collects the complement, inverted when the word is stored.  ia[h][c]: registers 16h .. 16h+15, chain c.
+template <class C, int LT, int PH, int TIE_SIMD, bool STORE, int Q>
+__device__ __forceinline__ void cta_bfly_arith_at(uint32_t (&x)[CtaShape<C, LT>::NL], const uint2* tbl_ph, const uint32_t pt, uint32_t (&ia)[2][2], uint32_t* xout) {
+    using S = CtaShape<C, LT>;
+    static_assert(TIE_SIMD == 0 || TIE_SIMD == 1, "the saturating flavour keeps the predicate form");
+    constexpr int bit = 1 << (S::LB - 1 - PH);
+    if constexpr ((Q & bit) == 0) {
+        constexpr int q0 = Q, q1 = Q | bit;
+        constexpr uint32_t jq = rotl_bits(uint32_t(q0) << S::LOGT, PH, S::SB);
+        constexpr uint32_t pq = bfly_pattern<C>(jq);
+        // {total_error, inverted_error} of pattern pq ^ pt (scalar.h:66-73, 107); pt is a byte offset that also selects the table set
+        const uint2 e = *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(tbl_ph) + ((pq << 3) ^ pt));
+        uint32_t m0, m1, t0, t1;
+        if constexpr (TIE_SIMD == 0) {
+            const uint32_t a0 = __vadd2(x[q0], e.x), a1 = __vadd2(x[q0], e.y);          // scalar.h:113, 115
+            m0 = __viaddmin_u16x2(x[q1], e.y, a0);                                      // scalar.h:114, 127
+            m1 = __viaddmin_u16x2(x[q1], e.x, a1);                                      // scalar.h:116, 128
+            t0 = a0 - m0;                                                               // != 0 per half  <=>  path 1 strictly better
+            t1 = a1 - m1;                                                               // (m <= a in both halves: no borrow crosses)
+        } else {
+            const uint32_t b0 = __vadd2(x[q1], e.y), b1 = __vadd2(x[q1], e.x);
+            m0 = __viaddmin_u16x2(x[q0], e.x, b0);
+            m1 = __viaddmin_u16x2(x[q0], e.y, b1);
+            t0 = b0 - m0;                                                               // != 0 per half  <=>  path 0 strictly better
+            t1 = b1 - m1;
+        }
+        x[q0] = m0;
+        x[q1] = m1;
+        const uint32_t d0 = __vminu2(t0, 0x00010001u), d1 = __vminu2(t1, 0x00010001u);
+        ia[q0 >> 4][(q0 >> 3) & 1] += d0 << (q0 & 15);
+        ia[q1 >> 4][(q1 >> 3) & 1] += d1 << (q1 & 15);
+        if constexpr (STORE) { xout[q0] = x[q0]; xout[q1] = x[q1]; }      // slot((t << LB) | q) = slot(t << LB) + q
+    }
+}
+template <class C, int LT, int PH, int TIE_SIMD, bool STORE, int... Qs>
+__device__ __forceinline__ void cta_bfly_arith_all(uint32_t (&x)[CtaShape<C, LT>::NL], const uint2* tbl_ph, const uint32_t pt, uint32_t (&ia)[2][2], uint32_t* xout,
+                                                   std::integer_sequence<int, Qs...>) {
+    (cta_bfly_arith_at<C, LT, PH, TIE_SIMD, STORE, Qs>(x, tbl_ph, pt, ia, xout), ...);
+}
+
 // STORE (last phase of a full group): both results go straight to the other exchange buffer, xout = buffer + slot(t << LB), so that
 // the stores of the exchange run under the butterflies of the phase instead of behind a barrier
 template <class C, int LT, int PH, int TIE_SIMD, bool STORE, int Q>
@@ -175,7 +225,8 @@ __device__ __forceinline__ void cta_bfly_at(uint32_t (&x)[CtaShape<C, LT>::NL], 
         constexpr uint32_t jq = rotl_bits(uint32_t(q0) << S::LOGT, PH, S::SB);
         constexpr uint32_t pq = bfly_pattern<C>(jq);
         constexpr bool SAT = Sat<TIE_SIMD>::value;  // saturating flavour, see acs_pair.cuh
-        const uint2 e = tbl_ph[pq ^ pt];            // {total_error, inverted_error} of pattern pq ^ pt   (scalar.h:66-73, 107)
+        // {total_error, inverted_error} of pattern pq ^ pt (scalar.h:66-73, 107); pt is a byte offset that also selects the table set
+        const uint2 e = *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(tbl_ph) + ((pq << 3) ^ pt));
         const uint32_t a0 = metric_add<SAT>(x[q0], e.x), b0 = metric_add<SAT>(x[q1], e.y);     // scalar.h:113-114
         const uint32_t a1 = metric_add<SAT>(x[q0], e.y), b1 = metric_add<SAT>(x[q1], e.x);     // scalar.h:115-116
         bool h0, l0, h1, l1, dA0, dB0, dA1, dB1;
@@ -215,6 +266,20 @@ struct CtaKernel {
     // dec_row: this thread's W words of the row.  NL = 32: {A word, B word}; NL = 16: one word, A bits | B bits << 16
     template <int PH, bool STORE = false>
     static __device__ __forceinline__ void step(uint32_t (&x)[NL], const uint2* tbl, const uint32_t (&pt)[LB], uint32_t* dec_row, uint32_t* xout = nullptr) {
+        static_assert(NL == 32 || NL == 16, "decision word packing assumes 32 or 16 registers per thread");
+        if constexpr (!Sat<TIE_SIMD>::value) {
+            uint32_t ia[2][2] = {{0u, 0u}, {0u, 0u}};
+            cta_bfly_arith_all<C, LT, PH, TIE_SIMD, STORE>(x, tbl + PH * NP, pt[PH], ia, xout, std::make_integer_sequence<int, NL>{});
+            constexpr uint32_t inv = TIE_SIMD ? 0xffffffffu : 0u;      // the SIMD tie-break collected the complement
+            const uint32_t lo = ia[0][0] + ia[0][1];                   // A bits 0..15 | B bits 0..15 << 16
+            if constexpr (NL == 32) {
+                const uint32_t hi = ia[1][0] + ia[1][1];               // A bits 16..31 | B bits 16..31 << 16
+                *reinterpret_cast<uint2*>(dec_row) = make_uint2(__byte_perm(lo, hi, 0x5410) ^ inv, __byte_perm(lo, hi, 0x7632) ^ inv);
+            } else {
+                dec_row[0] = lo ^ inv;
+            }
+            return;
+        }
         constexpr int NACC = CtaAcc<NL>::value;
         float fn[2][NACC][CTA_CHAINS];
 #pragma unroll
@@ -235,7 +300,6 @@ struct CtaKernel {
             }
         }
         // byte k of a frame's bits = mantissa byte 0 of accumulator k (registers 8k .. 8k+7)
-        static_assert(NL == 32 || NL == 16, "decision word packing assumes 32 or 16 registers per thread");
         if constexpr (NL == 32) {
             const uint32_t a01 = __byte_perm(__float_as_uint(fa[0][0]), __float_as_uint(fa[0][1]), 0x0040);
             const uint32_t a23 = __byte_perm(__float_as_uint(fa[0][2]), __float_as_uint(fa[0][3]), 0x0040);
@@ -274,8 +338,8 @@ __global__ void __launch_bounds__(CtaShape<C, LT>::T, 1) acs_cta_kernel(const Ac
     // Two exchange buffers and two table sets, used in turn (cur): buffer cur = the metrics at the start of the current group (read
     // back by the exchange, kept for the rollback), the other one takes the results of the group while it still runs.
     uint32_t* xch0 = smem;                                            // [2][NS (skewed)]
-    uint2* tbl0 = reinterpret_cast<uint2*>(smem + 2 * S::XCH_WORDS);  // [2][LB][NP] {total, inverted}
-    uint32_t* red = smem + 2 * S::XCH_WORDS + 2 * S::TBL_WORDS;       // [WARPS] reduction scratch
+    uint2* tbl0 = reinterpret_cast<uint2*>(smem + 2 * S::XCH_WORDS);  // [2 sets, TBL_SET_BYTES apart][LB][NP] {total, inverted}
+    uint32_t* red = smem + 2 * S::XCH_WORDS + 2 * (S::TBL_SET_BYTES / 4);   // [WARPS] reduction scratch
     uint32_t* flag = red + S::WARPS;                                  // [0..1] trigger flag of the groups in turn, [2] replay scratch
     static_assert(S::WARPS + 3 <= 64, "scratch words");
 
@@ -287,10 +351,10 @@ __global__ void __launch_bounds__(CtaShape<C, LT>::T, 1) acs_cta_kernel(const Ac
     uint16_t* mA = p.metrics + fA * C::NS;
     uint16_t* mB = p.metrics + fB * C::NS;
 
-    // lane part of the branch pattern per phase
+    // lane part of the branch pattern per phase, as byte offset into the table of the phase (+ the table set, see the loop)
     uint32_t pt[LB];
 #pragma unroll
-    for (int n = 0; n < LB; n++) pt[n] = bfly_pattern_dyn<C>(rotl_bits(t, n, SB));
+    for (int n = 0; n < LB; n++) pt[n] = bfly_pattern_dyn<C>(rotl_bits(t, n, SB)) << 3;
 
     int ph = int(p.dec_row0 % uint32_t(LB));
     uint32_t x[NL];
@@ -373,8 +437,8 @@ __global__ void __launch_bounds__(CtaShape<C, LT>::T, 1) acs_cta_kernel(const Ac
         uint32_t* drow = dec + size_t(done) * S::T * W;
         uint32_t* xcur = xch0 + size_t(cur) * S::XCH_WORDS;
         uint32_t* xnew = xch0 + size_t(cur ^ 1u) * S::XCH_WORDS;
-        const uint2* tcur = tbl0 + size_t(cur) * (S::TBL_WORDS / 2);
-        uint2* tnew = tbl0 + size_t(cur ^ 1u) * (S::TBL_WORDS / 2);
+        const uint2* tcur = tbl0;                          // the set is selected by bit 12 of pt[]
+        uint2* tnew = tbl0 + size_t(cur ^ 1u) * (S::TBL_SET_BYTES / 8);
 
         // ---- tables of the NEXT group (it starts at phase 0) into the other set - every thread left that set at the barrier of the
         //      previous group, or at the one behind its replay -, symbols of the group after that on their way
@@ -471,6 +535,8 @@ __global__ void __launch_bounds__(CtaShape<C, LT>::T, 1) acs_cta_kernel(const Ac
 #pragma unroll
             for (int q = 0; q < NL; q++) x[q] = xnew[S::slot((uint32_t(q) << LOGT) | t)];
             cur ^= 1u;
+#pragma unroll
+            for (int n = 0; n < LB; n++) pt[n] ^= S::TBL_SET_BYTES;
             ph = 0;
         } else {
             ph += int(span);                                 // the call ends inside an exchange period (streaming API)
