@@ -35,10 +35,10 @@ struct CtaShape {
     static constexpr int NP = C::NP;                 // branch patterns
     static constexpr int WARPS = T / 32;
     static constexpr size_t XCH_WORDS = size_t(C::NS) + size_t(C::NS) / 32 + 32;   // skewed by one word per 32
-    static constexpr size_t TBL_WORDS = size_t(LB) * NP * 2;
+    static constexpr size_t TBL_WORDS = size_t(LB) * NP * 4;          // [LB][NP] 16-byte slots {own entry, partner's entry}
     // Exchange buffer and tables are double-buffered.  The two table sets lie a power of two apart, so that "which set" is one bit of
     // the per-thread byte offset a fetch XORs its pattern into - the base stays a constant the load takes as immediate.
-    static constexpr uint32_t TBL_SET_BYTES = 4096;
+    static constexpr uint32_t TBL_SET_BYTES = 8192;
     static_assert(TBL_WORDS * 4 <= TBL_SET_BYTES, "a table set must fit its slot");
     static constexpr size_t SMEM_BYTES = (2 * XCH_WORDS + 64) * 4 + 2 * TBL_SET_BYTES;
     // Skew instead of XOR so that every access is (per-thread base) + (compile-time offset): the exchange writes position
@@ -55,9 +55,7 @@ struct CtaShape {
 // and few enough addresses that ptxas keeps them in registers for the whole kernel (no XOR per fetch).  The three low rows of M are
 // chosen so that the 8 lanes of a quarter warp read 8 different 16-byte bank groups (profiles/microbench/lds128_merge.cu: an LDS.128
 // is served a quarter warp at a time, lanes of different quarters never share a wavefront).
-// Used by acs_hist_cta.cuh (8.85 instead of 10.4 ms per wave of 148 frames).  The frame-pair kernel below keeps one LDS.64 per
-// butterfly: with the paired fetch ptxas spills the 40 slot addresses it then wants to keep (48 bytes of stack, 27 LDL in the loop)
-// and a wave of 148 pairs takes 14.55 instead of 14.05 ms (B200, config 5).
+// Used by acs_hist_cta.cuh (quads of 4-byte entries) and by the frame-pair kernel below (pairs of {total, inverted}).
 // Slot coordinates of the table of one phase: index bit i of pattern p = parity(p & row[i]); pb = the pairing register bit.
 struct PairMap {
     uint32_t row[8];
@@ -174,86 +172,88 @@ constexpr int CTA_CHAINS = VITB_CTA_CHAINS;          // chains per decision byte
 //     d = min(a - m, 1) per half (a plain 32-bit subtraction: m <= a in both halves);  word += d << q                          (scalar.h:113-128; A bits in the low half, B in the high)
 // 5 instructions per new state for both frames instead of 5.9.  The SIMD tie-break (a tie selects path 1) uses the path-1 sum as
 // the explicit one and collects the complement, inverted when the word is stored.  ia[h][c]: registers 16h .. 16h+15, chain c.
-template <class C, int LT, int PH, int TIE_SIMD, bool STORE, int Q>
-__device__ __forceinline__ void cta_bfly_arith_at(uint32_t (&x)[CtaShape<C, LT>::NL], const uint2* tbl_ph, const uint32_t pt, uint32_t (&ia)[2][2], uint32_t* xout) {
-    using S = CtaShape<C, LT>;
+template <class C, int LT, int TIE_SIMD, bool STORE, int q0, int q1>
+__device__ __forceinline__ void cta_bfly_arith_one(uint32_t (&x)[CtaShape<C, LT>::NL], const uint32_t ex, const uint32_t ey, uint32_t (&ia)[2][2], uint32_t* xout) {
     static_assert(TIE_SIMD == 0 || TIE_SIMD == 1, "the saturating flavour keeps the predicate form");
-    constexpr int bit = 1 << (S::LB - 1 - PH);
-    if constexpr ((Q & bit) == 0) {
-        constexpr int q0 = Q, q1 = Q | bit;
-        constexpr uint32_t jq = rotl_bits(uint32_t(q0) << S::LOGT, PH, S::SB);
-        constexpr uint32_t pq = bfly_pattern<C>(jq);
-        // {total_error, inverted_error} of pattern pq ^ pt (scalar.h:66-73, 107); pt is a byte offset that also selects the table set
-        const uint2 e = *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(tbl_ph) + ((pq << 3) ^ pt));
-        uint32_t m0, m1, t0, t1;
-        if constexpr (TIE_SIMD == 0) {
-            const uint32_t a0 = __vadd2(x[q0], e.x), a1 = __vadd2(x[q0], e.y);          // scalar.h:113, 115
-            m0 = __viaddmin_u16x2(x[q1], e.y, a0);                                      // scalar.h:114, 127
-            m1 = __viaddmin_u16x2(x[q1], e.x, a1);                                      // scalar.h:116, 128
-            t0 = a0 - m0;                                                               // != 0 per half  <=>  path 1 strictly better
-            t1 = a1 - m1;                                                               // (m <= a in both halves: no borrow crosses)
-        } else {
-            const uint32_t b0 = __vadd2(x[q1], e.y), b1 = __vadd2(x[q1], e.x);
-            m0 = __viaddmin_u16x2(x[q0], e.x, b0);
-            m1 = __viaddmin_u16x2(x[q0], e.y, b1);
-            t0 = b0 - m0;                                                               // != 0 per half  <=>  path 0 strictly better
-            t1 = b1 - m1;
-        }
-        x[q0] = m0;
-        x[q1] = m1;
-        const uint32_t d0 = __vminu2(t0, 0x00010001u), d1 = __vminu2(t1, 0x00010001u);
-        ia[q0 >> 4][(q0 >> 3) & 1] += d0 << (q0 & 15);
-        ia[q1 >> 4][(q1 >> 3) & 1] += d1 << (q1 & 15);
-        if constexpr (STORE) { xout[q0] = x[q0]; xout[q1] = x[q1]; }      // slot((t << LB) | q) = slot(t << LB) + q
+    uint32_t m0, m1, t0, t1;
+    if constexpr (TIE_SIMD == 0) {
+        const uint32_t a0 = __vadd2(x[q0], ex), a1 = __vadd2(x[q0], ey);            // scalar.h:113, 115
+        m0 = __viaddmin_u16x2(x[q1], ey, a0);                                       // scalar.h:114, 127
+        m1 = __viaddmin_u16x2(x[q1], ex, a1);                                       // scalar.h:116, 128
+        t0 = a0 - m0;                                                               // != 0 per half  <=>  path 1 strictly better
+        t1 = a1 - m1;                                                               // (m <= a in both halves: no borrow crosses)
+    } else {
+        const uint32_t b0 = __vadd2(x[q1], ey), b1 = __vadd2(x[q1], ex);
+        m0 = __viaddmin_u16x2(x[q0], ex, b0);
+        m1 = __viaddmin_u16x2(x[q0], ey, b1);
+        t0 = b0 - m0;                                                               // != 0 per half  <=>  path 0 strictly better
+        t1 = b1 - m1;
     }
-}
-template <class C, int LT, int PH, int TIE_SIMD, bool STORE, int... Qs>
-__device__ __forceinline__ void cta_bfly_arith_all(uint32_t (&x)[CtaShape<C, LT>::NL], const uint2* tbl_ph, const uint32_t pt, uint32_t (&ia)[2][2], uint32_t* xout,
-                                                   std::integer_sequence<int, Qs...>) {
-    (cta_bfly_arith_at<C, LT, PH, TIE_SIMD, STORE, Qs>(x, tbl_ph, pt, ia, xout), ...);
+    x[q0] = m0;
+    x[q1] = m1;
+    const uint32_t d0 = __vminu2(t0, 0x00010001u), d1 = __vminu2(t1, 0x00010001u);
+    ia[q0 >> 4][(q0 >> 3) & 1] += d0 << (q0 & 15);
+    ia[q1 >> 4][(q1 >> 3) & 1] += d1 << (q1 & 15);
+    if constexpr (STORE) { xout[q0] = x[q0]; xout[q1] = x[q1]; }      // slot((t << LB) | q) = slot(t << LB) + q
 }
 
 // STORE (last phase of a full group): both results go straight to the other exchange buffer, xout = buffer + slot(t << LB), so that
 // the stores of the exchange run under the butterflies of the phase instead of behind a barrier
-template <class C, int LT, int PH, int TIE_SIMD, bool STORE, int Q>
-__device__ __forceinline__ void cta_bfly_at(uint32_t (&x)[CtaShape<C, LT>::NL], const uint2* tbl_ph, const uint32_t pt, float (&fa)[2][CtaAcc<CtaShape<C, LT>::NL>::value][CTA_CHAINS],
-                                            uint32_t* xout) {
+template <class C, int LT, int TIE_SIMD, bool STORE, int q0, int q1>
+__device__ __forceinline__ void cta_bfly_pred_one(uint32_t (&x)[CtaShape<C, LT>::NL], const uint32_t ex, const uint32_t ey,
+                                                  float (&fa)[2][CtaAcc<CtaShape<C, LT>::NL>::value][CTA_CHAINS], uint32_t* xout) {
     using S = CtaShape<C, LT>;
-    constexpr int bit = 1 << (S::LB - 1 - PH);
-    if constexpr ((Q & bit) == 0) {
-        constexpr int q0 = Q, q1 = Q | bit;
-        constexpr uint32_t jq = rotl_bits(uint32_t(q0) << S::LOGT, PH, S::SB);
-        constexpr uint32_t pq = bfly_pattern<C>(jq);
-        constexpr bool SAT = Sat<TIE_SIMD>::value;  // saturating flavour, see acs_pair.cuh
-        // {total_error, inverted_error} of pattern pq ^ pt (scalar.h:66-73, 107); pt is a byte offset that also selects the table set
-        const uint2 e = *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(tbl_ph) + ((pq << 3) ^ pt));
-        const uint32_t a0 = metric_add<SAT>(x[q0], e.x), b0 = metric_add<SAT>(x[q1], e.y);     // scalar.h:113-114
-        const uint32_t a1 = metric_add<SAT>(x[q0], e.y), b1 = metric_add<SAT>(x[q1], e.x);     // scalar.h:115-116
-        bool h0, l0, h1, l1, dA0, dB0, dA1, dB1;
-        if constexpr (!TIE_SIMD) {
-            x[q0] = __vibmin_u16x2(a0, b0, &h0, &l0);
-            x[q1] = __vibmin_u16x2(a1, b1, &h1, &l1);
-            dA0 = !l0; dB0 = !h0; dA1 = !l1; dB1 = !h1;
-        } else {
-            x[q0] = __vibmin_u16x2(b0, a0, &h0, &l0);
-            x[q1] = __vibmin_u16x2(b1, a1, &h1, &l1);
-            dA0 = l0; dB0 = h0; dA1 = l1; dB1 = h1;
-        }
-        constexpr int NACC = CtaAcc<S::NL>::value;
-        constexpr int acc0 = (q0 >> 3) % NACC, acc1 = (q1 >> 3) % NACC, n0 = ((q0 & 7) * CTA_CHAINS) >> 3, n1 = ((q1 & 7) * CTA_CHAINS) >> 3;
-        constexpr float w0 = float(1u << (q0 & 7)), w1 = float(1u << (q1 & 7));
-        if (dA0) fa[0][acc0][n0] += w0;
-        if (dB0) fa[1][acc0][n0] += w0;
-        if (dA1) fa[0][acc1][n1] += w1;
-        if (dB1) fa[1][acc1][n1] += w1;
-        if constexpr (STORE) { xout[q0] = x[q0]; xout[q1] = x[q1]; }      // slot((t << LB) | q) = slot(t << LB) + q
+    constexpr bool SAT = Sat<TIE_SIMD>::value;  // saturating flavour, see acs_pair.cuh
+    const uint32_t a0 = metric_add<SAT>(x[q0], ex), b0 = metric_add<SAT>(x[q1], ey);     // scalar.h:113-114
+    const uint32_t a1 = metric_add<SAT>(x[q0], ey), b1 = metric_add<SAT>(x[q1], ex);     // scalar.h:115-116
+    bool h0, l0, h1, l1, dA0, dB0, dA1, dB1;
+    if constexpr (!TIE_SIMD) {
+        x[q0] = __vibmin_u16x2(a0, b0, &h0, &l0);
+        x[q1] = __vibmin_u16x2(a1, b1, &h1, &l1);
+        dA0 = !l0; dB0 = !h0; dA1 = !l1; dB1 = !h1;
+    } else {
+        x[q0] = __vibmin_u16x2(b0, a0, &h0, &l0);
+        x[q1] = __vibmin_u16x2(b1, a1, &h1, &l1);
+        dA0 = l0; dB0 = h0; dA1 = l1; dB1 = h1;
     }
+    constexpr int NACC = CtaAcc<S::NL>::value;
+    constexpr int acc0 = (q0 >> 3) % NACC, acc1 = (q1 >> 3) % NACC, n0 = ((q0 & 7) * CTA_CHAINS) >> 3, n1 = ((q1 & 7) * CTA_CHAINS) >> 3;
+    constexpr float w0 = float(1u << (q0 & 7)), w1 = float(1u << (q1 & 7));
+    if (dA0) fa[0][acc0][n0] += w0;
+    if (dB0) fa[1][acc0][n0] += w0;
+    if (dA1) fa[0][acc1][n1] += w1;
+    if (dB1) fa[1][acc1][n1] += w1;
+    if constexpr (STORE) { xout[q0] = x[q0]; xout[q1] = x[q1]; }      // slot((t << LB) | q) = slot(t << LB) + q
 }
 
-template <class C, int LT, int PH, int TIE_SIMD, bool STORE, int... Qs>
-__device__ __forceinline__ void cta_bfly_all(uint32_t (&x)[CtaShape<C, LT>::NL], const uint2* tbl_ph, const uint32_t pt, float (&fa)[2][CtaAcc<CtaShape<C, LT>::NL>::value][CTA_CHAINS],
-                                             uint32_t* xout, std::integer_sequence<int, Qs...>) {
-    (cta_bfly_at<C, LT, PH, TIE_SIMD, STORE, Qs>(x, tbl_ph, pt, fa, xout), ...);
+// the two butterflies (Q, Q | bit) and (Q | pbit, Q | pbit | bit) of a pair: one 16-byte table fetch (PairMap above); pt is the
+// thread's byte offset into the table of the phase and also selects the table set (CtaShape::TBL_SET_BYTES)
+template <class C, int LT, int PH, int TIE_SIMD, bool STORE, int Q, class Acc>
+__device__ __forceinline__ void cta_bfly_pair_at(uint32_t (&x)[CtaShape<C, LT>::NL], const uint4* tbl_ph, const uint32_t pt, Acc& acc, uint32_t* xout) {
+    using S = CtaShape<C, LT>;
+    constexpr PairMap M = pair_map<C, LT, false, 1>(PH);
+    static_assert(M.pb[0] >= 0, "no pairing bit with a non-zero pattern");
+    static_assert(pair_map_conflict_free<C, LT, false, 1>(PH), "table fetch with shared-memory bank conflicts inside a quarter warp");
+    constexpr int bit = 1 << (S::LB - 1 - PH), pbit = 1 << M.pb[0];
+    if constexpr ((Q & (bit | pbit)) == 0) {
+        constexpr uint32_t ia = pair_apply(M, C::R, bfly_pattern<C>(rotl_bits(uint32_t(Q) << S::LOGT, PH, S::SB)));
+        static_assert(pair_apply(M, C::R, bfly_pattern<C>(rotl_bits(uint32_t(Q | pbit) << S::LOGT, PH, S::SB))) == (ia ^ 1u),
+                      "paired butterflies must sit in one table slot");
+        // {total_error, inverted_error} of both butterflies   (scalar.h:66-73, 107)
+        const uint4 e = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(tbl_ph) + ((ia << 4) ^ pt));
+        if constexpr (Sat<TIE_SIMD>::value) {
+            cta_bfly_pred_one<C, LT, TIE_SIMD, STORE, Q, Q | bit>(x, e.x, e.y, acc, xout);
+            cta_bfly_pred_one<C, LT, TIE_SIMD, STORE, Q | pbit, Q | pbit | bit>(x, e.z, e.w, acc, xout);
+        } else {
+            cta_bfly_arith_one<C, LT, TIE_SIMD, STORE, Q, Q | bit>(x, e.x, e.y, acc, xout);
+            cta_bfly_arith_one<C, LT, TIE_SIMD, STORE, Q | pbit, Q | pbit | bit>(x, e.z, e.w, acc, xout);
+        }
+    }
+}
+template <class C, int LT, int PH, int TIE_SIMD, bool STORE, class Acc, int... Qs>
+__device__ __forceinline__ void cta_bfly_all(uint32_t (&x)[CtaShape<C, LT>::NL], const uint4* tbl_ph, const uint32_t pt, Acc& acc, uint32_t* xout,
+                                             std::integer_sequence<int, Qs...>) {
+    (cta_bfly_pair_at<C, LT, PH, TIE_SIMD, STORE, Qs>(x, tbl_ph, pt, acc, xout), ...);
 }
 
 template <class C, int LT, int SH, int TIE_SIMD>
@@ -265,11 +265,11 @@ struct CtaKernel {
     static constexpr int W = NL > 16 ? 2 : 1;     // 32-bit decision words per thread and step
     // dec_row: this thread's W words of the row.  NL = 32: {A word, B word}; NL = 16: one word, A bits | B bits << 16
     template <int PH, bool STORE = false>
-    static __device__ __forceinline__ void step(uint32_t (&x)[NL], const uint2* tbl, const uint32_t (&pt)[LB], uint32_t* dec_row, uint32_t* xout = nullptr) {
+    static __device__ __forceinline__ void step(uint32_t (&x)[NL], const uint4* tbl, const uint32_t (&pt)[LB], uint32_t* dec_row, uint32_t* xout = nullptr) {
         static_assert(NL == 32 || NL == 16, "decision word packing assumes 32 or 16 registers per thread");
         if constexpr (!Sat<TIE_SIMD>::value) {
             uint32_t ia[2][2] = {{0u, 0u}, {0u, 0u}};
-            cta_bfly_arith_all<C, LT, PH, TIE_SIMD, STORE>(x, tbl + PH * NP, pt[PH], ia, xout, std::make_integer_sequence<int, NL>{});
+            cta_bfly_all<C, LT, PH, TIE_SIMD, STORE>(x, tbl + PH * NP, pt[PH], ia, xout, std::make_integer_sequence<int, NL>{});
             constexpr uint32_t inv = TIE_SIMD ? 0xffffffffu : 0u;      // the SIMD tie-break collected the complement
             const uint32_t lo = ia[0][0] + ia[0][1];                   // A bits 0..15 | B bits 0..15 << 16
             if constexpr (NL == 32) {
@@ -287,7 +287,7 @@ struct CtaKernel {
 #pragma unroll
             for (int c = 0; c < CTA_CHAINS; c++) { fn[0][a][c] = c ? 0.f : 8388608.f; fn[1][a][c] = c ? 0.f : 8388608.f; }
         }
-        cta_bfly_all<C, LT, PH, TIE_SIMD, STORE>(x, tbl + PH * NP, pt[PH], fn, xout, std::make_integer_sequence<int, NL>{});
+        if constexpr (Sat<TIE_SIMD>::value) cta_bfly_all<C, LT, PH, TIE_SIMD, STORE>(x, tbl + PH * NP, pt[PH], fn, xout, std::make_integer_sequence<int, NL>{});
         float fa[2][NACC];
 #pragma unroll
         for (int a = 0; a < NACC; a++) {
@@ -338,7 +338,8 @@ __global__ void __launch_bounds__(CtaShape<C, LT>::T, 1) acs_cta_kernel(const Ac
     // Two exchange buffers and two table sets, used in turn (cur): buffer cur = the metrics at the start of the current group (read
     // back by the exchange, kept for the rollback), the other one takes the results of the group while it still runs.
     uint32_t* xch0 = smem;                                            // [2][NS (skewed)]
-    uint2* tbl0 = reinterpret_cast<uint2*>(smem + 2 * S::XCH_WORDS);  // [2 sets, TBL_SET_BYTES apart][LB][NP] {total, inverted}
+    uint4* tbl0 = reinterpret_cast<uint4*>(smem + 2 * S::XCH_WORDS);  // [2 sets, TBL_SET_BYTES apart][LB][NP] {total, inverted} of slot idx, of slot idx ^ 1
+    static_assert((2 * S::XCH_WORDS) % 4 == 0, "16-byte table slots");
     uint32_t* red = smem + 2 * S::XCH_WORDS + 2 * (S::TBL_SET_BYTES / 4);   // [WARPS] reduction scratch
     uint32_t* flag = red + S::WARPS;                                  // [0..1] trigger flag of the groups in turn, [2] replay scratch
     static_assert(S::WARPS + 3 <= 64, "scratch words");
@@ -351,10 +352,11 @@ __global__ void __launch_bounds__(CtaShape<C, LT>::T, 1) acs_cta_kernel(const Ac
     uint16_t* mA = p.metrics + fA * C::NS;
     uint16_t* mB = p.metrics + fB * C::NS;
 
-    // lane part of the branch pattern per phase, as byte offset into the table of the phase (+ the table set, see the loop)
+    // thread part of the table slot per phase, as byte offset into the table of the phase (+ the table set, see the loop)
     uint32_t pt[LB];
+    pair_thread_slots<C, LT, false, 1>(pt, t, std::make_integer_sequence<int, LB>{});
 #pragma unroll
-    for (int n = 0; n < LB; n++) pt[n] = bfly_pattern_dyn<C>(rotl_bits(t, n, SB)) << 3;
+    for (int n = 0; n < LB; n++) pt[n] <<= 4;
 
     int ph = int(p.dec_row0 % uint32_t(LB));
     uint32_t x[NL];
@@ -383,7 +385,7 @@ __global__ void __launch_bounds__(CtaShape<C, LT>::T, 1) acs_cta_kernel(const Ac
     uint32_t* dec = static_cast<uint32_t*>(p.dec) + ((size_t(pair) * p.dec_rows + p.dec_row0) * S::T + t) * W;
 
     // branch metric tables {total, inverted} of the steps of one group, built by the first LB*NP threads (one entry each)
-    auto build_tables = [&](uint2* tbl, uint32_t first_step, int first_phase, uint32_t n) {
+    auto build_tables = [&](uint4* tbl, uint32_t first_step, int first_phase, uint32_t n) {
         if (t < uint32_t(LB * NP)) {
             const int tph = int(t) / NP;
             const uint32_t pat = t % NP;
@@ -404,7 +406,10 @@ __global__ void __launch_bounds__(CtaShape<C, LT>::T, 1) acs_cta_kernel(const Ac
                     }
                 }
                 if constexpr (Sat<TIE_SIMD>::value) inv = __vsubus2(p.max_err2, tot);     // avx_u16.h:106: max_error -sat total
-                tbl[tph * NP + pat] = make_uint2(tot, inv);
+                const uint32_t idx = pair_apply_phase<C, LT, false, 1>(uint32_t(tph), pat, std::make_integer_sequence<int, LB>{});
+                uint2* t2 = reinterpret_cast<uint2*>(tbl + size_t(tph) * NP);
+                t2[2 * idx] = make_uint2(tot, inv);                    // own member of its slot,
+                t2[2 * (idx ^ 1u) + 1] = make_uint2(tot, inv);         // partner member of the neighbouring one
             }
         }
     };
@@ -437,8 +442,8 @@ __global__ void __launch_bounds__(CtaShape<C, LT>::T, 1) acs_cta_kernel(const Ac
         uint32_t* drow = dec + size_t(done) * S::T * W;
         uint32_t* xcur = xch0 + size_t(cur) * S::XCH_WORDS;
         uint32_t* xnew = xch0 + size_t(cur ^ 1u) * S::XCH_WORDS;
-        const uint2* tcur = tbl0;                          // the set is selected by bit 12 of pt[]
-        uint2* tnew = tbl0 + size_t(cur ^ 1u) * (S::TBL_SET_BYTES / 8);
+        const uint4* tcur = tbl0;                          // the set is selected by a bit of pt[]
+        uint4* tnew = tbl0 + size_t(cur ^ 1u) * (S::TBL_SET_BYTES / 16);
 
         // ---- tables of the NEXT group (it starts at phase 0) into the other set - every thread left that set at the barrier of the
         //      previous group, or at the one behind its replay -, symbols of the group after that on their way
