@@ -183,6 +183,11 @@ def test_cta_exchange_skew_is_conflict_free():
             for q in range(NL):
                 assert len({slot((t << LB) | q) % 32 for t in lanes}) == 32
                 assert len({slot((q << LOGT) | t) % 32 for t in lanes}) == 32
+        # the split form the kernels use (per-thread offset + compile-time offset: CtaShape::rd_off / wr_off / RD_STRIDE)
+        for t in range(T):
+            for q in range(NL):
+                assert slot((q << LOGT) | t) == (t + (t >> 5)) + q * (T + T // 32)
+                assert slot((t << LB) | q) == slot(t << LB) + q
 
 
 def test_frame_range_partitions_exactly():

@@ -45,6 +45,13 @@ struct CtaShape {
     // (t << LB) | q -> word 33t + q (LB = 5) and reads (q << LOGT) | t -> word q * (T + T/32) + t + (t >> 5); both hit 32 distinct
     // banks per warp (tests/test_host_cpu.py::test_cta_exchange_skew_is_conflict_free).
     static __host__ __device__ constexpr uint32_t slot(uint32_t phi) { return phi + (phi >> 5); }
+    // the same, split into a per-thread offset and a compile-time one (the buffers alternate, so their base is a run-time value and
+    // ptxas would otherwise recompute the whole expression for every register and group):
+    //   slot((q << LOGT) | t) = rd_off(t) + q * RD_STRIDE,   slot((t << LB) | q) = wr_off(t) + q   (q < 2^LB <= 32)
+    static constexpr uint32_t RD_STRIDE = uint32_t(T) + uint32_t(T) / 32;
+    static __host__ __device__ constexpr uint32_t rd_off(uint32_t t) { return t + (t >> 5); }
+    static __host__ __device__ constexpr uint32_t wr_off(uint32_t t) { return slot(t << LB); }
+    static_assert(LB <= 5 && LOGT >= 5, "split form of slot()");
 };
 
 // TABLE FETCH BY BUTTERFLY PAIRS (OR QUADS).  The entry of a butterfly is T[pq ^ pt] (pq: pattern of the register bits, a compile-time constant;
@@ -345,6 +352,7 @@ __global__ void __launch_bounds__(CtaShape<C, LT>::T, 1) acs_cta_kernel(const Ac
     static_assert(S::WARPS + 3 <= 64, "scratch words");
 
     const uint32_t t = threadIdx.x, pair = blockIdx.x;
+    const uint32_t rd_off = S::rd_off(t), wr_off = S::wr_off(t);
     const size_t fA = size_t(pair) * 2, fB = fA + 1;
     // the grid covers whole 64-frame blocks of the packed stream: pairs behind the last frame have nothing to decode (they used to
     // decode padding: 888 frames ran 448 CTAs, one more wave than 444 on 148 SMs)
@@ -429,7 +437,7 @@ __global__ void __launch_bounds__(CtaShape<C, LT>::T, 1) acs_cta_kernel(const Ac
     uint32_t done = 0, cur = 0;
     // prologue: buffer 0 holds the metrics at the start of the first group, table set 0 its tables
 #pragma unroll
-    for (int q = 0; q < NL; q++) xch0[S::slot((uint32_t(q) << LOGT) | t)] = x[q];
+    for (int q = 0; q < NL; q++) xch0[rd_off + uint32_t(q) * S::RD_STRIDE] = x[q];
     if (p.n_steps) {
         build_tables(tbl0, 0u, ph, group_span(0u, ph));
         prefetch_symbols(group_span(0u, ph));
@@ -459,7 +467,7 @@ __global__ void __launch_bounds__(CtaShape<C, LT>::T, 1) acs_cta_kernel(const Ac
         if (ph == 0 && span == uint32_t(LB)) {
             auto fast_phase = [&](auto PHc) {
                 constexpr int PH = decltype(PHc)::value;
-                Kn::template step<PH, PH == LB - 1>(x, tcur, pt, drow + size_t(PH) * S::T * W, xnew + S::slot(t << LB));
+                Kn::template step<PH, PH == LB - 1>(x, tcur, pt, drow + size_t(PH) * S::T * W, xnew + wr_off);
                 mx = __vmaxu2(mx, x[0]);
             };
             fast_phase(std::integral_constant<int, 0>{});
@@ -482,7 +490,7 @@ __global__ void __launch_bounds__(CtaShape<C, LT>::T, 1) acs_cta_kernel(const Ac
             if constexpr (LB > 4) run_phase(std::integral_constant<int, 4>{});
             if (full) {                                      // a group that started inside an exchange period (streaming API)
 #pragma unroll
-                for (int q = 0; q < NL; q++) xnew[S::slot((t << LB) | uint32_t(q))] = x[q];
+                for (int q = 0; q < NL; q++) xnew[wr_off + uint32_t(q)] = x[q];
             }
         }
         if (t == 0) {
@@ -496,7 +504,7 @@ __global__ void __launch_bounds__(CtaShape<C, LT>::T, 1) acs_cta_kernel(const Ac
         if (any_trig) {
             // ---- roll back and replay step by step with the reference's renormalisation (scalar.h:48-50, 139-153)
 #pragma unroll
-            for (int q = 0; q < NL; q++) x[q] = xcur[S::slot((uint32_t(q) << LOGT) | t)];
+            for (int q = 0; q < NL; q++) x[q] = xcur[rd_off + uint32_t(q) * S::RD_STRIDE];
             auto replay_phase = [&](auto PHc) {
                 constexpr int PH = decltype(PHc)::value;
                 if (PH >= ph && uint32_t(PH - ph) < span) {
@@ -528,7 +536,7 @@ __global__ void __launch_bounds__(CtaShape<C, LT>::T, 1) acs_cta_kernel(const Ac
             if (full) {
                 // the exchange of the replayed group: value at (q, t) moves to PHI' = (t << LB) | q
 #pragma unroll
-                for (int q = 0; q < NL; q++) xnew[S::slot((t << LB) | uint32_t(q))] = x[q];
+                for (int q = 0; q < NL; q++) xnew[wr_off + uint32_t(q)] = x[q];
             }
             __syncthreads();
         }
@@ -538,7 +546,7 @@ __global__ void __launch_bounds__(CtaShape<C, LT>::T, 1) acs_cta_kernel(const Ac
             // ---- exchange, read side: the layout is back to PHI = s.  The buffer just read is the rollback copy of the next group;
             //      the other one is written again only at the end of the next group, behind every thread's loads.
 #pragma unroll
-            for (int q = 0; q < NL; q++) x[q] = xnew[S::slot((uint32_t(q) << LOGT) | t)];
+            for (int q = 0; q < NL; q++) x[q] = xnew[rd_off + uint32_t(q) * S::RD_STRIDE];
             cur ^= 1u;
 #pragma unroll
             for (int n = 0; n < LB; n++) pt[n] ^= S::TBL_SET_BYTES;

@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(HistCtaShape<C>::T, MINB) acs_hist_cta_kernel(
     static_assert(H::WARPS + 3 <= 64, "scratch words");
 
     const uint32_t t = threadIdx.x;
+    const uint32_t rd_off = S::rd_off(t), wr_off = S::wr_off(t);      // exchange addresses: per-thread part (acs_cta.cuh)
     const size_t f = blockIdx.x;
     const HistConsts c = hist_consts<1>(p);
 
@@ -254,7 +255,7 @@ __global__ void __launch_bounds__(HistCtaShape<C>::T, MINB) acs_hist_cta_kernel(
     uint32_t done = 0, cur = 0;
     // prologue: buffer 0 holds the registers at the start of group 0, table set 0 its tables
 #pragma unroll
-    for (int q = 0; q < NL; q++) xch0[S::slot((uint32_t(q) << LOGT) | t)] = x[q];
+    for (int q = 0; q < NL; q++) xch0[rd_off + uint32_t(q) * S::RD_STRIDE] = x[q];
     if (p.n_steps) build_tables(tbl0, 0u, p.n_steps < uint32_t(LB) ? p.n_steps : uint32_t(LB));
     prefetch_symbols(uint32_t(LB));
     __syncthreads();
@@ -283,7 +284,7 @@ __global__ void __launch_bounds__(HistCtaShape<C>::T, MINB) acs_hist_cta_kernel(
             constexpr int PH = decltype(PHc)::value;
             constexpr bool GUARD = decltype(guard_tag)::value;
             if constexpr (GUARD) { if (uint32_t(PH) >= span) return; }
-            run_bfly(PHc, std::integral_constant<bool, !GUARD>{}, tcur, xnew + S::slot(t << LB));
+            run_bfly(PHc, std::integral_constant<bool, !GUARD>{}, tcur, xnew + wr_off);
             mx = max(mx, x[0]);
             pst++;
             if constexpr (PH != LB - 1) { if (pst == uint32_t(HB)) emit_record(std::integral_constant<int, LB - 2 - PH>{}); }     // after the last phase: behind the exchange
@@ -307,7 +308,7 @@ __global__ void __launch_bounds__(HistCtaShape<C>::T, MINB) acs_hist_cta_kernel(
         if (any_trig) {
             // ---- roll back (registers and record bookkeeping) and replay step by step with the reference's renormalisation
 #pragma unroll
-            for (int q = 0; q < NL; q++) x[q] = xcur[S::slot((uint32_t(q) << LOGT) | t)];
+            for (int q = 0; q < NL; q++) x[q] = xcur[rd_off + uint32_t(q) * S::RD_STRIDE];
             pst = pst0; r = r0;
             auto replay_phase = [&](auto PHc) {
                 constexpr int PH = decltype(PHc)::value;
@@ -336,7 +337,7 @@ __global__ void __launch_bounds__(HistCtaShape<C>::T, MINB) acs_hist_cta_kernel(
             if (full) {
                 // the exchange of the replayed group: value at (q, t) moves to PHI' = (t << LB) | q
 #pragma unroll
-                for (int q = 0; q < NL; q++) xnew[S::slot((t << LB) | uint32_t(q))] = x[q];
+                for (int q = 0; q < NL; q++) xnew[wr_off + uint32_t(q)] = x[q];
             }
             __syncthreads();
         }
@@ -346,14 +347,14 @@ __global__ void __launch_bounds__(HistCtaShape<C>::T, MINB) acs_hist_cta_kernel(
             // ---- exchange, read side: positions back to PHI = s.  The buffer just read is the rollback copy of the next group; the
             //      other one is written again only in the last phase of the next group, behind every thread's loads.
 #pragma unroll
-            for (int q = 0; q < NL; q++) x[q] = xnew[S::slot((uint32_t(q) << LOGT) | t)];
+            for (int q = 0; q < NL; q++) x[q] = xnew[rd_off + uint32_t(q) * S::RD_STRIDE];
             cur ^= 1u;
             if (pst == uint32_t(HB)) {
                 emit_record(std::integral_constant<int, LB - 1>{});   // records are cut in the layout the traceback expects: PHI = rotr^(steps mod 5)(s)
                 // the rollback copy must match the registers the next group starts from (history fields cleared); every thread
                 // rewrites exactly the words it has just read and will read back on a rollback: no barrier needed
 #pragma unroll
-                for (int q = 0; q < NL; q++) xnew[S::slot((uint32_t(q) << LOGT) | t)] = x[q];
+                for (int q = 0; q < NL; q++) xnew[rd_off + uint32_t(q) * S::RD_STRIDE] = x[q];
             }
         }
     }
