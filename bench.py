@@ -517,7 +517,7 @@ def main():
     # Issue-slot roofline of the kernel that ran (the binding bound for every configuration: DESIGN.md section 3): one
     # warp-instruction per clock per SM sub-partition (32 lanes) at the kernel's own MINIMUM instruction count per add-compare-select
     # of one frame: survivor-history kernels 4 per butterfly = 1.0 (uint8 metrics, two frames per register) / 2.0 (uint16 metrics,
-    # one frame per register); predicate kernels 10 per butterfly of two frames = 2.5.
+    # one frame per register); decision-row kernels 10 per butterfly of two frames = 2.5.
     if kernel_name.startswith("acs_hist"):
         ipa = 1.0 if dc.soft_bytes == 1 else 2.0
     else:
