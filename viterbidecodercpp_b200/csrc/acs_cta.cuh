@@ -155,6 +155,26 @@ __device__ __forceinline__ uint32_t pair_apply_phase(uint32_t ph, uint32_t p, st
     ((idx = (ph == uint32_t(PHs)) ? pair_apply_dyn<C, LOGT, EXCL_NEXT, NV, PHs>(p) : idx), ...);
     return idx;
 }
+// the pattern that sits at slot index idx (inverse of pair_apply): XOR of the patterns of the index bits
+template <class C, int LOGT, bool EXCL_NEXT, int NV>
+__host__ __device__ constexpr uint32_t pair_column(int PH, int k) {
+    const PairMap m = pair_map<C, LOGT, EXCL_NEXT, NV>(PH);
+    for (uint32_t p = 0; p < (1u << C::R); p++)
+        if (pair_apply(m, C::R, p) == (1u << k)) return p;
+    return 0u;
+}
+template <class C, int LOGT, bool EXCL_NEXT, int NV, int PH, int... Ks>
+__device__ __forceinline__ uint32_t pair_unapply_dyn_impl(uint32_t idx, std::integer_sequence<int, Ks...>) {
+    uint32_t p = 0;
+    ((p ^= ((idx >> Ks) & 1u) ? std::integral_constant<uint32_t, pair_column<C, LOGT, EXCL_NEXT, NV>(PH, Ks)>::value : 0u), ...);
+    return p;
+}
+template <class C, int LOGT, bool EXCL_NEXT, int NV, int... PHs>
+__device__ __forceinline__ uint32_t pair_unapply_phase(uint32_t ph, uint32_t idx, std::integer_sequence<int, PHs...>) {
+    uint32_t p = 0;
+    ((p = (ph == uint32_t(PHs)) ? pair_unapply_dyn_impl<C, LOGT, EXCL_NEXT, NV, PHs>(idx, std::make_integer_sequence<int, C::R>{}) : p), ...);
+    return p;
+}
 // slot part of thread t for every phase
 template <class C, int LOGT, bool EXCL_NEXT, int NV, int... PHs>
 __device__ __forceinline__ void pair_thread_slots(uint32_t (&mpt)[sizeof...(PHs)], uint32_t t, std::integer_sequence<int, PHs...>) {

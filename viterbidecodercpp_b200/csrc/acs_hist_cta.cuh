@@ -168,30 +168,28 @@ __global__ void __launch_bounds__(HistCtaShape<C>::T, MINB) acs_hist_cta_kernel(
     uint32_t* rec = static_cast<uint32_t*>(p.dec) + f * size_t(n_periods) * (size_t(C::NS) / 2) + t * 4;
     const int16_t* row = reinterpret_cast<const int16_t*>(static_cast<const uint8_t*>(p.sym) + f * p.sym_row_bytes);
 
-    // branch metric tables of the n steps of the group that starts at first_step, one pattern per thread (320 of the 512), stored as
-    // a member of the four slots that use it, plain and with the next step's tag added
+    // Branch metric tables of the n steps of the group that starts at first_step: thread t < LB * NP fills slot (t % NP) of step
+    // (t / NP) - its own pattern is the one that sits at that slot index, the other three members of the slot are the values of the
+    // lanes t ^ 1, t ^ 2, t ^ 3 (shuffles: the whole warp belongs to one step) - plain and with the next step's tag added.
+    const uint32_t b_tph = t / NP, b_slot = t % NP;
+    const uint32_t b_pat = pair_unapply_phase<C, LOGT, true, 2>(b_tph, b_slot, std::make_integer_sequence<int, LB>{});
     auto build_tables = [&](uint4* tbl, uint32_t first_step, uint32_t n) {
-        if (t < uint32_t(LB * NP)) {
-            const uint32_t tph = t / NP, pat = t % NP;
-            if (tph < n) {
-                const int16_t* sy = row + size_t(first_step + tph) * R;
-                uint32_t tot = 0;
+        if (t < uint32_t(LB * NP) && b_tph < n) {                   // uniform per warp: NP is a multiple of 32
+            const uint32_t step = first_step + b_tph;
+            const int16_t* sy = reinterpret_cast<const int16_t*>(reinterpret_cast<const char*>(row) + step * uint32_t(R * sizeof(int16_t)));
+            uint32_t tot = 0;
 #pragma unroll
-                for (int i = 0; i < R; i++) {
-                    const uint32_t sv = uint32_t(uint16_t(__ldg(sy + i))) << 16;
-                    const uint32_t lo = sv + c.c_low, hi = c.c_high - sv;       // s - low, high - s  (scalar.h:96-105 for s in [low, high])
-                    tot += ((pat >> i) & 1u) ? hi : lo;     // viterbi_branch_table.h:52 + scalar.h:66-73
-                }
-                // the tag of the next step; none behind a record cut (the cut sets it)
-                const uint32_t nxt = (2u << ((first_step + tph) % uint32_t(HB))) & 0xffffu;
-                const uint32_t idx = pair_apply_phase<C, LOGT, true, 2>(tph, pat, std::make_integer_sequence<int, LB>{});
-                uint32_t* tw = reinterpret_cast<uint32_t*>(tbl + size_t(tph) * 2 * NP);
-#pragma unroll
-                for (uint32_t j = 0; j < 4; j++) {                              // member j of slot idx ^ j
-                    tw[(idx ^ j) * 4 + j] = tot;
-                    tw[(NP + (idx ^ j)) * 4 + j] = tot + nxt;
-                }
+            for (int i = 0; i < R; i++) {
+                const uint32_t sv = uint32_t(uint16_t(__ldg(sy + i))) << 16;
+                const uint32_t lo = sv + c.c_low, hi = c.c_high - sv;       // s - low, high - s  (scalar.h:96-105 for s in [low, high])
+                tot += ((b_pat >> i) & 1u) ? hi : lo;       // viterbi_branch_table.h:52 + scalar.h:66-73
             }
+            const uint32_t t1 = __shfl_xor_sync(0xffffffffu, tot, 1), t2 = __shfl_xor_sync(0xffffffffu, tot, 2), t3 = __shfl_xor_sync(0xffffffffu, tot, 3);
+            // the tag of the next step; none behind a record cut (the cut sets it)
+            const uint32_t nxt = (2u << (step % uint32_t(HB))) & 0xffffu;
+            uint4* dst = tbl + size_t(b_tph) * 2 * NP + b_slot;
+            dst[0] = make_uint4(tot, t1, t2, t3);
+            dst[NP] = make_uint4(tot + nxt, t1 + nxt, t2 + nxt, t3 + nxt);
         }
     };
 
