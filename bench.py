@@ -482,7 +482,7 @@ def main():
         t_frame = time.perf_counter() - t0
         assert (out1 == d_out[0].cpu().numpy()).all(), "streaming calls and batch call disagree on frame 0"
         streaming = {"update_one_step_us": t_small * 1e6, "whole_frame_update_get_error_chainback_ms": t_frame * 1e3,
-                     "note": "host clock, synchronous calls through the C ABI (H2D of the symbols, ingest, ACS kernel, D2H of the result per call)"}
+                     "note": "host clock, synchronous calls through the C ABI (calls of up to 64 KB of symbols: staged in mapped pinned memory, ingest kernel + ACS kernel + one synchronize, the result read from mapped memory; larger calls: H2D copy, the two kernels, D2H copy)"}
 
     strong = None if args.no_strong else strong_cfg5(torch, dist, v, world, rank, local_rank, dev)
     multi = None

@@ -73,7 +73,9 @@ int vitb_set_traceback_length(vitb_decoder* h, size_t traceback_length);        
 int vitb_get_traceback_length(const vitb_decoder* h, size_t* traceback_length); /* core.h:189-192 */
 int vitb_reset(vitb_decoder* h, size_t starting_state);                         /* core.h:202-211 */
 /* Decoder::update<uint64_t>(base, symbols, N) (scalar.h:28-55): `symbols` is a HOST array of N soft_t, N % R == 0, may be called
- * repeatedly; *accumulated_error receives the sum of renormalisation minima of THIS call. */
+ * repeatedly; *accumulated_error receives the sum of renormalisation minima of THIS call.  One synchronous round trip per call
+ * (calls of up to 64 KB of symbols are staged in mapped pinned memory: two kernel launches and one synchronize, ~30 us on a B200;
+ * the batch calls below are the fast path). */
 int vitb_update(vitb_decoder* h, const void* symbols, size_t n_symbols, uint64_t* accumulated_error);
 int vitb_get_error(vitb_decoder* h, size_t end_state, uint32_t* error);         /* core.h:195-199; VITB_END_STATE_BEST: the minimum */
 int vitb_chainback(vitb_decoder* h, uint8_t* bytes_out, size_t total_bits, size_t end_state); /* core.h:214-236; or VITB_END_STATE_BEST */

@@ -80,6 +80,25 @@ struct DeviceBuffer {
     void release() { if (ptr) cudaFree(ptr); ptr = nullptr; bytes = 0; }
 };
 
+// Pinned host memory mapped into the device's address space: the streaming calls stage their (small) input there and take their
+// result from there, so that a call is two kernel launches and one synchronize - no copy calls.
+struct MappedBuffer {
+    void* host = nullptr;
+    void* dev = nullptr;
+    size_t bytes = 0;
+    cudaError_t reserve(size_t need) {
+        if (need <= bytes) return cudaSuccess;
+        release();
+        cudaError_t e = cudaHostAlloc(&host, need, cudaHostAllocMapped | cudaHostAllocPortable);
+        if (e != cudaSuccess) { host = nullptr; return e; }
+        e = cudaHostGetDevicePointer(&dev, host, 0);
+        if (e != cudaSuccess) { cudaFreeHost(host); host = nullptr; return e; }
+        bytes = need;
+        return cudaSuccess;
+    }
+    void release() { if (host) cudaFreeHost(host); host = nullptr; dev = nullptr; bytes = 0; }
+};
+
 // Workspace of one chunk of a batch call.  acs_done: recorded on the caller's stream behind the ACS kernel (the traceback on
 // tb_stream waits for it); tb_done: recorded on tb_stream behind the chunk's last kernel / copy (the next ACS that reuses the slot,
 // and whoever wants the results, wait for it).
@@ -134,6 +153,7 @@ struct vitb_decoder {
     int32_t unpunctured_value = 0;
     // single-frame streaming state (one 64-frame block, frame 0 is the user's)
     DeviceBuffer s_pk, s_dec, s_metrics, s_acc, s_in, s_out;
+    MappedBuffer s_map;                 // streaming calls: [0, 512) accumulated minima of the call, [512, ...) the call's symbols
     DeviceBuffer g_tx, g_sym, g_cnt;     // host-pointer conveniences of the device-side front end
     size_t traceback_length = 0;
     size_t current_decoded_bit = 0;
@@ -795,6 +815,7 @@ int vitb_destroy(vitb_decoder* h) {
     if (h->acs_stream) cudaStreamDestroy(h->acs_stream);
     for (DeviceBuffer* b : {&h->pk, &h->d_in, &h->d_out, &h->d_accout, &h->d_finout, &h->map, &h->end_states, &h->win_count,
                             &h->s_pk, &h->s_dec, &h->s_metrics, &h->s_acc, &h->s_in, &h->s_out, &h->g_tx, &h->g_sym, &h->g_cnt}) b->release();
+    h->s_map.release();
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     for (cudaEvent_t e : h->copy_ev) cudaEventDestroy(e);
     if (h->batch_done) cudaEventDestroy(h->batch_done);
@@ -938,20 +959,37 @@ int vitb_update(vitb_decoder* h, const void* symbols, size_t n_symbols, uint64_t
     if (steps == 0) return VITB_OK;
     VITB_CUDA(h, cudaSetDevice(h->prm.device));
     const size_t sb = size_t(h->prm.soft_bytes);
-    VITB_CUDA(h, h->s_in.reserve(n_symbols * sb));
     VITB_CUDA(h, h->s_pk.reserve(n_symbols * 32 * 4));
-    VITB_CUDA(h, cudaMemcpyAsync(h->s_in.ptr, symbols, n_symbols * sb, cudaMemcpyHostToDevice, h->stream));
-    VITB_CUDA(h, cudaMemsetAsync(h->s_acc.ptr, 0, 64 * 8, h->stream));       // update() returns the minima of THIS call (scalar.h:42)
+    // Calls of up to 64 KB of symbols (the reference's programs call update once per trellis step or per puncture segment:
+    // run_punctured_decoder.cpp, puncture_code_helpers.h:32-52) go through mapped pinned memory: the ingest kernel reads the symbols
+    // from there, the ACS kernel leaves the call's accumulated minima there - two launches and one synchronize per call.
+    constexpr size_t MAP_ACC_BYTES = 512, MAP_SYM_BYTES = 64 * 1024;
+    const bool mapped = n_symbols * sb <= MAP_SYM_BYTES && !getenv("VITB_NO_MAPPED_STREAMING");
+    const void* d_sym;
+    uint64_t* d_acc;
+    if (mapped) {
+        VITB_CUDA(h, h->s_map.reserve(MAP_ACC_BYTES + MAP_SYM_BYTES));
+        memcpy(static_cast<char*>(h->s_map.host) + MAP_ACC_BYTES, symbols, n_symbols * sb);
+        memset(h->s_map.host, 0, MAP_ACC_BYTES);                                // update() returns the minima of THIS call (scalar.h:42)
+        d_sym = static_cast<const char*>(h->s_map.dev) + MAP_ACC_BYTES;
+        d_acc = static_cast<uint64_t*>(h->s_map.dev);
+    } else {
+        VITB_CUDA(h, h->s_in.reserve(n_symbols * sb));
+        VITB_CUDA(h, cudaMemcpyAsync(h->s_in.ptr, symbols, n_symbols * sb, cudaMemcpyHostToDevice, h->stream));
+        VITB_CUDA(h, cudaMemsetAsync(h->s_acc.ptr, 0, 64 * 8, h->stream));
+        d_sym = h->s_in.ptr;
+        d_acc = static_cast<uint64_t*>(h->s_acc.ptr);
+    }
 
     IngestParams ip{};
-    ip.symbols = h->s_in.ptr; ip.row_stride = n_symbols; ip.n_frames = 1; ip.n_sym = uint32_t(n_symbols);
+    ip.symbols = d_sym; ip.row_stride = n_symbols; ip.n_frames = 1; ip.n_sym = uint32_t(n_symbols);
     ip.depuncture_map = nullptr; ip.fill_value = 0; ip.pk = static_cast<uint32_t*>(h->s_pk.ptr); ip.ppw = uint32_t(h->entry->ppw);
     VITB_CUDA(h, run_ingest(h, ip, 1, h->stream));
 
     AcsParams a{};
     fill_acs_params(h, a);
     a.pk = static_cast<const uint32_t*>(h->s_pk.ptr); a.dec = h->s_dec.ptr;
-    a.metrics = static_cast<uint16_t*>(h->s_metrics.ptr); a.acc = static_cast<uint64_t*>(h->s_acc.ptr);
+    a.metrics = static_cast<uint16_t*>(h->s_metrics.ptr); a.acc = d_acc;
     a.n_blocks = 1;      // warp block 0 holds the user's frame (frame 0); its other frames decode zeros and are ignored
     a.n_frames = 1;
     a.n_steps = uint32_t(steps); a.dec_rows = uint32_t(rows); a.dec_row0 = uint32_t(h->current_decoded_bit);
@@ -960,8 +998,9 @@ int vitb_update(vitb_decoder* h, const void* symbols, size_t n_symbols, uint64_t
     if (h->entry->generic) VITB_CUDA(h, h->entry->launch_generic(a, h->gcode, h->stream));
     else VITB_CUDA(h, h->entry->launch(a, h->stream));
     uint64_t acc = 0;
-    VITB_CUDA(h, cudaMemcpyAsync(&acc, h->s_acc.ptr, 8, cudaMemcpyDeviceToHost, h->stream));
+    if (!mapped) VITB_CUDA(h, cudaMemcpyAsync(&acc, h->s_acc.ptr, 8, cudaMemcpyDeviceToHost, h->stream));
     VITB_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (mapped) acc = *static_cast<volatile uint64_t*>(h->s_map.host);
     h->current_decoded_bit += steps;                                                        // scalar.h:52
     if (accumulated_error) *accumulated_error = acc;
     return VITB_OK;
