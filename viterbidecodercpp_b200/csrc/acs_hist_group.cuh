@@ -1,4 +1,5 @@
-// acs_hist_group.cuh -- survivor-history add-compare-select for K = 9 with uint16_t error metrics: ONE FRAME OVER T = 4 LANES.
+// acs_hist_group.cuh -- survivor-history add-compare-select with uint16_t error metrics, ONE FRAME OVER T = 4 LANES: K = 9 (the
+// default for batches that fill the GPU) and K = 7 (small batches: a quarter of the registers per lane, four times the warps).
 //
 // The survivor-history idea of acs_hist.cuh (register = metric << 16 | last <= 16 decisions of the survivor path into that state;
 // a butterfly is 2 adds + 2 fused add-min, no predicates, one record per 16 steps instead of a decision row per step) needs the
@@ -31,7 +32,14 @@ namespace vitb {
 template <class C>
 struct HistGroupShape {
     static constexpr int LOGT = 2, T = 4, SB = C::SB, LB = SB - LOGT, NL = 1 << LB, NW = NL / 2, FPW = 32 / T, WARPS = 2;
-    static_assert(SB == 8 && (C::R % 2) == 0, "built for K = 9 codes with an even number of symbols per step");
+    // K = 9: 64 registers per lane, exchange every 6 steps; K = 7 (small batches, see below): 16 registers, every 4 steps
+    static_assert((SB == 8 || SB == 6) && ((LB * C::R) % 2) == 0, "built for K = 9 and K = 7; an exchange period must be whole 32-bit words of symbols");
+    // can a 16-step record end behind phase PH of an exchange period (other than its last one)?
+    static __host__ __device__ constexpr bool record_may_end_after(int PH) {
+        int g = LB, b = 16;
+        while (b) { const int r = g % b; g = b; b = r; }          // gcd(LB, 16)
+        return PH != LB - 1 && ((PH + 1) % g) == 0;
+    }
     // shared-memory word of position PHI' for frame fw of the warp: rows of 32 words, XOR swizzle so that the 64 writes of a lane
     // ((t << LB) | q: consecutive q) and its 64 reads ((q << LOGT) | t) both touch 32 distinct banks per warp instruction
     static __host__ __device__ constexpr uint32_t slot(uint32_t fw, uint32_t phi) {
@@ -39,6 +47,11 @@ struct HistGroupShape {
         return qp * 32u + ((fw * uint32_t(T) + tp) ^ ((qp >> (LB - LOGT)) & uint32_t(T - 1)));
     }
 };
+
+template <class F, int... PHs>
+__device__ __forceinline__ void hg_for_each_phase(F&& f, std::integer_sequence<int, PHs...>) {
+    (f(std::integral_constant<int, PHs>{}), ...);
+}
 
 // one in-place butterfly at compile-time phase PH on registers Q and Q | bit
 template <class C, int PH, int TIE_SIMD, int Q>
@@ -167,12 +180,12 @@ __global__ void __launch_bounds__(32 * HistGroupShape<C>::WARPS, 7) acs_hist_gro
 
     // exchange after LB phases: the value at (q, t) moves to PHI' = (t << LB) | q, read back as PHI' = (q << LOGT) | t.  With the
     // swizzle of HistGroupShape::slot both sides reduce to four base addresses per lane plus compile-time offsets:
-    //   write (q, t): row (t << 4) | (q >> 2), column (4 fw + (q & 3)) ^ t      read q: row q, column (4 fw + t) ^ ((q >> 4) & 3)
+    //   write (q, t): row (t << (LB-2)) | (q >> 2), column (4 fw + (q & 3)) ^ t      read q: row q, column (4 fw + t) ^ ((q >> (LB-2)) & 3)
     uint32_t* wr_base[4];
     const uint32_t* rd_base[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        wr_base[k] = my_xch + (t << 4) * 32u + ((fw * 4u + uint32_t(k)) ^ t);
+        wr_base[k] = my_xch + (t << (LB - LOGT)) * 32u + ((fw * 4u + uint32_t(k)) ^ t);
         rd_base[k] = my_xch + ((fw * 4u + t) ^ uint32_t(k));
     }
     auto exchange = [&]() {
@@ -181,7 +194,7 @@ __global__ void __launch_bounds__(32 * HistGroupShape<C>::WARPS, 7) acs_hist_gro
         for (int q = 0; q < NL; q++) wr_base[q & 3][(q >> 2) * 32] = x[q];
         __syncwarp();
 #pragma unroll
-        for (int q = 0; q < NL; q++) x[q] = rd_base[(q >> 4) & 3][q * 32];
+        for (int q = 0; q < NL; q++) x[q] = rd_base[(q >> (LB - LOGT)) & 3][q * 32];
     };
 
     uint32_t tag = 1u, pst = 0, r = 0, pend = 0u;
@@ -217,13 +230,16 @@ __global__ void __launch_bounds__(32 * HistGroupShape<C>::WARPS, 7) acs_hist_gro
         hg_step<C, PH, TIE_SIMD, CONSISTENT>(x, sym, fold_bits, c, tag, lane, acc, pend);
         tag <<= 1;
         pst++;
-        if constexpr (PH == 1 || PH == 3) {         // (after phase 5 the record is cut behind the exchange, see the loop)
+        if constexpr (S::record_may_end_after(PH)) {     // (after the last phase the record is cut behind the exchange, see the loop)
             if (pst == uint32_t(HB)) emit_record();
         }
     };
 
     using NoGuard = std::false_type;
     using Guard = std::true_type;
+    auto all_phases = [&](auto guard_tag, uint32_t n0_, auto seq) {
+        hg_for_each_phase([&](auto phc) { do_phase(phc, guard_tag, n0_); }, seq);
+    };
     uint32_t n0 = 0, w0 = uint32_t(WPP);
 #pragma unroll 1
     for (; n0 + LB <= p.n_steps; n0 += LB, w0 += uint32_t(WPP)) {      // complete exchange periods
@@ -234,23 +250,14 @@ __global__ void __launch_bounds__(32 * HistGroupShape<C>::WARPS, 7) acs_hist_gro
             const uint32_t w = w0 + uint32_t(j);
             nxt[j] = __ldg(row + (w < maxw ? w : maxw));
         }
-        do_phase(std::integral_constant<int, 0>{}, NoGuard{}, n0);
-        do_phase(std::integral_constant<int, 1>{}, NoGuard{}, n0);
-        do_phase(std::integral_constant<int, 2>{}, NoGuard{}, n0);
-        do_phase(std::integral_constant<int, 3>{}, NoGuard{}, n0);
-        do_phase(std::integral_constant<int, 4>{}, NoGuard{}, n0);
-        do_phase(std::integral_constant<int, 5>{}, NoGuard{}, n0);
+        all_phases(NoGuard{}, n0, std::make_integer_sequence<int, LB>{});
         exchange();                                 // a full period ran: positions back to PHI = s
         if (pst == uint32_t(HB)) emit_record();     // records are cut in the layout the traceback expects: PHI = rotr^(steps mod 6)(s)
     }
     if (n0 < p.n_steps) {                           // the incomplete last period: guarded steps, no exchange
 #pragma unroll
         for (int j = 0; j < WPP; j++) cur[j] = nxt[j];
-        do_phase(std::integral_constant<int, 0>{}, Guard{}, n0);
-        do_phase(std::integral_constant<int, 1>{}, Guard{}, n0);
-        do_phase(std::integral_constant<int, 2>{}, Guard{}, n0);
-        do_phase(std::integral_constant<int, 3>{}, Guard{}, n0);
-        do_phase(std::integral_constant<int, 4>{}, Guard{}, n0);
+        all_phases(Guard{}, n0, std::make_integer_sequence<int, LB - 1>{});
     }
     if (pst) emit_record();                         // last, partial record (its pst is still needed for the SIMD tie-break mask)
     const uint32_t ph = p.n_steps % uint32_t(LB);
@@ -259,12 +266,13 @@ __global__ void __launch_bounds__(32 * HistGroupShape<C>::WARPS, 7) acs_hist_gro
 
     // final metrics in logical order: state s sits at PHI = rotr^ph(s)   (core.h:195-199 reads old_metrics[end_state])
     uint16_t* m = p.metrics + f * C::NS;
-    switch (ph) {
-#define VITB_HG_WB(PH_) case PH_: _Pragma("unroll") for (int q = 0; q < NL; q++) m[rotl_bits((uint32_t(q) << LOGT) | t, PH_, SB)] = uint16_t(x[q] >> 16); break;
-        VITB_HG_WB(0) VITB_HG_WB(1) VITB_HG_WB(2) VITB_HG_WB(3) VITB_HG_WB(4)
-        default: _Pragma("unroll") for (int q = 0; q < NL; q++) m[rotl_bits((uint32_t(q) << LOGT) | t, 5, SB)] = uint16_t(x[q] >> 16); break;
-#undef VITB_HG_WB
-    }
+    hg_for_each_phase([&](auto phc) {
+        constexpr int PH = decltype(phc)::value;
+        if (ph == uint32_t(PH)) {
+#pragma unroll
+            for (int q = 0; q < NL; q++) m[rotl_bits((uint32_t(q) << LOGT) | t, PH, SB)] = uint16_t(x[q] >> 16);
+        }
+    }, std::make_integer_sequence<int, LB>{});
     if (t == 0) p.acc[f] = acc;
 }
 

@@ -34,6 +34,7 @@ static const std::vector<KernelEntry>& registry() {
         register_generic(entries);
         register_k9_hist_group(entries);
         register_k15_hist_cta(entries);
+        register_k7_hist_group(entries);
     });
     return entries;
 }
@@ -116,7 +117,7 @@ struct vitb_decoder {
     vitb_params prm{};
     std::vector<const KernelEntry*> variants;   // every compiled lanes-per-pair variant of this code/config, ascending logt
     const KernelEntry* entry = nullptr;         // variant used by the single-frame streaming API (fixes its decision layout)
-    const KernelEntry* hg_entry = nullptr;      // frame-over-4-lanes survivor-history kernel (K = 9, uint16_t metrics), batch calls only
+    const KernelEntry* hg_entry = nullptr;      // frame-over-4-lanes (K = 9, K = 7) / frame-per-CTA (K = 15) survivor-history kernel, uint16_t metrics, batch calls only
     const KernelEntry* last_batch = nullptr;    // variant the last batch call selected
     bool last_batch_hist = false;               // ... and whether it ran as the survivor-history kernel (acs_hist.cuh)
     std::string name_buf, name_override;        // name_override: a batch call that used two kernels (cta_wave_split)
@@ -466,7 +467,16 @@ int decode_chunk_dev(vitb_decoder* h, const KernelEntry* e, const void* d_symbol
         const bool forced = h->forced_variant == entry_variant(a);
         if (a->layout == LAYOUT_HISTGROUP) {
             const bool direct_ok = (row_bytes0 % 4 == 0) && row_bytes0 >= 4 && (reinterpret_cast<uintptr_t>(d_symbols) % 4 == 0);
-            hg = direct_ok && (forced || (h->forced_variant == 0 && (n_frames + 7) / 8 >= size_t(h->n_sm) * 2));
+            // K = 9: the default once its 8 frames per warp fill the GPU.  K = 7: the one-lane history kernel (32 frames per warp,
+            // 16 instructions per add-compare-select pair fewer) is the faster one as soon as every scheduler has a warp of it; below
+            // that a frame over 4 lanes brings four times the warps (run_simple, 8192 frames: 256 warps on 592 schedulers)
+            // (measured, B200, ACS only: Voyager soft16 4096 frames 0.173 -> 0.106 ms, 8192 frames 0.175 -> 0.145 ms, 12 288 frames
+            // 0.175 -> 0.182 ms; DAB R = 1/4, whose 16-entry branch metric table is paid per lane: 8192 frames 1.53 -> 1.60 ms, 4096 frames
+            // 1.53 -> 1.49 ms - pinned only)
+            const size_t one_lane_warps = (n_frames + 31) / 32;
+            const bool auto_ok = (h->prm.K == 9) ? ((n_frames + 7) / 8 >= size_t(h->n_sm) * 2)
+                                                 : (h->prm.R <= 3 && one_lane_warps < size_t(h->n_sm) * 2);
+            hg = direct_ok && (forced || (h->forced_variant == 0 && auto_ok));
         } else {
             // One frame per CTA: 1.5 times the instructions per frame of the packed decision-row kernel (acs_cta.cuh, a frame PAIR per
             // CTA: 14.0 ms per wave of 148 pairs against 10.4 ms per wave of 148 frames, config 5), but half the granularity: it takes
@@ -555,7 +565,8 @@ int decode_chunk_dev(vitb_decoder* h, const KernelEntry* e, const void* d_symbol
         // segments per frame, 0.677 ms with one; profiles/r02_summary.md)
         // (Only behind the one-lane kernels, whose few CTAs leave room on every SM: the K = 9 kernel fills the register files, the
         // traceback then runs in its tail anyway and is better off segmented - config 3 pipelined: 4.83 ms single chain, 4.64 segmented.)
-        const bool gentle = h->overlap_hint && !hg && !hc;
+        // (The K = 7 lane-group kernel is a small-batch kernel: its CTAs leave room too.)
+        const bool gentle = h->overlap_hint && !(hg && K == 9) && !hc;
         const size_t want_seg = gentle ? 1 : (seg_target + n_frames - 1) / n_frames;
         size_t seg_records = (n_periods + want_seg - 1) / want_seg;
         if (seg_records < 4 * overlap && !gentle) seg_records = 4 * overlap;

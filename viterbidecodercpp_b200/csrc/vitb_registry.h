@@ -186,6 +186,7 @@ KernelEntry make_hist_group_entry(const char* name) {
     for (int i = 0; i < C::R; i++) e.G[i] = C::G[i];
     e.sh = 0; e.tie = TIE_SIMD; e.consistent = CONSISTENT ? 1 : 0; e.logt = HistGroupShape<C>::LOGT; e.name = name;
     e.layout = LAYOUT_HISTGROUP; e.ppw = 0; e.dec_words = 0;
+    if (C::K == 7) e.variant_id = 104;       // 4 lanes per FRAME; 4 alone is the decision-row kernel with 4 lanes per frame pair
     e.launch_hist = &launch_hist_group<C, TIE_SIMD, CONSISTENT>;
     return e;
 }
@@ -237,6 +238,7 @@ void register_small(std::vector<KernelEntry>& v);
 void register_generic(std::vector<KernelEntry>& v);
 void register_k9_hist_group(std::vector<KernelEntry>& v);
 void register_k15_hist_cta(std::vector<KernelEntry>& v);
+void register_k7_hist_group(std::vector<KernelEntry>& v);
 void register_k7r2_t1(std::vector<KernelEntry>& v);
 void register_k7r2_t2(std::vector<KernelEntry>& v);
 void register_k7r2_t4(std::vector<KernelEntry>& v);
