@@ -173,7 +173,11 @@ int vitb_set_profiling(vitb_decoder* h, int enabled);
 int vitb_get_stage_ms(vitb_decoder* h, float ms[4]);
 /* Kernel variants: a frame pair can be spread over 1, 2, 4 ... lanes (more lanes = more warps for small batches).  By default the
  * variant is chosen per batch call from the batch size; vitb_set_variant pins it (0 = automatic).  vitb_get_variants lists the
- * compiled lanes-per-pair settings of this handle's code and returns their number. */
+ * compiled lanes-per-pair settings of this handle's code and returns their number.  Numbers above 100 name batch-only
+ * survivor-history kernels that share a lane count with a decision-row kernel: 104 = K = 7, uint16_t metrics, one FRAME over 4
+ * lanes (the small-batch kernel); 256 = K = 15, uint16_t metrics, one frame per 512-thread CTA.  A pinned batch-only variant
+ * applies when its input requirements hold (unpunctured rows, 4-byte aligned for the lane-group kernels); otherwise the call falls
+ * back to the automatic choice. */
 int vitb_set_variant(vitb_decoder* h, int lanes_per_pair);
 int vitb_get_variants(const vitb_decoder* h, int* lanes_per_pair, int capacity);
 /* One-lane-per-pair variants (K <= 7) decode whole-frame batches with the survivor-history kernel (csrc/acs_hist.cuh: decisions ride
