@@ -169,24 +169,30 @@ def test_hist_group_record_position_of_a_state():
 
 
 def test_cta_exchange_skew_is_conflict_free():
-    """csrc/acs_cta.cuh CtaShape::slot(phi) = phi + (phi >> 5): the exchange's warp-wide stores ((t << LB) | q, fixed q) and loads
-    ((q << LOGT) | t, fixed q) hit 32 distinct banks, and slots never collide"""
+    """csrc/acs_cta.cuh CtaShape::slot(phi) = phi + 4 * (phi >> 5): the exchange's loads ((q << LOGT) | t, fixed q) hit 32 distinct
+    banks per warp, its stores - 2^LB consecutive words per thread, as STS.128, served a quarter warp at a time - 8 distinct 16-byte
+    bank groups per quarter warp (and 32 distinct banks per warp as scalar stores), slots never collide and stay 16-byte aligned"""
     SB = 14
     for LOGT in (9, 10):
         LB, T = SB - LOGT, 1 << LOGT
         NL = 1 << LB
-        slot = lambda phi: phi + (phi >> 5)
+        slot = lambda phi: phi + ((phi >> 5) << 2)
         assert len({slot(p) for p in range(1 << SB)}) == 1 << SB
-        assert max(slot(p) for p in range(1 << SB)) < (1 << SB) + (1 << SB) // 32 + 32
+        assert max(slot(p) for p in range(1 << SB)) < (1 << SB) + (1 << SB) // 8 + 32
         for w in range(T // 32):
             lanes = range(32 * w, 32 * w + 32)
             for q in range(NL):
-                assert len({slot((t << LB) | q) % 32 for t in lanes}) == 32
                 assert len({slot((q << LOGT) | t) % 32 for t in lanes}) == 32
+            for q4 in range(0, NL, 4):
+                for quarter in range(4):
+                    ts = range(32 * w + 8 * quarter, 32 * w + 8 * quarter + 8)
+                    words = [slot((t << LB) | q4) for t in ts]
+                    assert all(x % 4 == 0 for x in words)
+                    assert len({(x % 32) // 4 for x in words}) == 8
         # the split form the kernels use (per-thread offset + compile-time offset: CtaShape::rd_off / wr_off / RD_STRIDE)
         for t in range(T):
             for q in range(NL):
-                assert slot((q << LOGT) | t) == (t + (t >> 5)) + q * (T + T // 32)
+                assert slot((q << LOGT) | t) == (t + ((t >> 5) << 2)) + q * (T + T // 8)
                 assert slot((t << LB) | q) == slot(t << LB) + q
 
 

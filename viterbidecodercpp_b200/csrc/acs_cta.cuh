@@ -34,7 +34,7 @@ struct CtaShape {
     static constexpr int NL = 1 << LB;               // packed registers per thread
     static constexpr int NP = C::NP;                 // branch patterns
     static constexpr int WARPS = T / 32;
-    static constexpr size_t XCH_WORDS = size_t(C::NS) + size_t(C::NS) / 32 + 32;   // skewed by one word per 32
+    static constexpr size_t XCH_WORDS = size_t(C::NS) + size_t(C::NS) / 8 + 32;    // skewed by four words per 32
     static constexpr size_t TBL_WORDS = size_t(LB) * NP * 4;          // [LB][NP] 16-byte slots {own entry, partner's entry}
     // Exchange buffer and tables are double-buffered.  The two table sets lie a power of two apart, so that "which set" is one bit of
     // the per-thread byte offset a fetch XORs its pattern into - the base stays a constant the load takes as immediate.
@@ -42,16 +42,19 @@ struct CtaShape {
     static_assert(TBL_WORDS * 4 <= TBL_SET_BYTES, "a table set must fit its slot");
     static constexpr size_t SMEM_BYTES = (2 * XCH_WORDS + 64) * 4 + 2 * TBL_SET_BYTES;
     // Skew instead of XOR so that every access is (per-thread base) + (compile-time offset): the exchange writes position
-    // (t << LB) | q -> word 33t + q (LB = 5) and reads (q << LOGT) | t -> word q * (T + T/32) + t + (t >> 5); both hit 32 distinct
-    // banks per warp (tests/test_host_cpu.py::test_cta_exchange_skew_is_conflict_free).
-    static __host__ __device__ constexpr uint32_t slot(uint32_t phi) { return phi + (phi >> 5); }
+    // (t << LB) | q -> word 36t + q (LB = 5) and reads (q << LOGT) | t -> word q * (T + T/8) + t + 4 (t >> 5); conflict-free on both
+    // sides (tests/test_host_cpu.py::test_cta_exchange_skew_is_conflict_free).
+    static __host__ __device__ constexpr uint32_t slot(uint32_t phi) { return phi + ((phi >> 5) << 2); }
     // the same, split into a per-thread offset and a compile-time one (the buffers alternate, so their base is a run-time value and
     // ptxas would otherwise recompute the whole expression for every register and group):
     //   slot((q << LOGT) | t) = rd_off(t) + q * RD_STRIDE,   slot((t << LB) | q) = wr_off(t) + q   (q < 2^LB <= 32)
-    static constexpr uint32_t RD_STRIDE = uint32_t(T) + uint32_t(T) / 32;
-    static __host__ __device__ constexpr uint32_t rd_off(uint32_t t) { return t + (t >> 5); }
+    static constexpr uint32_t RD_STRIDE = uint32_t(T) + uint32_t(T) / 8;
+    static __host__ __device__ constexpr uint32_t rd_off(uint32_t t) { return t + ((t >> 5) << 2); }
     static __host__ __device__ constexpr uint32_t wr_off(uint32_t t) { return slot(t << LB); }
-    static_assert(LB <= 5 && LOGT >= 5, "split form of slot()");
+    static_assert(LB <= 5 && LB >= 2 && LOGT >= 5, "split form of slot()");
+    // Four words of skew per 32 (not one) keep a thread's 2^LB consecutive words 16-byte aligned: the write side of the exchange is
+    // STS.128 - a quarter warp of them hits 8 different bank groups (36 t and 16 t + 4 (t >> 1) modulo 32 words, t = 8k .. 8k+7) -,
+    // the read side stays 32 consecutive words per warp and register.
 };
 
 // TABLE FETCH BY BUTTERFLY PAIRS (OR QUADS).  The entry of a butterfly is T[pq ^ pt] (pq: pattern of the register bits, a compile-time constant;
@@ -192,6 +195,14 @@ template <int NL> struct CtaAcc { static constexpr int value = NL >= 32 ? 4 : (N
 #endif
 constexpr int CTA_CHAINS = VITB_CTA_CHAINS;          // chains per decision byte (1, 2 or 4)
 
+// store registers x[Q0 .. Q0+3] of a thread into the exchange buffer with one STS.128 (xout + Q0 is 16-byte aligned: wr_off is a
+// multiple of 4 words and so is Q0)
+template <int Q0, int NL>
+__device__ __forceinline__ void cta_store4(uint32_t* xout, const uint32_t (&x)[NL]) {
+    static_assert(Q0 % 4 == 0 && Q0 + 3 < NL, "aligned group of four registers");
+    *reinterpret_cast<uint4*>(xout + Q0) = make_uint4(x[Q0], x[Q0 + 1], x[Q0 + 2], x[Q0 + 3]);
+}
+
 // ARITHMETIC DECISIONS (the wrapping flavours).  The predicate form below pays ~1.4 instructions per decision bit on top of its
 // 4 adds + 2 min per butterfly (predicated FADD / FSEL + FADD, 89 of 290 instructions per step, and the kernel is issue bound).
 // Here the min is fused with one of the adds and the decision is read off the result:
@@ -221,7 +232,6 @@ __device__ __forceinline__ void cta_bfly_arith_one(uint32_t (&x)[CtaShape<C, LT>
     const uint32_t d0 = __vminu2(t0, 0x00010001u), d1 = __vminu2(t1, 0x00010001u);
     ia[q0 >> 4][(q0 >> 3) & 1] += d0 << (q0 & 15);
     ia[q1 >> 4][(q1 >> 3) & 1] += d1 << (q1 & 15);
-    if constexpr (STORE) { xout[q0] = x[q0]; xout[q1] = x[q1]; }      // slot((t << LB) | q) = slot(t << LB) + q
 }
 
 // STORE (last phase of a full group): both results go straight to the other exchange buffer, xout = buffer + slot(t << LB), so that
@@ -250,7 +260,6 @@ __device__ __forceinline__ void cta_bfly_pred_one(uint32_t (&x)[CtaShape<C, LT>:
     if (dB0) fa[1][acc0][n0] += w0;
     if (dA1) fa[0][acc1][n1] += w1;
     if (dB1) fa[1][acc1][n1] += w1;
-    if constexpr (STORE) { xout[q0] = x[q0]; xout[q1] = x[q1]; }      // slot((t << LB) | q) = slot(t << LB) + q
 }
 
 // the two butterflies (Q, Q | bit) and (Q | pbit, Q | pbit | bit) of a pair: one 16-byte table fetch (PairMap above); pt is the
@@ -274,6 +283,13 @@ __device__ __forceinline__ void cta_bfly_pair_at(uint32_t (&x)[CtaShape<C, LT>::
         } else {
             cta_bfly_arith_one<C, LT, TIE_SIMD, STORE, Q, Q | bit>(x, e.x, e.y, acc, xout);
             cta_bfly_arith_one<C, LT, TIE_SIMD, STORE, Q | pbit, Q | pbit | bit>(x, e.z, e.w, acc, xout);
+        }
+        if constexpr (STORE) {                      // slot((t << LB) | q) = slot(t << LB) + q
+            if constexpr (bit == 1 && pbit == 2) {
+                cta_store4<Q>(xout, x);             // the pair's four registers are Q .. Q+3
+            } else {
+                xout[Q] = x[Q]; xout[Q | bit] = x[Q | bit]; xout[Q | pbit] = x[Q | pbit]; xout[Q | pbit | bit] = x[Q | pbit | bit];
+            }
         }
     }
 }
@@ -510,7 +526,7 @@ __global__ void __launch_bounds__(CtaShape<C, LT>::T, 1) acs_cta_kernel(const Ac
             if constexpr (LB > 4) run_phase(std::integral_constant<int, 4>{});
             if (full) {                                      // a group that started inside an exchange period (streaming API)
 #pragma unroll
-                for (int q = 0; q < NL; q++) xnew[wr_off + uint32_t(q)] = x[q];
+                for (int q = 0; q < NL; q += 4) *reinterpret_cast<uint4*>(xnew + wr_off + q) = make_uint4(x[q], x[q + 1], x[q + 2], x[q + 3]);
             }
         }
         if (t == 0) {
@@ -556,7 +572,7 @@ __global__ void __launch_bounds__(CtaShape<C, LT>::T, 1) acs_cta_kernel(const Ac
             if (full) {
                 // the exchange of the replayed group: value at (q, t) moves to PHI' = (t << LB) | q
 #pragma unroll
-                for (int q = 0; q < NL; q++) xnew[wr_off + uint32_t(q)] = x[q];
+                for (int q = 0; q < NL; q += 4) *reinterpret_cast<uint4*>(xnew + wr_off + q) = make_uint4(x[q], x[q + 1], x[q + 2], x[q + 3]);
             }
             __syncthreads();
         }

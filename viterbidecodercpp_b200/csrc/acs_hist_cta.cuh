@@ -105,11 +105,16 @@ __device__ __forceinline__ void hc_bfly_quad_at(uint32_t (&x)[HistCtaShape<C>::N
         hc_bfly(x[Q | p1], x[Q | p1 | bit], e.y, cq);
         hc_bfly(x[Q | p2], x[Q | p2 | bit], e.z, cq);
         hc_bfly(x[Q | p1 | p2], x[Q | p1 | p2 | bit], e.w, cq);
-        if constexpr (STORE) {
+        if constexpr (STORE) {                               // xout = buffer + slot(t << LB): slot((t << LB) | q) = slot(t << LB) + q
+            if constexpr (bit == 1 && p1 == 2 && p2 == 4) {
+                cta_store4<Q>(xout, x);                      // the quad's eight registers are Q .. Q+7: two STS.128
+                cta_store4<Q + 4>(xout, x);
+            } else {
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                constexpr int qs[8] = {Q, Q | bit, Q | p1, Q | p1 | bit, Q | p2, Q | p2 | bit, Q | p1 | p2, Q | p1 | p2 | bit};
-                xout[qs[k]] = x[qs[k]];                      // xout = buffer + slot(t << LB): slot((t << LB) | q) = slot(t << LB) + q
+                for (int k = 0; k < 8; k++) {
+                    constexpr int qs[8] = {Q, Q | bit, Q | p1, Q | p1 | bit, Q | p2, Q | p2 | bit, Q | p1 | p2, Q | p1 | p2 | bit};
+                    xout[qs[k]] = x[qs[k]];
+                }
             }
         }
     }
@@ -335,7 +340,7 @@ __global__ void __launch_bounds__(HistCtaShape<C>::T, MINB) acs_hist_cta_kernel(
             if (full) {
                 // the exchange of the replayed group: value at (q, t) moves to PHI' = (t << LB) | q
 #pragma unroll
-                for (int q = 0; q < NL; q++) xnew[wr_off + uint32_t(q)] = x[q];
+                for (int q = 0; q < NL; q += 4) *reinterpret_cast<uint4*>(xnew + wr_off + q) = make_uint4(x[q], x[q + 1], x[q + 2], x[q + 3]);
             }
             __syncthreads();
         }
