@@ -137,7 +137,8 @@ __device__ __forceinline__ void hc_thread_slots(uint32_t (&mpt)[sizeof...(PHs)],
 }
 
 // grid = number of frames, block = 512, dynamic shared memory = HistCtaShape::SMEM_BYTES.  Whole frames only (no resume).
-// MINB: CTAs per SM the register allocation is made for (1: 128 registers per thread; 2: 64 registers - measured slower, it spills)
+// MINB: CTAs per SM the register allocation is made for.  1: 128 registers per thread.  (2 = 64 registers was measured slower when
+// the kernel still fitted twice per SM - it spilled -; with the double-buffered exchange, 168 KB of shared memory, it no longer does.)
 template <class C, int TIE_SIMD, int MINB>
 __global__ void __launch_bounds__(HistCtaShape<C>::T, MINB) acs_hist_cta_kernel(const AcsParams p) {
     using H = HistCtaShape<C>;

@@ -203,13 +203,6 @@ KernelEntry make_hist_group_entry(const char* name) {
 template <class C, int TIE_SIMD>
 cudaError_t launch_hist_cta(const AcsParams& p, cudaStream_t s) {
     using H = HistCtaShape<C>;
-    static const int minb = getenv("VITB_HC_MINB") ? atoi(getenv("VITB_HC_MINB")) : 1;      // experiment knob: CTAs per SM
-    if (minb == 2) {
-        const cudaError_t e = cudaFuncSetAttribute(acs_hist_cta_kernel<C, TIE_SIMD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(H::SMEM_BYTES));
-        if (e != cudaSuccess) return e;
-        acs_hist_cta_kernel<C, TIE_SIMD, 2><<<p.n_frames, H::T, H::SMEM_BYTES, s>>>(p);
-        return cudaGetLastError();
-    }
     const cudaError_t e = cudaFuncSetAttribute(acs_hist_cta_kernel<C, TIE_SIMD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(H::SMEM_BYTES));
     if (e != cudaSuccess) return e;
     acs_hist_cta_kernel<C, TIE_SIMD, 1><<<p.n_frames, H::T, H::SMEM_BYTES, s>>>(p);
