@@ -265,3 +265,19 @@ def test_reference_adapter_and_cuda_slot_compile_against_the_reference_headers(t
                    'int main() { return simd_type_list_with_cuda().back() == SIMD_CUDA ? 0 : 1; }\n')
     subprocess.run(["g++", "-std=c++17", "-mavx2", "-msse4.2", "-Wall", "-fsyntax-only", "-I", inc, "-I", "/root/reference/include", "-I", "/root/reference/examples",
                     "-I", os.path.join(ROOT, "oracle", "ref_programs"), str(cpp)], check=True)
+
+
+def test_k15_table_slot_maps_compile_time_checks(tmp_path):
+    """tests/host_programs/pair_map_check.cu: the slot maps of the K = 15 kernels' table fetch (csrc/acs_cta.cuh PairMap) are
+    bijections, put the butterflies of a pair / quad into one 16-byte slot and keep quarter warps free of bank conflicts - checked by
+    static_asserts over the same constexpr evaluation the kernels use, so compiling the program IS the test"""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not found")
+    exe = tmp_path / "pair_map_check"
+    subprocess.check_call([nvcc, "-std=c++17", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets",
+                           "-I", os.path.join(ROOT, "viterbidecodercpp_b200", "csrc"), "-o", str(exe),
+                           os.path.join(ROOT, "tests", "host_programs", "pair_map_check.cu")])
+    assert "pair maps ok" in subprocess.check_output([str(exe)]).decode()
