@@ -132,25 +132,35 @@ def test_exchange_swizzle_is_conflict_free():
         assert seen == set(range(NL * 32))
     for SB, g in [(4, 2), (6, 1), (6, 2), (6, 3), (8, 3), (8, 4), (8, 5)]:
         check(SB, g)
-    check(8, 2)       # csrc/acs_hist_group.cuh (HistGroupShape::slot): one frame over 4 lanes, 64 registers per lane
 
 
-def test_hist_group_exchange_base_addresses_match_the_slot_function():
-    """acs_hist_group_kernel addresses its exchange through four base pointers per lane plus compile-time offsets; they must be the
-    slot function above: write (q, t) -> PHI' = (t << 6) | q, read q -> PHI' = (q << 2) | t"""
-    g, LB = 2, 6
+def test_hist_group_exchange_layout():
+    """csrc/acs_hist_group.cuh (HistGroupShape::slot), one frame over 4 lanes, K = 9 (64 registers per lane) and K = 7 (16): the slots
+    are a bijection; a lane's four consecutive registers are one aligned 16-byte group and the 8 lanes of a quarter warp write 8
+    different groups (STS.128 is served a quarter warp at a time); every warp-wide load hits 32 distinct banks; and the base addresses
+    the kernel uses - one per lane for the stores, four for the loads, plus compile-time offsets - are that slot function"""
+    g = 2
     T = 1 << g
+    for LB in (6, 4):
+        NL = 1 << LB
 
-    def slot(fw, phi):
-        qp, tp = phi >> g, phi & (T - 1)
-        return qp * 32 + ((fw * T + tp) ^ ((qp >> (LB - g)) & (T - 1)))
-    for lane in range(32):
-        fw, t = lane >> g, lane & (T - 1)
-        wr_base = [(t << 4) * 32 + ((fw * 4 + k) ^ t) for k in range(4)]
-        rd_base = [((fw * 4 + t) ^ k) for k in range(4)]
-        for q in range(64):
-            assert wr_base[q & 3] + (q >> 2) * 32 == slot(fw, (t << LB) | q)
-            assert rd_base[(q >> 4) & 3] + q * 32 == slot(fw, (q << g) | t)
+        def slot(fw, phi):
+            qp, tp = phi >> g, phi & (T - 1)
+            return qp * 32 + ((fw + 2 * (qp >> (LB - g))) & 7) * 4 + tp
+        assert {slot(lane >> g, (q << g) | (lane & 3)) for lane in range(32) for q in range(NL)} == set(range(NL * 32))
+        for q in range(NL):
+            assert len({slot(lane >> g, (q << g) | (lane & 3)) % 32 for lane in range(32)}) == 32
+        for q4 in range(0, NL, 4):
+            for quarter in range(4):
+                words = [slot(lane >> g, ((lane & 3) << LB) | q4) for lane in range(8 * quarter, 8 * quarter + 8)]
+                assert all(w % 4 == 0 for w in words) and len({(w % 32) // 4 for w in words}) == 8
+        for lane in range(32):
+            fw, t = lane >> g, lane & (T - 1)
+            wr_base = (t << (LB - g)) * 32 + ((fw + 2 * t) & 7) * 4
+            rd_base = [((fw + 2 * k) & 7) * 4 + t for k in range(4)]
+            for q in range(NL):
+                assert wr_base + (q >> 2) * 32 + (q & 3) == slot(fw, (t << LB) | q)
+                assert rd_base[(q >> (LB - g)) & 3] + q * 32 == slot(fw, (q << g) | t)
 
 
 def test_hist_group_record_position_of_a_state():

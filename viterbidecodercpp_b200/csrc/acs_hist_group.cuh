@@ -40,11 +40,13 @@ struct HistGroupShape {
         while (b) { const int r = g % b; g = b; b = r; }          // gcd(LB, 16)
         return PH != LB - 1 && ((PH + 1) % g) == 0;
     }
-    // shared-memory word of position PHI' for frame fw of the warp: rows of 32 words, XOR swizzle so that the 64 writes of a lane
-    // ((t << LB) | q: consecutive q) and its 64 reads ((q << LOGT) | t) both touch 32 distinct banks per warp instruction
+    // shared-memory word of position PHI' for frame fw of the warp: rows of 32 words = 8 groups of 4; position (qp, tp) sits in row
+    // qp, group (fw + 2 * (qp >> (LB - 2))) mod 8, word tp.  A lane writes (t << LB) | q for consecutive q: four consecutive q are one
+    // aligned group (STS.128), and the 8 lanes of a quarter warp - two frames x four t - hit 8 different groups; its reads
+    // ((q << LOGT) | t, fixed q) touch 32 distinct banks per warp instruction.
     static __host__ __device__ constexpr uint32_t slot(uint32_t fw, uint32_t phi) {
         const uint32_t qp = phi >> LOGT, tp = phi & uint32_t(T - 1);
-        return qp * 32u + ((fw * uint32_t(T) + tp) ^ ((qp >> (LB - LOGT)) & uint32_t(T - 1)));
+        return qp * 32u + ((fw + 2u * (qp >> (LB - LOGT))) & 7u) * 4u + tp;
     }
 };
 
@@ -144,7 +146,7 @@ template <class C, int TIE_SIMD, bool CONSISTENT>
 __global__ void __launch_bounds__(32 * HistGroupShape<C>::WARPS, 7) acs_hist_group_kernel(const AcsParams p) {
     using S = HistGroupShape<C>;
     constexpr int R = C::R, NL = S::NL, NW = S::NW, LB = S::LB, LOGT = S::LOGT, T = S::T, SB = S::SB, HB = 16;
-    __shared__ uint32_t xch[S::WARPS][NL * 32];
+    __shared__ __align__(16) uint32_t xch[S::WARPS][NL * 32];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, blk = blockIdx.x * (blockDim.x >> 5) + warp;
     if (blk >= p.n_blocks) return;
     const uint32_t fw = lane >> LOGT, t = lane & uint32_t(T - 1);
@@ -179,19 +181,17 @@ __global__ void __launch_bounds__(32 * HistGroupShape<C>::WARPS, 7) acs_hist_gro
     for (int j = 0; j < WPP; j++) nxt[j] = __ldg(row + (uint32_t(j) < maxw ? uint32_t(j) : maxw));
 
     // exchange after LB phases: the value at (q, t) moves to PHI' = (t << LB) | q, read back as PHI' = (q << LOGT) | t.  With the
-    // swizzle of HistGroupShape::slot both sides reduce to four base addresses per lane plus compile-time offsets:
-    //   write (q, t): row (t << (LB-2)) | (q >> 2), column (4 fw + (q & 3)) ^ t      read q: row q, column (4 fw + t) ^ ((q >> (LB-2)) & 3)
-    uint32_t* wr_base[4];
+    // layout of HistGroupShape::slot the write side is one base address per lane and 16-byte stores of four registers, the read side
+    // four base addresses per lane plus compile-time offsets:
+    //   write (q, t): row (t << (LB-2)) | (q >> 2), group (fw + 2 t) & 7, word q & 3      read q: row q, group (fw + 2 (q >> (LB-2))) & 7, word t
+    uint32_t* wr_base = my_xch + (t << (LB - LOGT)) * 32u + ((fw + 2u * t) & 7u) * 4u;
     const uint32_t* rd_base[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        wr_base[k] = my_xch + (t << (LB - LOGT)) * 32u + ((fw * 4u + uint32_t(k)) ^ t);
-        rd_base[k] = my_xch + ((fw * 4u + t) ^ uint32_t(k));
-    }
+    for (int k = 0; k < 4; k++) rd_base[k] = my_xch + ((fw + 2u * uint32_t(k)) & 7u) * 4u + t;
     auto exchange = [&]() {
         __syncwarp();
 #pragma unroll
-        for (int q = 0; q < NL; q++) wr_base[q & 3][(q >> 2) * 32] = x[q];
+        for (int q = 0; q < NL; q += 4) *reinterpret_cast<uint4*>(wr_base + (q >> 2) * 32) = make_uint4(x[q], x[q + 1], x[q + 2], x[q + 3]);
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < NL; q++) x[q] = rd_base[(q >> (LB - LOGT)) & 3][q * 32];
